@@ -1,0 +1,189 @@
+"""Host-side mirror of the reference's interface for the hot path.
+
+``process_qsos`` takes what the MATLAB script ``process_qsos.m`` reads from its ``.mat`` inputs
+(process_qsos.m:4-49) and returns the variables it saves (process_qsos.m:236-244) with the
+same names and shapes, plus ``map_z_dlas`` / ``map_log_nhis`` / ``map_inds``
+(generate_ascii_catalog.m:73-80).  ``voigt`` mirrors the MEX signature
+``profile = voigt(lambdas, z, N [, num_lines])`` (voigt.c:8-13,253-304; default 31 lines).
+
+All compute happens in libgpdla.so (hand-written sm_100a CUDA) through the C ABI of
+``include/gpdla.h``.  PyTorch is used only for device buffers and streams in the
+device-resident entry points.  There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from .params import DEFAULT, Parameters
+
+RESULT_NAMES = ["min_z_dlas", "max_z_dlas", "log_priors_no_dla", "log_priors_dla", "log_likelihoods_no_dla",
+                "log_likelihoods_dla", "log_posteriors_no_dla", "log_posteriors_dla", "model_posteriors",
+                "p_no_dlas", "p_dlas", "map_z_dlas", "map_log_nhis"]
+
+
+def _f64(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _dp(a: np.ndarray):
+    return a.ctypes.data_as(_lib.c_double_p)
+
+
+def pad_spectra(spectra: Dict) -> Dict[str, np.ndarray]:
+    """Ragged cell arrays (preload_qsos.m:73-79) -> padded ``[Q x L_max]`` planes + lengths."""
+    if "lengths" in spectra:
+        return spectra
+    W = spectra["all_wavelengths"]
+    Q = len(W)
+    lengths = np.array([len(w) for w in W], dtype=np.int32)
+    L_max = max(int(lengths.max()) if Q else 1, 1)
+    out = dict(wavelengths=np.zeros((Q, L_max)), flux=np.zeros((Q, L_max)),
+               noise_variance=np.ones((Q, L_max)), pixel_mask=np.ones((Q, L_max), dtype=np.uint8),
+               lengths=lengths, z_qsos=_f64(spectra["z_qsos"]))
+    for q in range(Q):
+        n = lengths[q]
+        out["wavelengths"][q, :n] = spectra["all_wavelengths"][q]
+        out["flux"][q, :n] = spectra["all_flux"][q]
+        out["noise_variance"][q, :n] = spectra["all_noise_variance"][q]
+        out["pixel_mask"][q, :n] = np.asarray(spectra["all_pixel_mask"][q]).astype(np.uint8)
+    return out
+
+
+class DLAProcessor:
+    """A libgpdla context holding the learned null model, the DLA samples and the prior
+    catalogue on one GPU (what process_qsos.m:4-40 loads once before its quasar loop)."""
+
+    def __init__(self, model: Dict, samples: Dict, prior: Dict, params: Parameters = DEFAULT, device: int = 0,
+                 batch_quasars: int = 0):
+        self._lib = _lib.load()
+        self._ctx = ctypes.c_void_p()
+        _lib.check(self._lib.gpdla_create(ctypes.byref(self._ctx), int(device)))
+        self.device = int(device)
+        self.params = params
+        p = _lib.GpdlaParams()
+        self._lib.gpdla_default_parameters(ctypes.byref(p))
+        p.min_lambda, p.max_lambda = params.min_lambda, params.max_lambda
+        p.prior_z_qso_increase = params.prior_z_qso_increase
+        p.min_z_cut, p.max_z_cut = params.min_z_cut, params.max_z_cut
+        p.pixel_spacing, p.num_lines, p.batch_quasars = params.pixel_spacing, params.num_lines, int(batch_quasars)
+        _lib.check(self._lib.gpdla_set_parameters(self._ctx, ctypes.byref(p)), self._ctx)
+        rest, mu, M, lw = (_f64(model[k]) for k in ("rest_wavelengths", "mu", "M", "log_omega"))
+        if M.shape != (rest.size, M.shape[1]) or mu.size != rest.size or lw.size != rest.size:
+            raise ValueError("model arrays must be rest_wavelengths (n,), mu (n,), M (n, k), log_omega (n,)")
+        self.k = int(M.shape[1])
+        _lib.check(self._lib.gpdla_set_model(self._ctx, _dp(rest), rest.size, _dp(mu), _dp(M), self.k, _dp(lw),
+                                             float(model["log_c_0"]), float(model["log_tau_0"]),
+                                             float(model["log_beta"])), self._ctx)
+        off, lnhi, nhi = (_f64(samples[k]).ravel() for k in ("offset_samples", "log_nhi_samples", "nhi_samples"))
+        self.num_dla_samples = int(off.size)
+        _lib.check(self._lib.gpdla_set_samples(self._ctx, _dp(off), _dp(lnhi), _dp(nhi), off.size), self._ctx)
+        pz = _f64(prior["z_qsos"]).ravel()
+        pd = np.ascontiguousarray(np.asarray(prior["dla_ind"]).astype(np.uint8)).ravel()
+        _lib.check(self._lib.gpdla_set_prior(self._ctx, _dp(pz), pd.ctypes.data_as(_lib.c_u8_p), pz.size), self._ctx)
+
+    def close(self):
+        if getattr(self, "_ctx", None) is not None and self._ctx:
+            self._lib.gpdla_destroy(self._ctx)
+            self._ctx = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.gpdla_launch_count(self._ctx))
+
+    # ---------------------------------------------------------------- host buffers (the drop-in call)
+    def process(self, spectra: Dict, return_sample_log_likelihoods: bool = True) -> Dict[str, np.ndarray]:
+        sp = pad_spectra(spectra)
+        W, F, V = _f64(sp["wavelengths"]), _f64(sp["flux"]), _f64(sp["noise_variance"])
+        Mk = np.ascontiguousarray(sp["pixel_mask"], dtype=np.uint8)
+        lengths = np.ascontiguousarray(sp["lengths"], dtype=np.int32)
+        z = _f64(sp["z_qsos"])
+        Q, L_max = W.shape
+        S = self.num_dla_samples
+        out = {n: np.full((Q, 2) if n == "model_posteriors" else (Q,), np.nan) for n in RESULT_NAMES}
+        out["map_inds"] = np.full(Q, -1, dtype=np.int64)
+        if return_sample_log_likelihoods:
+            out["sample_log_likelihoods_dla"] = np.full((Q, S), np.nan)
+        res = _lib.GpdlaResults()
+        for n in _lib.RESULT_F64:
+            setattr(res, n, out[n].ctypes.data if n in out else None)
+        res.map_inds = out["map_inds"].ctypes.data
+        vp = lambda a: ctypes.c_void_p(a.ctypes.data)
+        _lib.check(self._lib.gpdla_process_qsos(self._ctx, Q, L_max, vp(W), vp(F), vp(V), vp(Mk), vp(lengths),
+                                                vp(z), ctypes.byref(res)), self._ctx)
+        return out
+
+    # ---------------------------------------------------------------- device-resident buffers
+    def process_device(self, wavelengths, flux, noise_variance, pixel_mask, lengths, z_qsos,
+                       return_sample_log_likelihoods: bool = False, out: Optional[Dict] = None) -> Dict:
+        """Inputs are CUDA tensors (float64 [Q x L_max], uint8 mask, int32 lengths, float64 z);
+        returns CUDA tensors.  Asynchronous on torch's current stream."""
+        import torch
+        Q, L_max = wavelengths.shape
+        dev = wavelengths.device
+        assert dev.type == "cuda" and dev.index == self.device
+        for t, dt in ((wavelengths, torch.float64), (flux, torch.float64), (noise_variance, torch.float64),
+                      (pixel_mask, torch.uint8), (lengths, torch.int32), (z_qsos, torch.float64)):
+            assert t.is_cuda and t.dtype == dt and t.is_contiguous()
+        if out is None:
+            out = {n: torch.empty((Q, 2) if n == "model_posteriors" else (Q,), dtype=torch.float64, device=dev)
+                   for n in RESULT_NAMES}
+            out["map_inds"] = torch.empty(Q, dtype=torch.int64, device=dev)
+            if return_sample_log_likelihoods:
+                out["sample_log_likelihoods_dla"] = torch.empty((Q, self.num_dla_samples), dtype=torch.float64,
+                                                                device=dev)
+        res = _lib.GpdlaResults()
+        for n in _lib.RESULT_F64:
+            setattr(res, n, out[n].data_ptr() if n in out else None)
+        res.map_inds = out["map_inds"].data_ptr()
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(self._lib.gpdla_process_qsos_device(
+            self._ctx, Q, L_max, wavelengths.data_ptr(), flux.data_ptr(), noise_variance.data_ptr(),
+            pixel_mask.data_ptr(), lengths.data_ptr(), z_qsos.data_ptr(), ctypes.byref(res),
+            ctypes.c_void_p(stream)), self._ctx)
+        return out
+
+
+def process_qsos(model: Dict, samples: Dict, spectra: Dict, prior: Dict, params: Parameters = DEFAULT,
+                 device: int = 0, return_sample_log_likelihoods: bool = True) -> Dict[str, np.ndarray]:
+    """Run the DLA detection algorithm on the given objects (process_qsos.m)."""
+    proc = DLAProcessor(model, samples, prior, params, device)
+    try:
+        return proc.process(spectra, return_sample_log_likelihoods)
+    finally:
+        proc.close()
+
+
+def voigt(lambdas: Sequence[float], z: float, N: float, num_lines: int = _lib.MAX_LINES) -> np.ndarray:
+    """``profile = voigt(lambdas, z, N [, num_lines])`` (voigt.c:253-304): Voigt absorption profile of the
+    first ``num_lines`` Lyman-series members for a cloud of column density ``N`` (cm^-2) at redshift ``z``,
+    convolved with the 7-pixel instrument profile; returns ``len(lambdas) - 6`` values."""
+    lib = _lib.load()
+    lam = _f64(lambdas).ravel()
+    out = np.empty(max(lam.size - 6, 0))
+    _lib.check(lib.gpdla_voigt(_dp(lam), lam.size, float(z), float(N), int(num_lines), _dp(out)))
+    return out
+
+
+def voigt_batch(lambdas, z, N, num_lines: int = _lib.MAX_LINES):
+    """Device-resident batched ``voigt``: CUDA float64 tensors ``lambdas`` (P,), ``z`` (S,), ``N`` (S,) ->
+    ``(S, P - 6)`` CUDA tensor, on torch's current stream."""
+    import torch
+    lib = _lib.load()
+    assert lambdas.is_cuda and lambdas.dtype == torch.float64 and z.dtype == torch.float64 and N.dtype == torch.float64
+    lambdas, z, N = lambdas.contiguous(), z.contiguous(), N.contiguous()
+    out = torch.empty((z.numel(), lambdas.numel() - 6), dtype=torch.float64, device=lambdas.device)
+    with torch.cuda.device(lambdas.device):
+        stream = torch.cuda.current_stream().cuda_stream
+        _lib.check(lib.gpdla_voigt_batch_device(lambdas.data_ptr(), lambdas.numel(), z.data_ptr(), N.data_ptr(),
+                                                z.numel(), int(num_lines), out.data_ptr(), ctypes.c_void_p(stream)))
+    return out

@@ -1,0 +1,463 @@
+// C ABI of libgpdla.so (see include/gpdla.h).  Host-side runtime: context, device workspaces,
+// batching of quasars, kernel dispatch.  No CPU compute path exists in this library.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/gpdla.h"
+#include "gpdla_kernels.cuh"
+
+using namespace gpdla;
+
+// ---------------------------------------------------------------------------- Lyman series data
+// Physical data of the hydrogen Lyman series, members 1..31 (the same atomic data the reference
+// tabulates at voigt.c:31-134): wavelength (cm), oscillator strength, transition rate (1/s).
+namespace {
+struct LymanLine { double wavelength_cm, f, Gamma; };
+const LymanLine kLyman[MAX_LINES] = {
+    {1.2156701e-05, 0.416400, 6.265e+08},  {1.0257223e-05, 0.079120, 1.897e+08},
+    {9.725368e-06, 0.029000, 8.127e+07},   {9.497431e-06, 0.013940, 4.204e+07},
+    {9.378035e-06, 0.007799, 2.450e+07},   {9.307483e-06, 0.004814, 1.236e+07},
+    {9.262257e-06, 0.003183, 8.255e+06},   {9.231504e-06, 0.002216, 5.785e+06},
+    {9.209631e-06, 0.001605, 4.210e+06},   {9.193514e-06, 0.00120, 3.160e+06},
+    {9.181294e-06, 0.000921, 2.432e+06},   {9.171806e-06, 0.0007226, 1.911e+06},
+    {9.16429e-06, 0.000577, 1.529e+06},    {9.15824e-06, 0.000469, 1.243e+06},
+    {9.15329e-06, 0.000386, 1.024e+06},    {9.14919e-06, 0.000321, 8.533e+05},
+    {9.14576e-06, 0.000270, 7.186e+05},    {9.14286e-06, 0.000230, 6.109e+05},
+    {9.14039e-06, 0.000197, 5.237e+05},    {9.13826e-06, 0.000170, 4.523e+05},
+    {9.13641e-06, 0.000148, 3.933e+05},    {9.13480e-06, 0.000129, 3.443e+05},
+    {9.13339e-06, 0.000114, 3.030e+05},    {9.13215e-06, 0.000101, 2.679e+05},
+    {9.13104e-06, 0.000089, 2.382e+05},    {9.13006e-06, 0.000080, 2.127e+05},
+    {9.12918e-06, 0.000071, 1.907e+05},    {9.12839e-06, 0.000064, 1.716e+05},
+    {9.12768e-06, 0.000058, 1.550e+05},    {9.12703e-06, 0.000053, 1.405e+05},
+    {9.12645e-06, 0.000048, 1.277e+05}};
+const double kC = 2.99792458e+10;               // speed of light, cm/s           voigt.c:22
+const double kE = 4.803204672997660e-10;        // elementary charge, statC       voigt.c:27
+const double kMe = 9.10938356e-28;              // electron mass, g               voigt.c:25
+const double kSigma = 9.08537121627923800e+05;  // Gaussian width b/sqrt2, cm/s   voigt.c:41
+// BOSS instrument profile, R = 2000, 1e-4 dex pixels, +-3 pixels             voigt.c:242-251
+const double kInstrument[7] = {2.17460992138080811e-03, 4.11623059580451742e-02, 2.40309364651846963e-01,
+                               4.32707438937454059e-01, 2.40309364651846963e-01, 4.11623059580451742e-02,
+                               2.17460992138080811e-03};
+
+void fill_line_constants(LineConstants* lc) {
+  for (int i = 0; i < MAX_LINES; ++i) {
+    lc->tw[i] = kLyman[i].wavelength_cm;
+    // voigt.c:141-143: M_PI * e * e * oscillator_strength * transition_wavelength / (m_e * c)
+    lc->lc[i] = M_PI * kE * kE * kLyman[i].f * kLyman[i].wavelength_cm / (kMe * kC);
+    // voigt.c:186: Gamma * transition_wavelength / (4 * M_PI)
+    lc->gam[i] = kLyman[i].Gamma * kLyman[i].wavelength_cm / (4 * M_PI);
+    lc->y[i] = lc->gam[i] / sqrt(2.0) / kSigma;
+    lc->y2[i] = lc->y[i] * lc->y[i];
+    lc->kcore[i] = lc->lc[i] / (sqrt(2.0 * M_PI) * kSigma);
+    lc->kwing[i] = lc->kcore[i] * lc->y[i] / sqrt(M_PI);
+  }
+  for (int i = 0; i < 7; ++i) lc->ip[i] = kInstrument[i];
+  lc->c = kC;
+  lc->inv_s2s = 1.0 / (sqrt(2.0) * kSigma);
+}
+
+thread_local std::string g_err;   // errors of the context-free entry points
+
+#define CUDA_TRY(expr, errstr)                                                              \
+  do {                                                                                      \
+    cudaError_t e__ = (expr);                                                               \
+    if (e__ != cudaSuccess) {                                                               \
+      char buf__[512];                                                                      \
+      snprintf(buf__, sizeof buf__, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+      (errstr) = buf__;                                                                     \
+      return GPDLA_ERR_CUDA;                                                                \
+    }                                                                                       \
+  } while (0)
+
+int upload_line_constants(std::string& err) {
+  int dev = -1;
+  CUDA_TRY(cudaGetDevice(&dev), err);
+  static std::vector<char> done;   // per device
+  if ((int)done.size() <= dev) done.resize(dev + 1, 0);
+  if (done[dev]) return GPDLA_OK;
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, dev), err);
+  if (prop.major != 10) {
+    err = "libgpdla.so is built for sm_100a (B200) only; device is sm_" + std::to_string(prop.major) +
+          std::to_string(prop.minor);
+    return GPDLA_ERR_CUDA;
+  }
+  LineConstants lc;
+  fill_line_constants(&lc);
+  CUDA_TRY(cudaMemcpyToSymbol(c_lines, &lc, sizeof lc), err);
+  done[dev] = 1;
+  return GPDLA_OK;
+}
+
+template <class T>
+int dev_upload(T** dst, const T* src, size_t n, std::string& err) {
+  if (*dst) { cudaFree(*dst); *dst = nullptr; }
+  CUDA_TRY(cudaMalloc(dst, std::max<size_t>(n, 1) * sizeof(T)), err);
+  CUDA_TRY(cudaMemcpy(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice), err);
+  return GPDLA_OK;
+}
+}  // namespace
+
+struct gpdla_ctx {
+  int device = 0;
+  std::string err;
+  uint64_t launches = 0;
+  gpdla_params params;
+  // null model
+  double *d_rest = nullptr, *d_mu = nullptr, *d_M = nullptr, *d_log_omega = nullptr;
+  int n_rest = 0, k = 0;
+  double c_0 = 0, tau_0 = 0, beta = 0;
+  // DLA samples
+  double *d_offset = nullptr, *d_log_nhi = nullptr, *d_nhi = nullptr;
+  int64_t S = 0;
+  // prior catalogue
+  double* d_prior_z = nullptr;
+  uint8_t* d_prior_dla = nullptr;
+  int64_t n_prior = -1;
+  // per-batch workspace
+  int ws_batch = 0, ws_npix = 0, ws_k = 0;
+  int64_t ws_S = 0;
+  QuasarMeta* d_meta = nullptr;
+  double *d_lam = nullptr, *d_pix = nullptr, *d_Mq = nullptr, *d_P = nullptr, *d_sll = nullptr, *d_scratch = nullptr;
+  int64_t* d_scratch_i = nullptr;
+  // staging for the host entry point
+  size_t st_bytes = 0;
+  void* d_stage = nullptr;
+};
+
+static void free_workspace(gpdla_ctx* c) {
+  cudaFree(c->d_meta); cudaFree(c->d_lam); cudaFree(c->d_pix); cudaFree(c->d_Mq); cudaFree(c->d_P);
+  cudaFree(c->d_sll); cudaFree(c->d_scratch); cudaFree(c->d_scratch_i);
+  c->d_meta = nullptr; c->d_lam = c->d_pix = c->d_Mq = c->d_P = c->d_sll = c->d_scratch = nullptr;
+  c->d_scratch_i = nullptr;
+  c->ws_batch = c->ws_npix = c->ws_k = 0; c->ws_S = 0;
+}
+
+static int ensure_workspace(gpdla_ctx* c, int batch, int npix) {
+  if (c->ws_batch >= batch && c->ws_npix == npix && c->ws_k == c->k && c->ws_S == c->S) return GPDLA_OK;
+  free_workspace(c);
+  using G = GramShape<20>;
+  const size_t B = batch;
+  CUDA_TRY(cudaMalloc(&c->d_meta, B * sizeof(QuasarMeta)), c->err);
+  CUDA_TRY(cudaMalloc(&c->d_lam, B * (npix + 8) * sizeof(double)), c->err);
+  CUDA_TRY(cudaMalloc(&c->d_pix, B * npix * 4 * sizeof(double)), c->err);
+  CUDA_TRY(cudaMalloc(&c->d_Mq, B * npix * c->k * sizeof(double)), c->err);
+  CUDA_TRY(cudaMalloc(&c->d_P, B * (npix / KC) * G::CHUNK_DOUBLES * sizeof(double)), c->err);
+  CUDA_TRY(cudaMalloc(&c->d_sll, B * c->S * sizeof(double)), c->err);
+  CUDA_TRY(cudaMalloc(&c->d_scratch, B * 16 * sizeof(double)), c->err);
+  CUDA_TRY(cudaMalloc(&c->d_scratch_i, B * sizeof(int64_t)), c->err);
+  c->ws_batch = batch; c->ws_npix = npix; c->ws_k = c->k; c->ws_S = c->S;
+  return GPDLA_OK;
+}
+
+template <int K, int WM, int WN, int MT, int NL>
+static int launch_loglik(gpdla_ctx* c, const LoglikArgs& la, int nq, cudaStream_t st) {
+  using Cfg = LoglikConfig<K, WM, WN, MT>;
+  auto kern = dla_loglik_kernel<K, WM, WN, MT, NL>;
+  const size_t smem = Cfg::smem_bytes(la.num_lines);
+  static size_t configured = 0;
+  if (configured < smem) {
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), c->err);
+    configured = smem;
+  }
+  dim3 grid((unsigned)((la.S + 1 + Cfg::TS - 1) / Cfg::TS), (unsigned)nq);
+  kern<<<grid, NTHREADS, smem, st>>>(la);
+  c->launches++;
+  CUDA_TRY(cudaGetLastError(), c->err);
+  return GPDLA_OK;
+}
+
+extern "C" {
+
+void gpdla_default_parameters(gpdla_params* p) {
+  const double c = 299792458.0;
+  p->min_lambda = 911.75; p->max_lambda = 1215.75;
+  p->lya_wavelength = 1215.6701; p->lyman_limit = 911.7633;
+  p->prior_z_qso_increase = (30000.0 * 1000.0) / c;
+  p->min_z_cut = (3000.0 * 1000.0) / c; p->max_z_cut = (3000.0 * 1000.0) / c;
+  p->pixel_spacing = 1e-4;
+  p->num_lines = 3;
+  p->batch_quasars = 0;
+}
+
+void gpdla_line_constants(double* tw, double* lcs, double* gam, double* ip) {
+  LineConstants lc;
+  fill_line_constants(&lc);
+  if (tw) memcpy(tw, lc.tw, sizeof lc.tw);
+  if (lcs) memcpy(lcs, lc.lc, sizeof lc.lc);
+  if (gam) memcpy(gam, lc.gam, sizeof lc.gam);
+  if (ip) memcpy(ip, lc.ip, sizeof lc.ip);
+}
+
+int gpdla_create(gpdla_ctx** out, int device) {
+  if (!out) return GPDLA_ERR_INVALID;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+    g_err = "no CUDA device " + std::to_string(device) + " (libgpdla.so has no CPU fallback)";
+    return GPDLA_ERR_CUDA;
+  }
+  gpdla_ctx* ctx = new gpdla_ctx;
+  ctx->device = device;
+  gpdla_default_parameters(&ctx->params);
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) { g_err = cudaGetErrorString(e); delete ctx; return GPDLA_ERR_CUDA; }
+  int rc = upload_line_constants(g_err);
+  if (rc != GPDLA_OK) { delete ctx; return rc; }
+  *out = ctx;
+  return GPDLA_OK;
+}
+
+void gpdla_destroy(gpdla_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  free_workspace(c);
+  cudaFree(c->d_rest); cudaFree(c->d_mu); cudaFree(c->d_M); cudaFree(c->d_log_omega);
+  cudaFree(c->d_offset); cudaFree(c->d_log_nhi); cudaFree(c->d_nhi);
+  cudaFree(c->d_prior_z); cudaFree(c->d_prior_dla); cudaFree(c->d_stage);
+  delete c;
+}
+
+const char* gpdla_last_error(const gpdla_ctx* c) { return c ? c->err.c_str() : g_err.c_str(); }
+uint64_t gpdla_launch_count(const gpdla_ctx* c) { return c ? c->launches : 0; }
+
+int gpdla_set_parameters(gpdla_ctx* c, const gpdla_params* p) {
+  if (!c || !p) return GPDLA_ERR_INVALID;
+  if (p->num_lines < 1 || p->num_lines > GPDLA_MAX_LINES || !(p->max_lambda > p->min_lambda) ||
+      p->batch_quasars < 0) {
+    c->err = "gpdla_set_parameters: invalid parameters";
+    return GPDLA_ERR_INVALID;
+  }
+  c->params = *p;
+  return GPDLA_OK;
+}
+
+int gpdla_set_model(gpdla_ctx* c, const double* rest, int32_t n_rest, const double* mu, const double* M, int32_t k,
+                    const double* log_omega, double log_c_0, double log_tau_0, double log_beta) {
+  if (!c || !rest || !mu || !M || !log_omega || n_rest < 2 || k < 1) return GPDLA_ERR_INVALID;
+  if (k != 20) {
+    c->err = "gpdla_set_model: rank k=" + std::to_string(k) + " not compiled in (available: 20)";
+    return GPDLA_ERR_UNSUPPORTED;
+  }
+  CUDA_TRY(cudaSetDevice(c->device), c->err);
+  int rc;
+  if ((rc = dev_upload(&c->d_rest, rest, n_rest, c->err))) return rc;
+  if ((rc = dev_upload(&c->d_mu, mu, n_rest, c->err))) return rc;
+  if ((rc = dev_upload(&c->d_M, M, (size_t)n_rest * k, c->err))) return rc;
+  if ((rc = dev_upload(&c->d_log_omega, log_omega, n_rest, c->err))) return rc;
+  c->n_rest = n_rest; c->k = k;
+  c->c_0 = exp(log_c_0); c->tau_0 = exp(log_tau_0); c->beta = exp(log_beta);   // process_qsos.m:84-86
+  return GPDLA_OK;
+}
+
+int gpdla_set_samples(gpdla_ctx* c, const double* offset, const double* log_nhi, const double* nhi, int64_t S) {
+  if (!c || !offset || !log_nhi || !nhi || S < 1) return GPDLA_ERR_INVALID;
+  CUDA_TRY(cudaSetDevice(c->device), c->err);
+  int rc;
+  if ((rc = dev_upload(&c->d_offset, offset, S, c->err))) return rc;
+  if ((rc = dev_upload(&c->d_log_nhi, log_nhi, S, c->err))) return rc;
+  if ((rc = dev_upload(&c->d_nhi, nhi, S, c->err))) return rc;
+  c->S = S;
+  return GPDLA_OK;
+}
+
+int gpdla_set_prior(gpdla_ctx* c, const double* z_qsos, const uint8_t* dla_ind, int64_t n) {
+  if (!c || n < 0 || (n > 0 && (!z_qsos || !dla_ind))) return GPDLA_ERR_INVALID;
+  CUDA_TRY(cudaSetDevice(c->device), c->err);
+  int rc;
+  if ((rc = dev_upload(&c->d_prior_z, z_qsos, n, c->err))) return rc;
+  if ((rc = dev_upload(&c->d_prior_dla, dla_ind, n, c->err))) return rc;
+  c->n_prior = n;
+  return GPDLA_OK;
+}
+
+int gpdla_process_qsos_device(gpdla_ctx* c, int64_t Q, int64_t L_max, const double* wavelengths, const double* flux,
+                              const double* noise_variance, const uint8_t* pixel_mask, const int32_t* lengths,
+                              const double* z_qsos, const gpdla_results* out, void* stream) {
+  if (!c) return GPDLA_ERR_INVALID;
+  if (Q < 0 || L_max < 1 || !out || (Q > 0 && (!wavelengths || !flux || !noise_variance || !pixel_mask || !lengths || !z_qsos))) {
+    c->err = "gpdla_process_qsos_device: invalid arguments";
+    return GPDLA_ERR_INVALID;
+  }
+  if (!c->d_M || !c->d_offset || c->n_prior < 0) {
+    c->err = "gpdla_process_qsos: set_model, set_samples and set_prior must be called first";
+    return GPDLA_ERR_STATE;
+  }
+  if (Q == 0) return GPDLA_OK;
+  CUDA_TRY(cudaSetDevice(c->device), c->err);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int npix = (int)((L_max + KC - 1) / KC) * KC;
+  int batch = c->params.batch_quasars > 0 ? c->params.batch_quasars : 296;
+  batch = (int)std::min<int64_t>(batch, Q);
+  int rc = ensure_workspace(c, batch, npix);
+  if (rc) return rc;
+  batch = c->ws_batch;
+  using G = GramShape<20>;
+
+  for (int64_t q0 = 0; q0 < Q; q0 += batch) {
+    const int nq = (int)std::min<int64_t>(batch, Q - q0);
+    PrepArgs pa;
+    pa.wavelengths = wavelengths + q0 * L_max; pa.flux = flux + q0 * L_max;
+    pa.noise_variance = noise_variance + q0 * L_max; pa.pixel_mask = pixel_mask + q0 * L_max;
+    pa.lengths = lengths + q0; pa.z_qsos = z_qsos + q0; pa.L_max = L_max;
+    pa.rest_wavelengths = c->d_rest; pa.mu = c->d_mu; pa.M = c->d_M; pa.log_omega = c->d_log_omega;
+    pa.n_rest = c->n_rest; pa.k = c->k; pa.c_0 = c->c_0; pa.tau_0 = c->tau_0; pa.beta = c->beta;
+    pa.prior_z_qsos = c->d_prior_z; pa.prior_dla_ind = c->d_prior_dla; pa.n_prior = c->n_prior;
+    pa.min_lambda = c->params.min_lambda; pa.max_lambda = c->params.max_lambda;
+    pa.lya_wavelength = c->params.lya_wavelength; pa.lyman_limit = c->params.lyman_limit;
+    pa.prior_z_qso_increase = c->params.prior_z_qso_increase; pa.min_z_cut = c->params.min_z_cut;
+    pa.max_z_cut = c->params.max_z_cut; pa.pixel_spacing = c->params.pixel_spacing;
+    pa.meta = c->d_meta; pa.lam_pad = c->d_lam; pa.pix = c->d_pix; pa.Mq = c->d_Mq; pa.NPIX = npix;
+    prepare_quasars_kernel<<<nq, NTHREADS, 0, st>>>(pa);
+    c->launches++;
+    CUDA_TRY(cudaGetLastError(), c->err);
+    build_gram_operand_kernel<20><<<dim3(npix / KC, nq), NTHREADS, 0, st>>>(c->d_Mq, c->d_meta, c->d_P, npix);
+    c->launches++;
+    CUDA_TRY(cudaGetLastError(), c->err);
+
+    double* sll = out->sample_log_likelihoods_dla ? out->sample_log_likelihoods_dla + q0 * c->S : c->d_sll;
+    double* llno = out->log_likelihoods_no_dla ? out->log_likelihoods_no_dla + q0 : c->d_scratch;
+    LoglikArgs la;
+    la.meta = c->d_meta; la.lam_pad = c->d_lam; la.pix = c->d_pix; la.P = c->d_P;
+    la.offset_samples = c->d_offset; la.nhi_samples = c->d_nhi; la.S = c->S;
+    la.num_lines = c->params.num_lines; la.NPIX = npix;
+    la.sample_log_likelihoods = sll; la.log_likelihoods_no_dla = llno;
+    if (c->params.num_lines == 3) rc = launch_loglik<20, 4, 2, 2, 3>(c, la, nq, st);
+    else rc = launch_loglik<20, 4, 2, 2, 0>(c, la, nq, st);
+    if (rc) return rc;
+
+    EvidenceArgs ea;
+    ea.meta = c->d_meta; ea.sample_log_likelihoods = sll; ea.log_likelihoods_no_dla = llno;
+    ea.offset_samples = c->d_offset; ea.log_nhi_samples = c->d_log_nhi; ea.S = c->S;
+    double* scr = c->d_scratch + batch;   // 15 more scratch columns of `batch` doubles
+    auto pick = [&](double* p, int col) { return p ? p + q0 : scr + (size_t)col * batch; };
+    ea.min_z_dlas = pick(out->min_z_dlas, 0); ea.max_z_dlas = pick(out->max_z_dlas, 1);
+    ea.log_priors_no_dla = pick(out->log_priors_no_dla, 2); ea.log_priors_dla = pick(out->log_priors_dla, 3);
+    ea.log_likelihoods_dla = pick(out->log_likelihoods_dla, 4);
+    ea.log_posteriors_no_dla = pick(out->log_posteriors_no_dla, 5);
+    ea.log_posteriors_dla = pick(out->log_posteriors_dla, 6);
+    ea.model_posteriors = out->model_posteriors ? out->model_posteriors + 2 * q0 : scr + (size_t)7 * batch;   // 2 cols
+    ea.p_no_dlas = pick(out->p_no_dlas, 9); ea.p_dlas = pick(out->p_dlas, 10);
+    ea.map_z_dlas = pick(out->map_z_dlas, 11); ea.map_log_nhis = pick(out->map_log_nhis, 12);
+    ea.map_inds = out->map_inds ? out->map_inds + q0 : c->d_scratch_i;
+    evidence_kernel<<<nq, NTHREADS, 0, st>>>(ea);
+    c->launches++;
+    CUDA_TRY(cudaGetLastError(), c->err);
+  }
+  return GPDLA_OK;
+}
+
+int gpdla_process_qsos(gpdla_ctx* c, int64_t Q, int64_t L_max, const double* wavelengths, const double* flux,
+                       const double* noise_variance, const uint8_t* pixel_mask, const int32_t* lengths,
+                       const double* z_qsos, const gpdla_results* out) {
+  if (!c) return GPDLA_ERR_INVALID;
+  if (Q < 0 || L_max < 1 || !out) { c->err = "gpdla_process_qsos: invalid arguments"; return GPDLA_ERR_INVALID; }
+  if (!c->d_M || !c->d_offset || c->n_prior < 0) {
+    c->err = "gpdla_process_qsos: set_model, set_samples and set_prior must be called first";
+    return GPDLA_ERR_STATE;
+  }
+  if (Q == 0) return GPDLA_OK;
+  CUDA_TRY(cudaSetDevice(c->device), c->err);
+  const size_t QL = (size_t)Q * L_max;
+  const bool want_sll = out->sample_log_likelihoods_dla != nullptr;
+  // one device staging block: 3 double planes + lengths/z + mask + 14 result columns (+ Q x S)
+  const size_t n_res = 14;
+  size_t bytes = 3 * QL * 8 + (size_t)Q * 8 + (n_res + 1) * Q * 8 + (size_t)Q * 8 + (size_t)Q * 4 + QL + 64 +
+                 (want_sll ? (size_t)Q * c->S * 8 : 0);
+  if (c->st_bytes < bytes) {
+    cudaFree(c->d_stage); c->d_stage = nullptr; c->st_bytes = 0;
+    CUDA_TRY(cudaMalloc(&c->d_stage, bytes), c->err);
+    c->st_bytes = bytes;
+  }
+  char* p = (char*)c->d_stage;
+  auto take = [&](size_t n) { char* r = p; p += (n + 15) / 16 * 16; return r; };
+  double* d_w = (double*)take(QL * 8); double* d_f = (double*)take(QL * 8); double* d_v = (double*)take(QL * 8);
+  double* d_z = (double*)take(Q * 8);
+  double* d_res = (double*)take((n_res + 1) * Q * 8);
+  int64_t* d_map = (int64_t*)take(Q * 8);
+  double* d_sll = want_sll ? (double*)take((size_t)Q * c->S * 8) : nullptr;
+  int32_t* d_len = (int32_t*)take(Q * 4);
+  uint8_t* d_m = (uint8_t*)take(QL);
+  cudaStream_t st = 0;
+  CUDA_TRY(cudaMemcpyAsync(d_w, wavelengths, QL * 8, cudaMemcpyHostToDevice, st), c->err);
+  CUDA_TRY(cudaMemcpyAsync(d_f, flux, QL * 8, cudaMemcpyHostToDevice, st), c->err);
+  CUDA_TRY(cudaMemcpyAsync(d_v, noise_variance, QL * 8, cudaMemcpyHostToDevice, st), c->err);
+  CUDA_TRY(cudaMemcpyAsync(d_m, pixel_mask, QL, cudaMemcpyHostToDevice, st), c->err);
+  CUDA_TRY(cudaMemcpyAsync(d_len, lengths, Q * 4, cudaMemcpyHostToDevice, st), c->err);
+  CUDA_TRY(cudaMemcpyAsync(d_z, z_qsos, Q * 8, cudaMemcpyHostToDevice, st), c->err);
+  gpdla_results dr;
+  dr.min_z_dlas = d_res + 0 * Q; dr.max_z_dlas = d_res + 1 * Q;
+  dr.log_priors_no_dla = d_res + 2 * Q; dr.log_priors_dla = d_res + 3 * Q;
+  dr.log_likelihoods_no_dla = d_res + 4 * Q; dr.log_likelihoods_dla = d_res + 5 * Q;
+  dr.log_posteriors_no_dla = d_res + 6 * Q; dr.log_posteriors_dla = d_res + 7 * Q;
+  dr.p_no_dlas = d_res + 8 * Q; dr.p_dlas = d_res + 9 * Q;
+  dr.map_z_dlas = d_res + 10 * Q; dr.map_log_nhis = d_res + 11 * Q;
+  dr.model_posteriors = d_res + 12 * Q;   // 2 columns
+  dr.map_inds = d_map;
+  dr.sample_log_likelihoods_dla = d_sll;
+  int rc = gpdla_process_qsos_device(c, Q, L_max, d_w, d_f, d_v, d_m, d_len, d_z, &dr, st);
+  if (rc) return rc;
+  double* hptr[12] = {out->min_z_dlas, out->max_z_dlas, out->log_priors_no_dla, out->log_priors_dla,
+                      out->log_likelihoods_no_dla, out->log_likelihoods_dla, out->log_posteriors_no_dla,
+                      out->log_posteriors_dla, out->p_no_dlas, out->p_dlas, out->map_z_dlas, out->map_log_nhis};
+  for (size_t i = 0; i < 12; ++i)
+    if (hptr[i]) CUDA_TRY(cudaMemcpyAsync(hptr[i], d_res + i * Q, Q * 8, cudaMemcpyDeviceToHost, st), c->err);
+  if (out->model_posteriors)
+    CUDA_TRY(cudaMemcpyAsync(out->model_posteriors, d_res + 12 * Q, 2 * Q * 8, cudaMemcpyDeviceToHost, st), c->err);
+  if (out->map_inds) CUDA_TRY(cudaMemcpyAsync(out->map_inds, d_map, Q * 8, cudaMemcpyDeviceToHost, st), c->err);
+  if (want_sll)
+    CUDA_TRY(cudaMemcpyAsync(out->sample_log_likelihoods_dla, d_sll, (size_t)Q * c->S * 8, cudaMemcpyDeviceToHost, st),
+             c->err);
+  CUDA_TRY(cudaStreamSynchronize(st), c->err);
+  return GPDLA_OK;
+}
+
+int gpdla_voigt_batch_device(const double* lambdas, int64_t num_points, const double* z, const double* N, int64_t S,
+                             int32_t num_lines, double* profile, void* stream) {
+  if (!lambdas || !z || !N || !profile || num_points < 7 || S < 1 || S > 65535 || num_lines < 1 ||
+      num_lines > GPDLA_MAX_LINES) {
+    g_err = "gpdla_voigt: invalid arguments (need num_points >= 7, 1 <= num_lines <= 31, 1 <= S <= 65535)";
+    return GPDLA_ERR_INVALID;
+  }
+  int rc = upload_line_constants(g_err);
+  if (rc) return rc;
+  const int64_t n_out = num_points - 6;
+  dim3 grid((unsigned)((n_out + NTHREADS - 1) / NTHREADS), (unsigned)S);
+  voigt_batch_kernel<<<grid, NTHREADS, 0, (cudaStream_t)stream>>>(lambdas, num_points, z, N, num_lines, profile);
+  CUDA_TRY(cudaGetLastError(), g_err);
+  return GPDLA_OK;
+}
+
+int gpdla_voigt(const double* lambdas, int64_t num_points, double z, double N, int32_t num_lines, double* profile) {
+  if (!lambdas || !profile || num_points < 7 || num_lines < 1 || num_lines > GPDLA_MAX_LINES || !(z > -1.0) ||
+      !isfinite(z) || !isfinite(N)) {
+    g_err = "gpdla_voigt: invalid arguments (need num_points >= 7, 1 <= num_lines <= 31, finite z > -1)";
+    return GPDLA_ERR_INVALID;
+  }
+  double* d = nullptr;
+  const size_t n_out = num_points - 6;
+  CUDA_TRY(cudaMalloc(&d, (num_points + n_out + 2) * sizeof(double)), g_err);
+  double zn[2] = {z, N};
+  cudaError_t e1 = cudaMemcpy(d, lambdas, num_points * sizeof(double), cudaMemcpyHostToDevice);
+  cudaError_t e2 = cudaMemcpy(d + num_points, zn, sizeof zn, cudaMemcpyHostToDevice);
+  int rc = GPDLA_ERR_CUDA;
+  if (e1 == cudaSuccess && e2 == cudaSuccess) {
+    rc = gpdla_voigt_batch_device(d, num_points, d + num_points, d + num_points + 1, 1, num_lines, d + num_points + 2, 0);
+    if (rc == GPDLA_OK) {
+      cudaError_t e3 = cudaMemcpy(profile, d + num_points + 2, n_out * sizeof(double), cudaMemcpyDeviceToHost);
+      if (e3 != cudaSuccess) { g_err = cudaGetErrorString(e3); rc = GPDLA_ERR_CUDA; }
+    }
+  } else {
+    g_err = cudaGetErrorString(e1 != cudaSuccess ? e1 : e2);
+  }
+  cudaFree(d);
+  return rc;
+}
+
+}  // extern "C"

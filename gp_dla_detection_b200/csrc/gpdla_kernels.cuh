@@ -1,0 +1,662 @@
+// sm_100a kernels of the per-quasar DLA model-selection hot path.
+//
+//   K0  prepare_quasars_kernel   process_qsos.m:96-181   window/mask, priors, model interpolation,
+//                                                        z range, padded grid, Gram operand P
+//   K1  voigt_batch_kernel       voigt.c:253-304         stand-alone absorption profiles (API `voigt`)
+//   K1+K2+K3 dla_loglik_kernel   process_qsos.m:185-199 + log_mvnpdf_low_rank.m:5-34, fused:
+//        Voigt profile -> weights -> FP64 DMMA Gram/projection -> Cholesky, log-det, quadratic form
+//   K4  evidence_kernel          process_qsos.m:203-233 + generate_ascii_catalog.m:73-80
+//
+// Reformulation: with a = absorption, d = a^2 omega^2 + v, w = a^2/d, u = a (y - a mu)/d
+//   B_s - I = sum_i w_i m_i m_i'   ->  [S x n] . [n x k(k+1)/2]   (operand P, shared by all samples)
+//   g_s     = sum_i u_i m_i        ->  [S x n] . [n x k]
+//   log p_s = -1/2 ( sum r^2/d - |R'^-1 g|^2 + sum log d + log det B + n log 2pi ),  R'R = B.
+#pragma once
+#include <stdint.h>
+#include "gpdla_math.cuh"
+
+namespace gpdla {
+
+constexpr int KC = 32;            // pixels per K-chunk of the Gram contraction
+constexpr int RAWW = 64;          // circular raw-profile buffer width (>= KC + 6, power of two)
+constexpr int NTHREADS = 256;     // 8 warps per CTA
+constexpr double LOG_2PI = 1.83787706640934534;   // log_mvnpdf_low_rank.m:7
+
+struct QuasarMeta {               // one per quasar, written by K0
+  int n_u;                        // pixels inside the modelled window (incl. masked)   process_qsos.m:104-108
+  int n;                          // pixels used (window & ~mask)                       process_qsos.m:110
+  int nchunks;                    // ceil(n_u / KC)
+  int first;                      // index of the first window pixel in the spectrum
+  double min_z_dla, max_z_dla;    // process_qsos.m:159-160
+  double log_prior_no_dla, log_prior_dla;   // process_qsos.m:128-131
+};
+
+template <int K>
+struct GramShape {
+  static constexpr int NPAIR = K * (K + 1) / 2;
+  static constexpr int WT = (NPAIR + 7) / 8;     // n8 tiles fed by the W operand
+  static constexpr int UT = (K + 7) / 8;         // n8 tiles fed by the U operand
+  static constexpr int NT = WT + UT;
+  static constexpr int NCOL = NT * 8;
+  // row stride of a P chunk in doubles: == 4 (mod 16) makes the DMMA B-fragment loads conflict-free
+  static constexpr int BSTR = NCOL + ((4 - NCOL % 16) + 16) % 16;
+  static constexpr int CHUNK_DOUBLES = KC * BSTR;
+  __host__ __device__ static constexpr int pair_index(int p, int q) { return p * K - p * (p - 1) / 2 + (q - p); }
+};
+
+constexpr int ASTR = KC + 4;      // row stride of the W/U operand tiles (== 4 mod 16)
+
+// ------------------------------------------------------------------------------------------
+// small helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// 1-D TMA bulk copy global -> shared, completion on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void dmma_884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------
+// K0: per-quasar preparation.  One CTA per quasar.
+struct PrepArgs {
+  // spectra, padded [Q x L_max]
+  const double* wavelengths;
+  const double* flux;
+  const double* noise_variance;
+  const uint8_t* pixel_mask;
+  const int32_t* lengths;
+  const double* z_qsos;
+  int64_t L_max;
+  // null model on the rest grid
+  const double* rest_wavelengths;
+  const double* mu;
+  const double* M;          // [n_rest x k] row-major
+  const double* log_omega;
+  int n_rest, k;
+  double c_0, tau_0, beta;
+  // prior catalogue
+  const double* prior_z_qsos;
+  const uint8_t* prior_dla_ind;
+  int64_t n_prior;
+  // parameters (set_parameters.m)
+  double min_lambda, max_lambda, lya_wavelength, lyman_limit, prior_z_qso_increase, min_z_cut, max_z_cut,
+      pixel_spacing;
+  // outputs
+  QuasarMeta* meta;
+  double* lam_pad;          // [Q x (NPIX + 8)]
+  double* pix;              // [Q x NPIX x 4]  (y, v, mu, omega2)
+  double* Mq;               // [Q x NPIX x k]  interpolated M rows (zero for masked / padding pixels)
+  int NPIX;
+};
+
+__device__ __forceinline__ double interp_linear(const double* xp, const double* fp, int stride, int j, double x) {
+  // numpy.interp / griddedInterpolant('linear') on the bracketing interval j (process_qsos.m:66-71)
+  double slope = (fp[(j + 1) * stride] - fp[j * stride]) / (xp[j + 1] - xp[j]);
+  return slope * (x - xp[j]) + fp[j * stride];
+}
+
+__global__ void __launch_bounds__(NTHREADS) prepare_quasars_kernel(PrepArgs a) {
+  const int q = blockIdx.x, tid = threadIdx.x;
+  const int64_t L = a.lengths[q];
+  const double z_qso = a.z_qsos[q];
+  const double* wl = a.wavelengths + q * a.L_max;
+  const double* fl = a.flux + q * a.L_max;
+  const double* nv = a.noise_variance + q * a.L_max;
+  const uint8_t* pm = a.pixel_mask + q * a.L_max;
+
+  __shared__ int s_first, s_last, s_n, s_nq, s_nd;
+  __shared__ double s_minw, s_maxw, s_minu, s_maxu;
+  __shared__ double red_min[NTHREADS / 32], red_max[NTHREADS / 32];
+  if (tid == 0) { s_first = 1 << 30; s_last = -1; s_n = 0; s_nq = 0; s_nd = 0; }
+  __syncthreads();
+
+  // window / mask (process_qsos.m:102-110); min/max of used and of window wavelengths
+  int first = 1 << 30, last = -1, n = 0;
+  double minw = INFINITY, maxw = -INFINITY, minu = INFINITY, maxu = -INFINITY;
+  for (int64_t i = tid; i < L; i += NTHREADS) {
+    double w = wl[i];
+    double rest = w / (1.0 + z_qso);
+    bool inwin = (rest >= a.min_lambda) && (rest <= a.max_lambda);
+    if (inwin) {
+      first = min(first, (int)i); last = max(last, (int)i);
+      minu = fmin(minu, w); maxu = fmax(maxu, w);
+      if (!pm[i]) { n++; minw = fmin(minw, w); maxw = fmax(maxw, w); }
+    }
+  }
+  // DLA existence prior counts (process_qsos.m:122-125)
+  int nq = 0, nd = 0;
+  const double zlim = z_qso + a.prior_z_qso_increase;
+  for (int64_t i = tid; i < a.n_prior; i += NTHREADS) {
+    bool less = a.prior_z_qsos[i] < zlim;
+    nq += less; nd += (less && a.prior_dla_ind[i]);
+  }
+  atomicMin(&s_first, first); atomicMax(&s_last, last);
+  atomicAdd(&s_n, n); atomicAdd(&s_nq, nq); atomicAdd(&s_nd, nd);
+  auto block_minmax = [&](double vmin, double vmax, double& omin, double& omax) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      vmin = fmin(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
+      vmax = fmax(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+    }
+    __syncthreads();
+    if ((tid & 31) == 0) { red_min[tid >> 5] = vmin; red_max[tid >> 5] = vmax; }
+    __syncthreads();
+    if (tid == 0) {
+      for (int w = 1; w < NTHREADS / 32; ++w) { vmin = fmin(vmin, red_min[w]); vmax = fmax(vmax, red_max[w]); }
+      omin = vmin; omax = vmax;
+    }
+  };
+  block_minmax(minw, maxw, s_minw, s_maxw);
+  block_minmax(minu, maxu, s_minu, s_maxu);
+  __syncthreads();
+
+  const int n_u = s_last >= s_first ? s_last - s_first + 1 : 0;
+  const int n_used = s_n;
+  const int NPIX = a.NPIX;
+  double* lam = a.lam_pad + (int64_t)q * (NPIX + 8);
+  double* pix = a.pix + (int64_t)q * NPIX * 4;
+  double* Mq = a.Mq + (int64_t)q * NPIX * a.k;
+
+  if (tid == 0) {
+    QuasarMeta m;
+    m.n_u = n_u; m.n = n_used; m.nchunks = (n_u + KC - 1) / KC; m.first = s_first;
+    // set_parameters.m:65-73
+    m.max_z_dla = (s_maxw / a.lya_wavelength - 1.0) - a.max_z_cut;
+    m.min_z_dla = fmax(s_minw / a.lya_wavelength - 1.0,
+                       a.lyman_limit * (1.0 + z_qso) / a.lya_wavelength - 1.0 + a.min_z_cut);
+    // process_qsos.m:128-131
+    m.log_prior_dla = log((double)s_nd) - log((double)s_nq);
+    m.log_prior_no_dla = log((double)(s_nq - s_nd)) - log((double)s_nq);
+    if (n_used == 0) { m.nchunks = 0; m.min_z_dla = NAN; m.max_z_dla = NAN; }
+    a.meta[q] = m;
+  }
+  if (n_used == 0) return;
+
+  // padded wavelength grid (process_qsos.m:168-176); pixels past the end continue the log grid
+  const double lo = log10(s_minu), hi = log10(s_maxu);
+  const int W3 = 3;
+  for (int p = tid; p < NPIX + 8; p += NTHREADS) {
+    double v;
+    if (p < W3) {
+      // logspace(lo - 3 ps, lo - ps, 3) = 10.^linspace(a, b, 3)
+      double a0 = lo - W3 * a.pixel_spacing, b0 = lo - a.pixel_spacing;
+      double ex = (p == W3 - 1) ? b0 : a0 + p * ((b0 - a0) / (W3 - 1));
+      v = exp10(ex);
+    } else if (p < W3 + n_u) {
+      v = wl[s_first + (p - W3)];
+    } else {
+      int t = p - (W3 + n_u);   // 0,1,2 are the reference's trailing pad; beyond that: filler
+      double a0 = hi + a.pixel_spacing, b0 = hi + W3 * a.pixel_spacing;
+      double ex = (t == W3 - 1) ? b0 : a0 + t * ((b0 - a0) / (W3 - 1));
+      v = exp10(ex);
+    }
+    lam[p] = v;
+  }
+
+  // per-pixel model interpolation (process_qsos.m:138-146)
+  const double x0 = a.rest_wavelengths[0];
+  const double inv_dx = (a.n_rest - 1) / (a.rest_wavelengths[a.n_rest - 1] - x0);
+  for (int i = tid; i < NPIX; i += NTHREADS) {
+    double y = 0.0, v = 1.0, mu = 0.0, om2 = 0.0;
+    bool used = false;
+    int j = 0;
+    double rest = 0.0;
+    if (i < n_u) {
+      int src = s_first + i;
+      double w = wl[src];
+      rest = w / (1.0 + z_qso);
+      used = !pm[src] && (rest >= a.min_lambda) && (rest <= a.max_lambda);
+      if (used) {
+        j = (int)((rest - x0) * inv_dx);
+        j = max(0, min(j, a.n_rest - 2));
+        while (j > 0 && a.rest_wavelengths[j] > rest) --j;
+        while (j < a.n_rest - 2 && a.rest_wavelengths[j + 1] <= rest) ++j;
+        y = fl[src]; v = nv[src];
+        mu = interp_linear(a.rest_wavelengths, a.mu, 1, j, rest);
+        double lw = interp_linear(a.rest_wavelengths, a.log_omega, 1, j, rest);
+        double lya_z = (w - a.lya_wavelength) / a.lya_wavelength;                 // :117-119
+        double scaling = 1.0 - exp(-a.tau_0 * pow(1.0 + lya_z, a.beta)) + a.c_0;   // :144
+        om2 = exp(2.0 * lw) * (scaling * scaling);                                 // :142,146
+      }
+    }
+    pix[i * 4 + 0] = y; pix[i * 4 + 1] = v; pix[i * 4 + 2] = mu; pix[i * 4 + 3] = om2;
+    for (int c = 0; c < a.k; ++c)
+      Mq[(int64_t)i * a.k + c] = used ? interp_linear(a.rest_wavelengths, a.M + c, a.k, j, rest) : 0.0;
+  }
+}
+
+// K0b: Gram operand P, chunked [Q][chunk][KC][BSTR]: columns pair_index(p,q) = M_ip M_iq, then the k
+// columns of M itself (projection), zero padding elsewhere.
+template <int K>
+__global__ void __launch_bounds__(NTHREADS) build_gram_operand_kernel(const double* __restrict__ Mq,
+                                                                      const QuasarMeta* __restrict__ meta,
+                                                                      double* __restrict__ P, int NPIX) {
+  using G = GramShape<K>;
+  const int q = blockIdx.y;
+  const int chunk = blockIdx.x;
+  if (chunk >= meta[q].nchunks) return;
+  __shared__ double sM[KC][K + 1];
+  const double* src = Mq + ((int64_t)q * NPIX + (int64_t)chunk * KC) * K;
+  for (int t = threadIdx.x; t < KC * K; t += NTHREADS) sM[t / K][t % K] = src[t];
+  __syncthreads();
+  double* dst = P + ((int64_t)q * (NPIX / KC) + chunk) * G::CHUNK_DOUBLES;
+  for (int t = threadIdx.x; t < G::CHUNK_DOUBLES; t += NTHREADS) {
+    int r = t / G::BSTR, c = t % G::BSTR;
+    double v = 0.0;
+    if (c < G::NPAIR) {
+      // invert pair_index: find p with pair_index(p,p) <= c
+      int p = 0;
+      while (p + 1 < K && G::pair_index(p + 1, p + 1) <= c) ++p;
+      int qq = p + (c - G::pair_index(p, p));
+      v = sM[r][p] * sM[r][qq];
+    } else if (c >= G::WT * 8 && c < G::WT * 8 + K) {
+      v = sM[r][c - G::WT * 8];
+    }
+    dst[t] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K1 (stand-alone): batched absorption profiles  A[s, i] = voigt(lambdas, z_s, N_s, num_lines)[i]
+// grid = (ceil(n_out / 256), S)
+__global__ void __launch_bounds__(NTHREADS) voigt_batch_kernel(const double* __restrict__ lambdas, int64_t num_points,
+                                                               const double* __restrict__ zs,
+                                                               const double* __restrict__ Ns, int num_lines,
+                                                               double* __restrict__ profile) {
+  __shared__ double s_raw[NTHREADS + 6];
+  __shared__ double s_mult[MAX_LINES];
+  const int64_t n_out = num_points - 6;
+  const int64_t s = blockIdx.y;
+  const int64_t i0 = (int64_t)blockIdx.x * NTHREADS;
+  const double z = zs[s], N = Ns[s];
+  if (threadIdx.x < num_lines) s_mult[threadIdx.x] = line_multiplier(threadIdx.x, z);
+  __syncthreads();
+  for (int t = threadIdx.x; t < NTHREADS + 6; t += NTHREADS) {
+    int64_t p = i0 + t;
+    if (p < num_points) {
+      double tau = tau_sum_generic(lambdas[p], s_mult, 1, num_lines);
+      s_raw[t] = exp(-N * tau);                       // voigt.c:291
+    }
+  }
+  __syncthreads();
+  int64_t i = i0 + threadIdx.x;
+  if (i < n_out) {
+    double acc = 0.0;
+#pragma unroll
+    for (int t = 0; t < 7; ++t) acc = fma(s_raw[threadIdx.x + t], c_lines.ip[t], acc);   // voigt.c:297-299
+    profile[s * n_out + i] = acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K1+K2+K3 fused: per-(quasar, sample-tile) log-likelihoods.
+struct LoglikArgs {
+  const QuasarMeta* meta;
+  const double* lam_pad;      // [Q x (NPIX + 8)]
+  const double* pix;          // [Q x NPIX x 4]
+  const double* P;            // [Q x NPIX/KC x KC x BSTR]
+  const double* offset_samples;
+  const double* nhi_samples;
+  int64_t S;                  // number of DLA samples; sample index S is the null model (absorption == 1)
+  int num_lines;
+  int NPIX;
+  double* sample_log_likelihoods;   // [Q x S]
+  double* log_likelihoods_no_dla;   // [Q]
+};
+
+template <int K, int WM, int WN, int MT>
+struct LoglikConfig {
+  using G = GramShape<K>;
+  static constexpr int TS = WM * MT * 8;               // samples per CTA
+  static constexpr int NTW = (G::NT + WN - 1) / WN;    // n8 tiles per warp
+  static constexpr int SPW = TS / (NTHREADS / 32);     // samples per warp in the producer phases
+  static_assert(WM * WN == NTHREADS / 32, "8 warps");
+  static_assert(TS % (NTHREADS / 32) == 0, "samples per warp");
+  static constexpr size_t B_BYTES = 2ull * G::CHUNK_DOUBLES * 8;
+  static constexpr size_t A_BYTES = 2ull * TS * ASTR * 8;
+  static constexpr size_t RAW_BYTES = (size_t)TS * RAWW * 8;
+  static constexpr size_t C_BYTES = (size_t)G::NCOL * TS * 8;      // epilogue staging, aliases the B buffers
+  static_assert(C_BYTES <= B_BYTES + A_BYTES + RAW_BYTES, "epilogue staging must fit");
+  __host__ __device__ static constexpr size_t smem_bytes(int num_lines) {
+    return B_BYTES + A_BYTES + RAW_BYTES + (size_t)TS * (num_lines + 4) * 8 + 64;
+  }
+};
+
+template <int K, int WM, int WN, int MT, int NL>
+__global__ void __launch_bounds__(NTHREADS, 1) dla_loglik_kernel(LoglikArgs args) {
+  using Cfg = LoglikConfig<K, WM, WN, MT>;
+  using G = GramShape<K>;
+  constexpr int TS = Cfg::TS, NTW = Cfg::NTW, SPW = Cfg::SPW;
+  const int q = blockIdx.y;
+  const QuasarMeta meta = args.meta[q];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t s0 = (int64_t)blockIdx.x * TS;
+  const int64_t S = args.S;
+
+  if (meta.nchunks == 0) {   // nothing usable in this spectrum: NaN results (process_qsos.m:74-82)
+    for (int i = tid; i < TS; i += NTHREADS) {
+      int64_t s = s0 + i;
+      if (s < S) args.sample_log_likelihoods[(int64_t)q * S + s] = NAN;
+      else if (s == S) args.log_likelihoods_no_dla[q] = NAN;
+    }
+    return;
+  }
+
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* Bt = reinterpret_cast<double*>(smem_raw);                       // [2][KC][BSTR]
+  double* Wt = reinterpret_cast<double*>(smem_raw + Cfg::B_BYTES);        // [TS][ASTR]
+  double* Ut = Wt + TS * ASTR;                                            // [TS][ASTR]
+  double* rawbuf = Ut + TS * ASTR;                                        // [TS][RAWW]
+  double* s_nhi = rawbuf + TS * RAWW;                                     // [TS]
+  double* s_q = s_nhi + TS;                                               // [TS]   sum r^2/d
+  double* s_ld = s_q + TS;                                                // [TS]   sum log d
+  double* s_mult = s_ld + TS;                                             // [num_lines][TS]
+  const int num_lines = (NL > 0) ? NL : args.num_lines;
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(s_mult + (size_t)TS * num_lines + TS);   // [2], 8-byte aligned
+  double* Cs = reinterpret_cast<double*>(smem_raw);                       // epilogue: [NCOL][TS]
+
+  // per-sample parameters: z_s (process_qsos.m:162-164), N_s, line multipliers (voigt.c:279)
+  for (int i = tid; i < TS; i += NTHREADS) {
+    int64_t s = s0 + i;
+    bool is_null = s >= S;
+    double z = is_null ? 0.0
+                       : __dadd_rn(meta.min_z_dla, __dmul_rn(meta.max_z_dla - meta.min_z_dla, args.offset_samples[s]));
+    s_nhi[i] = is_null ? -1.0 : args.nhi_samples[s];     // negative marks the null-model slot
+    for (int j = 0; j < num_lines; ++j) s_mult[j * TS + i] = line_multiplier(j, z);
+  }
+  if (tid == 0) {
+    mbar_init(&mbar[0], 1);
+    mbar_init(&mbar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  const double* lam = args.lam_pad + (int64_t)q * (args.NPIX + 8);
+  const double* pix = args.pix + (int64_t)q * args.NPIX * 4;
+  const double* Pq = args.P + (int64_t)q * (args.NPIX / KC) * G::CHUNK_DOUBLES;
+  constexpr uint32_t CHUNK_BYTES = G::CHUNK_DOUBLES * 8;
+
+  if (tid == 0) {
+    mbar_expect_tx(&mbar[0], CHUNK_BYTES);
+    tma_load_1d(Bt, Pq, CHUNK_BYTES, &mbar[0]);
+  }
+
+  // raw-profile evaluation for this warp's samples at padded pixel p
+  auto eval_raw = [&](int p) {
+    const double lambda = lam[p];
+#pragma unroll
+    for (int ss = 0; ss < SPW; ++ss) {
+      const int sl = warp * SPW + ss;
+      double tau;
+      if (NL == 3) tau = tau_sum_3(lambda, s_mult[sl], s_mult[TS + sl], s_mult[2 * TS + sl]);
+      else tau = tau_sum_generic(lambda, s_mult + sl, TS, num_lines);
+      rawbuf[sl * RAWW + (p & (RAWW - 1))] = exp(-s_nhi[sl] * tau);     // voigt.c:291
+    }
+  };
+  if (lane < 6) eval_raw(lane);   // leading pad pixels p = 0..5
+
+  // accumulators
+  double acc[MT][NTW][2];
+#pragma unroll
+  for (int mi = 0; mi < MT; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < NTW; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+  double qacc[SPW], ldm[SPW];
+  int lde[SPW];
+#pragma unroll
+  for (int ss = 0; ss < SPW; ++ss) { qacc[ss] = 0.0; ldm[ss] = 1.0; lde[ss] = 0; }
+
+  const int wm = warp % WM, wn = warp / WM;
+  const int gid = lane >> 2, tig = lane & 3;
+  const int nw_local = max(0, min(NTW, G::WT - wn * NTW));   // tiles of this warp fed by W (rest: U)
+
+  for (int c = 0; c < meta.nchunks; ++c) {
+    // ---- A1: raw profile for the KC new padded pixels
+    eval_raw(c * KC + 6 + lane);
+    __syncthreads();   // S1: raw visible; everyone is past the previous chunk's DMMA phase
+    if (tid == 0 && c + 1 < meta.nchunks) {
+      mbar_expect_tx(&mbar[(c + 1) & 1], CHUNK_BYTES);
+      tma_load_1d(Bt + ((c + 1) & 1) * G::CHUNK_DOUBLES, Pq + (int64_t)(c + 1) * G::CHUNK_DOUBLES, CHUNK_BYTES,
+                  &mbar[(c + 1) & 1]);
+    }
+    // ---- A2: instrument convolution + weights
+    {
+      const int i = c * KC + lane;
+      const double2 p01 = *reinterpret_cast<const double2*>(pix + (int64_t)i * 4);
+      const double2 p23 = *reinterpret_cast<const double2*>(pix + (int64_t)i * 4 + 2);
+      const double y = p01.x, v = p01.y, mu = p23.x, om2 = p23.y;
+#pragma unroll
+      for (int ss = 0; ss < SPW; ++ss) {
+        const int sl = warp * SPW + ss;
+        const double* rb = rawbuf + sl * RAWW;
+        double a = 0.0;
+#pragma unroll
+        for (int t = 0; t < 7; ++t) a = fma(rb[(i + t) & (RAWW - 1)], c_lines.ip[t], a);   // voigt.c:297-299
+        if (s_nhi[sl] < 0.0) a = 1.0;                    // null model: no absorption
+        const double a2 = a * a;
+        const double d = fma(a2, om2, v);                // dla_omega2 + noise variance  (process_qsos.m:194,198)
+        const double rd = fast_rcp(d);
+        const double r = fma(-a, mu, y);                 // y - dla_mu
+        const double t1 = r * rd;
+        Wt[sl * ASTR + lane] = a2 * rd;
+        Ut[sl * ASTR + lane] = a * t1;
+        qacc[ss] = fma(r, t1, qacc[ss]);
+        ldm[ss] *= d;
+      }
+      if ((c & 7) == 7) {   // keep the running product of d in range: move its exponent to an integer
+#pragma unroll
+        for (int ss = 0; ss < SPW; ++ss) {
+          int hi = __double2hiint(ldm[ss]);
+          int e = ((hi >> 20) & 0x7ff) - 1023;
+          lde[ss] += e;
+          ldm[ss] = __hiloint2double(hi - (e << 20), __double2loint(ldm[ss]));
+        }
+      }
+    }
+    __syncthreads();   // S2: operand tiles visible
+    mbar_wait(&mbar[c & 1], (c >> 1) & 1);
+    // ---- B: FP64 tensor-core contraction  acc += [W|U] (TS x KC) . P_chunk (KC x NCOL)
+    {
+      const double* Bc = Bt + (c & 1) * G::CHUNK_DOUBLES;
+#pragma unroll
+      for (int ks = 0; ks < KC / 4; ++ks) {
+        double aw[MT], au[MT];
+#pragma unroll
+        for (int mi = 0; mi < MT; ++mi) {
+          const int row = (wm * MT + mi) * 8 + gid;
+          aw[mi] = Wt[row * ASTR + ks * 4 + tig];
+          au[mi] = Ut[row * ASTR + ks * 4 + tig];
+        }
+#pragma unroll
+        for (int ni = 0; ni < NTW; ++ni) {
+          const int t = wn * NTW + ni;
+          if (t < G::NT) {
+            const double b = Bc[(ks * 4 + tig) * G::BSTR + t * 8 + gid];
+#pragma unroll
+            for (int mi = 0; mi < MT; ++mi) dmma_884(acc[mi][ni][0], acc[mi][ni][1], ni < nw_local ? aw[mi] : au[mi], b);
+          }
+        }
+      }
+    }
+  }
+
+  // ---- per-sample scalars: sum r^2/d and sum log d
+#pragma unroll
+  for (int ss = 0; ss < SPW; ++ss) {
+    double qs = warp_sum(qacc[ss]);
+    double ld = warp_sum(log(ldm[ss]) + (double)lde[ss] * 0.693147180559945309417);
+    if (lane == 0) { s_q[warp * SPW + ss] = qs; s_ld[warp * SPW + ss] = ld; }
+  }
+  __syncthreads();   // all DMMA reads of Bt/Wt/Ut done -> staging may alias them
+#pragma unroll
+  for (int mi = 0; mi < MT; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < NTW; ++ni) {
+      const int t = wn * NTW + ni;
+      if (t < G::NT) {
+        const int row = (wm * MT + mi) * 8 + gid;
+        Cs[(t * 8 + tig * 2) * TS + row] = acc[mi][ni][0];
+        Cs[(t * 8 + tig * 2 + 1) * TS + row] = acc[mi][ni][1];
+      }
+    }
+  __syncthreads();
+
+  // ---- K3: Cholesky of B = I + C, log-det, projected quadratic form; one thread per sample
+  if (tid < TS) {
+    const int sl = tid;
+    double* Bs = Cs + sl;                      // element (p,q), p<=q at Bs[pair_index(p,q) * TS]
+    const double* gs = Cs + (G::WT * 8) * TS + sl;   // g_p at gs[p * TS]
+    double logdetB = 0.0, zz = 0.0;
+#pragma unroll
+    for (int p = 0; p < K; ++p) {
+      double colp[K];                          // R(r,p), r < p
+#pragma unroll
+      for (int r = 0; r < p; ++r) colp[r] = Bs[G::pair_index(r, p) * TS];
+      double dpp = Bs[G::pair_index(p, p) * TS] + 1.0;     // log_mvnpdf_low_rank.m:23
+#pragma unroll
+      for (int r = 0; r < p; ++r) dpp = fma(-colp[r], colp[r], dpp);
+      logdetB += log(dpp);                     // = 2 log R(p,p)                        :30
+      const double inv = 1.0 / sqrt(dpp);
+#pragma unroll
+      for (int qq = p + 1; qq < K; ++qq) {
+        double v = Bs[G::pair_index(p, qq) * TS];
+#pragma unroll
+        for (int r = 0; r < p; ++r) v = fma(-colp[r], Bs[G::pair_index(r, qq) * TS], v);
+        Bs[G::pair_index(p, qq) * TS] = v * inv;
+      }
+      // augmented column: forward substitution R' z = g
+      double zp = gs[p * TS];
+#pragma unroll
+      for (int r = 0; r < p; ++r) zp = fma(-colp[r], gs[r * TS], zp);
+      zp *= inv;
+      const_cast<double*>(gs)[p * TS] = zp;
+      zz = fma(zp, zp, zz);
+    }
+    const double quad = s_q[sl] - zz;          // y' K^-1 y                               :28
+    const double logdet = s_ld[sl] + logdetB;  //                                         :30
+    const double lp = -0.5 * (quad + logdet + (double)meta.n * LOG_2PI);   //             :32
+    const int64_t s = s0 + sl;
+    if (s < S) args.sample_log_likelihoods[(int64_t)q * S + s] = lp;
+    else if (s == S) args.log_likelihoods_no_dla[q] = lp;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K4: evidence, posteriors, MAP.  One CTA per quasar.
+struct EvidenceArgs {
+  const QuasarMeta* meta;
+  const double* sample_log_likelihoods;   // [Q x S]
+  const double* log_likelihoods_no_dla;   // [Q]
+  const double* offset_samples;
+  const double* log_nhi_samples;
+  int64_t S;
+  // outputs, each [Q] unless noted
+  double *min_z_dlas, *max_z_dlas, *log_priors_no_dla, *log_priors_dla, *log_likelihoods_dla, *log_posteriors_no_dla,
+      *log_posteriors_dla, *model_posteriors /*[Q x 2]*/, *p_no_dlas, *p_dlas, *map_z_dlas, *map_log_nhis;
+  int64_t* map_inds;
+};
+
+__global__ void __launch_bounds__(NTHREADS) evidence_kernel(EvidenceArgs a) {
+  const int q = blockIdx.x, tid = threadIdx.x;
+  const QuasarMeta meta = a.meta[q];
+  const double* ll = a.sample_log_likelihoods + (int64_t)q * a.S;
+  __shared__ double s_val[NTHREADS / 32];
+  __shared__ long long s_idx[NTHREADS / 32];
+  __shared__ double s_max;
+  __shared__ long long s_arg;
+  __shared__ int s_nan;
+
+  // max over samples, NaN-ignoring like MATLAB max (process_qsos.m:203); first index attaining it
+  double m = -INFINITY; long long arg = -1; int has_nan = 0;
+  for (int64_t s = tid; s < a.S; s += NTHREADS) {
+    double v = ll[s];
+    if (v != v) { has_nan = 1; continue; }
+    if (v > m || arg < 0) { m = v; arg = s; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    double om = __shfl_xor_sync(0xffffffffu, m, o);
+    long long oa = __shfl_xor_sync(0xffffffffu, arg, o);
+    if (oa >= 0 && (arg < 0 || om > m || (om == m && oa < arg))) { m = om; arg = oa; }
+  }
+  has_nan = __any_sync(0xffffffffu, has_nan);
+  if (tid == 0) s_nan = 0;
+  __syncthreads();
+  if ((tid & 31) == 0) { s_val[tid >> 5] = m; s_idx[tid >> 5] = arg; if (has_nan) atomicOr(&s_nan, 1); }
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < NTHREADS / 32; ++w) {
+      double om = s_val[w]; long long oa = s_idx[w];
+      if (oa >= 0 && (arg < 0 || om > m || (om == m && oa < arg))) { m = om; arg = oa; }
+    }
+    s_max = m; s_arg = arg;
+  }
+  __syncthreads();
+  m = s_max; arg = s_arg;
+  double sum = 0.0;
+  for (int64_t s = tid; s < a.S; s += NTHREADS) sum += exp(ll[s] - m);          // :205-207 (NaN propagates like mean)
+  sum = warp_sum(sum);
+  __syncthreads();
+  if ((tid & 31) == 0) s_val[tid >> 5] = sum;
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < NTHREADS / 32; ++w) sum += s_val[w];
+    const bool valid = meta.nchunks > 0;
+    double lldla = valid ? m + log(sum / (double)a.S) : NAN;                     // :209-210
+    double llno = a.log_likelihoods_no_dla[q];
+    double lpno = meta.log_prior_no_dla + llno;                                  // :153-154
+    double lpdla = meta.log_prior_dla + lldla;                                   // :212-213
+    a.min_z_dlas[q] = meta.min_z_dla; a.max_z_dlas[q] = meta.max_z_dla;
+    a.log_priors_no_dla[q] = meta.log_prior_no_dla; a.log_priors_dla[q] = meta.log_prior_dla;
+    a.log_likelihoods_dla[q] = lldla;
+    a.log_posteriors_no_dla[q] = valid ? lpno : NAN; a.log_posteriors_dla[q] = valid ? lpdla : NAN;
+    // model posteriors (process_qsos.m:224-233); MATLAB max ignores NaN
+    double mx = fmax(lpno, lpdla);
+    double e0 = exp(lpno - mx), e1 = exp(lpdla - mx);
+    double tot = e0 + e1;
+    double p0 = e0 / tot, p1 = e1 / tot;
+    if (!valid) { p0 = NAN; p1 = NAN; }
+    a.model_posteriors[2 * q] = p0; a.model_posteriors[2 * q + 1] = p1;
+    a.p_no_dlas[q] = p0; a.p_dlas[q] = 1.0 - p0;
+    // MAP (generate_ascii_catalog.m:73-80)
+    a.map_inds[q] = (valid && arg >= 0) ? arg : -1;
+    if (valid && arg >= 0) {
+      a.map_z_dlas[q] = __dadd_rn(meta.min_z_dla, __dmul_rn(meta.max_z_dla - meta.min_z_dla, a.offset_samples[arg]));
+      a.map_log_nhis[q] = a.log_nhi_samples[arg];
+    } else {
+      a.map_z_dlas[q] = NAN; a.map_log_nhis[q] = NAN;
+    }
+  }
+}
+
+}  // namespace gpdla

@@ -1,0 +1,133 @@
+// Device math for the DLA hot path: Lyman-series line data, FP64 Voigt/Faddeeva evaluation,
+// fast reciprocal.  sm_100a only.
+//
+// Replaces the arithmetic of the reference's voigt.c:277-292 (per-pixel sum over lines of
+// leading_constant * voigt(velocity, sigma, gamma), libcerf call at voigt.c:288) with a
+// branch-light scheme suited to SIMT: see tools/gen_voigt_tables.py for the derivation and
+// the fitted tables (voigt_tables.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include "voigt_tables.h"
+
+namespace gpdla {
+
+constexpr int MAX_LINES = 31;  // voigt.c:16
+
+// Per-line constants, filled on the host by init_line_constants() (gpdla_capi.cu) from the
+// Lyman-series data; layout shared with the host.
+struct LineConstants {
+  double tw[MAX_LINES];     // transition wavelengths (cm)              voigt.c:31-64
+  double lc[MAX_LINES];     // leading constants                         voigt.c:141-184
+  double gam[MAX_LINES];    // Lorentzian widths (cm/s)                  voigt.c:186-220
+  double y[MAX_LINES];      // gam / (sqrt2 sigma)
+  double y2[MAX_LINES];     // y^2
+  double kcore[MAX_LINES];  // lc / (sqrt(2 pi) sigma)
+  double kwing[MAX_LINES];  // kcore * y / sqrt(pi)
+  double ip[7];             // instrument profile                        voigt.c:242-251
+  double c;                 // speed of light (cm/s)                     voigt.c:22
+  double inv_s2s;           // 1 / (sqrt2 sigma)
+};
+
+__constant__ LineConstants c_lines;
+__constant__ double c_wing_a[GPDLA_VOIGT_DEG_A + 1] = GPDLA_VOIGT_WING_A;
+__constant__ double c_wing_b[GPDLA_VOIGT_DEG_B + 1] = GPDLA_VOIGT_WING_B;
+// core table lives in global memory (divergent indexing; constant cache would serialise)
+__device__ const double g_core_table[GPDLA_VOIGT_NINT * GPDLA_VOIGT_CORE_STRIDE] = GPDLA_VOIGT_CORE_TABLE;
+
+// 1/x to ~1 ulp for normal positive x: MUFU.RCP64H seed + two Newton steps (4 DFMA).
+__device__ __forceinline__ double fast_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  return r;
+}
+
+__device__ __forceinline__ double wing_poly_a(double u) {
+  double a = c_wing_a[GPDLA_VOIGT_DEG_A];
+#pragma unroll
+  for (int i = GPDLA_VOIGT_DEG_A - 1; i >= 0; --i) a = fma(a, u, c_wing_a[i]);
+  return a;
+}
+__device__ __forceinline__ double wing_poly_b(double u) {
+  double b = c_wing_b[GPDLA_VOIGT_DEG_B];
+#pragma unroll
+  for (int i = GPDLA_VOIGT_DEG_B - 1; i >= 0; --i) b = fma(b, u, c_wing_b[i]);
+  return b;
+}
+
+// tau_j / N for |x| >= X0 given u = 1/x^2.
+__device__ __forceinline__ double tau_wing(int j, double u) {
+  double a = wing_poly_a(u);
+  double b = wing_poly_b(u);
+  double t = c_lines.y2[j] * u;
+  return c_lines.kwing[j] * u * fma(-t, b, a);
+}
+
+// tau_j / N for |x| < X0 (rare: <= 7 pixels per line per sample).
+__device__ __noinline__ double tau_core(int j, double x) {
+  double ax = fabs(x);
+  int idx = (int)(ax * GPDLA_VOIGT_INV_H);
+  idx = idx < GPDLA_VOIGT_NINT ? idx : GPDLA_VOIGT_NINT - 1;
+  double t = fma(ax, 2.0 * GPDLA_VOIGT_INV_H, -(2.0 * idx + 1.0));   // (ax - centre)/(H/2)
+  const double* tab = g_core_table + idx * GPDLA_VOIGT_CORE_STRIDE;
+  double h1 = tab[GPDLA_VOIGT_DEG_H1];
+#pragma unroll
+  for (int i = GPDLA_VOIGT_DEG_H1 - 1; i >= 0; --i) h1 = fma(h1, t, tab[i]);
+  const double* tab3 = tab + GPDLA_VOIGT_DEG_H1 + 1;
+  double h3 = tab3[GPDLA_VOIGT_DEG_H3];
+#pragma unroll
+  for (int i = GPDLA_VOIGT_DEG_H3 - 1; i >= 0; --i) h3 = fma(h3, t, tab3[i]);
+  double x2 = x * x;
+  double e = exp(-x2);
+  double y = c_lines.y[j], y2 = c_lines.y2[j];
+  double p4 = fma(x2, fma(x2, 4.0, -12.0), 3.0) * (1.0 / 6.0);
+  double even = fma(y2, fma(y2, p4, fma(-2.0, x2, 1.0)), 1.0);   // 1 + y^2 (1-2x^2) + y^4 p4
+  double rew = fma(e, even, y * fma(y2, h3, h1));
+  return c_lines.kcore[j] * rew;
+}
+
+// multiplier of voigt.c:279, same operation order: c / (tw * (1 + z)) / 1e8
+__device__ __forceinline__ double line_multiplier(int j, double z) {
+  return c_lines.c / (c_lines.tw[j] * (1.0 + z)) / 1e8;
+}
+
+// Sum over lines of tau_j / N at wavelength `lambda` (Angstrom) -- generic line count, one
+// reciprocal per line.  mult[j * mstride] are the per-sample multipliers.
+__device__ __forceinline__ double tau_sum_generic(double lambda, const double* mult, int mstride, int num_lines) {
+  double total = 0.0;
+  for (int j = 0; j < num_lines; ++j) {
+    double v = __dsub_rn(__dmul_rn(lambda, mult[j * mstride]), c_lines.c);   // voigt.c:287 (no FMA contraction)
+    double x = v * c_lines.inv_s2s;
+    double x2 = x * x;
+    double tj;
+    if (x2 >= GPDLA_VOIGT_X0 * GPDLA_VOIGT_X0) tj = tau_wing(j, fast_rcp(x2));
+    else tj = tau_core(j, x);
+    total += tj;
+  }
+  return total;
+}
+
+// Three-line specialisation (num_lines = 3, set_parameters.m:63): the three reciprocals share
+// one MUFU + Newton sequence through a common denominator.
+__device__ __forceinline__ double tau_sum_3(double lambda, double m0, double m1, double m2) {
+  const double X02 = GPDLA_VOIGT_X0 * GPDLA_VOIGT_X0;
+  double x0 = __dsub_rn(__dmul_rn(lambda, m0), c_lines.c) * c_lines.inv_s2s;
+  double x1 = __dsub_rn(__dmul_rn(lambda, m1), c_lines.c) * c_lines.inv_s2s;
+  double x2 = __dsub_rn(__dmul_rn(lambda, m2), c_lines.c) * c_lines.inv_s2s;
+  double s0 = x0 * x0, s1 = x1 * x1, s2 = x2 * x2;
+  double c0 = fmax(s0, X02), c1 = fmax(s1, X02), c2 = fmax(s2, X02);   // x^2 <= 8e3^2: product < 3e23
+  double p12 = c1 * c2;
+  double r = fast_rcp(c0 * p12);
+  double u0 = r * p12, u1 = r * (c0 * c2), u2 = r * (c0 * c1);
+  double t0 = tau_wing(0, u0), t1 = tau_wing(1, u1), t2 = tau_wing(2, u2);
+  if (s0 < X02) t0 = tau_core(0, x0);
+  if (s1 < X02) t1 = tau_core(1, x1);
+  if (s2 < X02) t2 = tau_core(2, x2);
+  return (t0 + t1) + t2;
+}
+
+}  // namespace gpdla

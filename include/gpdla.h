@@ -1,0 +1,121 @@
+/* gpdla.h -- C ABI of libgpdla.so, the B200 (sm_100a) implementation of gp_dla_detection's
+ * per-quasar DLA model-selection hot path.
+ *
+ * Every entry point replaces one interface of the reference (paths are into the
+ * jibanCat/gp_dla_detection tree):
+ *
+ *   gpdla_voigt / gpdla_voigt_batch_device
+ *        the MEX function  profile = voigt(lambdas, z, N [, num_lines])     voigt.c:253-304
+ *        (call site process_qsos.m:187-188)
+ *   gpdla_set_model        load(learned_qso_model_*)  rest_wavelengths, mu, M, log_omega,
+ *                          log_c_0, log_tau_0, log_beta                      process_qsos.m:29-35
+ *   gpdla_set_samples      load(dla_samples)  offset_samples, log_nhi_samples, nhi_samples
+ *                                                                            process_qsos.m:37-40
+ *   gpdla_set_prior        prior.z_qsos, prior.dla_ind                       process_qsos.m:11-27
+ *   gpdla_set_parameters   the workspace variables of set_parameters.m       set_parameters.m:5-73
+ *   gpdla_process_qsos / gpdla_process_qsos_device
+ *        the body of the script process_qsos.m:63-233 (per-quasar loop, sample loop calling
+ *        voigt + log_mvnpdf_low_rank.m:5-34, log-sum-exp, model posteriors) plus the MAP
+ *        extraction of generate_ascii_catalog.m:73-80
+ *
+ * Plain pointers and sizes only; no CPU fallback -- every function needs a CUDA device of
+ * compute capability 10.0 and returns GPDLA_ERR_CUDA otherwise.  All functions are
+ * re-entrant per context; a context must not be used from two threads at once.
+ */
+#ifndef GPDLA_H
+#define GPDLA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GPDLA_OK 0
+#define GPDLA_ERR_INVALID 1      /* bad argument (sizes, NULL, num_lines outside 1..31, num_points < 7) */
+#define GPDLA_ERR_CUDA 2         /* CUDA runtime error; see gpdla_last_error */
+#define GPDLA_ERR_UNSUPPORTED 3  /* configuration not compiled in (e.g. rank k) */
+#define GPDLA_ERR_STATE 4        /* model / samples / prior not set */
+
+#define GPDLA_MAX_LINES 31       /* voigt.c:16 */
+
+typedef struct gpdla_ctx gpdla_ctx;
+
+/* set_parameters.m:5-73 (only what the hot path reads) */
+typedef struct {
+  double min_lambda;            /* :33  911.75  */
+  double max_lambda;            /* :34  1215.75 */
+  double lya_wavelength;        /* :5   1215.6701 */
+  double lyman_limit;           /* :7   911.7633 */
+  double prior_z_qso_increase;  /* :56  kms_to_z(30000) */
+  double min_z_cut;             /* :69  kms_to_z(3000) */
+  double max_z_cut;             /* :65  kms_to_z(3000) */
+  double pixel_spacing;         /* :60  1e-4 dex */
+  int32_t num_lines;            /* :63  3 */
+  int32_t batch_quasars;        /* quasars processed per launch group (workspace size); 0 = default */
+} gpdla_params;
+
+/* process_qsos.m:74-82,236-244 result variables; each array has Q entries unless noted.
+ * Pointers may be NULL (that output is skipped).  Host pointers for gpdla_process_qsos,
+ * device pointers for gpdla_process_qsos_device. */
+typedef struct {
+  double* min_z_dlas;
+  double* max_z_dlas;
+  double* log_priors_no_dla;
+  double* log_priors_dla;
+  double* log_likelihoods_no_dla;
+  double* log_likelihoods_dla;
+  double* log_posteriors_no_dla;
+  double* log_posteriors_dla;
+  double* model_posteriors;             /* [Q x 2] row-major (no DLA, DLA) */
+  double* p_no_dlas;
+  double* p_dlas;
+  double* sample_log_likelihoods_dla;   /* [Q x S] row-major; NULL = not returned */
+  double* map_z_dlas;                   /* generate_ascii_catalog.m:75-76 */
+  double* map_log_nhis;                 /* generate_ascii_catalog.m:80 */
+  int64_t* map_inds;                    /* 0-based arg-max sample, -1 if none */
+} gpdla_results;
+
+void gpdla_default_parameters(gpdla_params* p);
+
+int gpdla_create(gpdla_ctx** ctx, int device);
+void gpdla_destroy(gpdla_ctx* ctx);
+const char* gpdla_last_error(const gpdla_ctx* ctx);
+/* number of kernels this context has launched so far (for bench.py's gpu_launches) */
+uint64_t gpdla_launch_count(const gpdla_ctx* ctx);
+
+int gpdla_set_parameters(gpdla_ctx* ctx, const gpdla_params* p);
+/* M is [n_rest x k], C-contiguous (MATLAB's column-major 1217 x k transposed once by the caller) */
+int gpdla_set_model(gpdla_ctx* ctx, const double* rest_wavelengths, int32_t n_rest, const double* mu,
+                    const double* M, int32_t k, const double* log_omega, double log_c_0, double log_tau_0,
+                    double log_beta);
+int gpdla_set_samples(gpdla_ctx* ctx, const double* offset_samples, const double* log_nhi_samples,
+                      const double* nhi_samples, int64_t num_dla_samples);
+int gpdla_set_prior(gpdla_ctx* ctx, const double* z_qsos, const uint8_t* dla_ind, int64_t n_prior);
+
+/* Spectra are the cell arrays all_wavelengths / all_flux / all_noise_variance / all_pixel_mask of
+ * preload_qsos.m:73-79 padded to [Q x L_max] row-major, with `lengths[q]` valid pixels each. */
+int gpdla_process_qsos(gpdla_ctx* ctx, int64_t Q, int64_t L_max, const double* wavelengths, const double* flux,
+                       const double* noise_variance, const uint8_t* pixel_mask, const int32_t* lengths,
+                       const double* z_qsos, const gpdla_results* out);
+/* Same with every array (inputs and outputs) already resident on the context's device;
+ * `stream` is a cudaStream_t (NULL = default stream).  Asynchronous: returns after enqueueing. */
+int gpdla_process_qsos_device(gpdla_ctx* ctx, int64_t Q, int64_t L_max, const double* wavelengths,
+                              const double* flux, const double* noise_variance, const uint8_t* pixel_mask,
+                              const int32_t* lengths, const double* z_qsos, const gpdla_results* out, void* stream);
+
+/* voigt.c:253-304: profile has num_points - 6 entries.  Host buffers; runs on the current device. */
+int gpdla_voigt(const double* lambdas, int64_t num_points, double z, double N, int32_t num_lines, double* profile);
+/* Batched, device buffers: profile[s, :] = voigt(lambdas, z[s], N[s], num_lines), [S x (num_points-6)] */
+int gpdla_voigt_batch_device(const double* lambdas, int64_t num_points, const double* z, const double* N,
+                             int64_t S, int32_t num_lines, double* profile, void* stream);
+
+/* Lyman-series constants as the library computes them (voigt.c:31-220,242-251), for verification:
+ * each output has GPDLA_MAX_LINES entries (instrument_profile: 7).  Pure host function. */
+void gpdla_line_constants(double* transition_wavelengths, double* leading_constants, double* gammas,
+                          double* instrument_profile);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPDLA_H */
