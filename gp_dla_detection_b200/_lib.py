@@ -6,7 +6,7 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libgpdla.so")
+LIB_PATH = os.environ.get("GPDLA_LIB", os.path.join(HERE, "libgpdla.so"))   # GPDLA_LIB: debug builds only
 
 c_double_p = ctypes.POINTER(ctypes.c_double)
 c_u8_p = ctypes.POINTER(ctypes.c_uint8)
@@ -41,6 +41,8 @@ SYMBOLS = {
     "gpdla_destroy": (None, [ctypes.c_void_p]),
     "gpdla_last_error": (ctypes.c_char_p, [ctypes.c_void_p]),
     "gpdla_launch_count": (ctypes.c_uint64, [ctypes.c_void_p]),
+    "gpdla_set_profiling": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    "gpdla_profile_read": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double), c_i64_p]),
     "gpdla_set_parameters": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(GpdlaParams)]),
     "gpdla_set_model": (ctypes.c_int, [ctypes.c_void_p, c_double_p, ctypes.c_int32, c_double_p, c_double_p,
                                        ctypes.c_int32, c_double_p, ctypes.c_double, ctypes.c_double,

@@ -100,6 +100,15 @@ class DLAProcessor:
     def launch_count(self) -> int:
         return int(self._lib.gpdla_launch_count(self._ctx))
 
+    def set_profiling(self, enable: bool):
+        _lib.check(self._lib.gpdla_set_profiling(self._ctx, int(bool(enable))), self._ctx)
+
+    def profile_read(self):
+        """(summed ms, launches) of the fused log-likelihood kernel since the last read."""
+        ms, n = ctypes.c_double(), ctypes.c_int64()
+        _lib.check(self._lib.gpdla_profile_read(self._ctx, ctypes.byref(ms), ctypes.byref(n)), self._ctx)
+        return ms.value, n.value
+
     # ---------------------------------------------------------------- host buffers (the drop-in call)
     def process(self, spectra: Dict, return_sample_log_likelihoods: bool = True) -> Dict[str, np.ndarray]:
         sp = pad_spectra(spectra)

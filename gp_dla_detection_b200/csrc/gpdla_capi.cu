@@ -129,6 +129,9 @@ struct gpdla_ctx {
   // staging for the host entry point
   size_t st_bytes = 0;
   void* d_stage = nullptr;
+  // optional per-kernel timing of the dominant kernel (bench.py's roofline)
+  bool profiling = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
 };
 
 static void free_workspace(gpdla_ctx* c) {
@@ -167,9 +170,19 @@ static int launch_loglik(gpdla_ctx* c, const LoglikArgs& la, int nq, cudaStream_
     configured = smem;
   }
   dim3 grid((unsigned)((la.S + 1 + Cfg::TS - 1) / Cfg::TS), (unsigned)nq);
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (c->profiling) {
+    CUDA_TRY(cudaEventCreate(&e0), c->err);
+    CUDA_TRY(cudaEventCreate(&e1), c->err);
+    CUDA_TRY(cudaEventRecord(e0, st), c->err);
+  }
   kern<<<grid, NTHREADS, smem, st>>>(la);
   c->launches++;
   CUDA_TRY(cudaGetLastError(), c->err);
+  if (c->profiling) {
+    CUDA_TRY(cudaEventRecord(e1, st), c->err);
+    c->prof_events.emplace_back(e0, e1);
+  }
   return GPDLA_OK;
 }
 
@@ -226,6 +239,29 @@ void gpdla_destroy(gpdla_ctx* c) {
 
 const char* gpdla_last_error(const gpdla_ctx* c) { return c ? c->err.c_str() : g_err.c_str(); }
 uint64_t gpdla_launch_count(const gpdla_ctx* c) { return c ? c->launches : 0; }
+
+int gpdla_set_profiling(gpdla_ctx* c, int enable) {
+  if (!c) return GPDLA_ERR_INVALID;
+  c->profiling = enable != 0;
+  return GPDLA_OK;
+}
+
+int gpdla_profile_read(gpdla_ctx* c, double* loglik_ms, int64_t* loglik_launches) {
+  if (!c) return GPDLA_ERR_INVALID;
+  double total = 0;
+  int64_t n = 0;
+  for (auto& ev : c->prof_events) {
+    CUDA_TRY(cudaEventSynchronize(ev.second), c->err);
+    float ms = 0;
+    CUDA_TRY(cudaEventElapsedTime(&ms, ev.first, ev.second), c->err);
+    total += ms; ++n;
+    cudaEventDestroy(ev.first); cudaEventDestroy(ev.second);
+  }
+  c->prof_events.clear();
+  if (loglik_ms) *loglik_ms = total;
+  if (loglik_launches) *loglik_launches = n;
+  return GPDLA_OK;
+}
 
 int gpdla_set_parameters(gpdla_ctx* c, const gpdla_params* p) {
   if (!c || !p) return GPDLA_ERR_INVALID;
@@ -328,6 +364,19 @@ int gpdla_process_qsos_device(gpdla_ctx* c, int64_t Q, int64_t L_max, const doub
     la.offset_samples = c->d_offset; la.nhi_samples = c->d_nhi; la.S = c->S;
     la.num_lines = c->params.num_lines; la.NPIX = npix;
     la.sample_log_likelihoods = sll; la.log_likelihoods_no_dla = llno;
+    la.phase_cycles = nullptr;
+#ifdef GPDLA_PHASE_TIMING
+    {
+      static long long* d_phase = nullptr;
+      if (!d_phase) { cudaMalloc(&d_phase, 16 * sizeof(long long)); cudaMemset(d_phase, 0, 16 * sizeof(long long)); }
+      la.phase_cycles = d_phase;
+      long long h[16];
+      cudaMemcpy(h, d_phase, sizeof h, cudaMemcpyDeviceToHost);
+      fprintf(stderr, "[phase cycles so far] A1 %lld | S1wait %lld | A2 %lld | S2wait %lld | tma wait %lld | B %lld | loop %lld | epilogue %lld\n",
+              h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7]);
+      fprintf(stderr, "[core path] cycles %lld, warp-evals with core %lld of %lld\n", h[8], h[9], h[10]);
+    }
+#endif
     if (c->params.num_lines == 3) rc = launch_loglik<20, 4, 2, 2, 3>(c, la, nq, st);
     else rc = launch_loglik<20, 4, 2, 2, 0>(c, la, nq, st);
     if (rc) return rc;

@@ -305,7 +305,7 @@ __global__ void __launch_bounds__(NTHREADS) voigt_batch_kernel(const double* __r
     int64_t p = i0 + t;
     if (p < num_points) {
       double tau = tau_sum_generic(lambdas[p], s_mult, 1, num_lines);
-      s_raw[t] = exp(-N * tau);                       // voigt.c:291
+      s_raw[t] = exp_nonpos(-N * tau);                // voigt.c:291
     }
   }
   __syncthreads();
@@ -332,7 +332,16 @@ struct LoglikArgs {
   int NPIX;
   double* sample_log_likelihoods;   // [Q x S]
   double* log_likelihoods_no_dla;   // [Q]
+  long long* phase_cycles;          // debug builds (-DGPDLA_PHASE_TIMING): [16] summed cycles per phase
 };
+
+#ifdef GPDLA_PHASE_TIMING
+#define PHASE_T(var) long long var = clock64()
+#define PHASE_ADD(idx, t0, t1) do { if (tid == 0) atomicAdd((unsigned long long*)&args.phase_cycles[idx], (unsigned long long)((t1) - (t0))); } while (0)
+#else
+#define PHASE_T(var)
+#define PHASE_ADD(idx, t0, t1)
+#endif
 
 template <int K, int WM, int WN, int MT>
 struct LoglikConfig {
@@ -411,19 +420,55 @@ __global__ void __launch_bounds__(NTHREADS, 1) dla_loglik_kernel(LoglikArgs args
     tma_load_1d(Bt, Pq, CHUNK_BYTES, &mbar[0]);
   }
 
-  // raw-profile evaluation for this warp's samples at padded pixel p
+  // raw-profile evaluation for this warp's samples at padded pixel p.  The common (wing) path is one
+  // basic block over all SPW samples so their dependency chains interleave; pixels within X0 Doppler
+  // widths of a line centre (<= 7 per line per sample) are redone by the exact routine.
   auto eval_raw = [&](int p) {
     const double lambda = lam[p];
+    double tau[SPW];
+    if (NL == 3) {
+      unsigned coremask = 0;
 #pragma unroll
-    for (int ss = 0; ss < SPW; ++ss) {
-      const int sl = warp * SPW + ss;
-      double tau;
-      if (NL == 3) tau = tau_sum_3(lambda, s_mult[sl], s_mult[TS + sl], s_mult[2 * TS + sl]);
-      else tau = tau_sum_generic(lambda, s_mult + sl, TS, num_lines);
-      rawbuf[sl * RAWW + (p & (RAWW - 1))] = exp(-s_nhi[sl] * tau);     // voigt.c:291
+      for (int ss = 0; ss < SPW; ++ss) {
+        const int sl = warp * SPW + ss;
+        bool core;
+        tau[ss] = tau_sum_3_wing(lambda, s_mult[sl], s_mult[TS + sl], s_mult[2 * TS + sl], core);
+        coremask |= core ? (1u << ss) : 0u;
+      }
+      PHASE_T(t_c0);
+      if (coremask) {
+#pragma unroll
+        for (int ss = 0; ss < SPW; ++ss) {
+          const int sl = warp * SPW + ss;
+          if (coremask & (1u << ss))
+            tau[ss] = tau_sum_3_exact(lambda, s_mult[sl], s_mult[TS + sl], s_mult[2 * TS + sl]);
+        }
+      }
+#ifdef GPDLA_PHASE_TIMING
+      __syncwarp();
+      PHASE_T(t_c1);
+      const bool any_core = __any_sync(0xffffffffu, coremask != 0);
+      if (lane == 0) {
+        atomicAdd((unsigned long long*)&args.phase_cycles[8], (unsigned long long)(t_c1 - t_c0));
+        atomicAdd((unsigned long long*)&args.phase_cycles[9], (unsigned long long)(any_core ? 1 : 0));
+        atomicAdd((unsigned long long*)&args.phase_cycles[10], 1ull);
+      }
+#endif
+    } else {
+#pragma unroll
+      for (int ss = 0; ss < SPW; ++ss) tau[ss] = tau_sum_generic(lambda, s_mult + warp * SPW + ss, TS, num_lines);
     }
+    // all shared-memory loads before the first store: the compiler cannot prove s_nhi and rawbuf do
+    // not alias, and a load stuck behind a store would serialise the SPW exponentials
+    double e[SPW];
+#pragma unroll
+    for (int ss = 0; ss < SPW; ++ss) e[ss] = -s_nhi[warp * SPW + ss] * tau[ss];
+#pragma unroll
+    for (int ss = 0; ss < SPW; ++ss) e[ss] = exp_nonpos(e[ss]);                    // voigt.c:291
+#pragma unroll
+    for (int ss = 0; ss < SPW; ++ss) rawbuf[(warp * SPW + ss) * RAWW + (p & (RAWW - 1))] = e[ss];
   };
-  if (lane < 6) eval_raw(lane);   // leading pad pixels p = 0..5
+  eval_raw(lane < 6 ? lane : 5);   // leading pad pixels p = 0..5 (all lanes participate; extra lanes repeat p = 5)
 
   // accumulators
   double acc[MT][NTW][2];
@@ -440,10 +485,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) dla_loglik_kernel(LoglikArgs args
   const int gid = lane >> 2, tig = lane & 3;
   const int nw_local = max(0, min(NTW, G::WT - wn * NTW));   // tiles of this warp fed by W (rest: U)
 
+  PHASE_T(t_start);
   for (int c = 0; c < meta.nchunks; ++c) {
     // ---- A1: raw profile for the KC new padded pixels
+    PHASE_T(t_a1);
     eval_raw(c * KC + 6 + lane);
+    PHASE_T(t_a1e);
     __syncthreads();   // S1: raw visible; everyone is past the previous chunk's DMMA phase
+    PHASE_T(t_s1);
     if (tid == 0 && c + 1 < meta.nchunks) {
       mbar_expect_tx(&mbar[(c + 1) & 1], CHUNK_BYTES);
       tma_load_1d(Bt + ((c + 1) & 1) * G::CHUNK_DOUBLES, Pq + (int64_t)(c + 1) * G::CHUNK_DOUBLES, CHUNK_BYTES,
@@ -455,21 +504,27 @@ __global__ void __launch_bounds__(NTHREADS, 1) dla_loglik_kernel(LoglikArgs args
       const double2 p01 = *reinterpret_cast<const double2*>(pix + (int64_t)i * 4);
       const double2 p23 = *reinterpret_cast<const double2*>(pix + (int64_t)i * 4 + 2);
       const double y = p01.x, v = p01.y, mu = p23.x, om2 = p23.y;
+      // loads first (convolution), stores last: see the aliasing note in eval_raw
+      double a[SPW];
 #pragma unroll
       for (int ss = 0; ss < SPW; ++ss) {
         const int sl = warp * SPW + ss;
         const double* rb = rawbuf + sl * RAWW;
-        double a = 0.0;
+        double acc_a = 0.0;
 #pragma unroll
-        for (int t = 0; t < 7; ++t) a = fma(rb[(i + t) & (RAWW - 1)], c_lines.ip[t], a);   // voigt.c:297-299
-        if (s_nhi[sl] < 0.0) a = 1.0;                    // null model: no absorption
-        const double a2 = a * a;
+        for (int t = 0; t < 7; ++t) acc_a = fma(rb[(i + t) & (RAWW - 1)], c_lines.ip[t], acc_a);   // voigt.c:297-299
+        a[ss] = (s_nhi[sl] < 0.0) ? 1.0 : acc_a;        // null model: no absorption
+      }
+#pragma unroll
+      for (int ss = 0; ss < SPW; ++ss) {
+        const int sl = warp * SPW + ss;
+        const double a2 = a[ss] * a[ss];
         const double d = fma(a2, om2, v);                // dla_omega2 + noise variance  (process_qsos.m:194,198)
         const double rd = fast_rcp(d);
-        const double r = fma(-a, mu, y);                 // y - dla_mu
+        const double r = fma(-a[ss], mu, y);             // y - dla_mu
         const double t1 = r * rd;
         Wt[sl * ASTR + lane] = a2 * rd;
-        Ut[sl * ASTR + lane] = a * t1;
+        Ut[sl * ASTR + lane] = a[ss] * t1;
         qacc[ss] = fma(r, t1, qacc[ss]);
         ldm[ss] *= d;
       }
@@ -483,8 +538,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) dla_loglik_kernel(LoglikArgs args
         }
       }
     }
+    PHASE_T(t_a2e);
     __syncthreads();   // S2: operand tiles visible
+    PHASE_T(t_s2);
     mbar_wait(&mbar[c & 1], (c >> 1) & 1);
+    PHASE_T(t_mb);
     // ---- B: FP64 tensor-core contraction  acc += [W|U] (TS x KC) . P_chunk (KC x NCOL)
     {
       const double* Bc = Bt + (c & 1) * G::CHUNK_DOUBLES;
@@ -508,7 +566,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) dla_loglik_kernel(LoglikArgs args
         }
       }
     }
+    PHASE_T(t_be);
+    PHASE_ADD(0, t_a1, t_a1e); PHASE_ADD(1, t_a1e, t_s1); PHASE_ADD(2, t_s1, t_a2e); PHASE_ADD(3, t_a2e, t_s2);
+    PHASE_ADD(4, t_s2, t_mb); PHASE_ADD(5, t_mb, t_be);
   }
+  PHASE_T(t_loop_end);
+  PHASE_ADD(6, t_start, t_loop_end);
 
   // ---- per-sample scalars: sum r^2/d and sum log d
 #pragma unroll
@@ -569,6 +632,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) dla_loglik_kernel(LoglikArgs args
     if (s < S) args.sample_log_likelihoods[(int64_t)q * S + s] = lp;
     else if (s == S) args.log_likelihoods_no_dla[q] = lp;
   }
+#ifdef GPDLA_PHASE_TIMING
+  __syncthreads();
+  PHASE_T(t_end);
+  PHASE_ADD(7, t_loop_end, t_end);
+#endif
 }
 
 // ------------------------------------------------------------------------------------------

@@ -111,23 +111,56 @@ __device__ __forceinline__ double tau_sum_generic(double lambda, const double* m
   return total;
 }
 
-// Three-line specialisation (num_lines = 3, set_parameters.m:63): the three reciprocals share
-// one MUFU + Newton sequence through a common denominator.
-__device__ __forceinline__ double tau_sum_3(double lambda, double m0, double m1, double m2) {
+// Three-line specialisation (num_lines = 3, set_parameters.m:63), branch-free wing part: the three
+// reciprocals share one MUFU + Newton sequence through a common denominator.  Returns the sum with
+// every line evaluated by the wing formula (|x| clamped to X0) and sets `core` when some line is
+// inside |x| < X0, in which case the caller re-evaluates with tau_sum_3_exact().  Keeping this free
+// of control flow lets the compiler interleave the evaluations of several samples.
+__device__ __forceinline__ double tau_sum_3_wing(double lambda, double m0, double m1, double m2, bool& core) {
   const double X02 = GPDLA_VOIGT_X0 * GPDLA_VOIGT_X0;
   double x0 = __dsub_rn(__dmul_rn(lambda, m0), c_lines.c) * c_lines.inv_s2s;
   double x1 = __dsub_rn(__dmul_rn(lambda, m1), c_lines.c) * c_lines.inv_s2s;
   double x2 = __dsub_rn(__dmul_rn(lambda, m2), c_lines.c) * c_lines.inv_s2s;
   double s0 = x0 * x0, s1 = x1 * x1, s2 = x2 * x2;
+  core = fmin(s0, fmin(s1, s2)) < X02;
   double c0 = fmax(s0, X02), c1 = fmax(s1, X02), c2 = fmax(s2, X02);   // x^2 <= 8e3^2: product < 3e23
   double p12 = c1 * c2;
   double r = fast_rcp(c0 * p12);
   double u0 = r * p12, u1 = r * (c0 * c2), u2 = r * (c0 * c1);
-  double t0 = tau_wing(0, u0), t1 = tau_wing(1, u1), t2 = tau_wing(2, u2);
-  if (s0 < X02) t0 = tau_core(0, x0);
-  if (s1 < X02) t1 = tau_core(1, x1);
-  if (s2 < X02) t2 = tau_core(2, x2);
-  return (t0 + t1) + t2;
+  return (tau_wing(0, u0) + tau_wing(1, u1)) + tau_wing(2, u2);
+}
+
+// Exact three-line sum including core pixels (rare path; same summation order as voigt.c:285-290).
+__device__ __noinline__ double tau_sum_3_exact(double lambda, double m0, double m1, double m2) {
+  const double X02 = GPDLA_VOIGT_X0 * GPDLA_VOIGT_X0;
+  double m[3] = {m0, m1, m2};
+  double t[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    double x = __dsub_rn(__dmul_rn(lambda, m[j]), c_lines.c) * c_lines.inv_s2s;
+    double s = x * x;
+    t[j] = (s < X02) ? tau_core(j, x) : tau_wing(j, fast_rcp(s));
+  }
+  return (t[0] + t[1]) + t[2];
+}
+
+// exp(x) for x <= 0 (and small positive x), branch-free: Cody-Waite reduction, degree-11 polynomial
+// (tools/gen_voigt_tables.py), exponent assembled in integer registers.  Returns 0 below -708
+// (the reference's libm would return values < 2.3e-308 there).
+__constant__ double c_exp_poly[12] = GPDLA_EXP_POLY;
+__device__ __forceinline__ double exp_nonpos(double x) {
+  const double SHIFT = 6755399441055744.0;   // 1.5 * 2^52
+  double xc = fmax(x, -708.0);
+  double kd = fma(xc, 1.4426950408889634074, SHIFT);
+  int k = __double2loint(kd);
+  kd -= SHIFT;
+  double r = fma(kd, -6.93147180369123816490e-01, xc);
+  r = fma(kd, -1.90821492927058770002e-10, r);
+  double p = c_exp_poly[11];
+#pragma unroll
+  for (int i = 10; i >= 0; --i) p = fma(p, r, c_exp_poly[i]);
+  double res = __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+  return (x < -708.0) ? 0.0 : res;
 }
 
 }  // namespace gpdla

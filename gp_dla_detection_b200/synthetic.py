@@ -106,9 +106,11 @@ def make_spectra(model: dict, num_quasars: int, seed: int = SPECTRA_SEED, shard:
             lam, rest = lam[inside[:1217]], rest[inside[:1217]]
         L = lam.size
         rc = np.clip(rest, lam_rest[0], lam_rest[-1])
-        mu_i = np.interp(rc, lam_rest, mu)
-        M_i = np.stack([np.interp(rc, lam_rest, M[:, j]) for j in range(k)], axis=1)
-        om2 = np.exp(2 * np.interp(rc, lam_rest, log_omega))
+        jj = np.minimum(((rc - lam_rest[0]) / P.DEFAULT.dlambda).astype(np.int64), lam_rest.size - 2)
+        tt = (rc - lam_rest[jj]) / P.DEFAULT.dlambda
+        mu_i = mu[jj] + tt * (mu[jj + 1] - mu[jj])
+        M_i = M[jj] + tt[:, None] * (M[jj + 1] - M[jj])
+        om2 = np.exp(2 * (log_omega[jj] + tt * (log_omega[jj + 1] - log_omega[jj])))
         om2 = om2 * (1 - np.exp(-tau_0 * (lam / P.lya_wavelength) ** beta) + c_0) ** 2
         noise_variance = (0.1 + 0.4 * rng.random(L)) ** 2
         flux = mu_i + M_i @ rng.standard_normal(k) + np.sqrt(om2) * rng.standard_normal(L)

@@ -84,6 +84,12 @@ const char* gpdla_last_error(const gpdla_ctx* ctx);
 /* number of kernels this context has launched so far (for bench.py's gpu_launches) */
 uint64_t gpdla_launch_count(const gpdla_ctx* ctx);
 
+/* Optional timing of the dominant kernel (fused Voigt + Gram + Cholesky): when enabled, CUDA events
+ * bracket each of its launches on the launching stream; gpdla_profile_read waits for them, returns
+ * the summed milliseconds and the launch count since the last read, and resets. */
+int gpdla_set_profiling(gpdla_ctx* ctx, int enable);
+int gpdla_profile_read(gpdla_ctx* ctx, double* loglik_ms, int64_t* loglik_launches);
+
 int gpdla_set_parameters(gpdla_ctx* ctx, const gpdla_params* p);
 /* M is [n_rest x k], C-contiguous (MATLAB's column-major 1217 x k transposed once by the caller) */
 int gpdla_set_model(gpdla_ctx* ctx, const double* rest_wavelengths, int32_t n_rest, const double* mu,

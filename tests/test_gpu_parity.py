@@ -1,0 +1,235 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle and the golden vectors.
+
+Tolerances are BASELINE.json's north_star: same MAP sample index, log-likelihoods within 1e-8
+relative, p_dla within 1e-6 absolute (the asserts below are tighter where the path allows)."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import boss_grid
+
+LL_RTOL = 1e-8        # north_star tolerance on log-likelihoods
+LL_RTOL_TIGHT = 1e-10  # what this implementation is held to
+P_ATOL = 1e-6         # north_star tolerance on p_dla
+PROFILE_ATOL = 5e-15  # absorption profile, absolute (values in [0, 1])
+
+
+def load_golden_problem(golden_dir):
+    g = np.load(os.path.join(golden_dir, "process_qsos_small.npz"))
+    model = dict(rest_wavelengths=g["model_rest_wavelengths"], mu=g["model_mu"], M=g["model_M"],
+                 log_omega=g["model_log_omega"], log_c_0=g["model_scalars"][0], log_tau_0=g["model_scalars"][1],
+                 log_beta=g["model_scalars"][2])
+    samples = {k: g[k] for k in ("offset_samples", "log_nhi_samples", "nhi_samples")}
+    prior = dict(z_qsos=g["prior_z_qsos"], dla_ind=g["prior_dla_ind"])
+    spectra = {k: [g["%s_%d" % (k, q)] for q in range(3)]
+               for k in ("all_wavelengths", "all_flux", "all_noise_variance", "all_pixel_mask")}
+    spectra["z_qsos"] = g["z_qsos"]
+    expect = {k[4:]: g[k] for k in g.files if k.startswith("out_")}
+    return model, samples, spectra, prior, expect
+
+
+def assert_parity(res, ref, check_samples=True):
+    assert np.array_equal(res["map_inds"], ref["map_inds"])
+    for k in ("log_likelihoods_no_dla", "log_likelihoods_dla", "log_posteriors_no_dla", "log_posteriors_dla"):
+        assert np.allclose(res[k], ref[k], rtol=LL_RTOL_TIGHT, atol=0, equal_nan=True), k
+    if check_samples:
+        a, b = res["sample_log_likelihoods_dla"], ref["sample_log_likelihoods_dla"]
+        assert np.allclose(a, b, rtol=LL_RTOL_TIGHT, atol=0, equal_nan=True)
+    for k in ("p_dlas", "p_no_dlas"):
+        assert np.allclose(res[k], ref[k], rtol=0, atol=P_ATOL, equal_nan=True), k
+    assert np.allclose(res["model_posteriors"], ref["model_posteriors"], rtol=0, atol=P_ATOL, equal_nan=True)
+    for k in ("min_z_dlas", "max_z_dlas", "log_priors_no_dla", "log_priors_dla", "map_z_dlas", "map_log_nhis"):
+        assert np.allclose(res[k], ref[k], rtol=1e-14, atol=0, equal_nan=True), k
+
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def api():
+    from gp_dla_detection_b200 import api as A
+    return A
+
+
+def test_voigt_against_oracle(api):
+    from oracle import process_qsos_oracle as O
+    lam = boss_grid()
+    rng = np.random.default_rng(3)
+    cases = [(2.3, 1e21, 3), (2.1, 10 ** 20.3, 31), (2.5, 1e23, 3), (2.9, 1e20, 1), (2.2, 10 ** 19.5, 3)]
+    cases += [(rng.uniform(1.95, 2.95), 10 ** rng.uniform(20, 23), int(rng.choice([1, 2, 3, 7, 31]))) for _ in range(25)]
+    for z, N, nl in cases:
+        a, b = api.voigt(lam, z, N, nl), O.voigt(lam, z, N, nl)
+        assert a.shape == (lam.size - 6,)
+        assert np.max(np.abs(a - b)) <= PROFILE_ATOL, (z, N, nl)
+    assert np.array_equal(api.voigt(lam, 2.2, 0.0, 3), np.ones(lam.size - 6))   # N = 0: exactly no absorption
+    assert api.voigt(lam[:7], 2.2, 1e20, 3).shape == (1,)                       # minimum length
+
+
+def test_voigt_against_reference_golden_vectors(api, golden_dir):
+    g = np.load(os.path.join(golden_dir, "voigt_reference.npz"))
+    for i, (z, N, nl) in enumerate(g["cases"]):
+        lam = g["lambdas"] if z < 3.5 else g["lambdas_hi"]
+        assert np.max(np.abs(api.voigt(lam, z, N, int(nl)) - g["profile_%d" % i])) <= PROFILE_ATOL
+
+
+def test_voigt_core_pixels_dense_sweep(api):
+    """Sweep the line centre across a pixel in fine steps so every core-table interval is hit."""
+    from oracle import process_qsos_oracle as O
+    lam = boss_grid(200, 3.60)
+    for nl, logn in ((1, 12.5), (3, 13.0), (3, 14.0)):   # unsaturated: the core shape is visible
+        for dz in np.linspace(0, 3e-4, 41):
+            z = 2.3 + dz
+            a, b = api.voigt(lam, z, 10 ** logn, nl), O.voigt(lam, z, 10 ** logn, nl)
+            assert np.max(np.abs(a - b)) <= PROFILE_ATOL
+
+
+def test_voigt_errors(api):
+    from gp_dla_detection_b200._lib import GpdlaError
+    lam = boss_grid(50)
+    for bad in (dict(lambdas=lam[:6], z=2.0, N=1e20, num_lines=3), dict(lambdas=lam, z=2.0, N=1e20, num_lines=0),
+                dict(lambdas=lam, z=2.0, N=1e20, num_lines=32), dict(lambdas=lam, z=-1.5, N=1e20, num_lines=3)):
+        with pytest.raises(GpdlaError):
+            api.voigt(**bad)
+
+
+def test_voigt_batch_device(api):
+    import torch
+    from oracle import process_qsos_oracle as O
+    lam = boss_grid(700)
+    zs, Ns = np.linspace(2.0, 2.6, 9), 10 ** np.linspace(20, 22.5, 9)
+    out = api.voigt_batch(torch.from_numpy(lam).cuda(), torch.from_numpy(zs).cuda(), torch.from_numpy(Ns).cuda(), 3)
+    out = out.cpu().numpy()
+    for i in range(9):
+        assert np.max(np.abs(out[i] - O.voigt(lam, zs[i], Ns[i], 3))) <= PROFILE_ATOL
+
+
+def test_process_qsos_golden_small(api, golden_dir):
+    model, samples, spectra, prior, expect = load_golden_problem(golden_dir)
+    res = api.process_qsos(model, samples, spectra, prior)
+    assert_parity(res, expect)
+
+
+def test_process_qsos_full_size_against_oracle(api, synthetic_inputs):
+    """Reference configuration: 10 000 samples, k = 20, 3 lines, ~1250-pixel spectra."""
+    from oracle import process_qsos_oracle as O
+    si = synthetic_inputs
+    res = api.process_qsos(si["model"], si["samples"], si["spectra"], si["prior"])
+    ref = O.process_qsos(si["model"], si["samples"], si["spectra"], si["prior"], engine="c")
+    assert_parity(res, ref)
+    # north_star's own tolerance, stated explicitly
+    rel = np.abs(res["sample_log_likelihoods_dla"] - ref["sample_log_likelihoods_dla"]) / np.abs(ref["sample_log_likelihoods_dla"])
+    assert rel.max() < LL_RTOL
+    # injected DLAs are recovered: MAP within one sample spacing of the truth
+    sp = si["spectra"]
+    for q in np.flatnonzero(~np.isnan(sp["truth_z_dla"])):
+        assert res["p_dlas"][q] > 0.99
+        assert abs(res["map_z_dlas"][q] - sp["truth_z_dla"][q]) < 5e-3
+        assert abs(res["map_log_nhis"][q] - sp["truth_log_nhi"][q]) < 1.0   # noisy spectra: loose on N_HI
+
+
+def test_fixed_shape_1217_pixel_grid(api, synthetic_inputs):
+    from gp_dla_detection_b200 import synthetic as syn
+    from oracle import process_qsos_oracle as O
+    si = synthetic_inputs
+    sp = syn.make_spectra(si["model"], 2, seed=11, fixed_shape=True)
+    sub = np.arange(0, 10000, 10)
+    samples = {k: v[sub] for k, v in si["samples"].items()}
+    res = api.process_qsos(si["model"], samples, sp, si["prior"])
+    ref = O.process_qsos(si["model"], samples, sp, si["prior"], engine="c")
+    assert_parity(res, ref)
+
+
+def test_more_lyman_lines(api, synthetic_inputs):
+    from gp_dla_detection_b200.params import Parameters
+    from oracle import process_qsos_oracle as O
+    si = synthetic_inputs
+    sp = {k: v[:1] for k, v in si["spectra"].items()}
+    sub = np.arange(0, 10000, 40)
+    samples = {k: v[sub] for k, v in si["samples"].items()}
+    for nl in (1, 5, 31):
+        res = api.process_qsos(si["model"], samples, sp, si["prior"], params=Parameters(num_lines=nl))
+        ref = O.process_qsos(si["model"], samples, sp, si["prior"], num_lines=nl, engine="c")
+        assert_parity(res, ref)
+
+
+def test_ragged_masked_and_empty_spectra(api, synthetic_inputs):
+    from oracle import process_qsos_oracle as O
+    si = synthetic_inputs
+    sp = {k: ([x.copy() for x in v] if isinstance(v, list) else v.copy()) for k, v in si["spectra"].items()}
+    for k in ("all_wavelengths", "all_flux", "all_noise_variance", "all_pixel_mask"):
+        sp[k][0] = sp[k][0][500:]                      # blue end missing (BOSS coverage limit)
+        sp[k][2] = sp[k][2][:900]                      # red end missing
+    sp["all_pixel_mask"][1][200:260] = True            # a masked block
+    sp["all_flux"][1][200:260] = np.nan                # garbage under the mask must not leak
+    sp["all_pixel_mask"][3][:] = True                  # nothing usable: NaN results (process_qsos.m:74-82)
+    sub = np.arange(0, 10000, 20)
+    samples = {k: v[sub] for k, v in si["samples"].items()}
+    res = api.process_qsos(si["model"], samples, sp, si["prior"])
+    spo = {k: (v[:3] if isinstance(v, list) else v[:3]) for k, v in sp.items()}
+    spo["all_flux"][1] = np.where(sp["all_pixel_mask"][1], 0.0, sp["all_flux"][1])
+    ref = O.process_qsos(si["model"], samples, spo, si["prior"], engine="c")
+    assert_parity({k: v[:3] for k, v in res.items()}, ref)
+    for k in ("log_likelihoods_no_dla", "log_likelihoods_dla", "p_dlas", "map_z_dlas", "min_z_dlas"):
+        assert np.isnan(res[k][3]), k
+    assert res["map_inds"][3] == -1 and np.all(np.isnan(res["sample_log_likelihoods_dla"][3]))
+
+
+def test_batching_and_device_entry_agree_with_host_entry(api, synthetic_inputs):
+    import torch
+    from gp_dla_detection_b200 import synthetic as syn
+    si = synthetic_inputs
+    sp = syn.make_spectra(si["model"], 7, seed=21)
+    sub = np.arange(0, 10000, 50)
+    samples = {k: v[sub] for k, v in si["samples"].items()}
+    one = api.DLAProcessor(si["model"], samples, si["prior"]).process(sp)
+    small = api.DLAProcessor(si["model"], samples, si["prior"], batch_quasars=2).process(sp)
+    for k in one:
+        assert np.array_equal(one[k], small[k], equal_nan=True), k
+    proc = api.DLAProcessor(si["model"], samples, si["prior"], batch_quasars=3)
+    pad = api.pad_spectra(sp)
+    t = {k: torch.from_numpy(np.ascontiguousarray(v)).cuda() for k, v in pad.items()}
+    n0 = proc.launch_count
+    dev = proc.process_device(t["wavelengths"], t["flux"], t["noise_variance"], t["pixel_mask"], t["lengths"],
+                              t["z_qsos"], return_sample_log_likelihoods=True)
+    torch.cuda.synchronize()
+    assert proc.launch_count - n0 == 4 * 3            # 4 kernels per batch, 3 batches
+    for k in one:
+        assert np.array_equal(one[k], dev[k].cpu().numpy(), equal_nan=True), k
+
+
+def test_zero_column_density_reduces_to_null_model(api, synthetic_inputs):
+    """Size-independent property at the full 10 000-sample size: N_HI = 0 for every sample makes each
+    sample likelihood equal the null likelihood, so the DLA evidence equals the null evidence."""
+    si = synthetic_inputs
+    s0 = dict(si["samples"]); s0["nhi_samples"] = np.zeros_like(s0["nhi_samples"])
+    res = api.process_qsos(si["model"], s0, si["spectra"], si["prior"])
+    for q in range(len(si["spectra"]["z_qsos"])):
+        assert np.allclose(res["sample_log_likelihoods_dla"][q], res["log_likelihoods_no_dla"][q], rtol=1e-12, atol=0)
+    assert np.allclose(res["log_likelihoods_dla"], res["log_likelihoods_no_dla"], rtol=1e-12, atol=0)
+
+
+def test_sample_permutation_invariance(api, synthetic_inputs):
+    """Permuting the samples permutes the sample likelihoods bit-for-bit and leaves the evidence and MAP
+    parameters unchanged (checks tile/offset handling at full size)."""
+    si = synthetic_inputs
+    sp = {k: v[:2] for k, v in si["spectra"].items()}
+    perm = np.random.default_rng(5).permutation(10000)
+    sperm = {k: v[perm] for k, v in si["samples"].items()}
+    a = api.process_qsos(si["model"], si["samples"], sp, si["prior"])
+    b = api.process_qsos(si["model"], sperm, sp, si["prior"])
+    assert np.array_equal(a["sample_log_likelihoods_dla"][:, perm], b["sample_log_likelihoods_dla"])
+    assert np.allclose(a["log_likelihoods_dla"], b["log_likelihoods_dla"], rtol=1e-13, atol=0)
+    assert np.array_equal(a["map_z_dlas"], b["map_z_dlas"]) and np.array_equal(a["map_log_nhis"], b["map_log_nhis"])
+    assert np.array_equal(perm[b["map_inds"]], a["map_inds"])
+
+
+def test_state_errors(api, synthetic_inputs):
+    from gp_dla_detection_b200._lib import GpdlaError
+    si = synthetic_inputs
+    bad = dict(si["model"]); bad["M"] = bad["M"][:, :7]
+    with pytest.raises(GpdlaError):
+        api.DLAProcessor(bad, si["samples"], si["prior"])
+    empty = dict(all_wavelengths=[], all_flux=[], all_noise_variance=[], all_pixel_mask=[], z_qsos=np.zeros(0))
+    res = api.process_qsos(si["model"], si["samples"], empty, si["prior"])
+    assert res["p_dlas"].shape == (0,)
