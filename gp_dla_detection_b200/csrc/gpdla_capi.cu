@@ -91,6 +91,31 @@ int upload_line_constants(std::string& err) {
   LineConstants lc;
   fill_line_constants(&lc);
   CUDA_TRY(cudaMemcpyToSymbol(c_lines, &lc, sizeof lc), err);
+  {  // three-line wing tables in velocity units (see tau_sum_3_wing)
+    const double wa[GPDLA_VOIGT_DEG_A + 1] = GPDLA_VOIGT_WING_A;
+    const double wb[GPDLA_VOIGT_DEG_B + 1] = GPDLA_VOIGT_WING_B;
+    const double two_s2 = 2.0 * kSigma * kSigma;   // u = two_s2 * q
+    Wing3 w3;
+    for (int j = 0; j < 3; ++j) {
+      double sc = two_s2 * lc.kwing[j];
+      for (int i = 0; i <= GPDLA_VOIGT_DEG_A; ++i) { w3.a[j][i] = sc * wa[i]; sc *= two_s2; }
+      w3.yy[j] = two_s2 * lc.kwing[j] * lc.y2[j] * two_s2 * wb[0];
+    }
+    w3.b1 = wb[1] / wb[0] * two_s2;
+    w3.v2min = GPDLA_VOIGT_X0 * GPDLA_VOIGT_X0 * two_s2;
+    CUDA_TRY(cudaMemcpyToSymbol(c_wing3, &w3, sizeof w3), err);
+  }
+  {  // accumulator column -> augmented-triangle index of the epilogue staging area (rank 20)
+    constexpr int K = 20;
+    using G = GramShape<K>;
+    static short tab[MAX_NCOL];
+    for (int c = 0; c < MAX_NCOL; ++c) tab[c] = -1;
+    for (int p = 0; p < K; ++p) {
+      for (int q = p; q < K; ++q) tab[G::pair_index(p, q)] = (short)aug_index<K>(p, q);
+      tab[G::WT * 8 + p] = (short)aug_index<K>(p, K);
+    }
+    CUDA_TRY(cudaMemcpyToSymbol(c_stage_index, tab, sizeof tab), err);
+  }
   done[dev] = 1;
   return GPDLA_OK;
 }
@@ -159,10 +184,10 @@ static int ensure_workspace(gpdla_ctx* c, int batch, int npix) {
   return GPDLA_OK;
 }
 
-template <int K, int WM, int WN, int MT, int NL>
+template <int K, int NL>
 static int launch_loglik(gpdla_ctx* c, const LoglikArgs& la, int nq, cudaStream_t st) {
-  using Cfg = LoglikConfig<K, WM, WN, MT>;
-  auto kern = dla_loglik_kernel<K, WM, WN, MT, NL>;
+  using Cfg = LoglikConfig<K>;
+  auto kern = dla_loglik_kernel<K, NL>;
   const size_t smem = Cfg::smem_bytes(la.num_lines);
   static size_t configured = 0;
   if (configured < smem) {
@@ -377,8 +402,8 @@ int gpdla_process_qsos_device(gpdla_ctx* c, int64_t Q, int64_t L_max, const doub
       fprintf(stderr, "[core path] cycles %lld, warp-evals with core %lld of %lld\n", h[8], h[9], h[10]);
     }
 #endif
-    if (c->params.num_lines == 3) rc = launch_loglik<20, 4, 2, 2, 3>(c, la, nq, st);
-    else rc = launch_loglik<20, 4, 2, 2, 0>(c, la, nq, st);
+    if (c->params.num_lines == 3) rc = launch_loglik<20, 3>(c, la, nq, st);
+    else rc = launch_loglik<20, 0>(c, la, nq, st);
     if (rc) return rc;
 
     EvidenceArgs ea;

@@ -46,6 +46,14 @@ struct GramShape {
 
 constexpr int ASTR = KC + 4;      // row stride of the W/U operand tiles (== 4 mod 16)
 
+// Epilogue staging layout: the symmetric Gram (p <= q < K) and the projected vector (q = K) as one
+// augmented upper triangle, entry (p, q) at aug_index(p, q).  c_stage_index maps an accumulator column
+// to that index (-1 for padding columns); filled by the host for the compiled rank.
+template <int K>
+__host__ __device__ constexpr int aug_index(int p, int q) { return p * (K + 1) - p * (p - 1) / 2 + (q - p); }
+constexpr int MAX_NCOL = 1024;
+__constant__ short c_stage_index[MAX_NCOL];
+
 // ------------------------------------------------------------------------------------------
 // small helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -343,29 +351,38 @@ struct LoglikArgs {
 #define PHASE_ADD(idx, t0, t1)
 #endif
 
-template <int K, int WM, int WN, int MT>
+// Warp-autonomous schedule.  A CTA of 8 warps handles 64 samples of one quasar; warp w owns samples
+// [8w, 8w+8) end to end: it evaluates their Voigt profiles and weights for a chunk of KC pixels into its
+// private rows of the operand tiles, then runs the FP64 DMMA contraction of those 8 rows against the
+// shared P chunk (one m8 tile x all n8 tiles, accumulators in registers).  No CTA-wide barrier sits in
+// the main loop: the only shared resource is the double-buffered P chunk, brought in by 1-D TMA bulk
+// copies; the warp that finishes a chunk last re-arms that buffer.  Warps drift apart, so DMMA phases of
+// some warps overlap the latency-bound profile phases of others.
+template <int K>
 struct LoglikConfig {
   using G = GramShape<K>;
-  static constexpr int TS = WM * MT * 8;               // samples per CTA
-  static constexpr int NTW = (G::NT + WN - 1) / WN;    // n8 tiles per warp
-  static constexpr int SPW = TS / (NTHREADS / 32);     // samples per warp in the producer phases
-  static_assert(WM * WN == NTHREADS / 32, "8 warps");
-  static_assert(TS % (NTHREADS / 32) == 0, "samples per warp");
+  static constexpr int NWARPS = NTHREADS / 32;
+  static constexpr int SPW = 8;                        // samples per warp = one m8 tile
+  static constexpr int TS = NWARPS * SPW;              // samples per CTA
   static constexpr size_t B_BYTES = 2ull * G::CHUNK_DOUBLES * 8;
   static constexpr size_t A_BYTES = 2ull * TS * ASTR * 8;
   static constexpr size_t RAW_BYTES = (size_t)TS * RAWW * 8;
-  static constexpr size_t C_BYTES = (size_t)G::NCOL * TS * 8;      // epilogue staging, aliases the B buffers
-  static_assert(C_BYTES <= B_BYTES + A_BYTES + RAW_BYTES, "epilogue staging must fit");
+  // epilogue staging [(K+1)(K+2)/2 - 1 entries][CSTR], aliases the P buffers and the operand tiles;
+  // CSTR == 4 (mod 16): the four lanes of a quad read consecutive entries without bank conflicts
+  static constexpr int CSTR = TS + 4;
+  static constexpr size_t C_BYTES = (size_t)((K + 1) * (K + 2) / 2) * CSTR * 8;
+  static_assert(C_BYTES <= B_BYTES + A_BYTES, "epilogue staging must fit in the P buffers + operand tiles");
+  static_assert(G::NT * 4 <= 200, "accumulators must fit in registers (use a smaller rank)");
   __host__ __device__ static constexpr size_t smem_bytes(int num_lines) {
     return B_BYTES + A_BYTES + RAW_BYTES + (size_t)TS * (num_lines + 4) * 8 + 64;
   }
 };
 
-template <int K, int WM, int WN, int MT, int NL>
+template <int K, int NL>
 __global__ void __launch_bounds__(NTHREADS, 1) dla_loglik_kernel(LoglikArgs args) {
-  using Cfg = LoglikConfig<K, WM, WN, MT>;
+  using Cfg = LoglikConfig<K>;
   using G = GramShape<K>;
-  constexpr int TS = Cfg::TS, NTW = Cfg::NTW, SPW = Cfg::SPW;
+  constexpr int TS = Cfg::TS, SPW = Cfg::SPW, NT = G::NT, CSTR = Cfg::CSTR;
   const int q = blockIdx.y;
   const QuasarMeta meta = args.meta[q];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -391,8 +408,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) dla_loglik_kernel(LoglikArgs args
   double* s_ld = s_q + TS;                                                // [TS]   sum log d
   double* s_mult = s_ld + TS;                                             // [num_lines][TS]
   const int num_lines = (NL > 0) ? NL : args.num_lines;
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(s_mult + (size_t)TS * num_lines + TS);   // [2], 8-byte aligned
-  double* Cs = reinterpret_cast<double*>(smem_raw);                       // epilogue: [NCOL][TS]
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(s_mult + (size_t)TS * num_lines + TS);   // full[2]
+  int* s_done = reinterpret_cast<int*>(mbar + 2);                                        // [2] warps done with buffer
+  double* Cs = reinterpret_cast<double*>(smem_raw);                       // epilogue: [entries][CSTR]
 
   // per-sample parameters: z_s (process_qsos.m:162-164), N_s, line multipliers (voigt.c:279)
   for (int i = tid; i < TS; i += NTHREADS) {
@@ -403,22 +421,30 @@ __global__ void __launch_bounds__(NTHREADS, 1) dla_loglik_kernel(LoglikArgs args
     s_nhi[i] = is_null ? -1.0 : args.nhi_samples[s];     // negative marks the null-model slot
     for (int j = 0; j < num_lines; ++j) s_mult[j * TS + i] = line_multiplier(j, z);
   }
-  if (tid == 0) {
-    mbar_init(&mbar[0], 1);
-    mbar_init(&mbar[1], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-
   const double* lam = args.lam_pad + (int64_t)q * (args.NPIX + 8);
   const double* pix = args.pix + (int64_t)q * args.NPIX * 4;
   const double* Pq = args.P + (int64_t)q * (args.NPIX / KC) * G::CHUNK_DOUBLES;
   constexpr uint32_t CHUNK_BYTES = G::CHUNK_DOUBLES * 8;
-
   if (tid == 0) {
+    mbar_init(&mbar[0], 1);
+    mbar_init(&mbar[1], 1);
+    s_done[0] = 0; s_done[1] = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     mbar_expect_tx(&mbar[0], CHUNK_BYTES);
     tma_load_1d(Bt, Pq, CHUNK_BYTES, &mbar[0]);
+    if (meta.nchunks > 1) {
+      mbar_expect_tx(&mbar[1], CHUNK_BYTES);
+      tma_load_1d(Bt + G::CHUNK_DOUBLES, Pq + G::CHUNK_DOUBLES, CHUNK_BYTES, &mbar[1]);
+    }
   }
+  __syncthreads();
+
+  // this warp's private rows
+  double* myW = Wt + warp * SPW * ASTR;
+  double* myU = Ut + warp * SPW * ASTR;
+  double* myraw = rawbuf + warp * SPW * RAWW;
+  const double* mynhi = s_nhi + warp * SPW;
+  const double* mymult = s_mult + warp * SPW;
 
   // raw-profile evaluation for this warp's samples at padded pixel p.  The common (wing) path is one
   // basic block over all SPW samples so their dependency chains interleave; pixels within X0 Doppler
@@ -430,74 +456,48 @@ __global__ void __launch_bounds__(NTHREADS, 1) dla_loglik_kernel(LoglikArgs args
       unsigned coremask = 0;
 #pragma unroll
       for (int ss = 0; ss < SPW; ++ss) {
-        const int sl = warp * SPW + ss;
         bool core;
-        tau[ss] = tau_sum_3_wing(lambda, s_mult[sl], s_mult[TS + sl], s_mult[2 * TS + sl], core);
+        tau[ss] = tau_sum_3_wing(lambda, mymult[ss], mymult[TS + ss], mymult[2 * TS + ss], core);
         coremask |= core ? (1u << ss) : 0u;
       }
-      PHASE_T(t_c0);
       if (coremask) {
 #pragma unroll
-        for (int ss = 0; ss < SPW; ++ss) {
-          const int sl = warp * SPW + ss;
-          if (coremask & (1u << ss))
-            tau[ss] = tau_sum_3_exact(lambda, s_mult[sl], s_mult[TS + sl], s_mult[2 * TS + sl]);
-        }
+        for (int ss = 0; ss < SPW; ++ss)
+          if (coremask & (1u << ss)) tau[ss] = tau_sum_3_exact(lambda, mymult[ss], mymult[TS + ss], mymult[2 * TS + ss]);
       }
-#ifdef GPDLA_PHASE_TIMING
-      __syncwarp();
-      PHASE_T(t_c1);
-      const bool any_core = __any_sync(0xffffffffu, coremask != 0);
-      if (lane == 0) {
-        atomicAdd((unsigned long long*)&args.phase_cycles[8], (unsigned long long)(t_c1 - t_c0));
-        atomicAdd((unsigned long long*)&args.phase_cycles[9], (unsigned long long)(any_core ? 1 : 0));
-        atomicAdd((unsigned long long*)&args.phase_cycles[10], 1ull);
-      }
-#endif
     } else {
 #pragma unroll
-      for (int ss = 0; ss < SPW; ++ss) tau[ss] = tau_sum_generic(lambda, s_mult + warp * SPW + ss, TS, num_lines);
+      for (int ss = 0; ss < SPW; ++ss) tau[ss] = tau_sum_generic(lambda, mymult + ss, TS, num_lines);
     }
     // all shared-memory loads before the first store: the compiler cannot prove s_nhi and rawbuf do
     // not alias, and a load stuck behind a store would serialise the SPW exponentials
     double e[SPW];
 #pragma unroll
-    for (int ss = 0; ss < SPW; ++ss) e[ss] = -s_nhi[warp * SPW + ss] * tau[ss];
+    for (int ss = 0; ss < SPW; ++ss) e[ss] = -mynhi[ss] * tau[ss];
 #pragma unroll
     for (int ss = 0; ss < SPW; ++ss) e[ss] = exp_nonpos(e[ss]);                    // voigt.c:291
 #pragma unroll
-    for (int ss = 0; ss < SPW; ++ss) rawbuf[(warp * SPW + ss) * RAWW + (p & (RAWW - 1))] = e[ss];
+    for (int ss = 0; ss < SPW; ++ss) myraw[ss * RAWW + (p & (RAWW - 1))] = e[ss];
   };
-  eval_raw(lane < 6 ? lane : 5);   // leading pad pixels p = 0..5 (all lanes participate; extra lanes repeat p = 5)
+  eval_raw(lane < 6 ? lane : 5);   // leading pad pixels p = 0..5 (extra lanes repeat p = 5)
 
-  // accumulators
-  double acc[MT][NTW][2];
+  // accumulators: 8 samples x NCOL columns per warp
+  double acc[NT][2];
 #pragma unroll
-  for (int mi = 0; mi < MT; ++mi)
-#pragma unroll
-    for (int ni = 0; ni < NTW; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+  for (int ni = 0; ni < NT; ++ni) acc[ni][0] = acc[ni][1] = 0.0;
   double qacc[SPW], ldm[SPW];
   int lde[SPW];
 #pragma unroll
   for (int ss = 0; ss < SPW; ++ss) { qacc[ss] = 0.0; ldm[ss] = 1.0; lde[ss] = 0; }
-
-  const int wm = warp % WM, wn = warp / WM;
   const int gid = lane >> 2, tig = lane & 3;
-  const int nw_local = max(0, min(NTW, G::WT - wn * NTW));   // tiles of this warp fed by W (rest: U)
 
   PHASE_T(t_start);
   for (int c = 0; c < meta.nchunks; ++c) {
     // ---- A1: raw profile for the KC new padded pixels
     PHASE_T(t_a1);
     eval_raw(c * KC + 6 + lane);
+    __syncwarp();
     PHASE_T(t_a1e);
-    __syncthreads();   // S1: raw visible; everyone is past the previous chunk's DMMA phase
-    PHASE_T(t_s1);
-    if (tid == 0 && c + 1 < meta.nchunks) {
-      mbar_expect_tx(&mbar[(c + 1) & 1], CHUNK_BYTES);
-      tma_load_1d(Bt + ((c + 1) & 1) * G::CHUNK_DOUBLES, Pq + (int64_t)(c + 1) * G::CHUNK_DOUBLES, CHUNK_BYTES,
-                  &mbar[(c + 1) & 1]);
-    }
     // ---- A2: instrument convolution + weights
     {
       const int i = c * KC + lane;
@@ -508,23 +508,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) dla_loglik_kernel(LoglikArgs args
       double a[SPW];
 #pragma unroll
       for (int ss = 0; ss < SPW; ++ss) {
-        const int sl = warp * SPW + ss;
-        const double* rb = rawbuf + sl * RAWW;
+        const double* rb = myraw + ss * RAWW;
         double acc_a = 0.0;
 #pragma unroll
         for (int t = 0; t < 7; ++t) acc_a = fma(rb[(i + t) & (RAWW - 1)], c_lines.ip[t], acc_a);   // voigt.c:297-299
-        a[ss] = (s_nhi[sl] < 0.0) ? 1.0 : acc_a;        // null model: no absorption
+        a[ss] = (__double2hiint(mynhi[ss]) < 0) ? 1.0 : acc_a;   // null model (N marked negative): no absorption
       }
 #pragma unroll
       for (int ss = 0; ss < SPW; ++ss) {
-        const int sl = warp * SPW + ss;
         const double a2 = a[ss] * a[ss];
         const double d = fma(a2, om2, v);                // dla_omega2 + noise variance  (process_qsos.m:194,198)
         const double rd = fast_rcp(d);
         const double r = fma(-a[ss], mu, y);             // y - dla_mu
         const double t1 = r * rd;
-        Wt[sl * ASTR + lane] = a2 * rd;
-        Ut[sl * ASTR + lane] = a[ss] * t1;
+        myW[ss * ASTR + lane] = a2 * rd;
+        myU[ss * ASTR + lane] = a[ss] * t1;
         qacc[ss] = fma(r, t1, qacc[ss]);
         ldm[ss] *= d;
       }
@@ -538,37 +536,36 @@ __global__ void __launch_bounds__(NTHREADS, 1) dla_loglik_kernel(LoglikArgs args
         }
       }
     }
+    __syncwarp();
     PHASE_T(t_a2e);
-    __syncthreads();   // S2: operand tiles visible
-    PHASE_T(t_s2);
     mbar_wait(&mbar[c & 1], (c >> 1) & 1);
     PHASE_T(t_mb);
-    // ---- B: FP64 tensor-core contraction  acc += [W|U] (TS x KC) . P_chunk (KC x NCOL)
+    // ---- B: FP64 tensor-core contraction  acc += [W|U] (8 x KC) . P_chunk (KC x NCOL)
     {
       const double* Bc = Bt + (c & 1) * G::CHUNK_DOUBLES;
 #pragma unroll
       for (int ks = 0; ks < KC / 4; ++ks) {
-        double aw[MT], au[MT];
+        const double aw = myW[gid * ASTR + ks * 4 + tig];
+        const double au = myU[gid * ASTR + ks * 4 + tig];
+        const double* brow = Bc + (ks * 4 + tig) * G::BSTR + gid;
 #pragma unroll
-        for (int mi = 0; mi < MT; ++mi) {
-          const int row = (wm * MT + mi) * 8 + gid;
-          aw[mi] = Wt[row * ASTR + ks * 4 + tig];
-          au[mi] = Ut[row * ASTR + ks * 4 + tig];
-        }
-#pragma unroll
-        for (int ni = 0; ni < NTW; ++ni) {
-          const int t = wn * NTW + ni;
-          if (t < G::NT) {
-            const double b = Bc[(ks * 4 + tig) * G::BSTR + t * 8 + gid];
-#pragma unroll
-            for (int mi = 0; mi < MT; ++mi) dmma_884(acc[mi][ni][0], acc[mi][ni][1], ni < nw_local ? aw[mi] : au[mi], b);
-          }
-        }
+        for (int ni = 0; ni < NT; ++ni) dmma_884(acc[ni][0], acc[ni][1], ni < G::WT ? aw : au, brow[ni * 8]);
       }
     }
+    __syncwarp();
     PHASE_T(t_be);
-    PHASE_ADD(0, t_a1, t_a1e); PHASE_ADD(1, t_a1e, t_s1); PHASE_ADD(2, t_s1, t_a2e); PHASE_ADD(3, t_a2e, t_s2);
-    PHASE_ADD(4, t_s2, t_mb); PHASE_ADD(5, t_mb, t_be);
+    // ---- release the P buffer; the last warp to finish this chunk re-arms it with chunk c + 2
+    if (lane == 0 && c + 2 < meta.nchunks) {
+      const int done = atomicAdd(&s_done[c & 1], 1);
+      if (done == Cfg::NWARPS - 1) {
+        s_done[c & 1] = 0;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(&mbar[c & 1], CHUNK_BYTES);
+        tma_load_1d(Bt + (c & 1) * G::CHUNK_DOUBLES, Pq + (int64_t)(c + 2) * G::CHUNK_DOUBLES, CHUNK_BYTES,
+                    &mbar[c & 1]);
+      }
+    }
+    PHASE_ADD(0, t_a1, t_a1e); PHASE_ADD(2, t_a1e, t_a2e); PHASE_ADD(4, t_a2e, t_mb); PHASE_ADD(5, t_mb, t_be);
   }
   PHASE_T(t_loop_end);
   PHASE_ADD(6, t_start, t_loop_end);
@@ -580,57 +577,58 @@ __global__ void __launch_bounds__(NTHREADS, 1) dla_loglik_kernel(LoglikArgs args
     double ld = warp_sum(log(ldm[ss]) + (double)lde[ss] * 0.693147180559945309417);
     if (lane == 0) { s_q[warp * SPW + ss] = qs; s_ld[warp * SPW + ss] = ld; }
   }
-  __syncthreads();   // all DMMA reads of Bt/Wt/Ut done -> staging may alias them
+  __syncthreads();   // every warp is done with the P buffers -> the staging area may alias them
+  // C fragment: lane holds row gid, columns 2 tig, 2 tig + 1 of each n8 tile
 #pragma unroll
-  for (int mi = 0; mi < MT; ++mi)
-#pragma unroll
-    for (int ni = 0; ni < NTW; ++ni) {
-      const int t = wn * NTW + ni;
-      if (t < G::NT) {
-        const int row = (wm * MT + mi) * 8 + gid;
-        Cs[(t * 8 + tig * 2) * TS + row] = acc[mi][ni][0];
-        Cs[(t * 8 + tig * 2 + 1) * TS + row] = acc[mi][ni][1];
-      }
-    }
-  __syncthreads();
+  for (int ni = 0; ni < NT; ++ni) {
+    const int i0 = c_stage_index[ni * 8 + tig * 2], i1 = c_stage_index[ni * 8 + tig * 2 + 1];
+    if (i0 >= 0) Cs[i0 * CSTR + warp * SPW + gid] = acc[ni][0];
+    if (i1 >= 0) Cs[i1 * CSTR + warp * SPW + gid] = acc[ni][1];
+  }
+  __syncwarp();
 
-  // ---- K3: Cholesky of B = I + C, log-det, projected quadratic form; one thread per sample
-  if (tid < TS) {
-    const int sl = tid;
-    double* Bs = Cs + sl;                      // element (p,q), p<=q at Bs[pair_index(p,q) * TS]
-    const double* gs = Cs + (G::WT * 8) * TS + sl;   // g_p at gs[p * TS]
-    double logdetB = 0.0, zz = 0.0;
+  // ---- K3: Cholesky of B = I + C (upper, R'R = B) with the projected vector g as column K (forward
+  // substitution for free), log-det, quadratic form.  Four lanes per sample; for row p the columns
+  // q = p+1 .. K are dealt round-robin to the quad.  Fully unrolled: every index is an immediate.
+  {
+    const int sl = warp * SPW + (lane >> 2);          // sample handled by this lane quad
+    const int l4 = lane & 3;
+    double* Bs = Cs + sl;                              // entry (p, q) at Bs[aug_index<K>(p, q) * CSTR]
+    double prod0 = 1.0, prod1 = 1.0;
 #pragma unroll
     for (int p = 0; p < K; ++p) {
-      double colp[K];                          // R(r,p), r < p
+      double colp[K];                                  // R(r, p), r < p
 #pragma unroll
-      for (int r = 0; r < p; ++r) colp[r] = Bs[G::pair_index(r, p) * TS];
-      double dpp = Bs[G::pair_index(p, p) * TS] + 1.0;     // log_mvnpdf_low_rank.m:23
+      for (int r = 0; r < p; ++r) colp[r] = Bs[aug_index<K>(r, p) * CSTR];
+      double dpp = Bs[aug_index<K>(p, p) * CSTR] + 1.0;                       // log_mvnpdf_low_rank.m:23
 #pragma unroll
       for (int r = 0; r < p; ++r) dpp = fma(-colp[r], colp[r], dpp);
-      logdetB += log(dpp);                     // = 2 log R(p,p)                        :30
-      const double inv = 1.0 / sqrt(dpp);
+      if (p < K / 2) prod0 *= dpp; else prod1 *= dpp;                       // log det B = log prod R(p,p)^2   :30
+      const double inv = rsqrt(dpp);
 #pragma unroll
-      for (int qq = p + 1; qq < K; ++qq) {
-        double v = Bs[G::pair_index(p, qq) * TS];
+      for (int j = 0; j < (K - p + 3) / 4; ++j) {
+        const int qq = p + 1 + l4 + 4 * j;
+        if (qq <= K) {
+          double* dst = Bs + (aug_index<K>(p, p) + (qq - p)) * CSTR;
+          double v = *dst;
 #pragma unroll
-        for (int r = 0; r < p; ++r) v = fma(-colp[r], Bs[G::pair_index(r, qq) * TS], v);
-        Bs[G::pair_index(p, qq) * TS] = v * inv;
+          for (int r = 0; r < p; ++r) v = fma(-colp[r], Bs[(aug_index<K>(r, r) + (qq - r)) * CSTR], v);
+          *dst = v * inv;
+        }
       }
-      // augmented column: forward substitution R' z = g
-      double zp = gs[p * TS];
-#pragma unroll
-      for (int r = 0; r < p; ++r) zp = fma(-colp[r], gs[r * TS], zp);
-      zp *= inv;
-      const_cast<double*>(gs)[p * TS] = zp;
-      zz = fma(zp, zp, zz);
+      __syncwarp();
     }
-    const double quad = s_q[sl] - zz;          // y' K^-1 y                               :28
-    const double logdet = s_ld[sl] + logdetB;  //                                         :30
-    const double lp = -0.5 * (quad + logdet + (double)meta.n * LOG_2PI);   //             :32
-    const int64_t s = s0 + sl;
-    if (s < S) args.sample_log_likelihoods[(int64_t)q * S + s] = lp;
-    else if (s == S) args.log_likelihoods_no_dla[q] = lp;
+    double zsum = 0.0;                                 // |R'^-1 g|^2: column K now holds z
+#pragma unroll
+    for (int p = 0; p < K; ++p) { const double zp = Bs[aug_index<K>(p, K) * CSTR]; zsum = fma(zp, zp, zsum); }
+    if (l4 == 0) {
+      const double quad = s_q[sl] - zsum;                                   // y' K^-1 y                 :28
+      const double logdet = s_ld[sl] + log(prod0) + log(prod1);             //                           :30
+      const double lp = -0.5 * (quad + logdet + (double)meta.n * LOG_2PI);  //                           :32
+      const int64_t s = s0 + sl;
+      if (s < S) args.sample_log_likelihoods[(int64_t)q * S + s] = lp;
+      else if (s == S) args.log_likelihoods_no_dla[q] = lp;
+    }
   }
 #ifdef GPDLA_PHASE_TIMING
   __syncthreads();

@@ -35,16 +35,19 @@ __constant__ double c_wing_b[GPDLA_VOIGT_DEG_B + 1] = GPDLA_VOIGT_WING_B;
 // core table lives in global memory (divergent indexing; constant cache would serialise)
 __device__ const double g_core_table[GPDLA_VOIGT_NINT * GPDLA_VOIGT_CORE_STRIDE] = GPDLA_VOIGT_CORE_TABLE;
 
-// 1/x to ~1 ulp for normal positive x: MUFU.RCP64H seed + two Newton steps (4 DFMA).
+// 1/x to ~1 ulp for normal positive x: MUFU.RCP64H seed (>= 20 good bits) + one cubically convergent
+// step r (1 + e + e^2), e = 1 - x r  (3 DFMA; the MUFU runs on its own pipe).
 __device__ __forceinline__ double fast_rcp(double x) {
   double r;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-  double e = fma(-x, r, 1.0);
-  r = fma(r, e, r);
-  e = fma(-x, r, 1.0);
-  r = fma(r, e, r);
-  return r;
+  const double e = fma(-x, r, 1.0);
+  const double t = fma(e, e, e);
+  return fma(r, t, r);
 }
+
+// Comparisons of non-negative doubles through their high words: integer pipe instead of the FP64 pipe
+// (exact unless the operands agree in their top 32 bits, where the caller's threshold is soft anyway).
+__device__ __forceinline__ bool hi_less(double a, double b) { return __double2hiint(a) < __double2hiint(b); }
 
 __device__ __forceinline__ double wing_poly_a(double u) {
   double a = c_wing_a[GPDLA_VOIGT_DEG_A];
@@ -111,23 +114,40 @@ __device__ __forceinline__ double tau_sum_generic(double lambda, const double* m
   return total;
 }
 
-// Three-line specialisation (num_lines = 3, set_parameters.m:63), branch-free wing part: the three
-// reciprocals share one MUFU + Newton sequence through a common denominator.  Returns the sum with
-// every line evaluated by the wing formula (|x| clamped to X0) and sets `core` when some line is
-// inside |x| < X0, in which case the caller re-evaluates with tau_sum_3_exact().  Keeping this free
-// of control flow lets the compiler interleave the evaluations of several samples.
+// Three-line specialisation (num_lines = 3, set_parameters.m:63), branch-free wing part.
+// Works in velocity units: with q = 1/v^2 (v in cm/s), u = 2 sigma^2 q and
+//   tau_j / N = q [ A_j(q) - yy_j q B(u) ],   A_j(q) = 2 sigma^2 kwing_j A(2 sigma^2 q),  yy_j = 2 sigma^2 y_j^2 kwing_j 2 sigma^2
+// with the per-line coefficients c_wing3 precomputed on the host (one multiply less per line, no
+// separate x).  In the wings the velocity may use a fused multiply-add (relative effect on tau
+// < 2e-13 at |x| = X0, far below the parity budget); the exact routine keeps voigt.c:287's rounding.
+// Sets `core` when some line is within X0 Doppler widths, in which case the caller re-evaluates
+// with tau_sum_3_exact().  Free of control flow so that several samples interleave.
+struct Wing3 {
+  double a[3][GPDLA_VOIGT_DEG_A + 1];   // A_j coefficients in q
+  double yy[3];                          // coefficient of the y^3 H3 correction
+  double b1;                             // B(u) ~ 1 + b1 q  (q units)
+  double v2min;                          // X0^2 * 2 sigma^2: clamp / core threshold on v^2
+};
+__constant__ Wing3 c_wing3;
+
+__device__ __forceinline__ double tau_wing3_line(int j, double q) {
+  double a = c_wing3.a[j][GPDLA_VOIGT_DEG_A];
+#pragma unroll
+  for (int i = GPDLA_VOIGT_DEG_A - 1; i >= 0; --i) a = fma(a, q, c_wing3.a[j][i]);
+  const double b = fma(c_wing3.b1, q, 1.0);
+  const double t = c_wing3.yy[j] * q;
+  return q * fma(-t, b, a);
+}
+
 __device__ __forceinline__ double tau_sum_3_wing(double lambda, double m0, double m1, double m2, bool& core) {
-  const double X02 = GPDLA_VOIGT_X0 * GPDLA_VOIGT_X0;
-  double x0 = __dsub_rn(__dmul_rn(lambda, m0), c_lines.c) * c_lines.inv_s2s;
-  double x1 = __dsub_rn(__dmul_rn(lambda, m1), c_lines.c) * c_lines.inv_s2s;
-  double x2 = __dsub_rn(__dmul_rn(lambda, m2), c_lines.c) * c_lines.inv_s2s;
-  double s0 = x0 * x0, s1 = x1 * x1, s2 = x2 * x2;
-  core = fmin(s0, fmin(s1, s2)) < X02;
-  double c0 = fmax(s0, X02), c1 = fmax(s1, X02), c2 = fmax(s2, X02);   // x^2 <= 8e3^2: product < 3e23
-  double p12 = c1 * c2;
-  double r = fast_rcp(c0 * p12);
-  double u0 = r * p12, u1 = r * (c0 * c2), u2 = r * (c0 * c1);
-  return (tau_wing(0, u0) + tau_wing(1, u1)) + tau_wing(2, u2);
+  const double v0 = fma(lambda, m0, -c_lines.c), v1 = fma(lambda, m1, -c_lines.c), v2 = fma(lambda, m2, -c_lines.c);
+  double s0 = v0 * v0, s1 = v1 * v1, s2 = v2 * v2;
+  const double lim = c_wing3.v2min;
+  const bool k0 = hi_less(s0, lim), k1 = hi_less(s1, lim), k2 = hi_less(s2, lim);
+  core = k0 | k1 | k2;
+  s0 = k0 ? lim : s0; s1 = k1 ? lim : s1; s2 = k2 ? lim : s2;
+  const double q0 = fast_rcp(s0), q1 = fast_rcp(s1), q2 = fast_rcp(s2);
+  return (tau_wing3_line(0, q0) + tau_wing3_line(1, q1)) + tau_wing3_line(2, q2);
 }
 
 // Exact three-line sum including core pixels (rare path; same summation order as voigt.c:285-290).
@@ -150,17 +170,19 @@ __device__ __noinline__ double tau_sum_3_exact(double lambda, double m0, double 
 __constant__ double c_exp_poly[12] = GPDLA_EXP_POLY;
 __device__ __forceinline__ double exp_nonpos(double x) {
   const double SHIFT = 6755399441055744.0;   // 1.5 * 2^52
-  double xc = fmax(x, -708.0);
+  // x <= 0 (or tiny positive): "below -708" is an unsigned compare of the high word (integer pipe)
+  const bool tiny = (unsigned)__double2hiint(x) > 0xC0862000u;   // x < -708 (hi word of -708.0 is 0xC0862000)
+  const double xc = tiny ? -708.0 : x;
   double kd = fma(xc, 1.4426950408889634074, SHIFT);
-  int k = __double2loint(kd);
+  const int k = __double2loint(kd);
   kd -= SHIFT;
   double r = fma(kd, -6.93147180369123816490e-01, xc);
   r = fma(kd, -1.90821492927058770002e-10, r);
   double p = c_exp_poly[11];
 #pragma unroll
   for (int i = 10; i >= 0; --i) p = fma(p, r, c_exp_poly[i]);
-  double res = __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
-  return (x < -708.0) ? 0.0 : res;
+  const double res = __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+  return tiny ? 0.0 : res;
 }
 
 }  // namespace gpdla
