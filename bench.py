@@ -37,6 +37,15 @@ def fp64_peak():
         return 37.0, "nominal HGX B200 FP64 tensor (fallback)"
 
 
+def ncu_traffic():
+    """DRAM bytes of one dla_loglik_kernel launch (296-quasar batch) from the committed ncu --set full capture."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_loglik_full.json")))
+        return d["dram_bytes_per_launch"], d["Grid Size"]["value"]
+    except Exception:
+        return None, None
+
+
 class ClockSampler:
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -231,6 +240,7 @@ def main():
     if rank == 0:
         peak, peak_src = fp64_peak()
         achieved = flops_per_step * args.steps / (k_ms * 1e-3) * 1e-12 if k_ms > 0 else None
+        traffic, traffic_grid = ncu_traffic()
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -243,7 +253,10 @@ def main():
             "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": (achieved / peak) if achieved else None, "traffic": None,
+                         "frac": (achieved / peak) if achieved else None, "traffic": traffic,
+                         "traffic_note": "dram__bytes_read+write of one launch with grid %s (one 296-quasar batch; this "
+                                         "run launches the same batch size), ncu --set full" % traffic_grid,
+                         "algorithmic_flops_per_launch": flops_per_step * args.steps / max(int(k_n), 1),
                          "kernel": "dla_loglik_kernel (fused Voigt + FP64 DMMA Gram + Cholesky)",
                          "kernel_ms_per_step": k_ms / args.steps, "kernel_launches": int(k_n),
                          "kernel_share_of_step": k_ms / ms,
