@@ -34,6 +34,17 @@ class GpdlaResults(ctypes.Structure):
     _fields_ = [(n, ctypes.c_void_p) for n in RESULT_F64] + [("map_inds", ctypes.c_void_p)]
 
 
+MULTI_RESULT_FIELDS = ["min_z_dlas", "max_z_dlas", "log_priors_no_dla", "log_priors_lls", "log_priors_dla",
+                       "log_likelihoods_no_dla", "log_likelihoods_lls", "log_likelihoods_dla",
+                       "log_posteriors_no_dla", "log_posteriors_lls", "log_posteriors_dla", "model_posteriors",
+                       "p_no_dlas", "p_lls", "p_dlas", "MAP_z_dlas", "MAP_log_nhis", "MAP_inds",
+                       "sample_log_likelihoods_dla", "sample_log_likelihoods_lls", "base_sample_inds"]
+
+
+class GpdlaMultiResults(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p) for n in MULTI_RESULT_FIELDS]
+
+
 # every symbol include/gpdla.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "gpdla_default_parameters": (None, [ctypes.POINTER(GpdlaParams)]),
@@ -56,6 +67,14 @@ SYMBOLS = {
                                                  ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                                  ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(GpdlaResults),
                                                  ctypes.c_void_p]),
+    "gpdla_set_lls_samples": (ctypes.c_int, [ctypes.c_void_p, c_double_p, ctypes.c_int64, ctypes.c_double,
+                                             ctypes.c_double]),
+    "gpdla_process_qsos_multi": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64] + [ctypes.c_void_p] * 6
+                                 + [ctypes.c_int32, ctypes.c_void_p, ctypes.POINTER(GpdlaMultiResults)]),
+    "gpdla_process_qsos_multi_device": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64]
+                                        + [ctypes.c_void_p] * 6 + [ctypes.c_int32, ctypes.c_void_p,
+                                                                   ctypes.POINTER(GpdlaMultiResults), ctypes.c_void_p]),
+    "gpdla_matlab_default_rand": (None, [c_double_p, ctypes.c_int64]),
     "gpdla_voigt": (ctypes.c_int, [c_double_p, ctypes.c_int64, ctypes.c_double, ctypes.c_double, ctypes.c_int32,
                                    c_double_p]),
     "gpdla_voigt_batch_device": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p,

@@ -81,6 +81,11 @@ class DLAProcessor:
         off, lnhi, nhi = (_f64(samples[k]).ravel() for k in ("offset_samples", "log_nhi_samples", "nhi_samples"))
         self.num_dla_samples = int(off.size)
         _lib.check(self._lib.gpdla_set_samples(self._ctx, _dp(off), _dp(lnhi), _dp(nhi), off.size), self._ctx)
+        self.has_lls = "lls_nhi_samples" in samples and "Z_lls" in samples and "Z_dla" in samples
+        if self.has_lls:   # multi_dlas/set_lls_parameters.m:55-71
+            lls = _f64(samples["lls_nhi_samples"]).ravel()
+            _lib.check(self._lib.gpdla_set_lls_samples(self._ctx, _dp(lls), lls.size, float(samples["Z_lls"]),
+                                                       float(samples["Z_dla"])), self._ctx)
         pz = _f64(prior["z_qsos"]).ravel()
         pd = np.ascontiguousarray(np.asarray(prior["dla_ind"]).astype(np.uint8)).ravel()
         _lib.check(self._lib.gpdla_set_prior(self._ctx, _dp(pz), pd.ctypes.data_as(_lib.c_u8_p), pz.size), self._ctx)
@@ -131,6 +136,49 @@ class DLAProcessor:
                                                 vp(z), ctypes.byref(res)), self._ctx)
         return out
 
+    # ---------------------------------------------------------------- multi-DLA + sub-DLA + mean flux
+    def process_multi(self, spectra: Dict, max_dlas: int = 4, base_sample_inds: Optional[np.ndarray] = None,
+                      return_samples: bool = True) -> Dict[str, np.ndarray]:
+        """``process_qsos_multiple_dlas_meanflux`` (multi_dlas/process_qsos_multiple_dlas_meanflux.m): results
+        with the reference's names and shapes -- ``sample_log_likelihoods_dla`` (Q, S, max_dlas),
+        ``base_sample_inds`` (Q, S, max_dlas-1; 0-based), ``MAP_*`` (Q, max_dlas, max_dlas),
+        ``model_posteriors`` (Q, 2 + max_dlas).  ``base_sample_inds`` given as input (same shape) replaces
+        the built-in resampling (rng('default') + randsample) for parity runs."""
+        if not self.has_lls:
+            raise ValueError("samples must hold lls_nhi_samples, Z_lls and Z_dla for the multi-DLA path")
+        sp = pad_spectra(spectra)
+        W, F, V = _f64(sp["wavelengths"]), _f64(sp["flux"]), _f64(sp["noise_variance"])
+        Mk = np.ascontiguousarray(sp["pixel_mask"], dtype=np.uint8)
+        lengths = np.ascontiguousarray(sp["lengths"], dtype=np.int32)
+        z = _f64(sp["z_qsos"])
+        Q, L_max = W.shape
+        S, MD = self.num_dla_samples, int(max_dlas)
+        shapes = dict(log_priors_dla=(Q, MD), log_likelihoods_dla=(Q, MD), log_posteriors_dla=(Q, MD),
+                      model_posteriors=(Q, MD + 2), MAP_z_dlas=(Q, MD, MD), MAP_log_nhis=(Q, MD, MD))
+        out = {}
+        for n in _lib.MULTI_RESULT_FIELDS[:17]:
+            out[n] = np.full(shapes.get(n, (Q,)), np.nan)
+        out["MAP_inds"] = np.full((Q, MD, MD), -1, dtype=np.int64)
+        if return_samples:
+            out["sample_log_likelihoods_dla"] = np.full((Q, MD, S), np.nan)
+            out["sample_log_likelihoods_lls"] = np.full((Q, S), np.nan)
+            out["base_sample_inds"] = np.zeros((Q, max(MD - 1, 0), S), dtype=np.int32)
+        res = _lib.GpdlaMultiResults()
+        for n in _lib.MULTI_RESULT_FIELDS:
+            setattr(res, n, out[n].ctypes.data if n in out and out[n].size else None)
+        bin_ = None
+        if base_sample_inds is not None:
+            bin_ = np.ascontiguousarray(np.transpose(np.asarray(base_sample_inds), (0, 2, 1)), dtype=np.int32)
+            assert bin_.shape == (Q, MD - 1, S)
+        vp = lambda a: ctypes.c_void_p(a.ctypes.data)
+        _lib.check(self._lib.gpdla_process_qsos_multi(
+            self._ctx, Q, L_max, vp(W), vp(F), vp(V), vp(Mk), vp(lengths), vp(z), MD,
+            vp(bin_) if bin_ is not None else None, ctypes.byref(res)), self._ctx)
+        if return_samples:   # reference layout: (quasar, sample, level)
+            out["sample_log_likelihoods_dla"] = np.transpose(out["sample_log_likelihoods_dla"], (0, 2, 1))
+            out["base_sample_inds"] = np.transpose(out["base_sample_inds"], (0, 2, 1))
+        return out
+
     # ---------------------------------------------------------------- device-resident buffers
     def process_device(self, wavelengths, flux, noise_variance, pixel_mask, lengths, z_qsos,
                        return_sample_log_likelihoods: bool = False, out: Optional[Dict] = None) -> Dict:
@@ -170,6 +218,26 @@ def process_qsos(model: Dict, samples: Dict, spectra: Dict, prior: Dict, params:
         return proc.process(spectra, return_sample_log_likelihoods)
     finally:
         proc.close()
+
+
+def process_qsos_multiple_dlas_meanflux(model: Dict, samples: Dict, spectra: Dict, prior: Dict, max_dlas: int = 4,
+                                        params: Parameters = DEFAULT, device: int = 0,
+                                        base_sample_inds: Optional[np.ndarray] = None,
+                                        return_samples: bool = True, batch_quasars: int = 0) -> Dict[str, np.ndarray]:
+    """Multi-DLA / sub-DLA / mean-flux processing (multi_dlas/process_qsos_multiple_dlas_meanflux.m).
+    ``samples`` additionally holds ``lls_nhi_samples``, ``Z_lls``, ``Z_dla`` (set_lls_parameters.m)."""
+    proc = DLAProcessor(model, samples, prior, params, device, batch_quasars=batch_quasars)
+    try:
+        return proc.process_multi(spectra, max_dlas, base_sample_inds, return_samples)
+    finally:
+        proc.close()
+
+
+def matlab_default_rand(n: int) -> np.ndarray:
+    """First ``n`` numbers of MATLAB's ``rng('default'); rand`` stream as the library generates them."""
+    out = np.empty(int(n))
+    _lib.load().gpdla_matlab_default_rand(_dp(out), int(n))
+    return out
 
 
 def voigt(lambdas: Sequence[float], z: float, N: float, num_lines: int = _lib.MAX_LINES) -> np.ndarray:

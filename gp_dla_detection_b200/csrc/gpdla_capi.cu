@@ -6,6 +6,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <random>
 #include <string>
 #include <vector>
 
@@ -91,6 +92,21 @@ int upload_line_constants(std::string& err) {
   LineConstants lc;
   fill_line_constants(&lc);
   CUDA_TRY(cudaMemcpyToSymbol(c_lines, &lc, sizeof lc), err);
+  {  // Lyman-series forest data of the multi-DLA mean-flux suppression
+    ForestConstants fc;
+    fc.num_forest_lines = MAX_LINES;                       // set_parameters_multi.m:76
+    fc.prev_beta = 3.65;                                   // ...meanflux.m:37
+    const double prev_tau_0 = 0.0023;                      // ...meanflux.m:36
+    const double lya_wavelength = 1215.6701, lya_oscillator_strength = 0.416400;
+    for (int l = 0; l < MAX_LINES; ++l) fc.wavelength[l] = kLyman[l].wavelength_cm * 1e8;   // set_parameters_multi.m:77-109
+    for (int l = 0; l < MAX_LINES; ++l) {
+      // tau_0 * lambda_l * f_l / (lambda_1 * f_1) without the tau_0                         ...meanflux.m:255-256
+      fc.tau_ratio[l] = fc.wavelength[l] * kLyman[l].f / (fc.wavelength[0] * kLyman[0].f);
+      // prev_tau_0 * f_l / f_lya * lambda_l / lya_wavelength                               ...meanflux.m:271-273
+      fc.kim_tau[l] = prev_tau_0 * kLyman[l].f / lya_oscillator_strength * fc.wavelength[l] / lya_wavelength;
+    }
+    CUDA_TRY(cudaMemcpyToSymbol(c_forest, &fc, sizeof fc), err);
+  }
   {  // three-line wing tables in velocity units (see tau_sum_3_wing)
     const double wa[GPDLA_VOIGT_DEG_A + 1] = GPDLA_VOIGT_WING_A;
     const double wb[GPDLA_VOIGT_DEG_B + 1] = GPDLA_VOIGT_WING_B;
@@ -154,6 +170,14 @@ struct gpdla_ctx {
   // staging for the host entry point
   size_t st_bytes = 0;
   void* d_stage = nullptr;
+  // multi-DLA path
+  double* d_lls_nhi = nullptr;
+  double Z_lls = 0, Z_dla = 0;
+  double* d_uniforms = nullptr;       // [3 x S] rand stream of rng('default')
+  int mws_batch = 0, mws_npix = 0;
+  int64_t mws_S = 0;
+  double *d_acache = nullptr, *d_msll = nullptr, *d_mlls = nullptr, *d_cum = nullptr, *d_mscal = nullptr;
+  int32_t *d_partners = nullptr, *d_active = nullptr;
   // optional per-kernel timing of the dominant kernel (bench.py's roofline)
   bool profiling = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
@@ -184,17 +208,17 @@ static int ensure_workspace(gpdla_ctx* c, int batch, int npix) {
   return GPDLA_OK;
 }
 
-template <int K, int NL>
+template <int K, int NL, int MODE>
 static int launch_loglik(gpdla_ctx* c, const LoglikArgs& la, int nq, cudaStream_t st) {
   using Cfg = LoglikConfig<K>;
-  auto kern = dla_loglik_kernel<K, NL>;
+  auto kern = dla_loglik_kernel<K, NL, MODE>;
   const size_t smem = Cfg::smem_bytes(la.num_lines);
   static size_t configured = 0;
   if (configured < smem) {
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), c->err);
     configured = smem;
   }
-  dim3 grid((unsigned)((la.S + 1 + Cfg::TS - 1) / Cfg::TS), (unsigned)nq);
+  dim3 grid((unsigned)((la.S + (la.log_likelihoods_no_dla ? 1 : 0) + Cfg::TS - 1) / Cfg::TS), (unsigned)nq);
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (c->profiling) {
     CUDA_TRY(cudaEventCreate(&e0), c->err);
@@ -209,6 +233,35 @@ static int launch_loglik(gpdla_ctx* c, const LoglikArgs& la, int nq, cudaStream_
     c->prof_events.emplace_back(e0, e1);
   }
   return GPDLA_OK;
+}
+
+static int ensure_multi_workspace(gpdla_ctx* c, int batch, int npix) {
+  if (c->mws_batch >= batch && c->mws_npix == npix && c->mws_S == c->S) return GPDLA_OK;
+  cudaFree(c->d_acache); cudaFree(c->d_msll); cudaFree(c->d_mlls); cudaFree(c->d_cum); cudaFree(c->d_mscal);
+  cudaFree(c->d_partners); cudaFree(c->d_active);
+  c->d_acache = c->d_msll = c->d_mlls = c->d_cum = c->d_mscal = nullptr; c->d_partners = c->d_active = nullptr;
+  c->mws_batch = 0;
+  const size_t B = batch, S = (size_t)c->S;
+  CUDA_TRY(cudaMalloc(&c->d_acache, B * S * npix * sizeof(double)), c->err);
+  CUDA_TRY(cudaMalloc(&c->d_msll, B * 4 * S * sizeof(double)), c->err);
+  CUDA_TRY(cudaMalloc(&c->d_mlls, B * S * sizeof(double)), c->err);
+  CUDA_TRY(cudaMalloc(&c->d_cum, B * S * sizeof(double)), c->err);
+  CUDA_TRY(cudaMalloc(&c->d_mscal, B * 8 * sizeof(double)), c->err);
+  CUDA_TRY(cudaMalloc(&c->d_partners, B * 3 * S * sizeof(int32_t)), c->err);
+  CUDA_TRY(cudaMalloc(&c->d_active, B * sizeof(int32_t)), c->err);
+  c->mws_batch = batch; c->mws_npix = npix; c->mws_S = c->S;
+  return GPDLA_OK;
+}
+
+template <int MODE>
+static int launch_mode(gpdla_ctx* c, const LoglikArgs& la, int nq, cudaStream_t st) {
+  if (c->params.num_lines == 3) return launch_loglik<20, 3, MODE>(c, la, nq, st);
+  return launch_loglik<20, 0, MODE>(c, la, nq, st);
+}
+
+__global__ void fill_i32_kernel(int32_t* p, int32_t v, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
 }
 
 extern "C" {
@@ -259,6 +312,8 @@ void gpdla_destroy(gpdla_ctx* c) {
   cudaFree(c->d_rest); cudaFree(c->d_mu); cudaFree(c->d_M); cudaFree(c->d_log_omega);
   cudaFree(c->d_offset); cudaFree(c->d_log_nhi); cudaFree(c->d_nhi);
   cudaFree(c->d_prior_z); cudaFree(c->d_prior_dla); cudaFree(c->d_stage);
+  cudaFree(c->d_lls_nhi); cudaFree(c->d_uniforms); cudaFree(c->d_acache); cudaFree(c->d_msll); cudaFree(c->d_mlls);
+  cudaFree(c->d_cum); cudaFree(c->d_mscal); cudaFree(c->d_partners); cudaFree(c->d_active);
   delete c;
 }
 
@@ -375,6 +430,7 @@ int gpdla_process_qsos_device(gpdla_ctx* c, int64_t Q, int64_t L_max, const doub
     pa.prior_z_qso_increase = c->params.prior_z_qso_increase; pa.min_z_cut = c->params.min_z_cut;
     pa.max_z_cut = c->params.max_z_cut; pa.pixel_spacing = c->params.pixel_spacing;
     pa.meta = c->d_meta; pa.lam_pad = c->d_lam; pa.pix = c->d_pix; pa.Mq = c->d_Mq; pa.NPIX = npix;
+    pa.meanflux = 0;
     prepare_quasars_kernel<<<nq, NTHREADS, 0, st>>>(pa);
     c->launches++;
     CUDA_TRY(cudaGetLastError(), c->err);
@@ -389,6 +445,7 @@ int gpdla_process_qsos_device(gpdla_ctx* c, int64_t Q, int64_t L_max, const doub
     la.offset_samples = c->d_offset; la.nhi_samples = c->d_nhi; la.S = c->S;
     la.num_lines = c->params.num_lines; la.NPIX = npix;
     la.sample_log_likelihoods = sll; la.log_likelihoods_no_dla = llno;
+    la.sll_stride = c->S; la.acache = nullptr; la.partners = nullptr; la.num_partners = 0; la.active = nullptr;
     la.phase_cycles = nullptr;
 #ifdef GPDLA_PHASE_TIMING
     {
@@ -402,8 +459,8 @@ int gpdla_process_qsos_device(gpdla_ctx* c, int64_t Q, int64_t L_max, const doub
       fprintf(stderr, "[core path] cycles %lld, warp-evals with core %lld of %lld\n", h[8], h[9], h[10]);
     }
 #endif
-    if (c->params.num_lines == 3) rc = launch_loglik<20, 3>(c, la, nq, st);
-    else rc = launch_loglik<20, 0>(c, la, nq, st);
+    if (c->params.num_lines == 3) rc = launch_loglik<20, 3, 0>(c, la, nq, st);
+    else rc = launch_loglik<20, 0, 0>(c, la, nq, st);
     if (rc) return rc;
 
     EvidenceArgs ea;
@@ -488,6 +545,228 @@ int gpdla_process_qsos(gpdla_ctx* c, int64_t Q, int64_t L_max, const double* wav
   if (want_sll)
     CUDA_TRY(cudaMemcpyAsync(out->sample_log_likelihoods_dla, d_sll, (size_t)Q * c->S * 8, cudaMemcpyDeviceToHost, st),
              c->err);
+  CUDA_TRY(cudaStreamSynchronize(st), c->err);
+  return GPDLA_OK;
+}
+
+// ---------------------------------------------------------------------------- multi-DLA path
+void gpdla_matlab_default_rand(double* out, int64_t n) {
+  // rng('default') = Mersenne twister, seed 5489; rand = 53-bit doubles (genrand_res53)
+  std::mt19937 gen(5489u);
+  for (int64_t i = 0; i < n; ++i) {
+    const uint32_t a = gen() >> 5, b = gen() >> 6;
+    out[i] = (a * 67108864.0 + b) / 9007199254740992.0;
+  }
+}
+
+int gpdla_set_lls_samples(gpdla_ctx* c, const double* lls_nhi, int64_t S, double Z_lls, double Z_dla) {
+  if (!c || !lls_nhi || S < 1 || !(Z_lls > 0) || !(Z_dla > 0)) return GPDLA_ERR_INVALID;
+  if (c->S != S) { c->err = "gpdla_set_lls_samples: call gpdla_set_samples first (same sample count)"; return GPDLA_ERR_STATE; }
+  CUDA_TRY(cudaSetDevice(c->device), c->err);
+  int rc;
+  if ((rc = dev_upload(&c->d_lls_nhi, lls_nhi, S, c->err))) return rc;
+  std::vector<double> u(3 * (size_t)S);
+  gpdla_matlab_default_rand(u.data(), (int64_t)u.size());
+  if ((rc = dev_upload(&c->d_uniforms, u.data(), u.size(), c->err))) return rc;
+  c->Z_lls = Z_lls; c->Z_dla = Z_dla;
+  return GPDLA_OK;
+}
+
+int gpdla_process_qsos_multi_device(gpdla_ctx* c, int64_t Q, int64_t L_max, const double* wavelengths,
+                                    const double* flux, const double* noise_variance, const uint8_t* pixel_mask,
+                                    const int32_t* lengths, const double* z_qsos, int32_t max_dlas,
+                                    const int32_t* base_in, const gpdla_multi_results* out, void* stream) {
+  if (!c) return GPDLA_ERR_INVALID;
+  if (Q < 0 || L_max < 1 || !out || max_dlas < 1 || max_dlas > 4 ||
+      (Q > 0 && (!wavelengths || !flux || !noise_variance || !pixel_mask || !lengths || !z_qsos))) {
+    c->err = "gpdla_process_qsos_multi_device: invalid arguments (1 <= max_dlas <= 4)";
+    return GPDLA_ERR_INVALID;
+  }
+  const void* required[] = {out->min_z_dlas, out->max_z_dlas, out->log_priors_no_dla, out->log_priors_lls,
+                            out->log_priors_dla, out->log_likelihoods_no_dla, out->log_likelihoods_lls,
+                            out->log_likelihoods_dla, out->log_posteriors_no_dla, out->log_posteriors_lls,
+                            out->log_posteriors_dla, out->model_posteriors, out->p_no_dlas, out->p_lls, out->p_dlas,
+                            out->MAP_z_dlas, out->MAP_log_nhis, out->MAP_inds};
+  for (const void* r : required)
+    if (Q > 0 && !r) { c->err = "gpdla_process_qsos_multi_device: only the three large outputs may be NULL"; return GPDLA_ERR_INVALID; }
+  if (!c->d_M || !c->d_offset || c->n_prior < 0 || !c->d_lls_nhi) {
+    c->err = "gpdla_process_qsos_multi: set_model, set_samples, set_prior and set_lls_samples must be called first";
+    return GPDLA_ERR_STATE;
+  }
+  if (Q == 0) return GPDLA_OK;
+  CUDA_TRY(cudaSetDevice(c->device), c->err);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int npix = (int)((L_max + KC - 1) / KC) * KC;
+  int batch = c->params.batch_quasars > 0 ? c->params.batch_quasars : 148;
+  batch = (int)std::min<int64_t>(batch, Q);
+  int rc = ensure_workspace(c, batch, npix);
+  if (rc) return rc;
+  rc = ensure_multi_workspace(c, batch, npix);
+  if (rc) return rc;
+  batch = std::min(c->ws_batch, c->mws_batch);
+  const int64_t S = c->S;
+  const int MD = max_dlas;
+  const double min_z_sep = (3000.0 * 1000.0) / 299792458.0;   // kms_to_z(3000), ...meanflux.m:33
+
+  for (int64_t q0 = 0; q0 < Q; q0 += batch) {
+    const int nq = (int)std::min<int64_t>(batch, Q - q0);
+    PrepArgs pa;
+    pa.wavelengths = wavelengths + q0 * L_max; pa.flux = flux + q0 * L_max;
+    pa.noise_variance = noise_variance + q0 * L_max; pa.pixel_mask = pixel_mask + q0 * L_max;
+    pa.lengths = lengths + q0; pa.z_qsos = z_qsos + q0; pa.L_max = L_max;
+    pa.rest_wavelengths = c->d_rest; pa.mu = c->d_mu; pa.M = c->d_M; pa.log_omega = c->d_log_omega;
+    pa.n_rest = c->n_rest; pa.k = c->k; pa.c_0 = c->c_0; pa.tau_0 = c->tau_0; pa.beta = c->beta;
+    pa.prior_z_qsos = c->d_prior_z; pa.prior_dla_ind = c->d_prior_dla; pa.n_prior = c->n_prior;
+    pa.min_lambda = c->params.min_lambda; pa.max_lambda = c->params.max_lambda;
+    pa.lya_wavelength = c->params.lya_wavelength; pa.lyman_limit = c->params.lyman_limit;
+    pa.prior_z_qso_increase = c->params.prior_z_qso_increase; pa.min_z_cut = c->params.min_z_cut;
+    pa.max_z_cut = c->params.max_z_cut; pa.pixel_spacing = c->params.pixel_spacing;
+    pa.meta = c->d_meta; pa.lam_pad = c->d_lam; pa.pix = c->d_pix; pa.Mq = c->d_Mq; pa.NPIX = npix;
+    pa.meanflux = 1;
+    prepare_quasars_kernel<<<nq, NTHREADS, 0, st>>>(pa);
+    c->launches++;
+    CUDA_TRY(cudaGetLastError(), c->err);
+    build_gram_operand_kernel<20><<<dim3(npix / KC, nq), NTHREADS, 0, st>>>(c->d_Mq, c->d_meta, c->d_P, npix);
+    c->launches++;
+    fill_i32_kernel<<<(nq + 255) / 256, 256, 0, st>>>(c->d_active, 1, nq);
+    c->launches++;
+    CUDA_TRY(cudaMemsetAsync(c->d_partners, 0, (size_t)nq * 3 * c->S * sizeof(int32_t), st), c->err);   // :313 zeros
+    CUDA_TRY(cudaGetLastError(), c->err);
+
+    // where this batch's sample log-likelihoods live: caller's [Q x MD x S] array or the workspace
+    double* sll = out->sample_log_likelihoods_dla ? out->sample_log_likelihoods_dla + q0 * MD * S : c->d_msll;
+    const int64_t sll_stride = (int64_t)MD * S;
+    double* slls = out->sample_log_likelihoods_lls ? out->sample_log_likelihoods_lls + q0 * S : c->d_mlls;
+    int32_t* partners = c->d_partners;
+
+    LoglikArgs la;
+    la.meta = c->d_meta; la.lam_pad = c->d_lam; la.pix = c->d_pix; la.P = c->d_P;
+    la.offset_samples = c->d_offset; la.S = S; la.num_lines = c->params.num_lines; la.NPIX = npix;
+    la.acache = c->d_acache; la.partners = partners; la.active = c->d_active; la.phase_cycles = nullptr;
+
+    MultiLevelArgs ma;
+    ma.meta = c->d_meta; ma.S = S; ma.max_dlas = MD; ma.partners = partners;
+    ma.partners_in = base_in ? base_in + q0 * 3 * S : nullptr;
+    ma.active = c->d_active; ma.offset_samples = c->d_offset; ma.log_nhi_samples = c->d_log_nhi;
+    ma.uniforms = c->d_uniforms; ma.min_z_separation = min_z_sep; ma.cum_scratch = c->d_cum;
+    ma.map_z = out->MAP_z_dlas + q0 * MD * MD; ma.map_log_nhi = out->MAP_log_nhis + q0 * MD * MD;
+    ma.map_inds = out->MAP_inds + q0 * MD * MD;
+
+    // level 1 (+ null model), absorption rows cached                         ...meanflux.m:342-361
+    la.nhi_samples = c->d_nhi; la.sample_log_likelihoods = sll; la.sll_stride = sll_stride;
+    la.log_likelihoods_no_dla = out->log_likelihoods_no_dla + q0; la.num_partners = 0;
+    if ((rc = launch_mode<1>(c, la, nq, st))) return rc;
+    // sub-DLA model                                                           ...meanflux.m:365-380
+    la.nhi_samples = c->d_lls_nhi; la.sample_log_likelihoods = slls; la.sll_stride = S;
+    la.log_likelihoods_no_dla = nullptr;
+    if ((rc = launch_mode<0>(c, la, nq, st))) return rc;
+    ma.level = 0; ma.sll = slls; ma.sll_stride = S; ma.log_likelihoods = out->log_likelihoods_lls + q0;
+    multi_level_kernel<<<nq, NTHREADS, 0, st>>>(ma);
+    c->launches++;
+    for (int level = 1; level <= MD; ++level) {
+      if (level >= 2) {
+        la.nhi_samples = c->d_nhi; la.sample_log_likelihoods = sll + (int64_t)(level - 1) * S;
+        la.sll_stride = sll_stride; la.log_likelihoods_no_dla = nullptr; la.num_partners = level - 1;
+        if ((rc = launch_mode<2>(c, la, nq, st))) return rc;
+      }
+      ma.level = level; ma.sll = sll + (int64_t)(level - 1) * S; ma.sll_stride = sll_stride;
+      ma.log_likelihoods = out->log_likelihoods_dla + q0 * MD;
+      multi_level_kernel<<<nq, NTHREADS, 0, st>>>(ma);
+      c->launches++;
+      CUDA_TRY(cudaGetLastError(), c->err);
+    }
+    if (out->base_sample_inds && MD > 1) {   // [Q x (MD-1) x S] <- workspace [nq x 3 x S]
+      CUDA_TRY(cudaMemcpy2DAsync(out->base_sample_inds + q0 * (MD - 1) * S, (size_t)(MD - 1) * S * sizeof(int32_t),
+                                 partners, (size_t)3 * S * sizeof(int32_t), (size_t)(MD - 1) * S * sizeof(int32_t), nq,
+                                 cudaMemcpyDeviceToDevice, st), c->err);
+    }
+    MultiPosteriorArgs mp;
+    mp.meta = c->d_meta; mp.Q = nq; mp.max_dlas = MD; mp.Z_lls = c->Z_lls; mp.Z_dla = c->Z_dla;
+    mp.log_likelihoods_no_dla = out->log_likelihoods_no_dla + q0; mp.log_likelihoods_lls = out->log_likelihoods_lls + q0;
+    mp.log_likelihoods_dla = out->log_likelihoods_dla + q0 * MD;
+    mp.min_z_dlas = out->min_z_dlas + q0; mp.max_z_dlas = out->max_z_dlas + q0;
+    mp.log_priors_no_dla = out->log_priors_no_dla + q0; mp.log_priors_lls = out->log_priors_lls + q0;
+    mp.log_priors_dla = out->log_priors_dla + q0 * MD;
+    mp.log_posteriors_no_dla = out->log_posteriors_no_dla + q0; mp.log_posteriors_lls = out->log_posteriors_lls + q0;
+    mp.log_posteriors_dla = out->log_posteriors_dla + q0 * MD;
+    mp.model_posteriors = out->model_posteriors + q0 * (MD + 2);
+    mp.p_no_dlas = out->p_no_dlas + q0; mp.p_lls = out->p_lls + q0; mp.p_dlas = out->p_dlas + q0;
+    multi_posterior_kernel<<<(nq + 127) / 128, 128, 0, st>>>(mp);
+    c->launches++;
+    CUDA_TRY(cudaGetLastError(), c->err);
+  }
+  return GPDLA_OK;
+}
+
+int gpdla_process_qsos_multi(gpdla_ctx* c, int64_t Q, int64_t L_max, const double* wavelengths, const double* flux,
+                             const double* noise_variance, const uint8_t* pixel_mask, const int32_t* lengths,
+                             const double* z_qsos, int32_t max_dlas, const int32_t* base_in,
+                             const gpdla_multi_results* out) {
+  if (!c) return GPDLA_ERR_INVALID;
+  if (Q < 0 || L_max < 1 || !out || max_dlas < 1 || max_dlas > 4) {
+    c->err = "gpdla_process_qsos_multi: invalid arguments (1 <= max_dlas <= 4)";
+    return GPDLA_ERR_INVALID;
+  }
+  if (Q == 0) return GPDLA_OK;
+  CUDA_TRY(cudaSetDevice(c->device), c->err);
+  const size_t QL = (size_t)Q * L_max, S = (size_t)c->S, MD = max_dlas;
+  // device staging: inputs, then every output (small ones always, large ones when requested)
+  struct Item { void** dev; const void* host_in; void* host_out; size_t bytes; };
+  double *d_w, *d_f, *d_v, *d_z; uint8_t* d_m; int32_t *d_len, *d_bin = nullptr;
+  gpdla_multi_results dr;
+  memset(&dr, 0, sizeof dr);
+  std::vector<Item> items = {
+      {(void**)&d_w, wavelengths, nullptr, QL * 8}, {(void**)&d_f, flux, nullptr, QL * 8},
+      {(void**)&d_v, noise_variance, nullptr, QL * 8}, {(void**)&d_z, z_qsos, nullptr, (size_t)Q * 8},
+      {(void**)&d_len, lengths, nullptr, (size_t)Q * 4}, {(void**)&d_m, pixel_mask, nullptr, QL},
+      {(void**)&dr.min_z_dlas, nullptr, out->min_z_dlas, (size_t)Q * 8},
+      {(void**)&dr.max_z_dlas, nullptr, out->max_z_dlas, (size_t)Q * 8},
+      {(void**)&dr.log_priors_no_dla, nullptr, out->log_priors_no_dla, (size_t)Q * 8},
+      {(void**)&dr.log_priors_lls, nullptr, out->log_priors_lls, (size_t)Q * 8},
+      {(void**)&dr.log_priors_dla, nullptr, out->log_priors_dla, (size_t)Q * MD * 8},
+      {(void**)&dr.log_likelihoods_no_dla, nullptr, out->log_likelihoods_no_dla, (size_t)Q * 8},
+      {(void**)&dr.log_likelihoods_lls, nullptr, out->log_likelihoods_lls, (size_t)Q * 8},
+      {(void**)&dr.log_likelihoods_dla, nullptr, out->log_likelihoods_dla, (size_t)Q * MD * 8},
+      {(void**)&dr.log_posteriors_no_dla, nullptr, out->log_posteriors_no_dla, (size_t)Q * 8},
+      {(void**)&dr.log_posteriors_lls, nullptr, out->log_posteriors_lls, (size_t)Q * 8},
+      {(void**)&dr.log_posteriors_dla, nullptr, out->log_posteriors_dla, (size_t)Q * MD * 8},
+      {(void**)&dr.model_posteriors, nullptr, out->model_posteriors, (size_t)Q * (MD + 2) * 8},
+      {(void**)&dr.p_no_dlas, nullptr, out->p_no_dlas, (size_t)Q * 8},
+      {(void**)&dr.p_lls, nullptr, out->p_lls, (size_t)Q * 8},
+      {(void**)&dr.p_dlas, nullptr, out->p_dlas, (size_t)Q * 8},
+      {(void**)&dr.MAP_z_dlas, nullptr, out->MAP_z_dlas, (size_t)Q * MD * MD * 8},
+      {(void**)&dr.MAP_log_nhis, nullptr, out->MAP_log_nhis, (size_t)Q * MD * MD * 8},
+      {(void**)&dr.MAP_inds, nullptr, out->MAP_inds, (size_t)Q * MD * MD * 8}};
+  if (out->sample_log_likelihoods_dla)
+    items.push_back({(void**)&dr.sample_log_likelihoods_dla, nullptr, out->sample_log_likelihoods_dla, (size_t)Q * MD * S * 8});
+  if (out->sample_log_likelihoods_lls)
+    items.push_back({(void**)&dr.sample_log_likelihoods_lls, nullptr, out->sample_log_likelihoods_lls, (size_t)Q * S * 8});
+  if (out->base_sample_inds && MD > 1)
+    items.push_back({(void**)&dr.base_sample_inds, nullptr, out->base_sample_inds, (size_t)Q * (MD - 1) * S * 4});
+  std::vector<int32_t> bin3;
+  if (base_in && MD > 1) {   // caller's [Q x (MD-1) x S] -> internal [Q x 3 x S]
+    bin3.assign((size_t)Q * 3 * S, 0);
+    for (size_t q = 0; q < (size_t)Q; ++q)
+      memcpy(&bin3[q * 3 * S], base_in + q * (MD - 1) * S, (MD - 1) * S * sizeof(int32_t));
+    items.push_back({(void**)&d_bin, bin3.data(), nullptr, bin3.size() * 4});
+  }
+  size_t bytes = 256;
+  for (auto& it : items) bytes += (it.bytes + 255) / 256 * 256;
+  if (c->st_bytes < bytes) {
+    cudaFree(c->d_stage); c->d_stage = nullptr; c->st_bytes = 0;
+    CUDA_TRY(cudaMalloc(&c->d_stage, bytes), c->err);
+    c->st_bytes = bytes;
+  }
+  char* p = (char*)c->d_stage;
+  cudaStream_t st = 0;
+  for (auto& it : items) {
+    *it.dev = p; p += (it.bytes + 255) / 256 * 256;
+    if (it.host_in) CUDA_TRY(cudaMemcpyAsync(*it.dev, it.host_in, it.bytes, cudaMemcpyHostToDevice, st), c->err);
+  }
+  int rc = gpdla_process_qsos_multi_device(c, Q, L_max, d_w, d_f, d_v, d_m, d_len, d_z, max_dlas, d_bin, &dr, st);
+  if (rc) return rc;
+  for (auto& it : items)
+    if (it.host_out) CUDA_TRY(cudaMemcpyAsync(it.host_out, *it.dev, it.bytes, cudaMemcpyDeviceToHost, st), c->err);
   CUDA_TRY(cudaStreamSynchronize(st), c->err);
   return GPDLA_OK;
 }

@@ -29,7 +29,19 @@ struct QuasarMeta {               // one per quasar, written by K0
   int first;                      // index of the first window pixel in the spectrum
   double min_z_dla, max_z_dla;    // process_qsos.m:159-160
   double log_prior_no_dla, log_prior_dla;   // process_qsos.m:128-131
+  int prior_num_quasars, prior_num_dlas;    // the counts behind them (multi-DLA priors, ...meanflux.m:190-216)
 };
+
+// Lyman-series forest data for the mean-flux suppression of the multi-DLA path
+// (multi_dlas/set_parameters_multi.m:76-145, ...meanflux.m:36-37,243-293); filled by the host.
+struct ForestConstants {
+  double wavelength[MAX_LINES];     // all_transition_wavelengths (Angstrom) = cm value * 1e8
+  double tau_ratio[MAX_LINES];      // lambda_l f_l / (lambda_1 f_1)                       ...meanflux.m:255-256
+  double kim_tau[MAX_LINES];        // prev_tau_0 f_l / f_lya * lambda_l / lya_wavelength  ...meanflux.m:271-273
+  double prev_beta;                 // 3.65
+  int num_forest_lines;             // 31
+};
+__constant__ ForestConstants c_forest;
 
 template <int K>
 struct GramShape {
@@ -125,6 +137,7 @@ struct PrepArgs {
   double* pix;              // [Q x NPIX x 4]  (y, v, mu, omega2)
   double* Mq;               // [Q x NPIX x k]  interpolated M rows (zero for masked / padding pixels)
   int NPIX;
+  int meanflux;             // 1: Lyman-series mean-flux suppression + noise scaling (multi-DLA path)
 };
 
 __device__ __forceinline__ double interp_linear(const double* xp, const double* fp, int stride, int j, double x) {
@@ -204,6 +217,7 @@ __global__ void __launch_bounds__(NTHREADS) prepare_quasars_kernel(PrepArgs a) {
                        a.lyman_limit * (1.0 + z_qso) / a.lya_wavelength - 1.0 + a.min_z_cut);
     // process_qsos.m:128-131
     m.log_prior_dla = log((double)s_nd) - log((double)s_nq);
+    m.prior_num_quasars = s_nq; m.prior_num_dlas = s_nd;
     m.log_prior_no_dla = log((double)(s_nq - s_nd)) - log((double)s_nq);
     if (n_used == 0) { m.nchunks = 0; m.min_z_dla = NAN; m.max_z_dla = NAN; }
     a.meta[q] = m;
@@ -235,7 +249,7 @@ __global__ void __launch_bounds__(NTHREADS) prepare_quasars_kernel(PrepArgs a) {
   const double x0 = a.rest_wavelengths[0];
   const double inv_dx = (a.n_rest - 1) / (a.rest_wavelengths[a.n_rest - 1] - x0);
   for (int i = tid; i < NPIX; i += NTHREADS) {
-    double y = 0.0, v = 1.0, mu = 0.0, om2 = 0.0;
+    double y = 0.0, v = 1.0, mu = 0.0, om2 = 0.0, absorb = 1.0;
     bool used = false;
     int j = 0;
     double rest = 0.0;
@@ -253,13 +267,32 @@ __global__ void __launch_bounds__(NTHREADS) prepare_quasars_kernel(PrepArgs a) {
         mu = interp_linear(a.rest_wavelengths, a.mu, 1, j, rest);
         double lw = interp_linear(a.rest_wavelengths, a.log_omega, 1, j, rest);
         double lya_z = (w - a.lya_wavelength) / a.lya_wavelength;                 // :117-119
-        double scaling = 1.0 - exp(-a.tau_0 * pow(1.0 + lya_z, a.beta)) + a.c_0;   // :144
-        om2 = exp(2.0 * lw) * (scaling * scaling);                                 // :142,146
+        if (!a.meanflux) {
+          double scaling = 1.0 - exp(-a.tau_0 * pow(1.0 + lya_z, a.beta)) + a.c_0;   // :144
+          om2 = exp(2.0 * lw) * (scaling * scaling);                                 // :142,146
+        } else {
+          // multi_dlas/process_qsos_multiple_dlas_meanflux.m:245-293
+          double depth = a.tau_0 * pow(1.0 + lya_z, a.beta);                         // :245
+          for (int l = 1; l < c_forest.num_forest_lines; ++l) {                      // :247-259
+            double lyman_1pz = c_forest.wavelength[0] * (1.0 + lya_z) / c_forest.wavelength[l];
+            if (lyman_1pz <= 1.0 + z_qso) depth = depth + (a.tau_0 * c_forest.tau_ratio[l]) * pow(lyman_1pz, a.beta);
+          }
+          double scaling = 1.0 - exp(-depth) + a.c_0;                                // :261
+          om2 = exp(2.0 * lw) * (scaling * scaling);                                 // :263
+          double total = 0.0;
+          for (int l = 0; l < c_forest.num_forest_lines; ++l) {                      // :269-283
+            double zl = (w - c_forest.wavelength[l]) / c_forest.wavelength[l];       // :183-187
+            if (l == 0 || !(zl > z_qso)) total = total + c_forest.kim_tau[l] * pow(1.0 + zl, c_forest.prev_beta);
+          }
+          absorb = exp(-total);                                                      // :285
+          mu = mu * absorb;                                                          // :287
+          om2 = om2 * (absorb * absorb);                                             // :293
+        }
       }
     }
     pix[i * 4 + 0] = y; pix[i * 4 + 1] = v; pix[i * 4 + 2] = mu; pix[i * 4 + 3] = om2;
     for (int c = 0; c < a.k; ++c)
-      Mq[(int64_t)i * a.k + c] = used ? interp_linear(a.rest_wavelengths, a.M + c, a.k, j, rest) : 0.0;
+      Mq[(int64_t)i * a.k + c] = used ? interp_linear(a.rest_wavelengths, a.M + c, a.k, j, rest) * absorb : 0.0;   // :288
   }
 }
 
@@ -338,8 +371,15 @@ struct LoglikArgs {
   int64_t S;                  // number of DLA samples; sample index S is the null model (absorption == 1)
   int num_lines;
   int NPIX;
-  double* sample_log_likelihoods;   // [Q x S]
-  double* log_likelihoods_no_dla;   // [Q]
+  double* sample_log_likelihoods;   // [Q x S] (row stride sll_stride)
+  double* log_likelihoods_no_dla;   // [Q]; nullptr: no null-model slot (tiles cover S samples only)
+  int64_t sll_stride;               // elements between consecutive quasars' rows of sample_log_likelihoods
+  // multi-DLA levels (...meanflux.m:337-381): the convolved absorption of every sample is cached at level 1
+  // (MODE 1) and levels >= 2 (MODE 2) multiply cached rows instead of re-evaluating Voigt profiles
+  double* acache;                   // [Q x S x NPIX]
+  const int32_t* partners;          // [Q x 3 x S] 0-based base_sample_inds; level l uses rows 0..l-2
+  int num_partners;
+  const int32_t* active;            // [Q] or nullptr; 0 = quasar finished early (:460-464) -> NaN
   long long* phase_cycles;          // debug builds (-DGPDLA_PHASE_TIMING): [16] summed cycles per phase
 };
 
@@ -374,11 +414,13 @@ struct LoglikConfig {
   static_assert(C_BYTES <= B_BYTES + A_BYTES, "epilogue staging must fit in the P buffers + operand tiles");
   static_assert(G::NT * 4 <= 200, "accumulators must fit in registers (use a smaller rank)");
   __host__ __device__ static constexpr size_t smem_bytes(int num_lines) {
-    return B_BYTES + A_BYTES + RAW_BYTES + (size_t)TS * (num_lines + 4) * 8 + 64;
+    return B_BYTES + A_BYTES + RAW_BYTES + (size_t)TS * (num_lines + 4) * 8 + 64 + 3 * TS * 4;
   }
 };
 
-template <int K, int NL>
+// MODE 0: single-DLA / sub-DLA pass;  MODE 1: same, and the convolved absorption rows are stored in
+// args.acache;  MODE 2: multi-DLA level >= 2, absorption = product of cached rows (sample and partners).
+template <int K, int NL, int MODE>
 __global__ void __launch_bounds__(NTHREADS, 1) dla_loglik_kernel(LoglikArgs args) {
   using Cfg = LoglikConfig<K>;
   using G = GramShape<K>;
@@ -389,11 +431,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) dla_loglik_kernel(LoglikArgs args
   const int64_t s0 = (int64_t)blockIdx.x * TS;
   const int64_t S = args.S;
 
-  if (meta.nchunks == 0) {   // nothing usable in this spectrum: NaN results (process_qsos.m:74-82)
+  // nothing usable in this spectrum (process_qsos.m:74-82), or the level loop already ended for this
+  // quasar (...meanflux.m:460-464): NaN results
+  if (meta.nchunks == 0 || (args.active != nullptr && args.active[q] == 0)) {
     for (int i = tid; i < TS; i += NTHREADS) {
       int64_t s = s0 + i;
-      if (s < S) args.sample_log_likelihoods[(int64_t)q * S + s] = NAN;
-      else if (s == S) args.log_likelihoods_no_dla[q] = NAN;
+      if (s < S) args.sample_log_likelihoods[(int64_t)q * args.sll_stride + s] = NAN;
+      else if (s == S && args.log_likelihoods_no_dla) args.log_likelihoods_no_dla[q] = NAN;
     }
     return;
   }
@@ -410,6 +454,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dla_loglik_kernel(LoglikArgs args
   const int num_lines = (NL > 0) ? NL : args.num_lines;
   uint64_t* mbar = reinterpret_cast<uint64_t*>(s_mult + (size_t)TS * num_lines + TS);   // full[2]
   int* s_done = reinterpret_cast<int*>(mbar + 2);                                        // [2] warps done with buffer
+  int* s_part = s_done + 2;                                                               // [3][TS] partner samples (MODE 2)
   double* Cs = reinterpret_cast<double*>(smem_raw);                       // epilogue: [entries][CSTR]
 
   // per-sample parameters: z_s (process_qsos.m:162-164), N_s, line multipliers (voigt.c:279)
@@ -420,6 +465,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) dla_loglik_kernel(LoglikArgs args
                        : __dadd_rn(meta.min_z_dla, __dmul_rn(meta.max_z_dla - meta.min_z_dla, args.offset_samples[s]));
     s_nhi[i] = is_null ? -1.0 : args.nhi_samples[s];     // negative marks the null-model slot
     for (int j = 0; j < num_lines; ++j) s_mult[j * TS + i] = line_multiplier(j, z);
+    if (MODE == 2) {
+      for (int j = 0; j < args.num_partners; ++j)
+        s_part[j * TS + i] = is_null ? 0 : args.partners[((int64_t)q * 3 + j) * S + s];
+    }
   }
   const double* lam = args.lam_pad + (int64_t)q * (args.NPIX + 8);
   const double* pix = args.pix + (int64_t)q * args.NPIX * 4;
@@ -479,7 +528,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) dla_loglik_kernel(LoglikArgs args
 #pragma unroll
     for (int ss = 0; ss < SPW; ++ss) myraw[ss * RAWW + (p & (RAWW - 1))] = e[ss];
   };
-  eval_raw(lane < 6 ? lane : 5);   // leading pad pixels p = 0..5 (extra lanes repeat p = 5)
+  if (MODE != 2) eval_raw(lane < 6 ? lane : 5);   // leading pad pixels p = 0..5 (extra lanes repeat p = 5)
+  double* const cache_q = (MODE != 0) ? args.acache + (int64_t)q * S * args.NPIX : nullptr;
 
   // accumulators: 8 samples x NCOL columns per warp
   double acc[NT][2];
@@ -495,7 +545,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dla_loglik_kernel(LoglikArgs args
   for (int c = 0; c < meta.nchunks; ++c) {
     // ---- A1: raw profile for the KC new padded pixels
     PHASE_T(t_a1);
-    eval_raw(c * KC + 6 + lane);
+    if (MODE != 2) eval_raw(c * KC + 6 + lane);
     __syncwarp();
     PHASE_T(t_a1e);
     // ---- A2: instrument convolution + weights
@@ -506,13 +556,36 @@ __global__ void __launch_bounds__(NTHREADS, 1) dla_loglik_kernel(LoglikArgs args
       const double y = p01.x, v = p01.y, mu = p23.x, om2 = p23.y;
       // loads first (convolution), stores last: see the aliasing note in eval_raw
       double a[SPW];
+      if (MODE != 2) {
 #pragma unroll
-      for (int ss = 0; ss < SPW; ++ss) {
-        const double* rb = myraw + ss * RAWW;
-        double acc_a = 0.0;
+        for (int ss = 0; ss < SPW; ++ss) {
+          const double* rb = myraw + ss * RAWW;
+          double acc_a = 0.0;
 #pragma unroll
-        for (int t = 0; t < 7; ++t) acc_a = fma(rb[(i + t) & (RAWW - 1)], c_lines.ip[t], acc_a);   // voigt.c:297-299
-        a[ss] = (__double2hiint(mynhi[ss]) < 0) ? 1.0 : acc_a;   // null model (N marked negative): no absorption
+          for (int t = 0; t < 7; ++t) acc_a = fma(rb[(i + t) & (RAWW - 1)], c_lines.ip[t], acc_a);   // voigt.c:297-299
+          a[ss] = (__double2hiint(mynhi[ss]) < 0) ? 1.0 : acc_a;   // null model (N marked negative): no absorption
+        }
+        if (MODE == 1) {   // keep the level-1 absorption rows for the higher multi-DLA levels
+#pragma unroll
+          for (int ss = 0; ss < SPW; ++ss) {
+            const int64_t smp = s0 + warp * SPW + ss;
+            if (smp < S) cache_q[smp * args.NPIX + i] = a[ss];
+          }
+        }
+      } else {
+        // absorption = voigt(sample) .* voigt(partner 1) .* ...   (...meanflux.m:342-351), from the cache
+#pragma unroll
+        for (int ss = 0; ss < SPW; ++ss) {
+          const int64_t smp = min(s0 + warp * SPW + ss, S - 1);
+          a[ss] = cache_q[smp * args.NPIX + i];
+        }
+        for (int j = 0; j < args.num_partners; ++j) {
+          double b[SPW];
+#pragma unroll
+          for (int ss = 0; ss < SPW; ++ss) b[ss] = cache_q[(int64_t)s_part[j * TS + warp * SPW + ss] * args.NPIX + i];
+#pragma unroll
+          for (int ss = 0; ss < SPW; ++ss) a[ss] = a[ss] * b[ss];
+        }
       }
 #pragma unroll
       for (int ss = 0; ss < SPW; ++ss) {
@@ -626,8 +699,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) dla_loglik_kernel(LoglikArgs args
       const double logdet = s_ld[sl] + log(prod0) + log(prod1);             //                           :30
       const double lp = -0.5 * (quad + logdet + (double)meta.n * LOG_2PI);  //                           :32
       const int64_t s = s0 + sl;
-      if (s < S) args.sample_log_likelihoods[(int64_t)q * S + s] = lp;
-      else if (s == S) args.log_likelihoods_no_dla[q] = lp;
+      if (s < S) args.sample_log_likelihoods[(int64_t)q * args.sll_stride + s] = lp;
+      else if (s == S && args.log_likelihoods_no_dla) args.log_likelihoods_no_dla[q] = lp;
     }
   }
 #ifdef GPDLA_PHASE_TIMING
@@ -723,6 +796,218 @@ __global__ void __launch_bounds__(NTHREADS) evidence_kernel(EvidenceArgs a) {
       a.map_z_dlas[q] = NAN; a.map_log_nhis[q] = NAN;
     }
   }
+}
+
+// ------------------------------------------------------------------------------------------
+// Multi-DLA level post-processing (multi_dlas/process_qsos_multiple_dlas_meanflux.m:359-472).
+// One CTA per quasar, after the log-likelihood kernel of a level (or of the sub-DLA pass, level 0):
+// Occam term -log S per sample (:361,378), z-separation filter (:386-392), nan-LSE (:400-409,416-426),
+// MAP (:438-445), early exit (:460-464), weighted resampling with replacement (:466-472).
+struct MultiLevelArgs {
+  const QuasarMeta* meta;
+  double* sll;                  // this level's sample log-likelihoods, [Q] rows of S with stride sll_stride; in/out
+  int64_t sll_stride;
+  int64_t S;
+  int level;                    // 1..max_dlas; 0 = sub-DLA (LLS) pass
+  int max_dlas;
+  int32_t* partners;            // [Q x 3 x S] base_sample_inds (0-based), row level-1 written here
+  const int32_t* partners_in;   // optional given base_sample_inds [Q x 3 x S] (parity runs); nullptr = resample
+  int32_t* active;              // [Q] level loop still running
+  const double* offset_samples;
+  const double* log_nhi_samples;
+  const double* uniforms;       // [3 x S]: rand stream after rng('default'), S numbers per level (:143,471)
+  double min_z_separation;      // kms_to_z(3000), :33
+  double* cum_scratch;          // [Q x S]
+  double* log_likelihoods;      // level >= 1: [Q x max_dlas]; level 0: [Q] (log_likelihoods_lls)
+  double* map_z;                // [Q x max_dlas x max_dlas]
+  double* map_log_nhi;          // [Q x max_dlas x max_dlas]
+  int64_t* map_inds;            // [Q x max_dlas x max_dlas], 0-based, -1 = unset
+};
+
+__global__ void __launch_bounds__(NTHREADS) multi_level_kernel(MultiLevelArgs a) {
+  const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const QuasarMeta meta = a.meta[q];
+  const int64_t S = a.S;
+  const int L = a.level, MD = a.max_dlas;
+  double* ll = a.sll + (int64_t)q * a.sll_stride;
+  __shared__ double s_val[NTHREADS / 32], s_val2[NTHREADS / 32];
+  __shared__ long long s_idx[NTHREADS / 32];
+  __shared__ double s_max, s_sum, s_cnt, s_ev;
+  __shared__ long long s_arg;
+  __shared__ double s_scan[NTHREADS];
+
+  if (L >= 1 && tid < MD) {   // this level's MAP row starts unset (:129-131)
+    const int64_t o = ((int64_t)q * MD + (L - 1)) * MD + tid;
+    a.map_z[o] = NAN; a.map_log_nhi[o] = NAN; a.map_inds[o] = -1;
+  }
+  const bool live = meta.nchunks > 0 && a.active[q] != 0;
+  if (!live) {
+    if (tid == 0) {
+      if (L >= 1) a.log_likelihoods[(int64_t)q * MD + (L - 1)] = NAN; else a.log_likelihoods[q] = NAN;
+    }
+    return;
+  }
+  const double logS = log((double)S);
+  const double zmin = meta.min_z_dla, zspan = meta.max_z_dla - meta.min_z_dla;
+  const int32_t* part = a.partners + (int64_t)q * 3 * S;
+  auto zs = [&](int64_t s) { return __dadd_rn(zmin, __dmul_rn(zspan, a.offset_samples[s])); };
+
+  // ---- pass 1: Occam term, separation filter, nan-max with first index
+  double m = -INFINITY; long long arg = -1;
+  for (int64_t s = tid; s < S; s += NTHREADS) {
+    double v = ll[s] - logS;                                                       // :361 / :378
+    if (L >= 2) {                                                                  // :386-392
+      double z[4];
+      z[0] = zs(s);
+      for (int j = 0; j < L - 1; ++j) z[j + 1] = zs(part[(int64_t)j * S + s]);
+      for (int i = 1; i < L; ++i) {                                                // insertion sort (<= 4 values)
+        double zi = z[i]; int k = i - 1;
+        while (k >= 0 && z[k] > zi) { z[k + 1] = z[k]; --k; }
+        z[k + 1] = zi;
+      }
+      bool close = false;
+      for (int i = 1; i < L; ++i) close |= (z[i] - z[i - 1]) < a.min_z_separation;
+      if (close) v = NAN;
+    }
+    ll[s] = v;
+    if (v == v && (arg < 0 || v > m)) { m = v; arg = s; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    double om = __shfl_xor_sync(0xffffffffu, m, o);
+    long long oa = __shfl_xor_sync(0xffffffffu, arg, o);
+    if (oa >= 0 && (arg < 0 || om > m || (om == m && oa < arg))) { m = om; arg = oa; }
+  }
+  if (lane == 0) { s_val[wid] = m; s_idx[wid] = arg; }
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < NTHREADS / 32; ++w) {
+      double om = s_val[w]; long long oa = s_idx[w];
+      if (oa >= 0 && (arg < 0 || om > m || (om == m && oa < arg))) { m = om; arg = oa; }
+    }
+    s_max = m; s_arg = arg;
+  }
+  __syncthreads();
+  m = s_max; arg = s_arg;
+
+  // ---- pass 2: nan-mean of exp(ll - max)
+  double sum = 0.0, cnt = 0.0;
+  for (int64_t s = tid; s < S; s += NTHREADS) {
+    double v = ll[s];
+    if (v == v) { sum += exp(v - m); cnt += 1.0; }
+  }
+  sum = warp_sum(sum); cnt = warp_sum(cnt);
+  __syncthreads();
+  if (lane == 0) { s_val[wid] = sum; s_val2[wid] = cnt; }
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < NTHREADS / 32; ++w) { sum += s_val[w]; cnt += s_val2[w]; }
+    s_sum = sum; s_cnt = cnt;
+    double ev = (arg >= 0) ? m + log(sum / cnt) - logS * (double)(L >= 1 ? L - 1 : 0) : NAN;   // :407-409 / :424-426
+    s_ev = ev;
+    if (L >= 1) a.log_likelihoods[(int64_t)q * MD + (L - 1)] = ev; else a.log_likelihoods[q] = ev;
+    if (L >= 1 && arg >= 0) {                                                      // :438-445
+      const int64_t o = ((int64_t)q * MD + (L - 1)) * MD;
+      a.map_inds[o] = arg; a.map_z[o] = zs(arg); a.map_log_nhi[o] = a.log_nhi_samples[arg];
+      for (int j = 0; j < L - 1; ++j) {
+        const long long k = part[(int64_t)j * S + arg];
+        a.map_inds[o + j + 1] = k; a.map_z[o + j + 1] = zs(k); a.map_log_nhi[o + j + 1] = a.log_nhi_samples[k];
+      }
+    }
+    if (L >= 1 && L < MD && !(ev == ev)) a.active[q] = 0;                          // :460-464
+  }
+  __syncthreads();
+  if (L < 1 || L >= MD || !(s_ev == s_ev)) return;                                 // :452-454, :460-464
+
+  // ---- resampling: base_sample_inds(level, :) = randsample(S, S, true, W)      :466-472
+  int32_t* out = a.partners + ((int64_t)q * 3 + (L - 1)) * S;
+  if (a.partners_in != nullptr) {
+    const int32_t* in = a.partners_in + ((int64_t)q * 3 + (L - 1)) * S;
+    for (int64_t s = tid; s < S; s += NTHREADS) out[s] = in[s];
+    return;
+  }
+  const double total = s_sum;
+  double* cum = a.cum_scratch + (int64_t)q * S;
+  const int64_t seg = (S + NTHREADS - 1) / NTHREADS;
+  const int64_t b = min((int64_t)tid * seg, S), e = min(b + seg, S);
+  double local = 0.0;
+  for (int64_t s = b; s < e; ++s) {
+    double v = ll[s];
+    local += (v == v) ? exp(v - m) / total : 0.0;                                  // W(nanind) = 0; p = w / sum(w)
+  }
+  s_scan[tid] = local;
+  __syncthreads();
+  if (tid == 0) {
+    double run = 0.0;
+    for (int t = 0; t < NTHREADS; ++t) { double x = s_scan[t]; s_scan[t] = run; run += x; }
+  }
+  __syncthreads();
+  double run = s_scan[tid];
+  for (int64_t s = b; s < e; ++s) {
+    double v = ll[s];
+    run += (v == v) ? exp(v - m) / total : 0.0;
+    cum[s] = fmin(run, 1.0);                                                       // edges = min([0 cumsum(p)], 1)
+  }
+  __syncthreads();
+  const double* u = a.uniforms + (int64_t)(L - 1) * S;
+  for (int64_t t = tid; t < S; t += NTHREADS) {
+    const double x = u[t];
+    int64_t lo = 0, hi = S - 1;            // number of interior edges cum[0..S-2] that are <= x
+    while (lo < hi) {
+      int64_t mid = (lo + hi) >> 1;
+      if (cum[mid] <= x) lo = mid + 1; else hi = mid;
+    }
+    out[t] = (int32_t)lo;
+  }
+}
+
+// Multi-DLA priors and model posteriors (...meanflux.m:190-216, 300-301, 411-413, 428-430, 482-495).
+struct MultiPosteriorArgs {
+  const QuasarMeta* meta;
+  int64_t Q;
+  int max_dlas;
+  double Z_lls, Z_dla;
+  const double* log_likelihoods_no_dla;   // [Q]
+  const double* log_likelihoods_lls;      // [Q]
+  const double* log_likelihoods_dla;      // [Q x max_dlas]
+  double *min_z_dlas, *max_z_dlas, *log_priors_no_dla, *log_priors_lls, *log_priors_dla /*[Q x max_dlas]*/;
+  double *log_posteriors_no_dla, *log_posteriors_lls, *log_posteriors_dla /*[Q x max_dlas]*/;
+  double *model_posteriors /*[Q x (2 + max_dlas)]*/, *p_no_dlas, *p_lls, *p_dlas;
+};
+
+__global__ void multi_posterior_kernel(MultiPosteriorArgs a) {
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= a.Q) return;
+  const QuasarMeta meta = a.meta[q];
+  const int MD = a.max_dlas;
+  const double nq = (double)meta.prior_num_quasars, nd = (double)meta.prior_num_dlas;
+  double pd[8];
+  const double p1 = nd / nq;
+  for (int j = 0; j < MD; ++j) pd[j] = pow(p1, (double)(j + 1));                   // :194
+  for (int j = 0; j < MD - 1; ++j) pd[j] = pd[j] - pd[j + 1];                      // :197-199
+  const double lp_lls_prior = log(nd) - log(nq) + log(a.Z_lls) - log(a.Z_dla);    // :208-210
+  const double lp_no_prior = log(nq - nd - a.Z_lls * nd / a.Z_dla) - log(nq);     // :214-216
+  a.min_z_dlas[q] = meta.min_z_dla; a.max_z_dlas[q] = meta.max_z_dla;
+  a.log_priors_no_dla[q] = lp_no_prior; a.log_priors_lls[q] = lp_lls_prior;
+  double lp[10];
+  lp[0] = lp_no_prior + a.log_likelihoods_no_dla[q];                               // :300-301
+  lp[1] = lp_lls_prior + a.log_likelihoods_lls[q];                                 // :428-430
+  for (int j = 0; j < MD; ++j) {
+    const double pr = log(pd[j]);                                                  // :204
+    a.log_priors_dla[q * MD + j] = pr;
+    lp[2 + j] = pr + a.log_likelihoods_dla[q * MD + j];                            // :411-413
+    a.log_posteriors_dla[q * MD + j] = lp[2 + j];
+  }
+  a.log_posteriors_no_dla[q] = lp[0]; a.log_posteriors_lls[q] = lp[1];
+  double mx = -INFINITY; bool any = false;
+  for (int j = 0; j < MD + 2; ++j) if (lp[j] == lp[j]) { mx = any ? fmax(mx, lp[j]) : lp[j]; any = true; }   // max ignores NaN
+  if (!any) mx = NAN;
+  double e[10], tot = 0.0;
+  for (int j = 0; j < MD + 2; ++j) { e[j] = exp(lp[j] - mx); tot += e[j]; }        // :485-488; sum propagates NaN
+  const double inv = 1.0 / tot;                                                    // :490-491
+  for (int j = 0; j < MD + 2; ++j) a.model_posteriors[q * (MD + 2) + j] = e[j] * inv;
+  const double p_no = e[0] * inv, p_l = e[1] * inv;
+  a.p_no_dlas[q] = p_no; a.p_lls[q] = p_l; a.p_dlas[q] = 1.0 - p_no - p_l;          // :493-495
 }
 
 }  // namespace gpdla

@@ -62,6 +62,9 @@ def make_samples(num_dla_samples: int = 10000, with_lls: bool = False) -> dict:
         u3 = _radical_inverse(idx, 5)
         out["lls_log_nhi_samples"] = 19.5 + 0.5 * u3
         out["lls_nhi_samples"] = 10.0 ** out["lls_log_nhi_samples"]
+        # partition functions of the column-density prior below / above 10^20 (set_lls_parameters.m:64-71);
+        # surrogate values for the synthetic prior (flat extrapolation below 20)
+        out["Z_lls"], out["Z_dla"] = 0.18, 0.82
     return out
 
 
@@ -83,8 +86,37 @@ def _voigt_raw(lam_obs: np.ndarray, z: float, nhi: float) -> np.ndarray:
     return np.exp(-nhi * lc * V)
 
 
+# Lyman series (wavelength in Angstrom, oscillator strength) for the mean-flux suppression of the multi-DLA
+# path (multi_dlas/set_parameters_multi.m:76-145)
+_LYMAN_A = np.array([1.2156701e-05, 1.0257223e-05, 9.725368e-06, 9.497431e-06, 9.378035e-06, 9.307483e-06,
+                     9.262257e-06, 9.231504e-06, 9.209631e-06, 9.193514e-06, 9.181294e-06, 9.171806e-06,
+                     9.16429e-06, 9.15824e-06, 9.15329e-06, 9.14919e-06, 9.14576e-06, 9.14286e-06, 9.14039e-06,
+                     9.13826e-06, 9.13641e-06, 9.13480e-06, 9.13339e-06, 9.13215e-06, 9.13104e-06, 9.13006e-06,
+                     9.12918e-06, 9.12839e-06, 9.12768e-06, 9.12703e-06, 9.12645e-06]) * 1e8
+_LYMAN_F = np.array([0.416400, 0.079120, 0.029000, 0.013940, 0.007799, 0.004814, 0.003183, 0.002216, 0.001605,
+                     0.00120, 0.000921, 0.0007226, 0.000577, 0.000469, 0.000386, 0.000321, 0.000270, 0.000230,
+                     0.000197, 0.000170, 0.000148, 0.000129, 0.000114, 0.000101, 0.000089, 0.000080, 0.000071,
+                     0.000064, 0.000058, 0.000053, 0.000048])
+
+
+def forest_suppression(lam: np.ndarray, z_qso: float, tau_0: float, beta: float):
+    """(mean-flux absorption, effective optical depth for the noise scaling) of the Lyman-series forest,
+    the model of multi_dlas/process_qsos_multiple_dlas_meanflux.m:243-285 (Kim et al. 2007 prior)."""
+    lya_1pz = lam / P.lya_wavelength
+    depth = tau_0 * lya_1pz ** beta
+    total = 0.0023 * lya_1pz ** 3.65
+    for l in range(1, _LYMAN_A.size):
+        onepz = lam / _LYMAN_A[l]
+        ok = onepz <= 1 + z_qso
+        ratio = _LYMAN_A[l] * _LYMAN_F[l] / (_LYMAN_A[0] * _LYMAN_F[0])
+        depth = depth + np.where(ok, tau_0 * ratio * onepz ** beta, 0.0)
+        total = total + np.where(ok, 0.0023 * ratio * onepz ** 3.65, 0.0)
+    return np.exp(-total), depth
+
+
 def make_spectra(model: dict, num_quasars: int, seed: int = SPECTRA_SEED, shard: int = 0,
-                 fixed_shape: bool = False, dla_fraction: float = 0.1) -> dict:
+                 fixed_shape: bool = False, dla_fraction: float = 0.1, meanflux: bool = False,
+                 max_injected: int = 1) -> dict:
     """BOSS-grid spectra shaped like preload_qsos.m:56-67 output (ragged lists).
 
     ``fixed_shape`` gives the 1217-pixel micro-benchmark variant of BASELINE.json: exactly
@@ -111,15 +143,21 @@ def make_spectra(model: dict, num_quasars: int, seed: int = SPECTRA_SEED, shard:
         mu_i = mu[jj] + tt * (mu[jj + 1] - mu[jj])
         M_i = M[jj] + tt[:, None] * (M[jj + 1] - M[jj])
         om2 = np.exp(2 * (log_omega[jj] + tt * (log_omega[jj + 1] - log_omega[jj])))
-        om2 = om2 * (1 - np.exp(-tau_0 * (lam / P.lya_wavelength) ** beta) + c_0) ** 2
+        if meanflux:   # the multi-DLA path's null model: forest-suppressed mean flux, Lyman-series noise
+            absorb, depth = forest_suppression(lam, z_qso, tau_0, beta)
+            om2 = om2 * (1 - np.exp(-depth) + c_0) ** 2 * absorb ** 2
+            mu_i, M_i = mu_i * absorb, M_i * absorb[:, None]
+        else:
+            om2 = om2 * (1 - np.exp(-tau_0 * (lam / P.lya_wavelength) ** beta) + c_0) ** 2
         noise_variance = (0.1 + 0.4 * rng.random(L)) ** 2
         flux = mu_i + M_i @ rng.standard_normal(k) + np.sqrt(om2) * rng.standard_normal(L)
         tz, tn = np.nan, np.nan
         if rng.random() < dla_fraction:
             zmin = max(lam.min() / P.lya_wavelength - 1, P.lyman_limit * (1 + z_qso) / P.lya_wavelength - 1 + P.DEFAULT.min_z_cut)
             zmax = lam.max() / P.lya_wavelength - 1 - P.DEFAULT.max_z_cut
-            tz, tn = rng.uniform(zmin, zmax), rng.uniform(20.0, 22.0)
-            flux = flux * _voigt_raw(lam, tz, 10.0 ** tn)
+            for _ in range(int(rng.integers(1, max_injected + 1))):   # truth_* keep the last injected system
+                tz, tn = rng.uniform(zmin, zmax), rng.uniform(20.0, 22.0)
+                flux = flux * _voigt_raw(lam, tz, 10.0 ** tn)
         flux = flux + np.sqrt(noise_variance) * rng.standard_normal(L)
         mask = np.zeros(L, dtype=bool) if fixed_shape else (rng.random(L) < 0.02)
         inside = (rest >= P.DEFAULT.min_lambda) & (rest <= P.DEFAULT.max_lambda)

@@ -110,6 +110,55 @@ int gpdla_process_qsos_device(gpdla_ctx* ctx, int64_t Q, int64_t L_max, const do
                               const double* flux, const double* noise_variance, const uint8_t* pixel_mask,
                               const int32_t* lengths, const double* z_qsos, const gpdla_results* out, void* stream);
 
+/* ---- multi-DLA + sub-DLA + mean-flux path: multi_dlas/process_qsos_multiple_dlas_meanflux.m:100-495 ----
+ *
+ * gpdla_set_lls_samples   lls_nhi_samples, Z_lls, Z_dla of multi_dlas/set_lls_parameters.m:55-71
+ * gpdla_process_qsos_multi(_device)
+ *     the per-quasar loop ...meanflux.m:141-480 (Lyman-series mean-flux suppression :243-293, level loop
+ *     :337-473 with Occam terms, z-separation filter, sub-DLA model, MAP, early exit, weighted resampling
+ *     seeded by rng('default') per quasar) and the model posteriors :482-495.
+ * Result variables as saved at ...meanflux.m:498-510.  Arrays with a level axis are [Q x max_dlas ...]
+ * row-major; base_sample_inds and MAP_inds are 0-based (MATLAB's are 1-based).  The three large arrays may be
+ * NULL (not returned).  `base_sample_inds_in` (NULL, or [Q x (max_dlas-1) x S], 0-based) replaces the
+ * library's own resampling -- for bit-reproducible parity runs against another implementation. */
+typedef struct {
+  double* min_z_dlas;
+  double* max_z_dlas;
+  double* log_priors_no_dla;
+  double* log_priors_lls;
+  double* log_priors_dla;              /* [Q x max_dlas] */
+  double* log_likelihoods_no_dla;
+  double* log_likelihoods_lls;
+  double* log_likelihoods_dla;         /* [Q x max_dlas] */
+  double* log_posteriors_no_dla;
+  double* log_posteriors_lls;
+  double* log_posteriors_dla;          /* [Q x max_dlas] */
+  double* model_posteriors;            /* [Q x (2 + max_dlas)]: no DLA, sub-DLA, 1..max_dlas DLAs */
+  double* p_no_dlas;
+  double* p_lls;
+  double* p_dlas;
+  double* MAP_z_dlas;                  /* [Q x max_dlas x max_dlas] */
+  double* MAP_log_nhis;                /* [Q x max_dlas x max_dlas] */
+  int64_t* MAP_inds;                   /* [Q x max_dlas x max_dlas], -1 = unset */
+  double* sample_log_likelihoods_dla;  /* [Q x max_dlas x S]; NULL = not returned */
+  double* sample_log_likelihoods_lls;  /* [Q x S]; NULL = not returned */
+  int32_t* base_sample_inds;           /* [Q x (max_dlas-1) x S]; NULL = not returned */
+} gpdla_multi_results;
+
+int gpdla_set_lls_samples(gpdla_ctx* ctx, const double* lls_nhi_samples, int64_t num_dla_samples, double Z_lls,
+                          double Z_dla);
+int gpdla_process_qsos_multi(gpdla_ctx* ctx, int64_t Q, int64_t L_max, const double* wavelengths,
+                             const double* flux, const double* noise_variance, const uint8_t* pixel_mask,
+                             const int32_t* lengths, const double* z_qsos, int32_t max_dlas,
+                             const int32_t* base_sample_inds_in, const gpdla_multi_results* out);
+int gpdla_process_qsos_multi_device(gpdla_ctx* ctx, int64_t Q, int64_t L_max, const double* wavelengths,
+                                    const double* flux, const double* noise_variance, const uint8_t* pixel_mask,
+                                    const int32_t* lengths, const double* z_qsos, int32_t max_dlas,
+                                    const int32_t* base_sample_inds_in, const gpdla_multi_results* out,
+                                    void* stream);
+/* The uniform random stream the resampling consumes (MATLAB rng('default'); rand): n values. Pure host. */
+void gpdla_matlab_default_rand(double* out, int64_t n);
+
 /* voigt.c:253-304: profile has num_points - 6 entries.  Host buffers; runs on the current device. */
 int gpdla_voigt(const double* lambdas, int64_t num_points, double z, double N, int32_t num_lines, double* profile);
 /* Batched, device buffers: profile[s, :] = voigt(lambdas, z[s], N[s], num_lines), [S x (num_points-6)] */

@@ -54,6 +54,23 @@ def main():
     for k, v in res.items():
         pack["out_" + k] = v
     np.savez_compressed(os.path.join(HERE, "process_qsos_small.npz"), **pack)
+    # ---- multi-DLA + sub-DLA + mean-flux: 2 quasars, 40 samples, 3 levels, literal numpy loop
+    from oracle import process_qsos_multi_oracle as MO
+    ms = syn.make_samples(10000, with_lls=True)
+    sub2 = np.arange(3, 10000, 251)[:40]
+    ms = {k: (v[sub2] if isinstance(v, np.ndarray) else v) for k, v in ms.items()}
+    msp = syn.make_spectra(model, 2, seed=123, dla_fraction=1.0, meanflux=True, max_injected=2)
+    mres = MO.process_qsos_multi(model, ms, msp, prior, Z_lls=ms["Z_lls"], Z_dla=ms["Z_dla"], max_dlas=3,
+                                 engine="numpy")
+    mpack = dict(offset_samples=ms["offset_samples"], log_nhi_samples=ms["log_nhi_samples"],
+                 nhi_samples=ms["nhi_samples"], lls_nhi_samples=ms["lls_nhi_samples"],
+                 Z=np.array([ms["Z_lls"], ms["Z_dla"]]), z_qsos=msp["z_qsos"])
+    for q in range(2):
+        for k in ("all_wavelengths", "all_flux", "all_noise_variance", "all_pixel_mask"):
+            mpack["%s_%d" % (k, q)] = msp[k][q]
+    for k, v in mres.items():
+        mpack["out_" + k] = v
+    np.savez_compressed(os.path.join(HERE, "process_qsos_multi_small.npz"), **mpack)
     print("wrote golden vectors:", {k: res[k] for k in ("log_likelihoods_no_dla", "log_likelihoods_dla", "p_dlas")})
 
 

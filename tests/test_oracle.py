@@ -168,3 +168,28 @@ def test_matlab_default_rng_stream():
     """rng('default') (multi-DLA resampling, ...meanflux.m:143) is MT19937 seed 5489."""
     r = np.random.RandomState(5489).rand(3)
     assert np.allclose(r, [0.8147236863931789, 0.9057919370756192, 0.1269868162935061], atol=1e-15)
+
+
+def test_multi_oracle_engines_agree(synthetic_inputs):
+    """Multi-DLA oracle: literal numpy loop vs the C engine, and the committed golden outputs."""
+    from gp_dla_detection_b200 import synthetic as syn
+    from oracle import process_qsos_multi_oracle as MO
+    si = synthetic_inputs
+    samples = syn.make_samples(10000, with_lls=True)
+    sub = np.arange(11, 10000, 400)
+    samples = {k: (v[sub] if isinstance(v, np.ndarray) else v) for k, v in samples.items()}
+    sp = syn.make_spectra(si["model"], 1, seed=77, dla_fraction=1.0, meanflux=True, max_injected=2)
+    kw = dict(Z_lls=samples["Z_lls"], Z_dla=samples["Z_dla"], max_dlas=3)
+    a = MO.process_qsos_multi(si["model"], samples, sp, si["prior"], engine="numpy", **kw)
+    b = MO.process_qsos_multi(si["model"], samples, sp, si["prior"], engine="c", **kw)
+    assert np.array_equal(a["base_sample_inds"], b["base_sample_inds"])
+    assert np.allclose(a["sample_log_likelihoods_dla"], b["sample_log_likelihoods_dla"], rtol=1e-12, equal_nan=True)
+    assert np.allclose(a["model_posteriors"], b["model_posteriors"], atol=1e-12, equal_nan=True)
+    assert abs(np.nansum(a["model_posteriors"]) - 1.0) < 1e-12
+    # prior identity asserted by the reference (...meanflux.m:202)
+    lp = np.exp(a["log_priors_dla"][0])
+    lpno, lplls, _ = MO.multi_priors(si["prior"]["z_qsos"], si["prior"]["dla_ind"], float(sp["z_qsos"][0]), 3,
+                                     samples["Z_lls"], samples["Z_dla"])
+    frac = np.count_nonzero(si["prior"]["dla_ind"][si["prior"]["z_qsos"] < sp["z_qsos"][0] + O.prior_z_qso_increase]) / \
+        np.count_nonzero(si["prior"]["z_qsos"] < sp["z_qsos"][0] + O.prior_z_qso_increase)
+    assert abs(lp.sum() - frac) < 1e-4
