@@ -121,19 +121,38 @@ int upload_line_constants(std::string& err) {
     w3.v2min = GPDLA_VOIGT_X0 * GPDLA_VOIGT_X0 * two_s2;
     CUDA_TRY(cudaMemcpyToSymbol(c_wing3, &w3, sizeof w3), err);
   }
-  {  // accumulator column -> augmented-triangle index of the epilogue staging area (rank 20)
-    constexpr int K = 20;
-    using G = GramShape<K>;
-    static short tab[MAX_NCOL];
-    for (int c = 0; c < MAX_NCOL; ++c) tab[c] = -1;
-    for (int p = 0; p < K; ++p) {
-      for (int q = p; q < K; ++q) tab[G::pair_index(p, q)] = (short)aug_index<K>(p, q);
-      tab[G::WT * 8 + p] = (short)aug_index<K>(p, K);
-    }
-    CUDA_TRY(cudaMemcpyToSymbol(c_stage_index, tab, sizeof tab), err);
-  }
   done[dev] = 1;
   return GPDLA_OK;
+}
+
+
+// accumulator column -> augmented-triangle index of the epilogue staging area, for rank K
+template <int K>
+static int upload_stage_index(std::string& err) {
+  using G = GramShape<K>;
+  static_assert(G::NCOL <= MAX_NCOL, "stage index table too small");
+  static short tab[MAX_NCOL];
+  for (int c = 0; c < MAX_NCOL; ++c) tab[c] = -1;
+  for (int p = 0; p < K; ++p) {
+    for (int q = p; q < K; ++q) tab[G::pair_index(p, q)] = (short)aug_index<K>(p, q);
+    tab[G::WT * 8 + p] = (short)aug_index<K>(p, K);
+  }
+  CUDA_TRY(cudaMemcpyToSymbol(c_stage_index, tab, sizeof tab), err);
+  return GPDLA_OK;
+}
+
+// rank dispatch: the ranks compiled into the library
+#define GPDLA_FOR_RANK(k, CALL)            \
+  switch (k) {                             \
+    case 10: { constexpr int K = 10; CALL; } break; \
+    case 20: { constexpr int K = 20; CALL; } break; \
+    default: break;                        \
+  }
+static bool rank_supported(int k) { return k == 10 || k == 20; }
+static size_t gram_chunk_doubles(int k) {
+  size_t r = 0;
+  GPDLA_FOR_RANK(k, r = GramShape<K>::CHUNK_DOUBLES);
+  return r;
 }
 
 template <class T>
@@ -194,13 +213,12 @@ static void free_workspace(gpdla_ctx* c) {
 static int ensure_workspace(gpdla_ctx* c, int batch, int npix) {
   if (c->ws_batch >= batch && c->ws_npix == npix && c->ws_k == c->k && c->ws_S == c->S) return GPDLA_OK;
   free_workspace(c);
-  using G = GramShape<20>;
   const size_t B = batch;
   CUDA_TRY(cudaMalloc(&c->d_meta, B * sizeof(QuasarMeta)), c->err);
   CUDA_TRY(cudaMalloc(&c->d_lam, B * (npix + 8) * sizeof(double)), c->err);
   CUDA_TRY(cudaMalloc(&c->d_pix, B * npix * 4 * sizeof(double)), c->err);
   CUDA_TRY(cudaMalloc(&c->d_Mq, B * npix * c->k * sizeof(double)), c->err);
-  CUDA_TRY(cudaMalloc(&c->d_P, B * (npix / KC) * G::CHUNK_DOUBLES * sizeof(double)), c->err);
+  CUDA_TRY(cudaMalloc(&c->d_P, B * (npix / KC) * gram_chunk_doubles(c->k) * sizeof(double)), c->err);
   CUDA_TRY(cudaMalloc(&c->d_sll, B * c->S * sizeof(double)), c->err);
   CUDA_TRY(cudaMalloc(&c->d_scratch, B * 16 * sizeof(double)), c->err);
   CUDA_TRY(cudaMalloc(&c->d_scratch_i, B * sizeof(int64_t)), c->err);
@@ -255,8 +273,10 @@ static int ensure_multi_workspace(gpdla_ctx* c, int batch, int npix) {
 
 template <int MODE>
 static int launch_mode(gpdla_ctx* c, const LoglikArgs& la, int nq, cudaStream_t st) {
-  if (c->params.num_lines == 3) return launch_loglik<20, 3, MODE>(c, la, nq, st);
-  return launch_loglik<20, 0, MODE>(c, la, nq, st);
+  int rc = GPDLA_ERR_UNSUPPORTED;
+  if (c->params.num_lines == 3) { GPDLA_FOR_RANK(c->k, (rc = launch_loglik<K, 3, MODE>(c, la, nq, st))); }
+  else { GPDLA_FOR_RANK(c->k, (rc = launch_loglik<K, 0, MODE>(c, la, nq, st))); }
+  return rc;
 }
 
 __global__ void fill_i32_kernel(int32_t* p, int32_t v, int64_t n) {
@@ -357,11 +377,16 @@ int gpdla_set_parameters(gpdla_ctx* c, const gpdla_params* p) {
 int gpdla_set_model(gpdla_ctx* c, const double* rest, int32_t n_rest, const double* mu, const double* M, int32_t k,
                     const double* log_omega, double log_c_0, double log_tau_0, double log_beta) {
   if (!c || !rest || !mu || !M || !log_omega || n_rest < 2 || k < 1) return GPDLA_ERR_INVALID;
-  if (k != 20) {
-    c->err = "gpdla_set_model: rank k=" + std::to_string(k) + " not compiled in (available: 20)";
+  if (!rank_supported(k)) {
+    c->err = "gpdla_set_model: rank k=" + std::to_string(k) + " not compiled in (available: 10, 20)";
     return GPDLA_ERR_UNSUPPORTED;
   }
   CUDA_TRY(cudaSetDevice(c->device), c->err);
+  {
+    int rcs = GPDLA_OK;
+    GPDLA_FOR_RANK(k, rcs = upload_stage_index<K>(c->err));
+    if (rcs) return rcs;
+  }
   int rc;
   if ((rc = dev_upload(&c->d_rest, rest, n_rest, c->err))) return rc;
   if ((rc = dev_upload(&c->d_mu, mu, n_rest, c->err))) return rc;
@@ -414,7 +439,6 @@ int gpdla_process_qsos_device(gpdla_ctx* c, int64_t Q, int64_t L_max, const doub
   int rc = ensure_workspace(c, batch, npix);
   if (rc) return rc;
   batch = c->ws_batch;
-  using G = GramShape<20>;
 
   for (int64_t q0 = 0; q0 < Q; q0 += batch) {
     const int nq = (int)std::min<int64_t>(batch, Q - q0);
@@ -434,7 +458,7 @@ int gpdla_process_qsos_device(gpdla_ctx* c, int64_t Q, int64_t L_max, const doub
     prepare_quasars_kernel<<<nq, NTHREADS, 0, st>>>(pa);
     c->launches++;
     CUDA_TRY(cudaGetLastError(), c->err);
-    build_gram_operand_kernel<20><<<dim3(npix / KC, nq), NTHREADS, 0, st>>>(c->d_Mq, c->d_meta, c->d_P, npix);
+    GPDLA_FOR_RANK(c->k, (build_gram_operand_kernel<K><<<dim3(npix / KC, nq), NTHREADS, 0, st>>>(c->d_Mq, c->d_meta, c->d_P, npix)));
     c->launches++;
     CUDA_TRY(cudaGetLastError(), c->err);
 
@@ -459,9 +483,7 @@ int gpdla_process_qsos_device(gpdla_ctx* c, int64_t Q, int64_t L_max, const doub
       fprintf(stderr, "[core path] cycles %lld, warp-evals with core %lld of %lld\n", h[8], h[9], h[10]);
     }
 #endif
-    if (c->params.num_lines == 3) rc = launch_loglik<20, 3, 0>(c, la, nq, st);
-    else rc = launch_loglik<20, 0, 0>(c, la, nq, st);
-    if (rc) return rc;
+    if ((rc = launch_mode<0>(c, la, nq, st))) return rc;
 
     EvidenceArgs ea;
     ea.meta = c->d_meta; ea.sample_log_likelihoods = sll; ea.log_likelihoods_no_dla = llno;
@@ -626,7 +648,7 @@ int gpdla_process_qsos_multi_device(gpdla_ctx* c, int64_t Q, int64_t L_max, cons
     prepare_quasars_kernel<<<nq, NTHREADS, 0, st>>>(pa);
     c->launches++;
     CUDA_TRY(cudaGetLastError(), c->err);
-    build_gram_operand_kernel<20><<<dim3(npix / KC, nq), NTHREADS, 0, st>>>(c->d_Mq, c->d_meta, c->d_P, npix);
+    GPDLA_FOR_RANK(c->k, (build_gram_operand_kernel<K><<<dim3(npix / KC, nq), NTHREADS, 0, st>>>(c->d_Mq, c->d_meta, c->d_P, npix)));
     c->launches++;
     fill_i32_kernel<<<(nq + 255) / 256, 256, 0, st>>>(c->d_active, 1, nq);
     c->launches++;
@@ -773,15 +795,15 @@ int gpdla_process_qsos_multi(gpdla_ctx* c, int64_t Q, int64_t L_max, const doubl
 
 int gpdla_voigt_batch_device(const double* lambdas, int64_t num_points, const double* z, const double* N, int64_t S,
                              int32_t num_lines, double* profile, void* stream) {
-  if (!lambdas || !z || !N || !profile || num_points < 7 || S < 1 || S > 65535 || num_lines < 1 ||
+  if (!lambdas || !z || !N || !profile || num_points < 7 || S < 1 || S > 2147483647LL || (num_points - 6 + NTHREADS - 1) / NTHREADS > 65535 || num_lines < 1 ||
       num_lines > GPDLA_MAX_LINES) {
-    g_err = "gpdla_voigt: invalid arguments (need num_points >= 7, 1 <= num_lines <= 31, 1 <= S <= 65535)";
+    g_err = "gpdla_voigt: invalid arguments (need 7 <= num_points <= 16.7M, 1 <= num_lines <= 31, S >= 1)";
     return GPDLA_ERR_INVALID;
   }
   int rc = upload_line_constants(g_err);
   if (rc) return rc;
   const int64_t n_out = num_points - 6;
-  dim3 grid((unsigned)((n_out + NTHREADS - 1) / NTHREADS), (unsigned)S);
+  dim3 grid((unsigned)S, (unsigned)((n_out + NTHREADS - 1) / NTHREADS));
   voigt_batch_kernel<<<grid, NTHREADS, 0, (cudaStream_t)stream>>>(lambdas, num_points, z, N, num_lines, profile);
   CUDA_TRY(cudaGetLastError(), g_err);
   return GPDLA_OK;

@@ -329,7 +329,7 @@ __global__ void __launch_bounds__(NTHREADS) build_gram_operand_kernel(const doub
 
 // ------------------------------------------------------------------------------------------
 // K1 (stand-alone): batched absorption profiles  A[s, i] = voigt(lambdas, z_s, N_s, num_lines)[i]
-// grid = (ceil(n_out / 256), S)
+// grid = (S, ceil(n_out / 256))
 __global__ void __launch_bounds__(NTHREADS) voigt_batch_kernel(const double* __restrict__ lambdas, int64_t num_points,
                                                                const double* __restrict__ zs,
                                                                const double* __restrict__ Ns, int num_lines,
@@ -337,8 +337,8 @@ __global__ void __launch_bounds__(NTHREADS) voigt_batch_kernel(const double* __r
   __shared__ double s_raw[NTHREADS + 6];
   __shared__ double s_mult[MAX_LINES];
   const int64_t n_out = num_points - 6;
-  const int64_t s = blockIdx.y;
-  const int64_t i0 = (int64_t)blockIdx.x * NTHREADS;
+  const int64_t s = blockIdx.x;
+  const int64_t i0 = (int64_t)blockIdx.y * NTHREADS;
   const double z = zs[s], N = Ns[s];
   if (threadIdx.x < num_lines) s_mult[threadIdx.x] = line_multiplier(threadIdx.x, z);
   __syncthreads();

@@ -224,6 +224,21 @@ def test_sample_permutation_invariance(api, synthetic_inputs):
     assert np.array_equal(perm[b["map_inds"]], a["map_inds"])
 
 
+def test_rank_and_sample_count_sweep(api, synthetic_inputs):
+    """BASELINE.json configs[4]: low-rank dimension k = 10 (k = 20 is covered above) and 1e3 / 3e4 samples."""
+    from gp_dla_detection_b200 import synthetic as syn
+    from oracle import process_qsos_oracle as O
+    si = synthetic_inputs
+    m10 = syn.make_model(10)
+    sp = syn.make_spectra(m10, 2, seed=31, dla_fraction=0.5)
+    s1k = syn.make_samples(1000)
+    assert_parity(api.process_qsos(m10, s1k, sp, si["prior"]), O.process_qsos(m10, s1k, sp, si["prior"], engine="c"))
+    s30k = syn.make_samples(30000)
+    sp1 = {k: v[:1] for k, v in si["spectra"].items()}
+    assert_parity(api.process_qsos(si["model"], s30k, sp1, si["prior"]),
+                  O.process_qsos(si["model"], s30k, sp1, si["prior"], engine="c"))
+
+
 def test_state_errors(api, synthetic_inputs):
     from gp_dla_detection_b200._lib import GpdlaError
     si = synthetic_inputs
