@@ -144,16 +144,19 @@ static int upload_stage_index(std::string& err) {
 // rank dispatch: the ranks compiled into the library
 #define GPDLA_FOR_RANK(k, CALL)            \
   switch (k) {                             \
-    case 10: { constexpr int K = 10; CALL; } break; \
-    case 20: { constexpr int K = 20; CALL; } break; \
+    case 10: { constexpr int K = 10, NSPLIT = 1; (void)NSPLIT; CALL; } break; \
+    case 20: { constexpr int K = 20, NSPLIT = 1; (void)NSPLIT; CALL; } break; \
+    case 40: { constexpr int K = 40, NSPLIT = 4; (void)NSPLIT; CALL; } break; \
     default: break;                        \
   }
-static bool rank_supported(int k) { return k == 10 || k == 20; }
-static size_t gram_chunk_doubles(int k) {
+static bool rank_supported(int k) { return k == 10 || k == 20 || k == 40; }
+static size_t gram_doubles_per_chunk_all_splits(int k) {
   size_t r = 0;
-  GPDLA_FOR_RANK(k, r = GramShape<K>::CHUNK_DOUBLES);
+  GPDLA_FOR_RANK(k, (r = (size_t)SplitShape<K, NSPLIT>::CHUNK_DOUBLES * NSPLIT));
   return r;
 }
+static int rank_splits(int k) { int r = 1; GPDLA_FOR_RANK(k, r = NSPLIT); return r; }
+static int rank_ncol(int k) { int r = 0; GPDLA_FOR_RANK(k, r = GramShape<K>::NCOL); return r; }
 
 template <class T>
 int dev_upload(T** dst, const T* src, size_t n, std::string& err) {
@@ -183,6 +186,7 @@ struct gpdla_ctx {
   // per-batch workspace
   int ws_batch = 0, ws_npix = 0, ws_k = 0;
   int64_t ws_S = 0;
+  double *d_gram = nullptr, *d_qld = nullptr;   // column-split ranks: global accumulator staging
   QuasarMeta* d_meta = nullptr;
   double *d_lam = nullptr, *d_pix = nullptr, *d_Mq = nullptr, *d_P = nullptr, *d_sll = nullptr, *d_scratch = nullptr;
   int64_t* d_scratch_i = nullptr;
@@ -204,7 +208,8 @@ struct gpdla_ctx {
 
 static void free_workspace(gpdla_ctx* c) {
   cudaFree(c->d_meta); cudaFree(c->d_lam); cudaFree(c->d_pix); cudaFree(c->d_Mq); cudaFree(c->d_P);
-  cudaFree(c->d_sll); cudaFree(c->d_scratch); cudaFree(c->d_scratch_i);
+  cudaFree(c->d_sll); cudaFree(c->d_scratch); cudaFree(c->d_scratch_i); cudaFree(c->d_gram); cudaFree(c->d_qld);
+  c->d_gram = c->d_qld = nullptr;
   c->d_meta = nullptr; c->d_lam = c->d_pix = c->d_Mq = c->d_P = c->d_sll = c->d_scratch = nullptr;
   c->d_scratch_i = nullptr;
   c->ws_batch = c->ws_npix = c->ws_k = 0; c->ws_S = 0;
@@ -218,25 +223,32 @@ static int ensure_workspace(gpdla_ctx* c, int batch, int npix) {
   CUDA_TRY(cudaMalloc(&c->d_lam, B * (npix + 8) * sizeof(double)), c->err);
   CUDA_TRY(cudaMalloc(&c->d_pix, B * npix * 4 * sizeof(double)), c->err);
   CUDA_TRY(cudaMalloc(&c->d_Mq, B * npix * c->k * sizeof(double)), c->err);
-  CUDA_TRY(cudaMalloc(&c->d_P, B * (npix / KC) * gram_chunk_doubles(c->k) * sizeof(double)), c->err);
+  CUDA_TRY(cudaMalloc(&c->d_P, B * (npix / KC) * gram_doubles_per_chunk_all_splits(c->k) * sizeof(double)), c->err);
   CUDA_TRY(cudaMalloc(&c->d_sll, B * c->S * sizeof(double)), c->err);
   CUDA_TRY(cudaMalloc(&c->d_scratch, B * 16 * sizeof(double)), c->err);
   CUDA_TRY(cudaMalloc(&c->d_scratch_i, B * sizeof(int64_t)), c->err);
+  if (rank_splits(c->k) > 1) {
+    const size_t rows = ((size_t)c->S + 1 + 63) / 64 * 64;
+    CUDA_TRY(cudaMalloc(&c->d_gram, B * rows * rank_ncol(c->k) * sizeof(double)), c->err);
+    CUDA_TRY(cudaMalloc(&c->d_qld, B * rows * 2 * sizeof(double)), c->err);
+  }
   c->ws_batch = batch; c->ws_npix = npix; c->ws_k = c->k; c->ws_S = c->S;
   return GPDLA_OK;
 }
 
-template <int K, int NL, int MODE>
-static int launch_loglik(gpdla_ctx* c, const LoglikArgs& la, int nq, cudaStream_t st) {
-  using Cfg = LoglikConfig<K>;
-  auto kern = dla_loglik_kernel<K, NL, MODE>;
+template <int K, int NL, int MODE, int NSPLIT>
+static int launch_loglik(gpdla_ctx* c, LoglikArgs la, int nq, cudaStream_t st) {
+  using Cfg = LoglikConfig<K, NSPLIT>;
+  auto kern = dla_loglik_kernel<K, NL, MODE, NSPLIT>;
   const size_t smem = Cfg::smem_bytes(la.num_lines);
   static size_t configured = 0;
   if (configured < smem) {
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), c->err);
     configured = smem;
   }
-  dim3 grid((unsigned)((la.S + (la.log_likelihoods_no_dla ? 1 : 0) + Cfg::TS - 1) / Cfg::TS), (unsigned)nq);
+  const unsigned tiles = (unsigned)((la.S + (la.log_likelihoods_no_dla ? 1 : 0) + Cfg::TS - 1) / Cfg::TS);
+  dim3 grid(tiles, (unsigned)nq, NSPLIT);
+  la.gram = c->d_gram; la.qld = c->d_qld; la.gram_rows = ((int64_t)c->S + 1 + 63) / 64 * 64;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (c->profiling) {
     CUDA_TRY(cudaEventCreate(&e0), c->err);
@@ -246,6 +258,15 @@ static int launch_loglik(gpdla_ctx* c, const LoglikArgs& la, int nq, cudaStream_
   kern<<<grid, NTHREADS, smem, st>>>(la);
   c->launches++;
   CUDA_TRY(cudaGetLastError(), c->err);
+  if (NSPLIT > 1) {
+    CholArgs ca;
+    ca.meta = la.meta; ca.gram = c->d_gram; ca.qld = c->d_qld; ca.gram_rows = la.gram_rows; ca.S = la.S;
+    ca.sample_log_likelihoods = la.sample_log_likelihoods; ca.sll_stride = la.sll_stride;
+    ca.log_likelihoods_no_dla = la.log_likelihoods_no_dla; ca.active = la.active;
+    cholesky_kernel<K><<<dim3((tiles * Cfg::TS + 31) / 32, (unsigned)nq), 128, 0, st>>>(ca);
+    c->launches++;
+    CUDA_TRY(cudaGetLastError(), c->err);
+  }
   if (c->profiling) {
     CUDA_TRY(cudaEventRecord(e1, st), c->err);
     c->prof_events.emplace_back(e0, e1);
@@ -274,8 +295,8 @@ static int ensure_multi_workspace(gpdla_ctx* c, int batch, int npix) {
 template <int MODE>
 static int launch_mode(gpdla_ctx* c, const LoglikArgs& la, int nq, cudaStream_t st) {
   int rc = GPDLA_ERR_UNSUPPORTED;
-  if (c->params.num_lines == 3) { GPDLA_FOR_RANK(c->k, (rc = launch_loglik<K, 3, MODE>(c, la, nq, st))); }
-  else { GPDLA_FOR_RANK(c->k, (rc = launch_loglik<K, 0, MODE>(c, la, nq, st))); }
+  if (c->params.num_lines == 3) { GPDLA_FOR_RANK(c->k, (rc = launch_loglik<K, 3, MODE, NSPLIT>(c, la, nq, st))); }
+  else { GPDLA_FOR_RANK(c->k, (rc = launch_loglik<K, 0, MODE, NSPLIT>(c, la, nq, st))); }
   return rc;
 }
 
@@ -378,7 +399,7 @@ int gpdla_set_model(gpdla_ctx* c, const double* rest, int32_t n_rest, const doub
                     const double* log_omega, double log_c_0, double log_tau_0, double log_beta) {
   if (!c || !rest || !mu || !M || !log_omega || n_rest < 2 || k < 1) return GPDLA_ERR_INVALID;
   if (!rank_supported(k)) {
-    c->err = "gpdla_set_model: rank k=" + std::to_string(k) + " not compiled in (available: 10, 20)";
+    c->err = "gpdla_set_model: rank k=" + std::to_string(k) + " not compiled in (available: 10, 20, 40)";
     return GPDLA_ERR_UNSUPPORTED;
   }
   CUDA_TRY(cudaSetDevice(c->device), c->err);
@@ -434,7 +455,7 @@ int gpdla_process_qsos_device(gpdla_ctx* c, int64_t Q, int64_t L_max, const doub
   CUDA_TRY(cudaSetDevice(c->device), c->err);
   cudaStream_t st = (cudaStream_t)stream;
   const int npix = (int)((L_max + KC - 1) / KC) * KC;
-  int batch = c->params.batch_quasars > 0 ? c->params.batch_quasars : 296;
+  int batch = c->params.batch_quasars > 0 ? c->params.batch_quasars : (rank_splits(c->k) > 1 ? 37 : 296);
   batch = (int)std::min<int64_t>(batch, Q);
   int rc = ensure_workspace(c, batch, npix);
   if (rc) return rc;
@@ -458,7 +479,7 @@ int gpdla_process_qsos_device(gpdla_ctx* c, int64_t Q, int64_t L_max, const doub
     prepare_quasars_kernel<<<nq, NTHREADS, 0, st>>>(pa);
     c->launches++;
     CUDA_TRY(cudaGetLastError(), c->err);
-    GPDLA_FOR_RANK(c->k, (build_gram_operand_kernel<K><<<dim3(npix / KC, nq), NTHREADS, 0, st>>>(c->d_Mq, c->d_meta, c->d_P, npix)));
+    GPDLA_FOR_RANK(c->k, (build_gram_operand_kernel<K, NSPLIT><<<dim3(npix / KC, nq, NSPLIT), NTHREADS, 0, st>>>(c->d_Mq, c->d_meta, c->d_P, npix)));
     c->launches++;
     CUDA_TRY(cudaGetLastError(), c->err);
 
@@ -619,7 +640,7 @@ int gpdla_process_qsos_multi_device(gpdla_ctx* c, int64_t Q, int64_t L_max, cons
   CUDA_TRY(cudaSetDevice(c->device), c->err);
   cudaStream_t st = (cudaStream_t)stream;
   const int npix = (int)((L_max + KC - 1) / KC) * KC;
-  int batch = c->params.batch_quasars > 0 ? c->params.batch_quasars : 148;
+  int batch = c->params.batch_quasars > 0 ? c->params.batch_quasars : (rank_splits(c->k) > 1 ? 37 : 148);
   batch = (int)std::min<int64_t>(batch, Q);
   int rc = ensure_workspace(c, batch, npix);
   if (rc) return rc;
@@ -648,7 +669,7 @@ int gpdla_process_qsos_multi_device(gpdla_ctx* c, int64_t Q, int64_t L_max, cons
     prepare_quasars_kernel<<<nq, NTHREADS, 0, st>>>(pa);
     c->launches++;
     CUDA_TRY(cudaGetLastError(), c->err);
-    GPDLA_FOR_RANK(c->k, (build_gram_operand_kernel<K><<<dim3(npix / KC, nq), NTHREADS, 0, st>>>(c->d_Mq, c->d_meta, c->d_P, npix)));
+    GPDLA_FOR_RANK(c->k, (build_gram_operand_kernel<K, NSPLIT><<<dim3(npix / KC, nq, NSPLIT), NTHREADS, 0, st>>>(c->d_Mq, c->d_meta, c->d_P, npix)));
     c->launches++;
     fill_i32_kernel<<<(nq + 255) / 256, 256, 0, st>>>(c->d_active, 1, nq);
     c->launches++;

@@ -56,6 +56,19 @@ struct GramShape {
   __host__ __device__ static constexpr int pair_index(int p, int q) { return p * K - p * (p - 1) / 2 + (q - p); }
 };
 
+// Column split: ranks whose 8 x NCOL accumulator tile does not fit one warp's registers (k = 40: 864
+// columns) are processed by NSPLIT CTAs per sample tile (grid.z), each owning NT / NSPLIT n8 tiles and
+// re-evaluating the (comparatively cheap) profile stage; the Cholesky then runs as a separate kernel.
+template <int K, int NSPLIT>
+struct SplitShape {
+  using G = GramShape<K>;
+  static_assert(G::NT % NSPLIT == 0, "n8 tiles must divide evenly among the column splits");
+  static constexpr int NTL = G::NT / NSPLIT;     // n8 tiles per CTA
+  static constexpr int NCOLL = NTL * 8;
+  static constexpr int BSTR = NCOLL + ((4 - NCOLL % 16) + 16) % 16;
+  static constexpr int CHUNK_DOUBLES = KC * BSTR;
+};
+
 constexpr int ASTR = KC + 4;      // row stride of the W/U operand tiles (== 4 mod 16)
 
 // Epilogue staging layout: the symmetric Gram (p <= q < K) and the projected vector (q = K) as one
@@ -298,30 +311,36 @@ __global__ void __launch_bounds__(NTHREADS) prepare_quasars_kernel(PrepArgs a) {
 
 // K0b: Gram operand P, chunked [Q][chunk][KC][BSTR]: columns pair_index(p,q) = M_ip M_iq, then the k
 // columns of M itself (projection), zero padding elsewhere.
-template <int K>
+template <int K, int NSPLIT>
 __global__ void __launch_bounds__(NTHREADS) build_gram_operand_kernel(const double* __restrict__ Mq,
                                                                       const QuasarMeta* __restrict__ meta,
                                                                       double* __restrict__ P, int NPIX) {
   using G = GramShape<K>;
+  using SS = SplitShape<K, NSPLIT>;
   const int q = blockIdx.y;
   const int chunk = blockIdx.x;
+  const int split = blockIdx.z;
   if (chunk >= meta[q].nchunks) return;
   __shared__ double sM[KC][K + 1];
   const double* src = Mq + ((int64_t)q * NPIX + (int64_t)chunk * KC) * K;
   for (int t = threadIdx.x; t < KC * K; t += NTHREADS) sM[t / K][t % K] = src[t];
   __syncthreads();
-  double* dst = P + ((int64_t)q * (NPIX / KC) + chunk) * G::CHUNK_DOUBLES;
-  for (int t = threadIdx.x; t < G::CHUNK_DOUBLES; t += NTHREADS) {
-    int r = t / G::BSTR, c = t % G::BSTR;
+  // layout [q][split][chunk][KC][BSTR]
+  double* dst = P + (((int64_t)q * NSPLIT + split) * (NPIX / KC) + chunk) * SS::CHUNK_DOUBLES;
+  for (int t = threadIdx.x; t < SS::CHUNK_DOUBLES; t += NTHREADS) {
+    int r = t / SS::BSTR, cl = t % SS::BSTR;
+    int c = split * SS::NCOLL + cl;          // global column
     double v = 0.0;
-    if (c < G::NPAIR) {
-      // invert pair_index: find p with pair_index(p,p) <= c
-      int p = 0;
-      while (p + 1 < K && G::pair_index(p + 1, p + 1) <= c) ++p;
-      int qq = p + (c - G::pair_index(p, p));
-      v = sM[r][p] * sM[r][qq];
-    } else if (c >= G::WT * 8 && c < G::WT * 8 + K) {
-      v = sM[r][c - G::WT * 8];
+    if (cl < SS::NCOLL) {
+      if (c < G::NPAIR) {
+        // invert pair_index: find p with pair_index(p,p) <= c
+        int p = 0;
+        while (p + 1 < K && G::pair_index(p + 1, p + 1) <= c) ++p;
+        int qq = p + (c - G::pair_index(p, p));
+        v = sM[r][p] * sM[r][qq];
+      } else if (c >= G::WT * 8 && c < G::WT * 8 + K) {
+        v = sM[r][c - G::WT * 8];
+      }
     }
     dst[t] = v;
   }
@@ -380,6 +399,10 @@ struct LoglikArgs {
   const int32_t* partners;          // [Q x 3 x S] 0-based base_sample_inds; level l uses rows 0..l-2
   int num_partners;
   const int32_t* active;            // [Q] or nullptr; 0 = quasar finished early (:460-464) -> NaN
+  // column-split ranks (NSPLIT > 1): accumulators and per-sample scalars leave through global memory
+  double* gram;                     // [Q x rows x NCOL], rows = sample tiles * 64
+  double* qld;                      // [Q x rows x 2]  (sum r^2/d, sum log d)
+  int64_t gram_rows;
   long long* phase_cycles;          // debug builds (-DGPDLA_PHASE_TIMING): [16] summed cycles per phase
 };
 
@@ -398,21 +421,22 @@ struct LoglikArgs {
 // the main loop: the only shared resource is the double-buffered P chunk, brought in by 1-D TMA bulk
 // copies; the warp that finishes a chunk last re-arms that buffer.  Warps drift apart, so DMMA phases of
 // some warps overlap the latency-bound profile phases of others.
-template <int K>
+template <int K, int NSPLIT>
 struct LoglikConfig {
   using G = GramShape<K>;
+  using SS = SplitShape<K, NSPLIT>;
   static constexpr int NWARPS = NTHREADS / 32;
   static constexpr int SPW = 8;                        // samples per warp = one m8 tile
   static constexpr int TS = NWARPS * SPW;              // samples per CTA
-  static constexpr size_t B_BYTES = 2ull * G::CHUNK_DOUBLES * 8;
+  static constexpr size_t B_BYTES = 2ull * SS::CHUNK_DOUBLES * 8;
   static constexpr size_t A_BYTES = 2ull * TS * ASTR * 8;
   static constexpr size_t RAW_BYTES = (size_t)TS * RAWW * 8;
   // epilogue staging [(K+1)(K+2)/2 - 1 entries][CSTR], aliases the P buffers and the operand tiles;
   // CSTR == 4 (mod 16): the four lanes of a quad read consecutive entries without bank conflicts
   static constexpr int CSTR = TS + 4;
   static constexpr size_t C_BYTES = (size_t)((K + 1) * (K + 2) / 2) * CSTR * 8;
-  static_assert(C_BYTES <= B_BYTES + A_BYTES, "epilogue staging must fit in the P buffers + operand tiles");
-  static_assert(G::NT * 4 <= 200, "accumulators must fit in registers (use a smaller rank)");
+  static_assert(NSPLIT > 1 || C_BYTES <= B_BYTES + A_BYTES, "epilogue staging must fit in the P buffers + operand tiles");
+  static_assert(SS::NTL * 4 <= 200, "accumulators must fit in registers (use more column splits)");
   __host__ __device__ static constexpr size_t smem_bytes(int num_lines) {
     return B_BYTES + A_BYTES + RAW_BYTES + (size_t)TS * (num_lines + 4) * 8 + 64 + 3 * TS * 4;
   }
@@ -420,11 +444,14 @@ struct LoglikConfig {
 
 // MODE 0: single-DLA / sub-DLA pass;  MODE 1: same, and the convolved absorption rows are stored in
 // args.acache;  MODE 2: multi-DLA level >= 2, absorption = product of cached rows (sample and partners).
-template <int K, int NL, int MODE>
+template <int K, int NL, int MODE, int NSPLIT>
 __global__ void __launch_bounds__(NTHREADS, 1) dla_loglik_kernel(LoglikArgs args) {
-  using Cfg = LoglikConfig<K>;
+  using Cfg = LoglikConfig<K, NSPLIT>;
   using G = GramShape<K>;
-  constexpr int TS = Cfg::TS, SPW = Cfg::SPW, NT = G::NT, CSTR = Cfg::CSTR;
+  using SS = SplitShape<K, NSPLIT>;
+  constexpr int TS = Cfg::TS, SPW = Cfg::SPW, NT = SS::NTL, CSTR = Cfg::CSTR;
+  const int split = (NSPLIT > 1) ? blockIdx.z : 0;
+  const int tile0 = split * SS::NTL;            // first global n8 tile of this CTA
   const int q = blockIdx.y;
   const QuasarMeta meta = args.meta[q];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -434,7 +461,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dla_loglik_kernel(LoglikArgs args
   // nothing usable in this spectrum (process_qsos.m:74-82), or the level loop already ended for this
   // quasar (...meanflux.m:460-464): NaN results
   if (meta.nchunks == 0 || (args.active != nullptr && args.active[q] == 0)) {
-    for (int i = tid; i < TS; i += NTHREADS) {
+    for (int i = tid; i < TS && split == 0; i += NTHREADS) {
       int64_t s = s0 + i;
       if (s < S) args.sample_log_likelihoods[(int64_t)q * args.sll_stride + s] = NAN;
       else if (s == S && args.log_likelihoods_no_dla) args.log_likelihoods_no_dla[q] = NAN;
@@ -472,8 +499,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) dla_loglik_kernel(LoglikArgs args
   }
   const double* lam = args.lam_pad + (int64_t)q * (args.NPIX + 8);
   const double* pix = args.pix + (int64_t)q * args.NPIX * 4;
-  const double* Pq = args.P + (int64_t)q * (args.NPIX / KC) * G::CHUNK_DOUBLES;
-  constexpr uint32_t CHUNK_BYTES = G::CHUNK_DOUBLES * 8;
+  const double* Pq = args.P + ((int64_t)q * NSPLIT + split) * (args.NPIX / KC) * SS::CHUNK_DOUBLES;
+  constexpr uint32_t CHUNK_BYTES = SS::CHUNK_DOUBLES * 8;
   if (tid == 0) {
     mbar_init(&mbar[0], 1);
     mbar_init(&mbar[1], 1);
@@ -483,7 +510,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dla_loglik_kernel(LoglikArgs args
     tma_load_1d(Bt, Pq, CHUNK_BYTES, &mbar[0]);
     if (meta.nchunks > 1) {
       mbar_expect_tx(&mbar[1], CHUNK_BYTES);
-      tma_load_1d(Bt + G::CHUNK_DOUBLES, Pq + G::CHUNK_DOUBLES, CHUNK_BYTES, &mbar[1]);
+      tma_load_1d(Bt + SS::CHUNK_DOUBLES, Pq + SS::CHUNK_DOUBLES, CHUNK_BYTES, &mbar[1]);
     }
   }
   __syncthreads();
@@ -565,7 +592,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dla_loglik_kernel(LoglikArgs args
           for (int t = 0; t < 7; ++t) acc_a = fma(rb[(i + t) & (RAWW - 1)], c_lines.ip[t], acc_a);   // voigt.c:297-299
           a[ss] = (__double2hiint(mynhi[ss]) < 0) ? 1.0 : acc_a;   // null model (N marked negative): no absorption
         }
-        if (MODE == 1) {   // keep the level-1 absorption rows for the higher multi-DLA levels
+        if (MODE == 1 && split == 0) {   // keep the level-1 absorption rows for the higher multi-DLA levels
 #pragma unroll
           for (int ss = 0; ss < SPW; ++ss) {
             const int64_t smp = s0 + warp * SPW + ss;
@@ -615,14 +642,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) dla_loglik_kernel(LoglikArgs args
     PHASE_T(t_mb);
     // ---- B: FP64 tensor-core contraction  acc += [W|U] (8 x KC) . P_chunk (KC x NCOL)
     {
-      const double* Bc = Bt + (c & 1) * G::CHUNK_DOUBLES;
+      const double* Bc = Bt + (c & 1) * SS::CHUNK_DOUBLES;
 #pragma unroll
       for (int ks = 0; ks < KC / 4; ++ks) {
         const double aw = myW[gid * ASTR + ks * 4 + tig];
         const double au = myU[gid * ASTR + ks * 4 + tig];
-        const double* brow = Bc + (ks * 4 + tig) * G::BSTR + gid;
+        const double* brow = Bc + (ks * 4 + tig) * SS::BSTR + gid;
 #pragma unroll
-        for (int ni = 0; ni < NT; ++ni) dmma_884(acc[ni][0], acc[ni][1], ni < G::WT ? aw : au, brow[ni * 8]);
+        for (int ni = 0; ni < NT; ++ni) dmma_884(acc[ni][0], acc[ni][1], (tile0 + ni) < G::WT ? aw : au, brow[ni * 8]);
       }
     }
     __syncwarp();
@@ -634,7 +661,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dla_loglik_kernel(LoglikArgs args
         s_done[c & 1] = 0;
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         mbar_expect_tx(&mbar[c & 1], CHUNK_BYTES);
-        tma_load_1d(Bt + (c & 1) * G::CHUNK_DOUBLES, Pq + (int64_t)(c + 2) * G::CHUNK_DOUBLES, CHUNK_BYTES,
+        tma_load_1d(Bt + (c & 1) * SS::CHUNK_DOUBLES, Pq + (int64_t)(c + 2) * SS::CHUNK_DOUBLES, CHUNK_BYTES,
                     &mbar[c & 1]);
       }
     }
@@ -649,6 +676,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) dla_loglik_kernel(LoglikArgs args
     double qs = warp_sum(qacc[ss]);
     double ld = warp_sum(log(ldm[ss]) + (double)lde[ss] * 0.693147180559945309417);
     if (lane == 0) { s_q[warp * SPW + ss] = qs; s_ld[warp * SPW + ss] = ld; }
+  }
+  __syncwarp();
+  if (NSPLIT > 1) {
+    // column-split ranks: accumulators (and, from split 0, the per-sample scalars) go to global memory;
+    // cholesky_kernel finishes the job
+    const int64_t row = s0 + warp * SPW + gid;
+    double* grow = args.gram + ((int64_t)q * args.gram_rows + row) * G::NCOL + tile0 * 8 + tig * 2;
+#pragma unroll
+    for (int ni = 0; ni < NT; ++ni) *reinterpret_cast<double2*>(grow + ni * 8) = make_double2(acc[ni][0], acc[ni][1]);
+    if (split == 0 && lane < SPW) {
+      double* qd = args.qld + ((int64_t)q * args.gram_rows + s0 + warp * SPW + lane) * 2;
+      qd[0] = s_q[warp * SPW + lane]; qd[1] = s_ld[warp * SPW + lane];
+    }
+    return;
   }
   __syncthreads();   // every warp is done with the P buffers -> the staging area may alias them
   // C fragment: lane holds row gid, columns 2 tig, 2 tig + 1 of each n8 tile
@@ -708,6 +749,58 @@ __global__ void __launch_bounds__(NTHREADS, 1) dla_loglik_kernel(LoglikArgs args
   PHASE_T(t_end);
   PHASE_ADD(7, t_loop_end, t_end);
 #endif
+}
+
+// ------------------------------------------------------------------------------------------
+// K3 for column-split ranks: Cholesky of B = I + C per sample straight from the global staging rows
+// (log_mvnpdf_low_rank.m:22-32).  Four lanes per sample, in place; runtime loops (k = 40: 21 kFLOP per
+// sample, ~1 % of the Gram).
+struct CholArgs {
+  const QuasarMeta* meta;
+  double* gram;                     // [Q x rows x NCOL]
+  const double* qld;                // [Q x rows x 2]
+  int64_t gram_rows;
+  int64_t S;
+  double* sample_log_likelihoods;
+  int64_t sll_stride;
+  double* log_likelihoods_no_dla;   // nullable
+  const int32_t* active;
+};
+
+template <int K>
+__global__ void __launch_bounds__(128) cholesky_kernel(CholArgs a) {
+  using G = GramShape<K>;
+  const int q = blockIdx.y;
+  const QuasarMeta meta = a.meta[q];
+  if (meta.nchunks == 0 || (a.active != nullptr && a.active[q] == 0)) return;   // NaNs already written
+  const int lane = threadIdx.x & 31, l4 = lane & 3;
+  const int64_t row = (int64_t)blockIdx.x * 32 + (threadIdx.x >> 2);
+  const bool valid_row = row < a.gram_rows;
+  double* Bs = a.gram + ((int64_t)q * a.gram_rows + (valid_row ? row : 0)) * G::NCOL;
+  auto col = [](int p, int qq) { return qq < K ? G::pair_index(p, qq) : G::WT * 8 + p; };   // column K = projected vector
+  double prod[4] = {1.0, 1.0, 1.0, 1.0};
+  for (int p = 0; p < K; ++p) {
+    double dpp = Bs[col(p, p)] + 1.0;                                            // :23
+    for (int r = 0; r < p; ++r) { const double c = Bs[col(r, p)]; dpp = fma(-c, c, dpp); }
+    prod[p & 3] *= dpp;
+    const double inv = rsqrt(dpp);
+    for (int qq = p + 1 + l4; qq <= K; qq += 4) {
+      double v = Bs[col(p, qq)];
+      for (int r = 0; r < p; ++r) v = fma(-Bs[col(r, p)], Bs[col(r, qq)], v);
+      Bs[col(p, qq)] = v * inv;
+    }
+    __syncwarp();
+  }
+  double zsum = 0.0;
+  for (int p = 0; p < K; ++p) { const double zp = Bs[col(p, K)]; zsum = fma(zp, zp, zsum); }
+  if (l4 == 0 && valid_row) {
+    const double* qd = a.qld + ((int64_t)q * a.gram_rows + row) * 2;
+    const double quad = qd[0] - zsum;                                            // :28
+    const double logdet = qd[1] + (log(prod[0]) + log(prod[1])) + (log(prod[2]) + log(prod[3]));   // :30
+    const double lp = -0.5 * (quad + logdet + (double)meta.n * LOG_2PI);         // :32
+    if (row < a.S) a.sample_log_likelihoods[(int64_t)q * a.sll_stride + row] = lp;
+    else if (row == a.S && a.log_likelihoods_no_dla) a.log_likelihoods_no_dla[q] = lp;
+  }
 }
 
 // ------------------------------------------------------------------------------------------

@@ -225,7 +225,7 @@ def test_sample_permutation_invariance(api, synthetic_inputs):
 
 
 def test_rank_and_sample_count_sweep(api, synthetic_inputs):
-    """BASELINE.json configs[4]: low-rank dimension k = 10 (k = 20 is covered above) and 1e3 / 3e4 samples."""
+    """BASELINE.json configs[4]: low-rank dimensions k = 10 and 40 (k = 20 is covered above), 1e3 / 3e4 samples."""
     from gp_dla_detection_b200 import synthetic as syn
     from oracle import process_qsos_oracle as O
     si = synthetic_inputs
@@ -233,6 +233,13 @@ def test_rank_and_sample_count_sweep(api, synthetic_inputs):
     sp = syn.make_spectra(m10, 2, seed=31, dla_fraction=0.5)
     s1k = syn.make_samples(1000)
     assert_parity(api.process_qsos(m10, s1k, sp, si["prior"]), O.process_qsos(m10, s1k, sp, si["prior"], engine="c"))
+    m40 = syn.make_model(40)                                      # column-split kernel + stand-alone Cholesky
+    sp40 = syn.make_spectra(m40, 3, seed=41, dla_fraction=0.5)
+    sp40["all_pixel_mask"][1][:] = True                            # an empty spectrum inside the batch
+    r40 = api.process_qsos(m40, s1k, sp40, si["prior"])
+    o40 = O.process_qsos(m40, s1k, sp40, si["prior"], engine="c")
+    assert_parity(r40, o40)
+    assert np.isnan(r40["log_likelihoods_dla"][1]) and np.all(np.isfinite(r40["log_likelihoods_dla"][[0, 2]]))
     s30k = syn.make_samples(30000)
     sp1 = {k: v[:1] for k, v in si["spectra"].items()}
     assert_parity(api.process_qsos(si["model"], s30k, sp1, si["prior"]),
