@@ -263,7 +263,14 @@ static int launch_loglik(gpdla_ctx* c, LoglikArgs la, int nq, cudaStream_t st) {
     ca.meta = la.meta; ca.gram = c->d_gram; ca.qld = c->d_qld; ca.gram_rows = la.gram_rows; ca.S = la.S;
     ca.sample_log_likelihoods = la.sample_log_likelihoods; ca.sll_stride = la.sll_stride;
     ca.log_likelihoods_no_dla = la.log_likelihoods_no_dla; ca.active = la.active;
-    cholesky_kernel<K><<<dim3((tiles * Cfg::TS + 31) / 32, (unsigned)nq), 128, 0, st>>>(ca);
+    static bool chol_configured = false;
+    if (!chol_configured) {
+      CUDA_TRY(cudaFuncSetAttribute(cholesky_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)cholesky_smem_bytes<K>()), c->err);
+      chol_configured = true;
+    }
+    cholesky_kernel<K><<<dim3(tiles * Cfg::TS / CHOL_SAMPLES, (unsigned)nq), CHOL_SAMPLES * 4,
+                         cholesky_smem_bytes<K>(), st>>>(ca);
     c->launches++;
     CUDA_TRY(cudaGetLastError(), c->err);
   }

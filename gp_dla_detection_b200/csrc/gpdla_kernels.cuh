@@ -753,8 +753,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) dla_loglik_kernel(LoglikArgs args
 
 // ------------------------------------------------------------------------------------------
 // K3 for column-split ranks: Cholesky of B = I + C per sample straight from the global staging rows
-// (log_mvnpdf_low_rank.m:22-32).  Four lanes per sample, in place; runtime loops (k = 40: 21 kFLOP per
-// sample, ~1 % of the Gram).
+// (log_mvnpdf_low_rank.m:22-32), staged through shared memory as an augmented triangle.  Four lanes per
+// sample; each lane keeps its columns of the current row in registers (k = 40: 21 kFLOP per sample).
 struct CholArgs {
   const QuasarMeta* meta;
   double* gram;                     // [Q x rows x NCOL]
@@ -767,33 +767,66 @@ struct CholArgs {
   const int32_t* active;
 };
 
+constexpr int CHOL_SAMPLES = 16;              // samples per CTA of cholesky_kernel
+constexpr int CHOL_STRIDE = CHOL_SAMPLES + 4;  // == 4 (mod 16): quad lanes read consecutive entries conflict-free
 template <int K>
-__global__ void __launch_bounds__(128) cholesky_kernel(CholArgs a) {
+constexpr size_t cholesky_smem_bytes() { return (size_t)((K + 1) * (K + 2) / 2) * CHOL_STRIDE * 8; }
+
+template <int K>
+__global__ void __launch_bounds__(CHOL_SAMPLES * 4) cholesky_kernel(CholArgs a) {
   using G = GramShape<K>;
+  constexpr int NQ = (K + 3) / 4 + 1;            // columns per quad lane, upper bound
   const int q = blockIdx.y;
   const QuasarMeta meta = a.meta[q];
   if (meta.nchunks == 0 || (a.active != nullptr && a.active[q] == 0)) return;   // NaNs already written
-  const int lane = threadIdx.x & 31, l4 = lane & 3;
-  const int64_t row = (int64_t)blockIdx.x * 32 + (threadIdx.x >> 2);
-  const bool valid_row = row < a.gram_rows;
-  double* Bs = a.gram + ((int64_t)q * a.gram_rows + (valid_row ? row : 0)) * G::NCOL;
-  auto col = [](int p, int qq) { return qq < K ? G::pair_index(p, qq) : G::WT * 8 + p; };   // column K = projected vector
+  extern __shared__ __align__(16) double Cs[];   // [aug entries][CHOL_STRIDE]
+  const int tid = threadIdx.x, l4 = tid & 3, sl = tid >> 2;
+  const int64_t row0 = (int64_t)blockIdx.x * CHOL_SAMPLES;
+  // stage the accumulator rows: coalesced along columns, scattered into the augmented triangle
+  const double* g0 = a.gram + ((int64_t)q * a.gram_rows + row0) * G::NCOL;
+  for (int c = tid; c < G::NCOL; c += CHOL_SAMPLES * 4) {   // one (divergent) table lookup per column
+    const int idx = c_stage_index[c];
+    if (idx >= 0) {
+#pragma unroll 8
+      for (int r = 0; r < CHOL_SAMPLES; ++r) Cs[idx * CHOL_STRIDE + r] = g0[(int64_t)r * G::NCOL + c];
+    }
+  }
+  __syncthreads();
+  double* Bs = Cs + sl;                           // entry (p, q) at Bs[aug_index<K>(p, q) * CHOL_STRIDE]
   double prod[4] = {1.0, 1.0, 1.0, 1.0};
   for (int p = 0; p < K; ++p) {
-    double dpp = Bs[col(p, p)] + 1.0;                                            // :23
-    for (int r = 0; r < p; ++r) { const double c = Bs[col(r, p)]; dpp = fma(-c, c, dpp); }
+    const int base_p = aug_index<K>(p, p);
+    double dpp = Bs[base_p * CHOL_STRIDE] + 1.0;                                   // :23
+    double v[NQ];
+#pragma unroll
+    for (int j = 0; j < NQ; ++j) {
+      const int qq = p + 1 + l4 + 4 * j;
+      v[j] = (qq <= K) ? Bs[(base_p + (qq - p)) * CHOL_STRIDE] : 0.0;
+    }
+#pragma unroll 2
+    for (int r = 0; r < p; ++r) {
+      const int base_r = aug_index<K>(r, r) - r;                                   // entry (r, x) at base_r + x
+      const double c = Bs[(base_r + p) * CHOL_STRIDE];
+      dpp = fma(-c, c, dpp);
+#pragma unroll
+      for (int j = 0; j < NQ; ++j) {
+        const int qq = p + 1 + l4 + 4 * j;
+        if (qq <= K) v[j] = fma(-c, Bs[(base_r + qq) * CHOL_STRIDE], v[j]);
+      }
+    }
     prod[p & 3] *= dpp;
     const double inv = rsqrt(dpp);
-    for (int qq = p + 1 + l4; qq <= K; qq += 4) {
-      double v = Bs[col(p, qq)];
-      for (int r = 0; r < p; ++r) v = fma(-Bs[col(r, p)], Bs[col(r, qq)], v);
-      Bs[col(p, qq)] = v * inv;
+#pragma unroll
+    for (int j = 0; j < NQ; ++j) {
+      const int qq = p + 1 + l4 + 4 * j;
+      if (qq <= K) Bs[(base_p + (qq - p)) * CHOL_STRIDE] = v[j] * inv;
     }
     __syncwarp();
   }
   double zsum = 0.0;
-  for (int p = 0; p < K; ++p) { const double zp = Bs[col(p, K)]; zsum = fma(zp, zp, zsum); }
-  if (l4 == 0 && valid_row) {
+  for (int p = 0; p < K; ++p) { const double zp = Bs[aug_index<K>(p, K) * CHOL_STRIDE]; zsum = fma(zp, zp, zsum); }
+  const int64_t row = row0 + sl;
+  if (l4 == 0) {
     const double* qd = a.qld + ((int64_t)q * a.gram_rows + row) * 2;
     const double quad = qd[0] - zsum;                                            // :28
     const double logdet = qd[1] + (log(prod[0]) + log(prod[1])) + (log(prod[2]) + log(prod[3]));   // :30
