@@ -123,11 +123,12 @@ def run_reference(args):
     value = per_step * args.steps / dt
     sample = "%d quasars x %d samples per step (bounded sample of the 10000-quasar workload)" % (per_step, NUM_SAMPLES)
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 0, "steps": args.steps,
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "configs[1]: 10000 synthetic DR12Q-shaped quasars, single-DLA, k=20, 10000 samples, "
-                               "3 Lyman lines", "sample": sample},
+                               "3 Lyman lines", "sample": sample,
+                   "note": "CPU arm: runs on rank 0's host cores only, whatever --gpus says"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
                          "note": "C restatement of process_qsos.m + voigt.c + log_mvnpdf_low_rank.m (oracle/c), "
                                  "OpenMP over samples like the reference's parfor; MATLAB/Octave/libcerf are absent"},

@@ -65,3 +65,21 @@ def test_product_never_imports_the_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
                 assert "libgpdla_oracle" not in src and "voigt_ref" not in src, f
+
+
+def test_ascii_catalog_writer_formats(tmp_path):
+    """generate_ascii_catalog.m:9-20,49-81: same printf formats, three-digit exponents, THING_ID only."""
+    from gp_dla_detection_b200 import catalog_writer as cw
+    res = dict(min_z_dlas=np.array([2.01234, 1.9]), max_z_dlas=np.array([2.98768, 3.1]),
+               log_priors_no_dla=np.array([-0.10382, -0.2]), log_priors_dla=np.array([-2.31655, -1.7]),
+               log_likelihoods_no_dla=np.array([-190.48437, -1.5e3]), log_likelihoods_dla=np.array([-221.16647, -1.4e3]),
+               model_posteriors=np.array([[1.0, 5.107e-15], [3.2e-101, 1.0]]), p_dlas=np.array([5.107e-15, 1.0]),
+               map_z_dlas=np.array([2.5, 2.25]), map_log_nhis=np.array([20.0092, 21.5]))
+    p = tmp_path / "results.dat"
+    cw.write_results(str(p), res, [12345, 987654321])
+    lines = p.read_text().splitlines()
+    assert lines[0] == "000012345 2.0123 2.9877 -0.10382 -2.31655 -1.90484e+02 -2.21166e+02 1.00000e+000 5.10700e-015 2.5000 20.0092"
+    assert lines[1] == "987654321 1.9000 3.1000 -0.20000 -1.70000 -1.50000e+03 -1.40000e+03 3.20000e-101 1.00000e+000 2.2500 21.5000"
+    s = tmp_path / "samples.dat"
+    cw.write_dla_samples(str(s), [0.5, 0.25], [20.2966751, 21.0])
+    assert s.read_text() == "0.500000 20.296675\n0.250000 21.000000\n"
