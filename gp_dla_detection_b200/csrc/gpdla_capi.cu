@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -236,17 +237,29 @@ static int ensure_workspace(gpdla_ctx* c, int batch, int npix) {
   return GPDLA_OK;
 }
 
+// schedule of the fused kernel: 1 = warp-specialised (one DMMA warp per SM sub-partition), 0 = warp-autonomous
+static int fused_schedule() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("GPDLA_SCHEDULE"); v = (e && e[0] == 'a') ? 0 : 1; }
+  return v;
+}
+
 template <int K, int NL, int MODE, int NSPLIT>
 static int launch_loglik(gpdla_ctx* c, LoglikArgs la, int nq, cudaStream_t st) {
+  const bool ws = fused_schedule() == 1;
   using Cfg = LoglikConfig<K, NSPLIT>;
-  auto kern = dla_loglik_kernel<K, NL, MODE, NSPLIT>;
-  const size_t smem = Cfg::smem_bytes(la.num_lines);
-  static size_t configured = 0;
-  if (configured < smem) {
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), c->err);
-    configured = smem;
+  using WCfg = WsConfig<K, NSPLIT>;
+  auto kern_wa = dla_loglik_kernel<K, NL, MODE, NSPLIT>;
+  auto kern_ws = dla_loglik_ws_kernel<K, NL, MODE, NSPLIT>;
+  const size_t smem = ws ? WCfg::smem_bytes(la.num_lines) : Cfg::smem_bytes(la.num_lines);
+  const int TS = ws ? WCfg::TS : Cfg::TS;
+  static size_t configured[2] = {0, 0};
+  if (configured[ws] < smem) {
+    if (ws) CUDA_TRY(cudaFuncSetAttribute(kern_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), c->err);
+    else CUDA_TRY(cudaFuncSetAttribute(kern_wa, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), c->err);
+    configured[ws] = smem;
   }
-  const unsigned tiles = (unsigned)((la.S + (la.log_likelihoods_no_dla ? 1 : 0) + Cfg::TS - 1) / Cfg::TS);
+  const unsigned tiles = (unsigned)((la.S + (la.log_likelihoods_no_dla ? 1 : 0) + TS - 1) / TS);
   dim3 grid(tiles, (unsigned)nq, NSPLIT);
   la.gram = c->d_gram; la.qld = c->d_qld; la.gram_rows = ((int64_t)c->S + 1 + 63) / 64 * 64;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -255,7 +268,8 @@ static int launch_loglik(gpdla_ctx* c, LoglikArgs la, int nq, cudaStream_t st) {
     CUDA_TRY(cudaEventCreate(&e1), c->err);
     CUDA_TRY(cudaEventRecord(e0, st), c->err);
   }
-  kern<<<grid, NTHREADS, smem, st>>>(la);
+  if (ws) kern_ws<<<grid, WS_THREADS, smem, st>>>(la);
+  else kern_wa<<<grid, NTHREADS, smem, st>>>(la);
   c->launches++;
   CUDA_TRY(cudaGetLastError(), c->err);
   if (NSPLIT > 1) {
@@ -269,7 +283,7 @@ static int launch_loglik(gpdla_ctx* c, LoglikArgs la, int nq, cudaStream_t st) {
                                     (int)cholesky_smem_bytes<K>()), c->err);
       chol_configured = true;
     }
-    cholesky_kernel<K><<<dim3(tiles * Cfg::TS / CHOL_SAMPLES, (unsigned)nq), CHOL_SAMPLES * 4,
+    cholesky_kernel<K><<<dim3(tiles * TS / CHOL_SAMPLES, (unsigned)nq), CHOL_SAMPLES * 4,
                          cholesky_smem_bytes<K>(), st>>>(ca);
     c->launches++;
     CUDA_TRY(cudaGetLastError(), c->err);
@@ -506,7 +520,7 @@ int gpdla_process_qsos_device(gpdla_ctx* c, int64_t Q, int64_t L_max, const doub
       la.phase_cycles = d_phase;
       long long h[16];
       cudaMemcpy(h, d_phase, sizeof h, cudaMemcpyDeviceToHost);
-      fprintf(stderr, "[phase cycles so far] A1 %lld | S1wait %lld | A2 %lld | S2wait %lld | tma wait %lld | B %lld | loop %lld | epilogue %lld\n",
+      fprintf(stderr, "[phase cycles so far] P:raw+conv %lld | P:wait_empty %lld | P:weights %lld | C:wait_full %lld | C:wait_tma %lld | C:dmma %lld | - %lld | C:epilogue %lld\n",
               h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7]);
       fprintf(stderr, "[core path] cycles %lld, warp-evals with core %lld of %lld\n", h[8], h[9], h[10]);
     }

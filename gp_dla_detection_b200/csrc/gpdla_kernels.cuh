@@ -409,9 +409,11 @@ struct LoglikArgs {
 #ifdef GPDLA_PHASE_TIMING
 #define PHASE_T(var) long long var = clock64()
 #define PHASE_ADD(idx, t0, t1) do { if (tid == 0) atomicAdd((unsigned long long*)&args.phase_cycles[idx], (unsigned long long)((t1) - (t0))); } while (0)
+#define WS_PHASE_ADD(w, idx, t0, t1) do { if (lane == 0 && warp == (w)) atomicAdd((unsigned long long*)&args.phase_cycles[idx], (unsigned long long)((t1) - (t0))); } while (0)
 #else
 #define PHASE_T(var)
 #define PHASE_ADD(idx, t0, t1)
+#define WS_PHASE_ADD(w, idx, t0, t1)
 #endif
 
 // Warp-autonomous schedule.  A CTA of 8 warps handles 64 samples of one quasar; warp w owns samples
@@ -441,6 +443,68 @@ struct LoglikConfig {
     return B_BYTES + A_BYTES + RAW_BYTES + (size_t)TS * (num_lines + 4) * 8 + 64 + 3 * TS * 4;
   }
 };
+
+// Epilogue shared by the fused kernels: stage one warp's 8 x NCOL accumulator tile through shared memory as
+// an augmented upper triangle and factorise it (K3).  `row0` = first sample row of this warp inside the CTA.
+template <int K, int NT, int CSTR>
+__device__ __forceinline__ void stage_and_factor(double (&acc)[NT][2], double* Cs, const double* s_q, const double* s_ld,
+                                                 int row0, int lane, const QuasarMeta& meta, const LoglikArgs& args,
+                                                 int q, int64_t s0) {
+  const int gid = lane >> 2, tig = lane & 3;
+  const int64_t S = args.S;
+  // C fragment: lane holds row gid, columns 2 tig, 2 tig + 1 of each n8 tile
+#pragma unroll
+  for (int ni = 0; ni < NT; ++ni) {
+    const int i0 = c_stage_index[ni * 8 + tig * 2], i1 = c_stage_index[ni * 8 + tig * 2 + 1];
+    if (i0 >= 0) Cs[i0 * CSTR + row0 + gid] = acc[ni][0];
+    if (i1 >= 0) Cs[i1 * CSTR + row0 + gid] = acc[ni][1];
+  }
+  __syncwarp();
+
+  // ---- K3: Cholesky of B = I + C (upper, R'R = B) with the projected vector g as column K (forward
+  // substitution for free), log-det, quadratic form.  Four lanes per sample; for row p the columns
+  // q = p+1 .. K are dealt round-robin to the quad.  Fully unrolled: every index is an immediate.
+  {
+    const int sl = row0 + (lane >> 2);          // sample handled by this lane quad
+    const int l4 = lane & 3;
+    double* Bs = Cs + sl;                              // entry (p, q) at Bs[aug_index<K>(p, q) * CSTR]
+    double prod0 = 1.0, prod1 = 1.0;
+#pragma unroll
+    for (int p = 0; p < K; ++p) {
+      double colp[K];                                  // R(r, p), r < p
+#pragma unroll
+      for (int r = 0; r < p; ++r) colp[r] = Bs[aug_index<K>(r, p) * CSTR];
+      double dpp = Bs[aug_index<K>(p, p) * CSTR] + 1.0;                       // log_mvnpdf_low_rank.m:23
+#pragma unroll
+      for (int r = 0; r < p; ++r) dpp = fma(-colp[r], colp[r], dpp);
+      if (p < K / 2) prod0 *= dpp; else prod1 *= dpp;                       // log det B = log prod R(p,p)^2   :30
+      const double inv = rsqrt(dpp);
+#pragma unroll
+      for (int j = 0; j < (K - p + 3) / 4; ++j) {
+        const int qq = p + 1 + l4 + 4 * j;
+        if (qq <= K) {
+          double* dst = Bs + (aug_index<K>(p, p) + (qq - p)) * CSTR;
+          double v = *dst;
+#pragma unroll
+          for (int r = 0; r < p; ++r) v = fma(-colp[r], Bs[(aug_index<K>(r, r) + (qq - r)) * CSTR], v);
+          *dst = v * inv;
+        }
+      }
+      __syncwarp();
+    }
+    double zsum = 0.0;                                 // |R'^-1 g|^2: column K now holds z
+#pragma unroll
+    for (int p = 0; p < K; ++p) { const double zp = Bs[aug_index<K>(p, K) * CSTR]; zsum = fma(zp, zp, zsum); }
+    if (l4 == 0) {
+      const double quad = s_q[sl] - zsum;                                   // y' K^-1 y                 :28
+      const double logdet = s_ld[sl] + log(prod0) + log(prod1);             //                           :30
+      const double lp = -0.5 * (quad + logdet + (double)meta.n * LOG_2PI);  //                           :32
+      const int64_t s = s0 + sl;
+      if (s < S) args.sample_log_likelihoods[(int64_t)q * args.sll_stride + s] = lp;
+      else if (s == S && args.log_likelihoods_no_dla) args.log_likelihoods_no_dla[q] = lp;
+    }
+  }
+}
 
 // MODE 0: single-DLA / sub-DLA pass;  MODE 1: same, and the convolved absorption rows are stored in
 // args.acache;  MODE 2: multi-DLA level >= 2, absorption = product of cached rows (sample and partners).
@@ -692,63 +756,346 @@ __global__ void __launch_bounds__(NTHREADS, 1) dla_loglik_kernel(LoglikArgs args
     return;
   }
   __syncthreads();   // every warp is done with the P buffers -> the staging area may alias them
-  // C fragment: lane holds row gid, columns 2 tig, 2 tig + 1 of each n8 tile
-#pragma unroll
-  for (int ni = 0; ni < NT; ++ni) {
-    const int i0 = c_stage_index[ni * 8 + tig * 2], i1 = c_stage_index[ni * 8 + tig * 2 + 1];
-    if (i0 >= 0) Cs[i0 * CSTR + warp * SPW + gid] = acc[ni][0];
-    if (i1 >= 0) Cs[i1 * CSTR + warp * SPW + gid] = acc[ni][1];
-  }
-  __syncwarp();
-
-  // ---- K3: Cholesky of B = I + C (upper, R'R = B) with the projected vector g as column K (forward
-  // substitution for free), log-det, quadratic form.  Four lanes per sample; for row p the columns
-  // q = p+1 .. K are dealt round-robin to the quad.  Fully unrolled: every index is an immediate.
-  {
-    const int sl = warp * SPW + (lane >> 2);          // sample handled by this lane quad
-    const int l4 = lane & 3;
-    double* Bs = Cs + sl;                              // entry (p, q) at Bs[aug_index<K>(p, q) * CSTR]
-    double prod0 = 1.0, prod1 = 1.0;
-#pragma unroll
-    for (int p = 0; p < K; ++p) {
-      double colp[K];                                  // R(r, p), r < p
-#pragma unroll
-      for (int r = 0; r < p; ++r) colp[r] = Bs[aug_index<K>(r, p) * CSTR];
-      double dpp = Bs[aug_index<K>(p, p) * CSTR] + 1.0;                       // log_mvnpdf_low_rank.m:23
-#pragma unroll
-      for (int r = 0; r < p; ++r) dpp = fma(-colp[r], colp[r], dpp);
-      if (p < K / 2) prod0 *= dpp; else prod1 *= dpp;                       // log det B = log prod R(p,p)^2   :30
-      const double inv = rsqrt(dpp);
-#pragma unroll
-      for (int j = 0; j < (K - p + 3) / 4; ++j) {
-        const int qq = p + 1 + l4 + 4 * j;
-        if (qq <= K) {
-          double* dst = Bs + (aug_index<K>(p, p) + (qq - p)) * CSTR;
-          double v = *dst;
-#pragma unroll
-          for (int r = 0; r < p; ++r) v = fma(-colp[r], Bs[(aug_index<K>(r, r) + (qq - r)) * CSTR], v);
-          *dst = v * inv;
-        }
-      }
-      __syncwarp();
-    }
-    double zsum = 0.0;                                 // |R'^-1 g|^2: column K now holds z
-#pragma unroll
-    for (int p = 0; p < K; ++p) { const double zp = Bs[aug_index<K>(p, K) * CSTR]; zsum = fma(zp, zp, zsum); }
-    if (l4 == 0) {
-      const double quad = s_q[sl] - zsum;                                   // y' K^-1 y                 :28
-      const double logdet = s_ld[sl] + log(prod0) + log(prod1);             //                           :30
-      const double lp = -0.5 * (quad + logdet + (double)meta.n * LOG_2PI);  //                           :32
-      const int64_t s = s0 + sl;
-      if (s < S) args.sample_log_likelihoods[(int64_t)q * args.sll_stride + s] = lp;
-      else if (s == S && args.log_likelihoods_no_dla) args.log_likelihoods_no_dla[q] = lp;
-    }
-  }
+  stage_and_factor<K, NT, CSTR>(acc, Cs, s_q, s_ld, warp * SPW, lane, meta, args, q, s0);
 #ifdef GPDLA_PHASE_TIMING
   __syncthreads();
   PHASE_T(t_end);
   PHASE_ADD(7, t_loop_end, t_end);
 #endif
+}
+
+// ------------------------------------------------------------------------------------------
+// Warp-specialised schedule.
+//
+// Measured on B200 (profiles/r01_fp64_mix.txt, r01_dmma_loop.txt): DMMA and DFMA share one pipe per SM
+// sub-partition and its arbiter favours DMMA -- while two warps of a sub-partition issue DMMA, DFMA warps
+// there do not progress at all; with one DMMA warp they get 31 % and the DMMA stream 62 %.  A lone DMMA warp
+// that also fetches its fragments from shared memory reaches only 78 % of the pipe, two warps reach ~100 %.
+// Tried and measured (ms per 296 quasars): 1 consumer + 2 producers per sub-partition 89.6-91.2 (shipped);
+// 2 consumers + 1 producer 132.5 (the producer only runs while both consumers wait, and a lone warp's
+// profile arithmetic is latency-bound); 2 consumers + 2 producers with setmaxnreg 97.7.  Roles, per CTA of
+// WS_CONSUMERS x 8 samples of one quasar (defaults: 4 consumers, 8 producers, 32 samples, 168 registers):
+//   * CONSUMER warps (0..NC-1, one per sub-partition): consumer c runs the FP64 DMMA contraction of sample
+//     rows 8c..8c+7 (one m8 tile x all n8 tiles, accumulators in 120 registers) against the shared P chunk;
+//   * PRODUCER warps (NC.., two per sub-partition): each makes 4 of a consumer's 8 rows per chunk -- Voigt raw
+//     profile, instrument convolution, weights w = a^2/d, u = a (y - a mu)/d, lane = pixel -- and accumulates
+//     the per-sample scalars sum r^2/d and prod d.
+// Rows travel through 2-stage full/empty mbarriers per consumer; P chunks arrive by 1-D TMA bulk copies into
+// a double buffer re-armed by the last consumer to finish.  No CTA-wide barrier in the main loop.
+constexpr int RAWS = KC + 8;      // raw-profile row: 6 carried-over pixels + KC new ones (+2 pad)
+#ifndef GPDLA_WS_CONSUMERS
+#define GPDLA_WS_CONSUMERS 4
+#define GPDLA_WS_PRODUCERS 8
+#endif
+constexpr int WS_CONSUMERS = GPDLA_WS_CONSUMERS, WS_PRODUCERS = GPDLA_WS_PRODUCERS;
+constexpr int WS_THREADS = 32 * (WS_CONSUMERS + WS_PRODUCERS);   // 384 -> 168 registers per thread
+constexpr int WS_STAGES = 2;      // operand-row stages between producer and consumer
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int K, int NSPLIT>
+struct WsConfig {
+  using G = GramShape<K>;
+  using SS = SplitShape<K, NSPLIT>;
+  static constexpr int SPW = 8;                         // samples per consumer = one m8 tile
+  static constexpr int SPB = 4;                         // samples per producer batch
+  static constexpr int TS = WS_CONSUMERS * SPW;         // 64 samples per CTA
+  static constexpr int SPP = TS / WS_PRODUCERS;         // 16 samples per producer
+  static constexpr size_t B_BYTES = 2ull * SS::CHUNK_DOUBLES * 8;
+  static constexpr size_t A_BYTES = (size_t)WS_STAGES * 2 * TS * ASTR * 8;     // W and U, WS_STAGES stages
+  static constexpr size_t RAW_BYTES = (size_t)TS * RAWS * 8;
+  static constexpr int CSTR = TS + 4;
+  static constexpr size_t C_BYTES = (size_t)((K + 1) * (K + 2) / 2) * CSTR * 8;
+  static_assert(NSPLIT > 1 || C_BYTES <= B_BYTES + A_BYTES, "epilogue staging must fit");
+  static_assert(SS::NTL * 4 + 40 <= 168, "accumulators must fit in the consumer's registers");
+  static constexpr int NBAR = 2 + 2 * WS_STAGES * WS_CONSUMERS;
+  __host__ __device__ static constexpr size_t smem_bytes(int num_lines) {
+    return B_BYTES + A_BYTES + RAW_BYTES + (size_t)TS * (num_lines + 4) * 8 + NBAR * 8 + 64 + 3 * TS * 4;
+  }
+};
+
+template <int K, int NL, int MODE, int NSPLIT>
+__global__ void __launch_bounds__(WS_THREADS, 1) dla_loglik_ws_kernel(LoglikArgs args) {
+  using Cfg = WsConfig<K, NSPLIT>;
+  using G = GramShape<K>;
+  using SS = SplitShape<K, NSPLIT>;
+  constexpr int TS = Cfg::TS, SPW = Cfg::SPW, SPB = Cfg::SPB, SPP = Cfg::SPP, NT = SS::NTL, CSTR = Cfg::CSTR;
+  const int split = (NSPLIT > 1) ? blockIdx.z : 0;
+  const int tile0 = split * SS::NTL;
+  const int q = blockIdx.y;
+  const QuasarMeta meta = args.meta[q];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t s0 = (int64_t)blockIdx.x * TS;
+  const int64_t S = args.S;
+
+  if (meta.nchunks == 0 || (args.active != nullptr && args.active[q] == 0)) {   // see dla_loglik_kernel
+    for (int i = tid; i < TS && split == 0; i += WS_THREADS) {
+      int64_t s = s0 + i;
+      if (s < S) args.sample_log_likelihoods[(int64_t)q * args.sll_stride + s] = NAN;
+      else if (s == S && args.log_likelihoods_no_dla) args.log_likelihoods_no_dla[q] = NAN;
+    }
+    return;
+  }
+
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* Bt = reinterpret_cast<double*>(smem_raw);                       // [2][KC][BSTR]
+  double* Wt = reinterpret_cast<double*>(smem_raw + Cfg::B_BYTES);        // [WS_STAGES][TS][ASTR]
+  double* Ut = Wt + WS_STAGES * TS * ASTR;                                // [WS_STAGES][TS][ASTR]
+  double* rawbuf = Ut + WS_STAGES * TS * ASTR;                            // [TS][RAWS]
+  double* s_nhi = rawbuf + TS * RAWS;                                     // [TS]
+  double* s_q = s_nhi + TS;                                               // [TS]   sum r^2/d
+  double* s_ld = s_q + TS;                                                // [TS]   sum log d
+  double* s_mult = s_ld + TS;                                             // [num_lines][TS]
+  const int num_lines = (NL > 0) ? NL : args.num_lines;
+  uint64_t* bar_p = reinterpret_cast<uint64_t*>(s_mult + (size_t)TS * num_lines + TS);   // P chunk full[2]
+  uint64_t* bar_full = bar_p + 2;                                          // [consumer][stage] rows ready
+  uint64_t* bar_empty = bar_full + WS_STAGES * WS_CONSUMERS;               // [consumer][stage] rows consumed
+  int* s_done = reinterpret_cast<int*>(bar_empty + WS_STAGES * WS_CONSUMERS);   // [2] consumers done with P buffer
+  int* s_part = s_done + 2;                                                // [3][TS] partner samples (MODE 2)
+  double* Cs = reinterpret_cast<double*>(smem_raw);                       // epilogue: [entries][CSTR]
+
+  for (int i = tid; i < TS; i += WS_THREADS) {                             // per-sample parameters
+    int64_t s = s0 + i;
+    bool is_null = s >= S;
+    double z = is_null ? 0.0
+                       : __dadd_rn(meta.min_z_dla, __dmul_rn(meta.max_z_dla - meta.min_z_dla, args.offset_samples[s]));
+    s_nhi[i] = is_null ? -1.0 : args.nhi_samples[s];     // negative marks the null-model slot
+    s_ld[i] = 0.0;
+    for (int j = 0; j < num_lines; ++j) s_mult[j * TS + i] = line_multiplier(j, z);
+    if (MODE == 2) {
+      for (int j = 0; j < args.num_partners; ++j)
+        s_part[j * TS + i] = is_null ? 0 : args.partners[((int64_t)q * 3 + j) * S + s];
+    }
+  }
+  const double* Pq = args.P + ((int64_t)q * NSPLIT + split) * (args.NPIX / KC) * SS::CHUNK_DOUBLES;
+  constexpr uint32_t CHUNK_BYTES = SS::CHUNK_DOUBLES * 8;
+  if (tid == 0) {
+    mbar_init(&bar_p[0], 1);
+    mbar_init(&bar_p[1], 1);
+    for (int i = 0; i < WS_STAGES * WS_CONSUMERS; ++i) { mbar_init(&bar_full[i], 64); mbar_init(&bar_empty[i], 32); }
+    s_done[0] = 0; s_done[1] = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_expect_tx(&bar_p[0], CHUNK_BYTES);
+    tma_load_1d(Bt, Pq, CHUNK_BYTES, &bar_p[0]);
+    if (meta.nchunks > 1) {
+      mbar_expect_tx(&bar_p[1], CHUNK_BYTES);
+      tma_load_1d(Bt + SS::CHUNK_DOUBLES, Pq + SS::CHUNK_DOUBLES, CHUNK_BYTES, &bar_p[1]);
+    }
+  }
+  __syncthreads();
+
+  double acc[NT][2];   // consumer accumulators (dead in producers)
+
+  if (warp >= WS_CONSUMERS) {
+    // =========================================================================== PRODUCER
+    const int pr = warp - WS_CONSUMERS;
+    const double* lam = args.lam_pad + (int64_t)q * (args.NPIX + 8);
+    const double* pix = args.pix + (int64_t)q * args.NPIX * 4;
+    double* const cache_q = (MODE != 0) ? args.acache + (int64_t)q * S * args.NPIX : nullptr;
+    // the CTA's 2 * WS_CONSUMERS batches of 4 sample rows are dealt round-robin to the producers:
+    // local batch b of producer pr is global batch j = pr + b * WS_PRODUCERS = rows 4 (j / NC) .. +4 of consumer j % NC
+    auto batch_consumer = [&](int b) { return (pr + b * WS_PRODUCERS) % WS_CONSUMERS; };
+    auto batch_row0 = [&](int b) { return batch_consumer(b) * SPW + ((pr + b * WS_PRODUCERS) / WS_CONSUMERS) * SPB; };
+
+    // raw (unconvolved) absorption of 4 samples (rows row0..row0+3) at one wavelength    voigt.c:282-292
+    auto eval_raw = [&](int row0, double lambda, double (&e)[SPB]) {
+      const double* mymult = s_mult + row0;
+      const double* mynhi = s_nhi + row0;
+      double tau[SPB];
+      if (NL == 3) {
+        unsigned coremask = 0;
+#pragma unroll
+        for (int ss = 0; ss < SPB; ++ss) {
+          bool core;
+          tau[ss] = tau_sum_3_wing(lambda, mymult[ss], mymult[TS + ss], mymult[2 * TS + ss], core);
+          coremask |= core ? (1u << ss) : 0u;
+        }
+        if (coremask) {
+#pragma unroll
+          for (int ss = 0; ss < SPB; ++ss)
+            if (coremask & (1u << ss)) tau[ss] = tau_sum_3_exact(lambda, mymult[ss], mymult[TS + ss], mymult[2 * TS + ss]);
+        }
+      } else {
+#pragma unroll
+        for (int ss = 0; ss < SPB; ++ss) tau[ss] = tau_sum_generic(lambda, mymult + ss, TS, num_lines);
+      }
+#pragma unroll
+      for (int ss = 0; ss < SPB; ++ss) e[ss] = -mynhi[ss] * tau[ss];
+#pragma unroll
+      for (int ss = 0; ss < SPB; ++ss) e[ss] = exp_nonpos(e[ss]);                  // voigt.c:291
+    };
+    if (MODE != 2) {   // leading pad pixels p = 0..5
+      const double lambda0 = lam[lane < 6 ? lane : 5];
+#pragma unroll
+      for (int b = 0; b < SPP / SPB; ++b) {
+        double e[SPB];
+        eval_raw(batch_row0(b), lambda0, e);
+        if (lane < 6) {
+#pragma unroll
+          for (int ss = 0; ss < SPB; ++ss) rawbuf[(batch_row0(b) + ss) * RAWS + lane] = e[ss];
+        }
+      }
+    }
+    double qacc[SPP], ldm[SPP];
+    int lde[SPP];
+#pragma unroll
+    for (int ss = 0; ss < SPP; ++ss) { qacc[ss] = 0.0; ldm[ss] = 1.0; lde[ss] = 0; }
+
+    // pixel data of the next chunk is fetched one chunk ahead (global/L2 latency off the critical path)
+    double lambda_n = lam[6 + lane];
+    double2 p01n = *reinterpret_cast<const double2*>(pix + (int64_t)lane * 4);
+    double2 p23n = *reinterpret_cast<const double2*>(pix + (int64_t)lane * 4 + 2);
+    for (int c = 0; c < meta.nchunks; ++c) {
+      const int stage = c % WS_STAGES;
+      const int i = c * KC + lane;
+      const double lambda = lambda_n;
+      const double y = p01n.x, v = p01n.y, mu = p23n.x, om2 = p23n.y;
+      if (c + 1 < meta.nchunks) {
+        lambda_n = lam[i + KC + 6];
+        p01n = *reinterpret_cast<const double2*>(pix + (int64_t)(i + KC) * 4);
+        p23n = *reinterpret_cast<const double2*>(pix + (int64_t)(i + KC) * 4 + 2);
+      }
+#pragma unroll
+      for (int b = 0; b < SPP / SPB; ++b) {
+        const int cons = batch_consumer(b), row0 = batch_row0(b);
+        double* myraw = rawbuf + row0 * RAWS;
+        double a[SPB];
+        if (MODE != 2) {
+          // ---- raw profile for the KC new padded pixels, then the instrument convolution (voigt.c:297-299)
+          double e[SPB];
+          eval_raw(row0, lambda, e);
+#pragma unroll
+          for (int ss = 0; ss < SPB; ++ss) myraw[ss * RAWS + 6 + lane] = e[ss];
+          __syncwarp();
+          double carry[SPB];
+#pragma unroll
+          for (int ss = 0; ss < SPB; ++ss) {
+            const double* rb = myraw + ss * RAWS;
+            double acc_a = 0.0;
+#pragma unroll
+            for (int t = 0; t < 7; ++t) acc_a = fma(rb[lane + t], c_lines.ip[t], acc_a);
+            carry[ss] = rb[KC + (lane < 6 ? lane : 0)];
+            a[ss] = (__double2hiint(s_nhi[row0 + ss]) < 0) ? 1.0 : acc_a;   // null model (N marked negative)
+          }
+          __syncwarp();
+          if (lane < 6) {
+#pragma unroll
+            for (int ss = 0; ss < SPB; ++ss) myraw[ss * RAWS + lane] = carry[ss];   // last 6 pixels -> front of the row
+          }
+          if (MODE == 1 && split == 0) {   // keep the level-1 absorption rows for the higher multi-DLA levels
+#pragma unroll
+            for (int ss = 0; ss < SPB; ++ss) {
+              const int64_t smp = s0 + row0 + ss;
+              if (smp < S) cache_q[smp * args.NPIX + i] = a[ss];
+            }
+          }
+        } else {
+          // absorption = voigt(sample) .* voigt(partner 1) .* ...   (...meanflux.m:342-351), from the cache
+#pragma unroll
+          for (int ss = 0; ss < SPB; ++ss) {
+            const int64_t smp = min(s0 + row0 + ss, S - 1);
+            a[ss] = cache_q[smp * args.NPIX + i];
+          }
+          for (int j = 0; j < args.num_partners; ++j) {
+            double bb[SPB];
+#pragma unroll
+            for (int ss = 0; ss < SPB; ++ss) bb[ss] = cache_q[(int64_t)s_part[j * TS + row0 + ss] * args.NPIX + i];
+#pragma unroll
+            for (int ss = 0; ss < SPB; ++ss) a[ss] = a[ss] * bb[ss];
+          }
+        }
+        // ---- weights into the consumer's operand rows of this stage, once it has released them
+        mbar_wait(&bar_empty[cons * WS_STAGES + stage], ((c / WS_STAGES) & 1) ^ 1);
+        double* dW = Wt + (stage * TS + row0) * ASTR + lane;
+        double* dU = Ut + (stage * TS + row0) * ASTR + lane;
+#pragma unroll
+        for (int ss = 0; ss < SPB; ++ss) {
+          const double a2 = a[ss] * a[ss];
+          const double d = fma(a2, om2, v);                // dla_omega2 + noise variance  (process_qsos.m:194,198)
+          const double rd = fast_rcp(d);
+          const double r = fma(-a[ss], mu, y);             // y - dla_mu
+          const double t1 = r * rd;
+          dW[ss * ASTR] = a2 * rd;
+          dU[ss * ASTR] = a[ss] * t1;
+          qacc[b * SPB + ss] = fma(r, t1, qacc[b * SPB + ss]);
+          ldm[b * SPB + ss] *= d;
+        }
+        mbar_arrive(&bar_full[cons * WS_STAGES + stage]);
+      }
+      if ((c & 7) == 7) {   // keep the running products of d in range: move their exponents to integers
+#pragma unroll
+        for (int ss = 0; ss < SPP; ++ss) {
+          int hi = __double2hiint(ldm[ss]);
+          int e2 = ((hi >> 20) & 0x7ff) - 1023;
+          lde[ss] += e2;
+          ldm[ss] = __hiloint2double(hi - (e2 << 20), __double2loint(ldm[ss]));
+        }
+      }
+    }
+#pragma unroll
+    for (int b = 0; b < SPP / SPB; ++b)
+#pragma unroll
+      for (int ss = 0; ss < SPB; ++ss) {   // per-sample scalars: sum r^2/d and sum log d
+        const double qs = warp_sum(qacc[b * SPB + ss]);
+        const double ld = warp_sum(log(ldm[b * SPB + ss]) + (double)lde[b * SPB + ss] * 0.693147180559945309417);
+        if (lane == 0) { s_q[batch_row0(b) + ss] = qs; s_ld[batch_row0(b) + ss] = ld; }
+      }
+  } else {
+    // =========================================================================== CONSUMER
+#pragma unroll
+    for (int ni = 0; ni < NT; ++ni) acc[ni][0] = acc[ni][1] = 0.0;
+    const int gid = lane >> 2, tig = lane & 3;
+    const double* rW0 = Wt + (warp * SPW + gid) * ASTR + tig;
+    const double* rU0 = Ut + (warp * SPW + gid) * ASTR + tig;
+    for (int c = 0; c < meta.nchunks; ++c) {
+      const int stage = c % WS_STAGES;           // operand-row stage
+      const int pbuf = c & 1;                    // P chunk buffer
+      mbar_wait(&bar_full[warp * WS_STAGES + stage], (c / WS_STAGES) & 1);
+      mbar_wait(&bar_p[pbuf], (c >> 1) & 1);
+      const double* Bc = Bt + pbuf * SS::CHUNK_DOUBLES + tig * SS::BSTR + gid;
+      const double* rW = rW0 + stage * TS * ASTR;
+      const double* rU = rU0 + stage * TS * ASTR;
+      // FP64 tensor-core contraction  acc += [W|U] (8 x KC) . P_chunk (KC x NCOL)
+#pragma unroll
+      for (int ks = 0; ks < KC / 4; ++ks) {
+        const double aw = rW[ks * 4];
+        const double au = rU[ks * 4];
+        const double* brow = Bc + ks * 4 * SS::BSTR;
+#pragma unroll
+        for (int ni = 0; ni < NT; ++ni) dmma_884(acc[ni][0], acc[ni][1], (tile0 + ni) < G::WT ? aw : au, brow[ni * 8]);
+      }
+      mbar_arrive(&bar_empty[warp * WS_STAGES + stage]);
+      __syncwarp();
+      // release the P buffer; the last consumer to finish this chunk re-arms it with chunk c + 2
+      if (lane == 0 && c + 2 < meta.nchunks) {
+        const int done = atomicAdd(&s_done[pbuf], 1);
+        if (done == WS_CONSUMERS - 1) {
+          s_done[pbuf] = 0;
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          mbar_expect_tx(&bar_p[pbuf], CHUNK_BYTES);
+          tma_load_1d(Bt + pbuf * SS::CHUNK_DOUBLES, Pq + (int64_t)(c + 2) * SS::CHUNK_DOUBLES, CHUNK_BYTES,
+                      &bar_p[pbuf]);
+        }
+      }
+    }
+  }
+  __syncthreads();   // all operand/P buffers are dead -> the staging area may alias them; s_q, s_ld are final
+  if (warp >= WS_CONSUMERS) return;
+  if (NSPLIT > 1) {   // column-split ranks: see dla_loglik_kernel
+    const int gid = lane >> 2, tig = lane & 3;
+    const int64_t row = s0 + warp * SPW + gid;
+    double* grow = args.gram + ((int64_t)q * args.gram_rows + row) * G::NCOL + tile0 * 8 + tig * 2;
+#pragma unroll
+    for (int ni = 0; ni < NT; ++ni) *reinterpret_cast<double2*>(grow + ni * 8) = make_double2(acc[ni][0], acc[ni][1]);
+    if (split == 0 && lane < SPW) {
+      double* qd = args.qld + ((int64_t)q * args.gram_rows + s0 + warp * SPW + lane) * 2;
+      qd[0] = s_q[warp * SPW + lane]; qd[1] = s_ld[warp * SPW + lane];
+    }
+    return;
+  }
+  stage_and_factor<K, NT, CSTR>(acc, Cs, s_q, s_ld, warp * SPW, lane, meta, args, q, s0);
 }
 
 // ------------------------------------------------------------------------------------------
