@@ -328,7 +328,15 @@ __global__ void __launch_bounds__(NTHREADS) build_gram_operand_kernel(const doub
   // layout [q][split][chunk][KC][BSTR]
   double* dst = P + (((int64_t)q * NSPLIT + split) * (NPIX / KC) + chunk) * SS::CHUNK_DOUBLES;
   for (int t = threadIdx.x; t < SS::CHUNK_DOUBLES; t += NTHREADS) {
-    int r = t / SS::BSTR, cl = t % SS::BSTR;
+    int r = t / SS::BSTR, pos = t % SS::BSTR;
+    // storage position -> local column: the two n8 tiles of a pair are interleaved so that one 16-byte
+    // shared-memory load fetches a lane's B fragments of both (position 16 j + 2 g + t  <->  tile 2j + t, column g)
+    int cl = pos;
+    if (pos < SS::NCOLL) {
+      const int j = pos / 16, w = pos % 16;
+      if (2 * j + 1 < SS::NTL) cl = (2 * j + (w & 1)) * 8 + (w >> 1);
+      else cl = (w < 8) ? 2 * j * 8 + w : SS::NCOLL;   // odd last tile: plain layout, rest padding
+    }
     int c = split * SS::NCOLL + cl;          // global column
     double v = 0.0;
     if (cl < SS::NCOLL) {
@@ -443,6 +451,23 @@ struct LoglikConfig {
     return B_BYTES + A_BYTES + RAW_BYTES + (size_t)TS * (num_lines + 4) * 8 + 64 + 3 * TS * 4;
   }
 };
+
+// One k4-step of the contraction for one warp: NT n8 tiles, B fragments fetched pairwise with 16-byte loads
+// from the pair-interleaved P chunk row `brow2` (= chunk + k * BSTR + 2 * gid).
+template <int NT, int WT>
+__device__ __forceinline__ void dmma_k4_step(double (&acc)[NT][2], double aw, double au, const double* brow2, int tile0,
+                                             int gid) {
+#pragma unroll
+  for (int j = 0; j < NT / 2; ++j) {
+    const double2 b = *reinterpret_cast<const double2*>(brow2 + j * 16);
+    dmma_884(acc[2 * j][0], acc[2 * j][1], (tile0 + 2 * j) < WT ? aw : au, b.x);
+    dmma_884(acc[2 * j + 1][0], acc[2 * j + 1][1], (tile0 + 2 * j + 1) < WT ? aw : au, b.y);
+  }
+  if (NT % 2) {
+    const double b = brow2[(NT / 2) * 16 - gid];   // plain layout of the odd last tile: position 16 (NT/2) + gid
+    dmma_884(acc[NT - 1][0], acc[NT - 1][1], (tile0 + NT - 1) < WT ? aw : au, b);
+  }
+}
 
 // Epilogue shared by the fused kernels: stage one warp's 8 x NCOL accumulator tile through shared memory as
 // an augmented upper triangle and factorise it (K3).  `row0` = first sample row of this warp inside the CTA.
@@ -711,9 +736,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dla_loglik_kernel(LoglikArgs args
       for (int ks = 0; ks < KC / 4; ++ks) {
         const double aw = myW[gid * ASTR + ks * 4 + tig];
         const double au = myU[gid * ASTR + ks * 4 + tig];
-        const double* brow = Bc + (ks * 4 + tig) * SS::BSTR + gid;
-#pragma unroll
-        for (int ni = 0; ni < NT; ++ni) dmma_884(acc[ni][0], acc[ni][1], (tile0 + ni) < G::WT ? aw : au, brow[ni * 8]);
+        dmma_k4_step<NT, G::WT>(acc, aw, au, Bc + (ks * 4 + tig) * SS::BSTR + 2 * gid, tile0, gid);
       }
     }
     __syncwarp();
@@ -1054,7 +1077,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) dla_loglik_ws_kernel(LoglikArgs
       const int pbuf = c & 1;                    // P chunk buffer
       mbar_wait(&bar_full[warp * WS_STAGES + stage], (c / WS_STAGES) & 1);
       mbar_wait(&bar_p[pbuf], (c >> 1) & 1);
-      const double* Bc = Bt + pbuf * SS::CHUNK_DOUBLES + tig * SS::BSTR + gid;
+      const double* Bc = Bt + pbuf * SS::CHUNK_DOUBLES + tig * SS::BSTR + 2 * gid;
       const double* rW = rW0 + stage * TS * ASTR;
       const double* rU = rU0 + stage * TS * ASTR;
       // FP64 tensor-core contraction  acc += [W|U] (8 x KC) . P_chunk (KC x NCOL)
@@ -1062,9 +1085,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) dla_loglik_ws_kernel(LoglikArgs
       for (int ks = 0; ks < KC / 4; ++ks) {
         const double aw = rW[ks * 4];
         const double au = rU[ks * 4];
-        const double* brow = Bc + ks * 4 * SS::BSTR;
-#pragma unroll
-        for (int ni = 0; ni < NT; ++ni) dmma_884(acc[ni][0], acc[ni][1], (tile0 + ni) < G::WT ? aw : au, brow[ni * 8]);
+        dmma_k4_step<NT, G::WT>(acc, aw, au, Bc + ks * 4 * SS::BSTR, tile0, gid);
       }
       mbar_arrive(&bar_empty[warp * WS_STAGES + stage]);
       __syncwarp();
