@@ -258,7 +258,7 @@ def main():
                          "traffic_note": "dram__bytes_read+write of one launch with grid %s (one 296-quasar batch; this "
                                          "run launches the same batch size), ncu --set full" % traffic_grid,
                          "algorithmic_flops_per_launch": flops_per_step * args.steps / max(int(k_n), 1),
-                         "kernel": "dla_loglik_kernel (fused Voigt + FP64 DMMA Gram + Cholesky)",
+                         "kernel": "dla_loglik_ws_kernel (fused Voigt + FP64 DMMA Gram + Cholesky, warp-specialised)",
                          "kernel_ms_per_step": k_ms / args.steps, "kernel_launches": int(k_n),
                          "kernel_share_of_step": k_ms / ms,
                          "algorithmic_flops_per_step": flops_per_step, "peak_source": peak_src,
