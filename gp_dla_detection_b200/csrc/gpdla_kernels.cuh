@@ -812,7 +812,10 @@ constexpr int RAWS = KC + 8;      // raw-profile row: 6 carried-over pixels + KC
 #endif
 constexpr int WS_CONSUMERS = GPDLA_WS_CONSUMERS, WS_PRODUCERS = GPDLA_WS_PRODUCERS;
 constexpr int WS_THREADS = 32 * (WS_CONSUMERS + WS_PRODUCERS);   // 384 -> 168 registers per thread
-constexpr int WS_STAGES = 2;      // operand-row stages between producer and consumer
+#ifndef GPDLA_WS_STAGES
+#define GPDLA_WS_STAGES 2
+#endif
+constexpr int WS_STAGES = GPDLA_WS_STAGES;   // operand-row stages between producer and consumer
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");

@@ -246,6 +246,18 @@ def test_rank_and_sample_count_sweep(api, synthetic_inputs):
                   O.process_qsos(si["model"], s30k, sp1, si["prior"], engine="c"))
 
 
+def test_tiny_and_odd_sample_counts(api, synthetic_inputs):
+    """Sample tiles are 32 wide: S = 1, 5, 33 exercise the partial-tile and null-slot handling."""
+    from oracle import process_qsos_oracle as O
+    si = synthetic_inputs
+    sp = {k: v[:2] for k, v in si["spectra"].items()}
+    for S in (1, 5, 33):
+        sub = np.arange(S) * 7 + 3
+        samples = {k: v[sub] for k, v in si["samples"].items()}
+        assert_parity(api.process_qsos(si["model"], samples, sp, si["prior"]),
+                      O.process_qsos(si["model"], samples, sp, si["prior"], engine="c"))
+
+
 def test_state_errors(api, synthetic_inputs):
     from gp_dla_detection_b200._lib import GpdlaError
     si = synthetic_inputs
