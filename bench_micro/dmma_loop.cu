@@ -28,7 +28,7 @@ __global__ void __launch_bounds__(128, 1) k_loop(double* out, long long* cyc, in
   for (int c = 0; c < chunks; ++c) {
     const double* Bc = Bt + tig * BSTR + gid;
 #pragma unroll
-    for (int ks = 0; ks < KC / 4; ++ks) {
+    for (int ks = 0; ks < (VARIANT == 3 ? 0 : KC / 4); ++ks) {
       const double aw = rW[ks * 4];
       const double* brow = Bc + ks * 4 * BSTR;
       if (VARIANT == 0) {
@@ -43,9 +43,37 @@ __global__ void __launch_bounds__(128, 1) k_loop(double* out, long long* cyc, in
           dmma(acc[ni][0], acc[ni][1], aw, b.x);
           dmma(acc[ni + 1][0], acc[ni + 1][1], aw, b.y);
         }
-      } else {
+      } else if (VARIANT == 2) {
 #pragma unroll
         for (int ni = 0; ni < NT; ++ni) dmma(acc[ni][0], acc[ni][1], aw, aw + ni);
+      }
+    }
+    if (VARIANT == 3) {
+      // explicit software pipeline: fragments of k4-step ks+1 are loaded (16-byte loads) into a second
+      // register set while the DMMAs of step ks issue
+      double2 cur[NT / 2], nxt[NT / 2];
+      double awc = rW[0], awn = 0.0;
+      {
+        const double2* b2 = reinterpret_cast<const double2*>(Bt + tig * BSTR) + gid;
+#pragma unroll
+        for (int j = 0; j < NT / 2; ++j) cur[j] = b2[j * 8];
+      }
+#pragma unroll
+      for (int ks = 0; ks < KC / 4; ++ks) {
+        if (ks + 1 < KC / 4) {
+          const double2* b2 = reinterpret_cast<const double2*>(Bt + ((ks + 1) * 4 + tig) * BSTR) + gid;
+          awn = rW[(ks + 1) * 4];
+#pragma unroll
+          for (int j = 0; j < NT / 2; ++j) nxt[j] = b2[j * 8];
+        }
+#pragma unroll
+        for (int j = 0; j < NT / 2; ++j) {
+          dmma(acc[2 * j][0], acc[2 * j][1], awc, cur[j].x);
+          dmma(acc[2 * j + 1][0], acc[2 * j + 1][1], awc, cur[j].y);
+        }
+#pragma unroll
+        for (int j = 0; j < NT / 2; ++j) cur[j] = nxt[j];
+        awc = awn;
       }
     }
   }
@@ -71,5 +99,6 @@ int main() {
   run<0>(out, dc, "LDS.64 per fragment");
   run<1>(out, dc, "LDS.128 per two fragments");
   run<2>(out, dc, "no smem loads");
+  run<3>(out, dc, "LDS.128 + register double buffer");
   return 0;
 }

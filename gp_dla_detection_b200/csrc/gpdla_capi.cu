@@ -253,11 +253,12 @@ static int launch_loglik(gpdla_ctx* c, LoglikArgs la, int nq, cudaStream_t st) {
   auto kern_ws = dla_loglik_ws_kernel<K, NL, MODE, NSPLIT>;
   const size_t smem = ws ? WCfg::smem_bytes(la.num_lines) : Cfg::smem_bytes(la.num_lines);
   const int TS = ws ? WCfg::TS : Cfg::TS;
-  static size_t configured[2] = {0, 0};
-  if (configured[ws] < smem) {
+  static size_t configured[2][64] = {};   // per schedule and device: function attributes are per device
+  const int dev = c->device & 63;
+  if (configured[ws][dev] < smem) {
     if (ws) CUDA_TRY(cudaFuncSetAttribute(kern_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), c->err);
     else CUDA_TRY(cudaFuncSetAttribute(kern_wa, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), c->err);
-    configured[ws] = smem;
+    configured[ws][dev] = smem;
   }
   const unsigned tiles = (unsigned)((la.S + (la.log_likelihoods_no_dla ? 1 : 0) + TS - 1) / TS);
   dim3 grid(tiles, (unsigned)nq, NSPLIT);
@@ -277,11 +278,11 @@ static int launch_loglik(gpdla_ctx* c, LoglikArgs la, int nq, cudaStream_t st) {
     ca.meta = la.meta; ca.gram = c->d_gram; ca.qld = c->d_qld; ca.gram_rows = la.gram_rows; ca.S = la.S;
     ca.sample_log_likelihoods = la.sample_log_likelihoods; ca.sll_stride = la.sll_stride;
     ca.log_likelihoods_no_dla = la.log_likelihoods_no_dla; ca.active = la.active;
-    static bool chol_configured = false;
-    if (!chol_configured) {
+    static bool chol_configured[64] = {};
+    if (!chol_configured[dev]) {
       CUDA_TRY(cudaFuncSetAttribute(cholesky_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)cholesky_smem_bytes<K>()), c->err);
-      chol_configured = true;
+      chol_configured[dev] = true;
     }
     cholesky_kernel<K><<<dim3(tiles * TS / CHOL_SAMPLES, (unsigned)nq), CHOL_SAMPLES * 4,
                          cholesky_smem_bytes<K>(), st>>>(ca);

@@ -258,6 +258,20 @@ def test_tiny_and_odd_sample_counts(api, synthetic_inputs):
                       O.process_qsos(si["model"], samples, sp, si["prior"], engine="c"))
 
 
+def test_two_devices_in_one_process(api, synthetic_inputs):
+    """Contexts on different GPUs of one process give identical results (per-device constants/attributes)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    si = synthetic_inputs
+    sub = np.arange(0, 10000, 25)
+    samples = {k: v[sub] for k, v in si["samples"].items()}
+    a = api.process_qsos(si["model"], samples, si["spectra"], si["prior"], device=0)
+    b = api.process_qsos(si["model"], samples, si["spectra"], si["prior"], device=1)
+    for k in a:
+        assert np.array_equal(a[k], b[k], equal_nan=True), k
+
+
 def test_state_errors(api, synthetic_inputs):
     from gp_dla_detection_b200._lib import GpdlaError
     si = synthetic_inputs
