@@ -272,6 +272,41 @@ def test_two_devices_in_one_process(api, synthetic_inputs):
         assert np.array_equal(a[k], b[k], equal_nan=True), k
 
 
+def test_fuzz_extreme_inputs(api, synthetic_inputs):
+    """Randomised spectra outside the synthetic generator's comfort zone: noise variances over 10 decades,
+    flux outliers and negative flux, heavy masking, redshifts up to 5.5, short spectra."""
+    from gp_dla_detection_b200 import synthetic as syn
+    from oracle import process_qsos_oracle as O
+    si = synthetic_inputs
+    rng = np.random.default_rng(2024)
+    sp = syn.make_spectra(si["model"], 16, seed=77, dla_fraction=0.5)
+    for q in range(16):
+        L = len(sp["all_flux"][q])
+        sp["all_noise_variance"][q] = 10.0 ** rng.uniform(-6, 4, L)
+        sp["all_flux"][q] = sp["all_flux"][q] + rng.standard_normal(L) * np.sqrt(sp["all_noise_variance"][q])
+        out = rng.random(L) < 0.01
+        sp["all_flux"][q][out] = rng.uniform(-50, 50, np.count_nonzero(out))
+        sp["all_pixel_mask"][q] = rng.random(L) < rng.choice([0.0, 0.05, 0.5])
+        if q % 4 == 0:
+            lo, n_keep = rng.integers(0, 900), rng.integers(210, 400)
+            for k in ("all_wavelengths", "all_flux", "all_noise_variance", "all_pixel_mask"):
+                sp[k][q] = sp[k][q][lo:lo + n_keep]
+    sp["all_wavelengths"][3] = sp["all_wavelengths"][3] * (1 + 5.5) / (1 + float(sp["z_qsos"][3]))   # same rest frame at z = 5.5
+    sp["z_qsos"][3] = 5.5
+    sub = np.arange(0, 10000, 33)
+    samples = {k: v[sub] for k, v in si["samples"].items()}
+    res = api.process_qsos(si["model"], samples, sp, si["prior"])
+    ref = O.process_qsos(si["model"], samples, sp, si["prior"], engine="c")
+    a, b = res["sample_log_likelihoods_dla"], ref["sample_log_likelihoods_dla"]
+    assert np.array_equal(np.isnan(a), np.isnan(b))
+    assert np.allclose(a, b, rtol=1e-9, atol=0, equal_nan=True)      # north_star: 1e-8
+    assert np.allclose(res["log_likelihoods_no_dla"], ref["log_likelihoods_no_dla"], rtol=1e-9, equal_nan=True)
+    assert np.allclose(res["p_dlas"], ref["p_dlas"], rtol=0, atol=P_ATOL, equal_nan=True)
+    ok = ~np.isnan(ref["log_likelihoods_dla"])
+    tie_free = np.array([np.sum(b[q] >= np.nanmax(b[q]) * (1 + 1e-12 * np.sign(-np.nanmax(b[q])))) == 1 if ok[q] else False for q in range(16)])
+    assert np.array_equal(res["map_inds"][tie_free], ref["map_inds"][tie_free])
+
+
 def test_state_errors(api, synthetic_inputs):
     from gp_dla_detection_b200._lib import GpdlaError
     si = synthetic_inputs
