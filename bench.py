@@ -37,10 +37,10 @@ def fp64_peak():
         return 37.0, "nominal HGX B200 FP64 tensor (fallback)"
 
 
-def ncu_traffic():
-    """DRAM bytes of one dla_loglik_kernel launch (296-quasar batch) from the committed ncu --set full capture."""
+def ncu_traffic(i8):
+    """DRAM bytes of one fused log-likelihood launch (296-quasar batch) from the committed ncu --set full capture."""
     try:
-        d = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_loglik_full.json")))
+        d = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_loglik_i8_full.json" if i8 else "r01_ncu_loglik_full.json")))
         return d["dram_bytes_per_launch"], d["Grid Size"]["value"]
     except Exception:
         return None, None
@@ -146,6 +146,8 @@ def main():
     ap.add_argument("--ref-quasars-per-step", type=int, default=8)
     ap.add_argument("--cpu-baseline-quasars", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gram-digits", type=int, default=0, choices=[-1, 0, 5, 6],
+                    help="Gram arithmetic: 0 default (INT8 tensor-core path, 6 digits), -1 FP64 DMMA, 5/6 INT8 digits")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -177,7 +179,7 @@ def main():
     n_pix = n_used - masked_in               # used pixels n_q
     flops_per_step = float(np.sum(n_pix) * NUM_SAMPLES * K_RANK * (K_RANK + 3))   # n k (k+3) per sample
 
-    proc = api.DLAProcessor(model, samples, prior, device=local_rank)
+    proc = api.DLAProcessor(model, samples, prior, device=local_rank, gram_digits=args.gram_digits)
     host = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in pad.items()}
     dtens = {k: v.to(dev) for k, v in host.items()}
     order = ("wavelengths", "flux", "noise_variance", "pixel_mask", "lengths", "z_qsos")
@@ -241,7 +243,42 @@ def main():
     if rank == 0:
         peak, peak_src = fp64_peak()
         achieved = flops_per_step * args.steps / (k_ms * 1e-3) * 1e-12 if k_ms > 0 else None
-        traffic, traffic_grid = ncu_traffic()
+        digits = args.gram_digits
+        if digits == 0:
+            digits = -1 if os.environ.get("GPDLA_GRAM", "").startswith("f") else (5 if os.environ.get("GPDLA_I8_DIGITS") == "5" else 6)
+        i8 = digits in (5, 6)
+        traffic, traffic_grid = ncu_traffic(i8)
+        roof = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                "frac": (achieved / peak) if achieved else None, "traffic": traffic,
+                "traffic_note": "dram__bytes_read+write of one launch with grid %s (one 296-quasar batch; this "
+                                "run launches the same batch size), ncu --set full" % traffic_grid,
+                "algorithmic_flops_per_launch": flops_per_step * args.steps / max(int(k_n), 1),
+                "kernel_ms_per_step": k_ms / args.steps, "kernel_launches": int(k_n),
+                "kernel_share_of_step": k_ms / ms,
+                "algorithmic_flops_per_step": flops_per_step, "peak_source": peak_src}
+        if i8:
+            # int8 operations the tcgen05 MMAs execute: per cluster (128 samples) and 32-pixel chunk, L(L+1)/2 slice
+            # pairs x (3 CTAs x N=80 + 1 CTA x N=32) columns x 128 rows x 32 pixels x 2
+            pairs = digits * (digits + 1) // 2
+            chunks = np.sum((n_used + 31) // 32)
+            clusters = (NUM_SAMPLES + 1 + 127) // 128
+            int8_ops = float(chunks) * clusters * pairs * 2.0 * 128 * 32 * (3 * 80 + 32)
+            roof.update({
+                "kernel": "dla_loglik_i8_kernel (fused Voigt + exact-product INT8 tcgen05 Gram, %d signed 8-bit digits per "
+                          "factor, s32 TMEM accumulators + Cholesky; 4-CTA clusters, DSMEM row-block exchange)" % digits,
+                "note": "achieved/peak = FP64-equivalent Gram rate (S n k(k+3) per quasar, SURVEY 8(d)) over the measured "
+                        "FP64 DMMA peak; the contraction itself runs as exact INT8 slice products on the tcgen05 tensor "
+                        "pipe, which leaves the FP64 pipe to the Voigt/weight arithmetic -- the stage that now bounds "
+                        "the kernel (ncu: FP64 pipe ~26 % busy, tensor pipe ~50 %, the producers' dependent-issue "
+                        "latency limits both; DESIGN.md 4.3)",
+                "int8_tensor": {"achieved_tops": int8_ops * args.steps / (k_ms * 1e-3) * 1e-12 if k_ms > 0 else None,
+                                "peak_tops": 4283.0, "peak_source": "profiles/r01_tcgen05_i8.txt (this pool's B200, N = 240)"},
+            })
+        else:
+            roof.update({
+                "kernel": "dla_loglik_ws_kernel (fused Voigt + FP64 DMMA Gram + Cholesky, warp-specialised)",
+                "note": "FP64 DMMA and DFMA share one pipe on B200 (measured): the fused kernel's Voigt/"
+                        "weight arithmetic competes with the Gram for the same 37 TFLOP/s"})
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -250,20 +287,12 @@ def main():
                                    "samples, %d Lyman lines, L_max=%d" % (Q, K_RANK, NUM_SAMPLES, NUM_LINES, L_max),
                        "quasars_per_gpu": Q, "l2": "inputs %.0f MB + per-batch workspace > 126 MB L2; no flush needed"
                                                    % (h2d / 1e6),
+                       "gram_arithmetic": ("exact-product int8 x int8 -> s32 slices of FP64 operands, %d digits (%d "
+                                           "fractional bits)" % (digits, 8 * digits - 1)) if i8 else "FP64 DMMA",
                        "sharding": "quasars split across ranks, no data-path collective; one all_gather of records"},
             "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": (achieved / peak) if achieved else None, "traffic": traffic,
-                         "traffic_note": "dram__bytes_read+write of one launch with grid %s (one 296-quasar batch; this "
-                                         "run launches the same batch size), ncu --set full" % traffic_grid,
-                         "algorithmic_flops_per_launch": flops_per_step * args.steps / max(int(k_n), 1),
-                         "kernel": "dla_loglik_ws_kernel (fused Voigt + FP64 DMMA Gram + Cholesky, warp-specialised)",
-                         "kernel_ms_per_step": k_ms / args.steps, "kernel_launches": int(k_n),
-                         "kernel_share_of_step": k_ms / ms,
-                         "algorithmic_flops_per_step": flops_per_step, "peak_source": peak_src,
-                         "note": "FP64 DMMA and DFMA share one pipe on B200 (measured): the fused kernel's Voigt/"
-                                 "weight arithmetic competes with the Gram for the same 37 TFLOP/s"},
+            "roofline": roof,
             "clocks": clocks,
         }
         if not args.no_cpu_baseline:

@@ -22,7 +22,8 @@ class GpdlaParams(ctypes.Structure):
                 ("lya_wavelength", ctypes.c_double), ("lyman_limit", ctypes.c_double),
                 ("prior_z_qso_increase", ctypes.c_double), ("min_z_cut", ctypes.c_double),
                 ("max_z_cut", ctypes.c_double), ("pixel_spacing", ctypes.c_double),
-                ("num_lines", ctypes.c_int32), ("batch_quasars", ctypes.c_int32)]
+                ("num_lines", ctypes.c_int32), ("batch_quasars", ctypes.c_int32),
+                ("gram_digits", ctypes.c_int32), ("reserved", ctypes.c_int32)]
 
 
 RESULT_F64 = ["min_z_dlas", "max_z_dlas", "log_priors_no_dla", "log_priors_dla", "log_likelihoods_no_dla",

@@ -58,7 +58,9 @@ class DLAProcessor:
     catalogue on one GPU (what process_qsos.m:4-40 loads once before its quasar loop)."""
 
     def __init__(self, model: Dict, samples: Dict, prior: Dict, params: Parameters = DEFAULT, device: int = 0,
-                 batch_quasars: int = 0):
+                 batch_quasars: int = 0, gram_digits: int = 0):
+        """``gram_digits``: arithmetic of the Gram contraction -- 0 default (exact-product INT8 tensor-core path
+        with 6 digits for k = 20, FP64 DMMA otherwise), -1 FP64 DMMA, 5 / 6 INT8 path with that many digits."""
         self._lib = _lib.load()
         self._ctx = ctypes.c_void_p()
         _lib.check(self._lib.gpdla_create(ctypes.byref(self._ctx), int(device)))
@@ -70,6 +72,7 @@ class DLAProcessor:
         p.prior_z_qso_increase = params.prior_z_qso_increase
         p.min_z_cut, p.max_z_cut = params.min_z_cut, params.max_z_cut
         p.pixel_spacing, p.num_lines, p.batch_quasars = params.pixel_spacing, params.num_lines, int(batch_quasars)
+        p.gram_digits = int(gram_digits)
         _lib.check(self._lib.gpdla_set_parameters(self._ctx, ctypes.byref(p)), self._ctx)
         rest, mu, M, lw = (_f64(model[k]) for k in ("rest_wavelengths", "mu", "M", "log_omega"))
         if M.shape != (rest.size, M.shape[1]) or mu.size != rest.size or lw.size != rest.size:
@@ -211,9 +214,9 @@ class DLAProcessor:
 
 
 def process_qsos(model: Dict, samples: Dict, spectra: Dict, prior: Dict, params: Parameters = DEFAULT,
-                 device: int = 0, return_sample_log_likelihoods: bool = True) -> Dict[str, np.ndarray]:
+                 device: int = 0, return_sample_log_likelihoods: bool = True, gram_digits: int = 0) -> Dict[str, np.ndarray]:
     """Run the DLA detection algorithm on the given objects (process_qsos.m)."""
-    proc = DLAProcessor(model, samples, prior, params, device)
+    proc = DLAProcessor(model, samples, prior, params, device, gram_digits=gram_digits)
     try:
         return proc.process(spectra, return_sample_log_likelihoods)
     finally:
@@ -223,10 +226,11 @@ def process_qsos(model: Dict, samples: Dict, spectra: Dict, prior: Dict, params:
 def process_qsos_multiple_dlas_meanflux(model: Dict, samples: Dict, spectra: Dict, prior: Dict, max_dlas: int = 4,
                                         params: Parameters = DEFAULT, device: int = 0,
                                         base_sample_inds: Optional[np.ndarray] = None,
-                                        return_samples: bool = True, batch_quasars: int = 0) -> Dict[str, np.ndarray]:
+                                        return_samples: bool = True, batch_quasars: int = 0,
+                                        gram_digits: int = 0) -> Dict[str, np.ndarray]:
     """Multi-DLA / sub-DLA / mean-flux processing (multi_dlas/process_qsos_multiple_dlas_meanflux.m).
     ``samples`` additionally holds ``lls_nhi_samples``, ``Z_lls``, ``Z_dla`` (set_lls_parameters.m)."""
-    proc = DLAProcessor(model, samples, prior, params, device, batch_quasars=batch_quasars)
+    proc = DLAProcessor(model, samples, prior, params, device, batch_quasars=batch_quasars, gram_digits=gram_digits)
     try:
         return proc.process_multi(spectra, max_dlas, base_sample_inds, return_samples)
     finally:

@@ -13,6 +13,7 @@
 
 #include "../../include/gpdla.h"
 #include "gpdla_kernels.cuh"
+#include "gpdla_i8_kernels.cuh"
 
 using namespace gpdla;
 
@@ -142,6 +143,24 @@ static int upload_stage_index(std::string& err) {
   return GPDLA_OK;
 }
 
+// INT8 path: accumulator column (CTA rank, n) -> augmented-triangle index
+template <int K, int L>
+static int upload_i8_stage_index(std::string& err) {
+  using Sh = i8::Shape<K, L>;
+  using G = GramShape<K>;
+  static short tab[i8::CLUSTER * 128];
+  for (auto& t : tab) t = -1;
+  for (int p = 0; p < K; ++p) {
+    for (int q = p; q < K; ++q) {
+      const int c = G::pair_index(p, q);
+      tab[(c / Sh::WCOLS) * 128 + c % Sh::WCOLS] = (short)aug_index<K>(p, q);
+    }
+    tab[i8::WCTAS * 128 + p] = (short)aug_index<K>(p, K);
+  }
+  CUDA_TRY(cudaMemcpyToSymbol(i8::c_i8_stage, tab, sizeof tab), err);
+  return GPDLA_OK;
+}
+
 // rank dispatch: the ranks compiled into the library
 #define GPDLA_FOR_RANK(k, CALL)            \
   switch (k) {                             \
@@ -191,6 +210,11 @@ struct gpdla_ctx {
   QuasarMeta* d_meta = nullptr;
   double *d_lam = nullptr, *d_pix = nullptr, *d_Mq = nullptr, *d_P = nullptr, *d_sll = nullptr, *d_scratch = nullptr;
   int64_t* d_scratch_i = nullptr;
+  // INT8 tensor-core Gram path (k = 20): digit operands and scales
+  int i8_batch = 0, i8_npix = 0;
+  double *d_pix2 = nullptr, *d_colscale = nullptr, *d_colinv = nullptr;
+  uint8_t* d_bop = nullptr;
+  int* d_status = nullptr;
   // staging for the host entry point
   size_t st_bytes = 0;
   void* d_stage = nullptr;
@@ -296,6 +320,125 @@ static int launch_loglik(gpdla_ctx* c, LoglikArgs la, int nq, cudaStream_t st) {
   return GPDLA_OK;
 }
 
+// Gram path: 8 = INT8 tcgen05 (k = 20 only; digits from GPDLA_I8_DIGITS, default 6), 0 = FP64 DMMA.
+// GPDLA_GRAM=f64 forces the FP64 kernels.
+constexpr int I8_K = 20;
+static int i8_default_digits() {
+  static int v = -2;
+  if (v == -2) {
+    const char* g = getenv("GPDLA_GRAM");
+    const char* d = getenv("GPDLA_I8_DIGITS");
+    if (g && g[0] == 'f') v = -1;
+    else v = (d && d[0] == '5') ? 5 : 6;
+  }
+  return v;
+}
+// digits of the INT8 path for this context, 0 = FP64 DMMA kernels
+static int i8_digits(const gpdla_ctx* c) {
+  int d = c->params.gram_digits;
+  if (d == 0) d = i8_default_digits();
+  return (c->k == I8_K && (d == 5 || d == 6)) ? d : 0;
+}
+static bool use_i8(const gpdla_ctx* c) { return i8_digits(c) > 0; }
+
+static int ensure_i8_workspace(gpdla_ctx* c, int batch, int npix) {
+  if (c->i8_batch >= batch && c->i8_npix == npix) return GPDLA_OK;
+  cudaFree(c->d_pix2); cudaFree(c->d_colscale); cudaFree(c->d_colinv); cudaFree(c->d_bop);
+  c->d_pix2 = c->d_colscale = c->d_colinv = nullptr; c->d_bop = nullptr; c->i8_batch = 0;
+  const size_t B = batch;
+  using Sh = i8::Shape<I8_K, 6>;    // the 6-digit layout is the larger one
+  CUDA_TRY(cudaMalloc(&c->d_pix2, B * npix * 2 * sizeof(double)), c->err);
+  CUDA_TRY(cudaMalloc(&c->d_colscale, B * Sh::NCOLTAB * sizeof(double)), c->err);
+  CUDA_TRY(cudaMalloc(&c->d_colinv, B * Sh::NCOLTAB * sizeof(double)), c->err);
+  CUDA_TRY(cudaMalloc(&c->d_bop, B * (npix / KC) * Sh::CHUNK_BYTES), c->err);
+  if (!c->d_status) {
+    CUDA_TRY(cudaMalloc(&c->d_status, sizeof(int)), c->err);
+    CUDA_TRY(cudaMemset(c->d_status, 0, sizeof(int)), c->err);
+  }
+  c->i8_batch = batch; c->i8_npix = npix;
+  return GPDLA_OK;
+}
+
+static i8::I8Args i8_args(gpdla_ctx* c) {
+  i8::I8Args xa;
+  xa.pix2 = c->d_pix2; xa.bop = c->d_bop; xa.colscale = c->d_colscale; xa.colinv = c->d_colinv; xa.status = c->d_status;
+  xa.phase = nullptr;
+  if (getenv("GPDLA_I8_PHASES")) {
+    static unsigned long long* d_phase = nullptr;
+    if (!d_phase) { cudaMalloc(&d_phase, 24 * sizeof(unsigned long long)); cudaMemset(d_phase, 0, 24 * sizeof(unsigned long long)); }
+    unsigned long long h[24];
+    cudaMemcpy(h, d_phase, sizeof h, cudaMemcpyDeviceToHost);
+    if (h[7]) fprintf(stderr, "[i8 phases, mean cycles since CTA start over %llu CTAs] - %llu | setup %llu | producer loop end %llu | acc final %llu | recombined %llu | cluster barrier %llu | factor end %llu\n",
+                      h[7], h[0] / h[7], h[1] / h[7], h[2] / h[7], h[3] / h[7], h[4] / h[7], h[5] / h[7], h[6] / h[7]);
+    if (h[7]) fprintf(stderr, "[i8 waits, mean cycles per CTA] producers: A-stage empty (per thread) %llu | mma: A full %llu | mma: B full %llu | loader: B empty %llu | sender: rows %llu | epilogue: accumulators %llu\n",
+                      h[9] / h[7] / 256, h[10] / h[7], h[11] / h[7], h[12] / h[7], h[13] / h[7], h[14] / h[7] / 4);
+    cudaMemset(d_phase, 0, sizeof h);
+    xa.phase = d_phase;
+  }
+  return xa;
+}
+
+// K0c + K0d: scales and digit planes of the B operand for a prepared batch
+template <int L>
+static int build_i8_operands_L(gpdla_ctx* c, int nq, int npix, cudaStream_t st) {
+  static bool uploaded[64] = {};
+  const int dev = c->device & 63;
+  if (!uploaded[dev]) {
+    int rc = upload_i8_stage_index<I8_K, L>(c->err);
+    if (rc) return rc;
+    uploaded[dev] = true;
+  }
+  i8::I8Args xa = i8_args(c);
+  i8::i8_scales_kernel<I8_K, L><<<nq, NTHREADS, 0, st>>>(c->d_meta, c->d_pix, c->d_Mq, xa, npix);
+  c->launches++;
+  CUDA_TRY(cudaGetLastError(), c->err);
+  i8::i8_build_operand_kernel<I8_K, L><<<dim3(npix / KC, nq), NTHREADS, 0, st>>>(c->d_meta, c->d_Mq, xa, npix);
+  c->launches++;
+  CUDA_TRY(cudaGetLastError(), c->err);
+  return GPDLA_OK;
+}
+static int build_i8_operands(gpdla_ctx* c, int nq, int npix, cudaStream_t st) {
+  int rc = ensure_i8_workspace(c, c->ws_batch, npix);
+  if (rc) return rc;
+  return i8_digits(c) == 5 ? build_i8_operands_L<5>(c, nq, npix, st) : build_i8_operands_L<6>(c, nq, npix, st);
+}
+
+template <int L, int NL, int MODE>
+static int launch_loglik_i8(gpdla_ctx* c, const LoglikArgs& la, int nq, cudaStream_t st) {
+  using Sh = i8::Shape<I8_K, L>;
+  auto kern = i8::dla_loglik_i8_kernel<I8_K, L, NL, MODE>;
+  const size_t smem = Sh::smem_bytes(la.num_lines);
+  static size_t configured[64] = {};
+  const int dev = c->device & 63;
+  if (configured[dev] < smem) {
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), c->err);
+    configured[dev] = smem;
+  }
+  const unsigned clusters = (unsigned)((la.S + (la.log_likelihoods_no_dla ? 1 : 0) + i8::TM - 1) / i8::TM);
+  dim3 grid(clusters * i8::CLUSTER, (unsigned)nq, 1);
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (c->profiling) {
+    CUDA_TRY(cudaEventCreate(&e0), c->err);
+    CUDA_TRY(cudaEventCreate(&e1), c->err);
+    CUDA_TRY(cudaEventRecord(e0, st), c->err);
+  }
+  kern<<<grid, i8::THREADS, smem, st>>>(la, i8_args(c));
+  c->launches++;
+  CUDA_TRY(cudaGetLastError(), c->err);
+  if (c->profiling) {
+    CUDA_TRY(cudaEventRecord(e1, st), c->err);
+    c->prof_events.emplace_back(e0, e1);
+  }
+  return GPDLA_OK;
+}
+
+template <int MODE>
+static int launch_mode_i8(gpdla_ctx* c, const LoglikArgs& la, int nq, cudaStream_t st) {
+  const bool l5 = i8_digits(c) == 5;
+  if (c->params.num_lines == 3) return l5 ? launch_loglik_i8<5, 3, MODE>(c, la, nq, st) : launch_loglik_i8<6, 3, MODE>(c, la, nq, st);
+  return l5 ? launch_loglik_i8<5, 0, MODE>(c, la, nq, st) : launch_loglik_i8<6, 0, MODE>(c, la, nq, st);
+}
+
 static int ensure_multi_workspace(gpdla_ctx* c, int batch, int npix) {
   if (c->mws_batch >= batch && c->mws_npix == npix && c->mws_S == c->S) return GPDLA_OK;
   cudaFree(c->d_acache); cudaFree(c->d_msll); cudaFree(c->d_mlls); cudaFree(c->d_cum); cudaFree(c->d_mscal);
@@ -322,6 +465,11 @@ static int launch_mode(gpdla_ctx* c, const LoglikArgs& la, int nq, cudaStream_t 
   return rc;
 }
 
+template <int MODE>
+static int launch_mode_any(gpdla_ctx* c, const LoglikArgs& la, int nq, cudaStream_t st) {
+  return use_i8(c) ? launch_mode_i8<MODE>(c, la, nq, st) : launch_mode<MODE>(c, la, nq, st);
+}
+
 __global__ void fill_i32_kernel(int32_t* p, int32_t v, int64_t n) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
@@ -338,6 +486,7 @@ void gpdla_default_parameters(gpdla_params* p) {
   p->pixel_spacing = 1e-4;
   p->num_lines = 3;
   p->batch_quasars = 0;
+  p->gram_digits = 0; p->reserved = 0;
 }
 
 void gpdla_line_constants(double* tw, double* lcs, double* gam, double* ip) {
@@ -375,6 +524,7 @@ void gpdla_destroy(gpdla_ctx* c) {
   cudaFree(c->d_rest); cudaFree(c->d_mu); cudaFree(c->d_M); cudaFree(c->d_log_omega);
   cudaFree(c->d_offset); cudaFree(c->d_log_nhi); cudaFree(c->d_nhi);
   cudaFree(c->d_prior_z); cudaFree(c->d_prior_dla); cudaFree(c->d_stage);
+  cudaFree(c->d_pix2); cudaFree(c->d_colscale); cudaFree(c->d_colinv); cudaFree(c->d_bop); cudaFree(c->d_status);
   cudaFree(c->d_lls_nhi); cudaFree(c->d_uniforms); cudaFree(c->d_acache); cudaFree(c->d_msll); cudaFree(c->d_mlls);
   cudaFree(c->d_cum); cudaFree(c->d_mscal); cudaFree(c->d_partners); cudaFree(c->d_active);
   delete c;
@@ -409,7 +559,7 @@ int gpdla_profile_read(gpdla_ctx* c, double* loglik_ms, int64_t* loglik_launches
 int gpdla_set_parameters(gpdla_ctx* c, const gpdla_params* p) {
   if (!c || !p) return GPDLA_ERR_INVALID;
   if (p->num_lines < 1 || p->num_lines > GPDLA_MAX_LINES || !(p->max_lambda > p->min_lambda) ||
-      p->batch_quasars < 0) {
+      p->batch_quasars < 0 || !(p->gram_digits == 0 || p->gram_digits == -1 || p->gram_digits == 5 || p->gram_digits == 6)) {
     c->err = "gpdla_set_parameters: invalid parameters";
     return GPDLA_ERR_INVALID;
   }
@@ -501,9 +651,13 @@ int gpdla_process_qsos_device(gpdla_ctx* c, int64_t Q, int64_t L_max, const doub
     prepare_quasars_kernel<<<nq, NTHREADS, 0, st>>>(pa);
     c->launches++;
     CUDA_TRY(cudaGetLastError(), c->err);
-    GPDLA_FOR_RANK(c->k, (build_gram_operand_kernel<K, NSPLIT><<<dim3(npix / KC, nq, NSPLIT), NTHREADS, 0, st>>>(c->d_Mq, c->d_meta, c->d_P, npix)));
-    c->launches++;
-    CUDA_TRY(cudaGetLastError(), c->err);
+    if (use_i8(c)) {
+      if ((rc = build_i8_operands(c, nq, npix, st))) return rc;
+    } else {
+      GPDLA_FOR_RANK(c->k, (build_gram_operand_kernel<K, NSPLIT><<<dim3(npix / KC, nq, NSPLIT), NTHREADS, 0, st>>>(c->d_Mq, c->d_meta, c->d_P, npix)));
+      c->launches++;
+      CUDA_TRY(cudaGetLastError(), c->err);
+    }
 
     double* sll = out->sample_log_likelihoods_dla ? out->sample_log_likelihoods_dla + q0 * c->S : c->d_sll;
     double* llno = out->log_likelihoods_no_dla ? out->log_likelihoods_no_dla + q0 : c->d_scratch;
@@ -526,7 +680,7 @@ int gpdla_process_qsos_device(gpdla_ctx* c, int64_t Q, int64_t L_max, const doub
       fprintf(stderr, "[core path] cycles %lld, warp-evals with core %lld of %lld\n", h[8], h[9], h[10]);
     }
 #endif
-    if ((rc = launch_mode<0>(c, la, nq, st))) return rc;
+    if ((rc = launch_mode_any<0>(c, la, nq, st))) return rc;
 
     EvidenceArgs ea;
     ea.meta = c->d_meta; ea.sample_log_likelihoods = sll; ea.log_likelihoods_no_dla = llno;
@@ -691,8 +845,12 @@ int gpdla_process_qsos_multi_device(gpdla_ctx* c, int64_t Q, int64_t L_max, cons
     prepare_quasars_kernel<<<nq, NTHREADS, 0, st>>>(pa);
     c->launches++;
     CUDA_TRY(cudaGetLastError(), c->err);
-    GPDLA_FOR_RANK(c->k, (build_gram_operand_kernel<K, NSPLIT><<<dim3(npix / KC, nq, NSPLIT), NTHREADS, 0, st>>>(c->d_Mq, c->d_meta, c->d_P, npix)));
-    c->launches++;
+    if (use_i8(c)) {
+      if ((rc = build_i8_operands(c, nq, npix, st))) return rc;
+    } else {
+      GPDLA_FOR_RANK(c->k, (build_gram_operand_kernel<K, NSPLIT><<<dim3(npix / KC, nq, NSPLIT), NTHREADS, 0, st>>>(c->d_Mq, c->d_meta, c->d_P, npix)));
+      c->launches++;
+    }
     fill_i32_kernel<<<(nq + 255) / 256, 256, 0, st>>>(c->d_active, 1, nq);
     c->launches++;
     CUDA_TRY(cudaMemsetAsync(c->d_partners, 0, (size_t)nq * 3 * c->S * sizeof(int32_t), st), c->err);   // :313 zeros
@@ -720,11 +878,11 @@ int gpdla_process_qsos_multi_device(gpdla_ctx* c, int64_t Q, int64_t L_max, cons
     // level 1 (+ null model), absorption rows cached                         ...meanflux.m:342-361
     la.nhi_samples = c->d_nhi; la.sample_log_likelihoods = sll; la.sll_stride = sll_stride;
     la.log_likelihoods_no_dla = out->log_likelihoods_no_dla + q0; la.num_partners = 0;
-    if ((rc = launch_mode<1>(c, la, nq, st))) return rc;
+    if ((rc = launch_mode_any<1>(c, la, nq, st))) return rc;
     // sub-DLA model                                                           ...meanflux.m:365-380
     la.nhi_samples = c->d_lls_nhi; la.sample_log_likelihoods = slls; la.sll_stride = S;
     la.log_likelihoods_no_dla = nullptr;
-    if ((rc = launch_mode<0>(c, la, nq, st))) return rc;
+    if ((rc = launch_mode_any<0>(c, la, nq, st))) return rc;
     ma.level = 0; ma.sll = slls; ma.sll_stride = S; ma.log_likelihoods = out->log_likelihoods_lls + q0;
     multi_level_kernel<<<nq, NTHREADS, 0, st>>>(ma);
     c->launches++;
@@ -732,7 +890,7 @@ int gpdla_process_qsos_multi_device(gpdla_ctx* c, int64_t Q, int64_t L_max, cons
       if (level >= 2) {
         la.nhi_samples = c->d_nhi; la.sample_log_likelihoods = sll + (int64_t)(level - 1) * S;
         la.sll_stride = sll_stride; la.log_likelihoods_no_dla = nullptr; la.num_partners = level - 1;
-        if ((rc = launch_mode<2>(c, la, nq, st))) return rc;
+        if ((rc = launch_mode_any<2>(c, la, nq, st))) return rc;
       }
       ma.level = level; ma.sll = sll + (int64_t)(level - 1) * S; ma.sll_stride = sll_stride;
       ma.log_likelihoods = out->log_likelihoods_dla + q0 * MD;

@@ -1,0 +1,609 @@
+// INT8 tensor-core (tcgen05, TMEM) variant of the fused per-sample log-likelihood kernel: the Gram and the
+// projection of log_mvnpdf_low_rank.m:22-28 leave the FP64 pipe.
+//
+// Exact-product scheme (prototype and error study: tools/ozaki_digits.py).  With a = absorption,
+// d = a^2 omega^2 + v, w = a^2/d, u = a (y - a mu)/d  (process_qsos.m:192-198):
+//   W'' = w cw,  cw_i = CAP (omega2_i + v_i)                      in [0, CAP]     (w is largest at a = 1)
+//   U'' = u cu,  cu_i = CAP / (b_i (|y_i| + |mu_i|)),  b_i = max_{0<=a<=1} a / (a^2 omega2_i + v_i)   in [-CAP, CAP]
+//   P''_ic = m_ip m_iq / cw_i 2^-e_c,   M''_ic = m_ic / cu_i 2^-e_c                  (column exponents, |.| <= CAP)
+// Every factor is rounded to F = 8 L - 1 fractional bits and cut into L signed 8-bit digits; the slice pairs
+// (i, j) with i + j >= L - 1 are contracted by tcgen05.mma kind::i8 into one s32 TMEM accumulator per
+// diagonal i + j (exact: |sum| < 2^27), and the diagonals are recombined in FP64.  L = 6 reproduces the FP64
+// Gram to 4e-15 of its scale (log-likelihoods to 8e-14), L = 5 to 9e-13 (1.4e-11).
+//
+// Schedule: a cluster of 4 CTAs owns 128 samples (MMA M) of one quasar.  Every CTA *produces* the W'' and U''
+// digits of 32 samples per 32-pixel chunk (8 producer warps: Voigt profile, instrument convolution, weights,
+// digits -- the FP64 work that remains) and ships its 32-row block to the peers that contract it with one bulk
+// shared-memory-to-shared-memory copy each (DSMEM, completion on the receiver's mbarrier).  CTAs 0..2
+// contract W'' with a third of the Gram columns each (N = 80), CTA 3 contracts U'' with M'' (N = 32): TMEM
+// holds L diagonals x N columns per CTA.  The P''/M'' digit chunk arrives by 1-D TMA.  After the last chunk
+// the accumulators are recombined, sent to the CTA that produced the sample (DSMEM stores) and factorised
+// there (factor_staged, the same Cholesky as the FP64 kernels).
+#pragma once
+#include "gpdla_kernels.cuh"
+
+namespace gpdla {
+namespace i8 {
+
+constexpr int CLUSTER = 4;
+constexpr int TS = 32;              // samples produced (and factorised) per CTA
+constexpr int TM = CLUSTER * TS;    // samples per cluster = MMA M
+constexpr int WCTAS = 3;            // CTAs contracting W''; the last CTA contracts U''
+constexpr int NPROD = 8;            // producer warps
+constexpr int SPB = TS / NPROD;     // samples per producer warp (interleaved in one instruction stream)
+constexpr int NCTRL = 4;            // control / epilogue warps (MMA issue, P loader, row-block sender, spare)
+constexpr int THREADS = 32 * (NCTRL + NPROD);
+constexpr int STAGES = 3;           // A-operand stages
+constexpr double CAP = 0.996;       // |x| <= CAP keeps the top signed digit within [-128, 127]
+constexpr int TMEM_COLS = 512;
+
+template <int K, int L>
+struct Shape {
+  using G = GramShape<K>;
+  static constexpr int WCOLS = (G::NPAIR + WCTAS - 1) / WCTAS;    // useful Gram columns per W CTA (70)
+  static constexpr int NW = (WCOLS + 15) / 16 * 16;               // MMA N of a W CTA (80)
+  static constexpr int NU = (K + 15) / 16 * 16;                   // MMA N of the U CTA (32)
+  static constexpr int NMAX = NW > NU ? NW : NU;
+  static constexpr int F = 8 * L - 1;                             // fractional bits
+  // A tile (128 samples x 32 pixels x L digits), K-major, no swizzle: 8-row x 16-byte core matrices,
+  // 128 B apart along K (LBO), the L digit planes of an 8-row group side by side, groups SBO apart
+  static constexpr int SBO_A = 256 * L;
+  static constexpr int ROWBLOCK = (TS / 8) * SBO_A;               // one CTA's 32 rows, all digit planes: contiguous
+  static constexpr int A_TILE = (TM / 8) * SBO_A;
+  static constexpr int BW_PLANE = NW * KC, BU_PLANE = NU * KC;    // bytes of one digit plane of the B operand
+  static constexpr int B_MAX = L * (BW_PLANE > BU_PLANE ? BW_PLANE : BU_PLANE);
+  static constexpr int CHUNK_BYTES = L * (WCTAS * BW_PLANE + BU_PLANE);   // all four CTAs' B operand, one chunk
+  static constexpr int B_BUF = B_MAX;
+  static constexpr int NCOLTAB = CLUSTER * NMAX;                  // per-quasar column table [rank][NMAX]
+  static constexpr int CSTR = TS + 4;
+  static constexpr int NENT = (K + 1) * (K + 2) / 2;
+  static_assert(L * NW <= TMEM_COLS, "diagonal accumulators must fit in TMEM");
+  static_assert(L >= 2 && L <= 7, "digit count");
+  __host__ __device__ static constexpr int b_offset(int rank) { return rank * L * BW_PLANE; }
+  __host__ __device__ static constexpr int b_bytes(int rank) { return L * (rank < WCTAS ? BW_PLANE : BU_PLANE); }
+  __host__ __device__ static constexpr uint64_t digit_bias() {
+    uint64_t b = 0;
+    for (int i = 0; i < L; ++i) b |= (uint64_t)0x80 << (8 * i);
+    return b;
+  }
+  __host__ __device__ static constexpr double magic() {   // x + magic has ulp 2^-F:  1.5 * 2^(52 - F)
+    double m = 1.5;
+    for (int i = 0; i < 52 - F; ++i) m *= 2.0;
+    return m;
+  }
+  static constexpr size_t OFF_A = 0;
+  static constexpr size_t OFF_SX = OFF_A + (size_t)STAGES * A_TILE;
+  static constexpr size_t OFF_B = OFF_SX + (size_t)STAGES * ROWBLOCK;
+  static constexpr size_t OFF_CS = OFF_B + 2ull * B_BUF;
+  static constexpr size_t OFF_RAW = OFF_CS + (size_t)NENT * CSTR * 8;
+  static constexpr size_t OFF_MISC = OFF_RAW + (size_t)TS * RAWS * 8;
+  __host__ __device__ static constexpr size_t smem_bytes(int num_lines) {
+    return OFF_MISC + (size_t)TS * (num_lines + 4) * 8 + 32 * 8 + 3 * TS * 4 + 64;
+  }
+};
+
+// accumulator column (rank, n) -> augmented-triangle index of the staging area (-1: padding column)
+__constant__ short c_i8_stage[CLUSTER * 128];
+
+struct I8Args {
+  double* pix2;            // [Q x NPIX x 2]  (cw, cu)
+  uint8_t* bop;            // [Q x NPIX/KC x CHUNK_BYTES]  digit planes of P'' (ranks 0..2) and M'' (rank 3)
+  double* colscale;        // [Q x 4 x NMAX]  2^(e_c - 2F + 8(L-1)): accumulator -> Gram entry
+  double* colinv;          // [Q x 4 x NMAX]  2^-e_c
+  int* status;             // != 0: a barrier wait timed out (kernel traps)
+  unsigned long long* phase;   // nullable: [16] summed cycles per phase (GPDLA_I8_PHASES)
+};
+
+// ------------------------------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+// wait with a deadline: a protocol error becomes a trapped kernel (CUDA error), not a hung GPU
+__device__ __forceinline__ void mbar_wait_d(uint64_t* bar, uint32_t parity, int* status, int code,
+                                            unsigned long long* phase = nullptr, unsigned backoff_ns = 0) {
+  const uint32_t a = smem_u32(bar);
+  const long long t0 = phase ? clock64() : 0;
+  for (uint32_t spins = 0;; ++spins) {
+    uint32_t ok;
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+    if (ok) break;
+    if (backoff_ns) __nanosleep(backoff_ns);
+    if (spins > 20000000u) {   // seconds: a protocol error, not a slow peer
+      if (status) atomicExch(status, code + 100 * (int)(cluster_ctarank() + 1));
+      __threadfence_system();
+      asm volatile("trap;");
+    }
+  }
+  if (phase) atomicAdd(&phase[8 + code], (unsigned long long)(clock64() - t0));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) { mbar_expect_tx(bar, bytes); }
+// shared::cta -> peer CTA's shared memory, completion (bytes) on the peer's mbarrier
+__device__ __forceinline__ void dsmem_bulk_copy(uint32_t dst_cluster, uint32_t src_cta, uint32_t bytes, uint32_t bar_cluster) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_cluster),
+               "r"(src_cta), "r"(bytes), "r"(bar_cluster)
+               : "memory");
+}
+__device__ __forceinline__ void st_cluster_f64(uint32_t addr, double v) {
+  asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
+}
+// K-major, no-swizzle shared-memory matrix descriptor (validated by bench_micro/tcgen05_i8.cu)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) |
+         (1ull << 46);
+}
+// kind::i8 instruction descriptor: D = s32, A = B = signed 8-bit, both K-major, N >> 3, M >> 4
+__host__ __device__ constexpr uint32_t make_idesc(int n) {
+  return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+}
+__device__ __forceinline__ void mma_i8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n}\n" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(0u)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mma_commit_multicast(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+
+// ------------------------------------------------------------------------------------------
+// K0c: per-pixel scales (cw, cu) and per-column exponents of the digit operands.  One CTA per quasar.
+template <int K, int L>
+__global__ void __launch_bounds__(NTHREADS) i8_scales_kernel(const QuasarMeta* __restrict__ meta, const double* __restrict__ pix,
+                                                             const double* __restrict__ Mq, I8Args xa, int NPIX) {
+  using Sh = Shape<K, L>;
+  using G = GramShape<K>;
+  const int q = blockIdx.x, tid = threadIdx.x;
+  const double* pq = pix + (int64_t)q * NPIX * 4;
+  double* p2 = xa.pix2 + (int64_t)q * NPIX * 2;
+  for (int i = tid; i < NPIX; i += NTHREADS) {
+    const double y = pq[i * 4 + 0], v = pq[i * 4 + 1], mu = pq[i * 4 + 2], om2 = pq[i * 4 + 3];
+    const double cw = CAP * (om2 + v);
+    // b = max over 0 <= a <= 1 of a / (a^2 om2 + v): at a = sqrt(v / om2) if that is < 1, else at a = 1
+    const double b = (v >= om2) ? 1.0 / (om2 + v) : 0.5 / sqrt(om2 * v);
+    const double yy = fabs(y) + fabs(mu);
+    const double cu = (yy > 0.0 && isfinite(b)) ? CAP / (b * yy) : 0.0;
+    p2[i * 2 + 0] = cw; p2[i * 2 + 1] = cu;
+  }
+  __syncthreads();
+  const int n_u = meta[q].n_u;
+  const double* mq = Mq + (int64_t)q * NPIX * K;
+  for (int idx = tid; idx < Sh::NCOLTAB; idx += NTHREADS) {
+    const int rank = idx / Sh::NMAX, n = idx % Sh::NMAX;
+    int p = -1, qq = 0;
+    if (rank < WCTAS) {
+      const int c = rank * Sh::WCOLS + n;
+      if (n < Sh::WCOLS && c < G::NPAIR) {
+        p = 0;
+        while (p + 1 < K && G::pair_index(p + 1, p + 1) <= c) ++p;
+        qq = p + (c - G::pair_index(p, p));
+      }
+    } else if (n < K) {
+      p = n;
+    }
+    double mx = 0.0;
+    if (p >= 0) {
+      for (int i = 0; i < n_u; ++i) {
+        double x;
+        if (rank < WCTAS) { const double cw = p2[i * 2]; x = cw > 0.0 ? __ddiv_rn(__dmul_rn(mq[i * K + p], mq[i * K + qq]), cw) : 0.0; }
+        else { const double cu = p2[i * 2 + 1]; x = cu > 0.0 ? __ddiv_rn(mq[i * K + p], cu) : 0.0; }
+        mx = fmax(mx, fabs(x));
+      }
+    }
+    int e = 0;
+    if (mx > 0.0 && isfinite(mx)) {
+      int ex;
+      const double m = frexp(mx, &ex);        // mx = m 2^ex, m in [0.5, 1)
+      e = (m <= CAP) ? ex : ex + 1;
+    }
+    xa.colscale[(int64_t)q * Sh::NCOLTAB + idx] = ldexp(1.0, e - 2 * Sh::F + 8 * (L - 1));
+    xa.colinv[(int64_t)q * Sh::NCOLTAB + idx] = ldexp(1.0, -e);
+  }
+}
+
+// K0d: digit planes of P'' and M'' in the tcgen05 K-major core-matrix layout, [Q][chunk][rank][digit][N x 32 B].
+template <int K, int L>
+__global__ void __launch_bounds__(NTHREADS) i8_build_operand_kernel(const QuasarMeta* __restrict__ meta,
+                                                                    const double* __restrict__ Mq, I8Args xa, int NPIX) {
+  using Sh = Shape<K, L>;
+  using G = GramShape<K>;
+  const int q = blockIdx.y, chunk = blockIdx.x;
+  if (chunk >= meta[q].nchunks) return;
+  __shared__ double sM[KC][K + 1];
+  __shared__ double sc[KC][2];
+  const double* src = Mq + ((int64_t)q * NPIX + (int64_t)chunk * KC) * K;
+  for (int t = threadIdx.x; t < KC * K; t += NTHREADS) sM[t / K][t % K] = src[t];
+  for (int t = threadIdx.x; t < KC * 2; t += NTHREADS) sc[t / 2][t % 2] = xa.pix2[((int64_t)q * NPIX + (int64_t)chunk * KC) * 2 + t];
+  __syncthreads();
+  uint8_t* dst = xa.bop + ((int64_t)q * (NPIX / KC) + chunk) * Sh::CHUNK_BYTES;
+  const double* cinv = xa.colinv + (int64_t)q * Sh::NCOLTAB;
+  constexpr int ROWS = WCTAS * Sh::NW + Sh::NU;
+  for (int t = threadIdx.x; t < ROWS * KC; t += NTHREADS) {
+    const int k = t % KC, row = t / KC;
+    const int rank = row < WCTAS * Sh::NW ? row / Sh::NW : WCTAS;
+    const int n = row - rank * Sh::NW;
+    const int N = rank < WCTAS ? Sh::NW : Sh::NU;
+    double x = 0.0;
+    if (rank < WCTAS) {
+      const int c = rank * Sh::WCOLS + n;
+      if (n < Sh::WCOLS && c < G::NPAIR) {
+        int p = 0;
+        while (p + 1 < K && G::pair_index(p + 1, p + 1) <= c) ++p;
+        const int qq = p + (c - G::pair_index(p, p));
+        const double cw = sc[k][0];
+        x = cw > 0.0 ? __ddiv_rn(__dmul_rn(sM[k][p], sM[k][qq]), cw) : 0.0;
+      }
+    } else if (n < K) {
+      const double cu = sc[k][1];
+      x = cu > 0.0 ? __ddiv_rn(sM[k][n], cu) : 0.0;
+    }
+    x = x * cinv[rank * Sh::NMAX + n];                       // exact: power of two
+    const long long X = __double2ll_rn(ldexp(x, Sh::F));     // |X| <= CAP 2^F
+    const uint64_t xb = ((uint64_t)X + Sh::digit_bias()) ^ Sh::digit_bias();
+    uint8_t* d0 = dst + Sh::b_offset(rank) + (n / 8) * 256 + (k / 16) * 128 + (n % 8) * 16 + (k % 16);
+#pragma unroll
+    for (int j = 0; j < L; ++j) d0[(size_t)j * N * KC] = (uint8_t)(xb >> (8 * j));
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K1+K2+K3 fused, INT8 tensor-core Gram.  grid = (4 * ceil((S + 1) / 128), quasars), cluster (4, 1, 1).
+template <int K, int L, int NL, int MODE>
+__global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(THREADS, 1) dla_loglik_i8_kernel(LoglikArgs args, I8Args xa) {
+  using Sh = Shape<K, L>;
+  constexpr int CSTR = Sh::CSTR;
+  const int q = blockIdx.y;
+  const QuasarMeta meta = args.meta[q];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();
+  const long long T0 = clock64();
+  auto phase_add = [&](int idx, long long t) { if (xa.phase && lane == 0) atomicAdd(&xa.phase[idx], (unsigned long long)(t - T0)); };
+  const int64_t s0 = (int64_t)(blockIdx.x / CLUSTER) * TM + (int64_t)rank * TS;   // first sample produced here
+  const int64_t S = args.S;
+
+  if (meta.nchunks == 0 || (args.active != nullptr && args.active[q] == 0)) {     // whole cluster takes this exit
+    for (int i = tid; i < TS; i += THREADS) {
+      const int64_t s = s0 + i;
+      if (s < S) args.sample_log_likelihoods[(int64_t)q * args.sll_stride + s] = NAN;
+      else if (s == S && args.log_likelihoods_no_dla) args.log_likelihoods_no_dla[q] = NAN;
+    }
+    return;
+  }
+
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  uint8_t* At = smem_raw + Sh::OFF_A;                                      // [STAGES][A_TILE]   MMA A operand
+  uint8_t* Sx = smem_raw + Sh::OFF_SX;                                     // [STAGES][ROWBLOCK] rows of the other kind
+  uint8_t* Bt = smem_raw + Sh::OFF_B;                                      // [2][B_BUF]
+  double* Cs = reinterpret_cast<double*>(smem_raw + Sh::OFF_CS);           // [NENT][CSTR] epilogue staging
+  double* rawbuf = reinterpret_cast<double*>(smem_raw + Sh::OFF_RAW);      // [TS][RAWS]
+  double* s_nhi = reinterpret_cast<double*>(smem_raw + Sh::OFF_MISC);      // [TS]
+  double* s_q = s_nhi + TS;                                                // [TS]  sum r^2/d
+  double* s_ld = s_q + TS;                                                 // [TS]  sum log d
+  double* s_mult = s_ld + TS;                                              // [num_lines][TS]
+  const int num_lines = (NL > 0) ? NL : args.num_lines;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_mult + (size_t)TS * num_lines + TS);
+  uint64_t* bar_full = bars;                    // [STAGES] A tile complete (own rows + 3 remote row blocks)
+  uint64_t* bar_empty = bar_full + STAGES;      // [STAGES] all four CTAs' MMAs have consumed the stage
+  uint64_t* bar_rows = bar_empty + STAGES;      // [STAGES] local producers have written their rows
+  uint64_t* bar_pfull = bar_rows + STAGES;      // [2] B chunk landed
+  uint64_t* bar_pempty = bar_pfull + 2;         // [2] B chunk consumed
+  uint64_t* bar_acc = bar_pempty + 2;           // accumulators final
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 24);
+  int* s_part = reinterpret_cast<int*>(bars + 32);                          // [3][TS] partner samples (MODE 2)
+
+  for (int i = tid; i < TS; i += THREADS) {                                 // per-sample parameters
+    const int64_t s = s0 + i;
+    const bool is_null = s >= S;
+    const double z = is_null ? 0.0
+                             : __dadd_rn(meta.min_z_dla, __dmul_rn(meta.max_z_dla - meta.min_z_dla, args.offset_samples[s]));
+    s_nhi[i] = is_null ? -1.0 : args.nhi_samples[s];     // negative marks the null-model slot
+    s_ld[i] = 0.0;
+    for (int j = 0; j < num_lines; ++j) s_mult[j * TS + i] = line_multiplier(j, z);
+    if (MODE == 2) {
+      for (int j = 0; j < args.num_partners; ++j)
+        s_part[j * TS + i] = is_null ? 0 : args.partners[((int64_t)q * 3 + j) * S + s];
+    }
+  }
+  if (tid == 0) {
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], CLUSTER); mbar_init(&bar_rows[i], NPROD); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&bar_pfull[i], 1); mbar_init(&bar_pempty[i], 1); }
+    mbar_init(bar_acc, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "n"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;");
+  const uint32_t tmem_base = *s_tmem;
+  cluster_sync_all();                  // every CTA's barriers are initialised before any remote traffic
+  if (warp == 0) phase_add(1, clock64());   // setup done
+
+  const int N = rank < WCTAS ? Sh::NW : Sh::NU;
+  const uint32_t b_bytes = (uint32_t)Sh::b_bytes(rank);
+  const uint8_t* bsrc = xa.bop + (int64_t)q * (args.NPIX / KC) * Sh::CHUNK_BYTES + Sh::b_offset(rank);
+  const int nchunks = meta.nchunks;
+
+  if (warp >= NCTRL) {
+    // =========================================================================== PRODUCER
+    // lane = pixel; the warp's 4 samples are interleaved in one instruction stream (12 dependency chains)
+    const int pr = warp - NCTRL;
+    const int row0 = pr * SPB;
+    const double* lam = args.lam_pad + (int64_t)q * (args.NPIX + 8);
+    const double* pix = args.pix + (int64_t)q * args.NPIX * 4;
+    const double* pix2 = xa.pix2 + (int64_t)q * args.NPIX * 2;
+    double* const cache_q = (MODE != 0) ? args.acache + (int64_t)q * S * args.NPIX : nullptr;
+    // digit destinations: the kind this CTA contracts goes straight into its A tile, the other into Sx
+    const uint32_t own_block = rank * Sh::ROWBLOCK;
+    uint8_t* const wdst0 = (rank < WCTAS) ? At + own_block : Sx;
+    uint8_t* const udst0 = (rank < WCTAS) ? Sx : At + own_block;
+    const uint32_t wstride = (rank < WCTAS) ? Sh::A_TILE : Sh::ROWBLOCK;   // bytes between stages
+    const uint32_t ustride = (rank < WCTAS) ? Sh::ROWBLOCK : Sh::A_TILE;
+    const uint32_t rowoff = (row0 / 8) * Sh::SBO_A + (row0 % 8) * 16 + (lane / 16) * 128 + (lane % 16);
+
+    auto eval_raw = [&](double lambda, double (&e)[SPB]) {        // voigt.c:282-292, 4 samples at one wavelength
+      const double* mymult = s_mult + row0;
+      const double* mynhi = s_nhi + row0;
+      double tau[SPB];
+      if (NL == 3) {
+        unsigned coremask = 0;
+#pragma unroll
+        for (int ss = 0; ss < SPB; ++ss) {
+          bool core;
+          tau[ss] = tau_sum_3_wing(lambda, mymult[ss], mymult[TS + ss], mymult[2 * TS + ss], core);
+          coremask |= core ? (1u << ss) : 0u;
+        }
+        if (coremask) {
+#pragma unroll
+          for (int ss = 0; ss < SPB; ++ss)
+            if (coremask & (1u << ss)) tau[ss] = tau_sum_3_exact(lambda, mymult[ss], mymult[TS + ss], mymult[2 * TS + ss]);
+        }
+      } else {
+#pragma unroll
+        for (int ss = 0; ss < SPB; ++ss) tau[ss] = tau_sum_generic(lambda, mymult + ss, TS, num_lines);
+      }
+#pragma unroll
+      for (int ss = 0; ss < SPB; ++ss) e[ss] = -mynhi[ss] * tau[ss];
+#pragma unroll
+      for (int ss = 0; ss < SPB; ++ss) e[ss] = exp_nonpos(e[ss]);                  // voigt.c:291
+    };
+    double* myraw = rawbuf + row0 * RAWS;
+    if (MODE != 2) {   // leading pad pixels p = 0..5
+      double e[SPB];
+      eval_raw(lam[lane < 6 ? lane : 5], e);
+      if (lane < 6) {
+#pragma unroll
+        for (int ss = 0; ss < SPB; ++ss) myraw[ss * RAWS + lane] = e[ss];
+      }
+    }
+    double qacc[SPB], ldm[SPB];
+    int lde[SPB];
+#pragma unroll
+    for (int ss = 0; ss < SPB; ++ss) { qacc[ss] = 0.0; ldm[ss] = 1.0; lde[ss] = 0; }
+
+    constexpr uint64_t BIAS = Sh::digit_bias();
+    const double MAGIC = Sh::magic();
+    const uint64_t KADD = BIAS - (uint64_t)__double_as_longlong(MAGIC);
+
+    // pixel data of the next chunk is fetched one chunk ahead (global/L2 latency off the critical path)
+    double lambda_n = lam[6 + lane];
+    double2 p01n = *reinterpret_cast<const double2*>(pix + (int64_t)lane * 4);
+    double2 p23n = *reinterpret_cast<const double2*>(pix + (int64_t)lane * 4 + 2);
+    double2 p45n = *reinterpret_cast<const double2*>(pix2 + (int64_t)lane * 2);
+    for (int c = 0; c < nchunks; ++c) {
+      const int stage = c % STAGES;
+      const int i = c * KC + lane;
+      const double lambda = lambda_n;
+      const double y = p01n.x, v = p01n.y, mu = p23n.x, om2 = p23n.y, cw = p45n.x, cu = p45n.y;
+      if (c + 1 < nchunks) {
+        lambda_n = lam[i + KC + 6];
+        p01n = *reinterpret_cast<const double2*>(pix + (int64_t)(i + KC) * 4);
+        p23n = *reinterpret_cast<const double2*>(pix + (int64_t)(i + KC) * 4 + 2);
+        p45n = *reinterpret_cast<const double2*>(pix2 + (int64_t)(i + KC) * 2);
+      }
+      double a[SPB];
+      if (MODE != 2) {
+        // ---- raw profile for the KC new padded pixels, then the instrument convolution (voigt.c:297-299)
+        double e[SPB];
+        eval_raw(lambda, e);
+#pragma unroll
+        for (int ss = 0; ss < SPB; ++ss) myraw[ss * RAWS + 6 + lane] = e[ss];
+        __syncwarp();
+        double carry[SPB];
+#pragma unroll
+        for (int ss = 0; ss < SPB; ++ss) {
+          const double* rb = myraw + ss * RAWS;
+          double acc_a = 0.0;
+#pragma unroll
+          for (int t = 0; t < 7; ++t) acc_a = fma(rb[lane + t], c_lines.ip[t], acc_a);
+          carry[ss] = rb[KC + (lane < 6 ? lane : 0)];
+          a[ss] = (__double2hiint(s_nhi[row0 + ss]) < 0) ? 1.0 : acc_a;   // null model (N marked negative)
+        }
+        __syncwarp();
+        if (lane < 6) {
+#pragma unroll
+          for (int ss = 0; ss < SPB; ++ss) myraw[ss * RAWS + lane] = carry[ss];   // last 6 pixels -> front of the row
+        }
+        if (MODE == 1) {   // keep the level-1 absorption rows for the higher multi-DLA levels
+#pragma unroll
+          for (int ss = 0; ss < SPB; ++ss) {
+            const int64_t smp = s0 + row0 + ss;
+            if (smp < S) cache_q[smp * args.NPIX + i] = a[ss];
+          }
+        }
+      } else {
+        // absorption = voigt(sample) .* voigt(partner 1) .* ...   (...meanflux.m:342-351), from the cache
+#pragma unroll
+        for (int ss = 0; ss < SPB; ++ss) {
+          const int64_t smp = min(s0 + row0 + ss, S - 1);
+          a[ss] = cache_q[smp * args.NPIX + i];
+        }
+        for (int j = 0; j < args.num_partners; ++j) {
+          double bb[SPB];
+#pragma unroll
+          for (int ss = 0; ss < SPB; ++ss) bb[ss] = cache_q[(int64_t)s_part[j * TS + row0 + ss] * args.NPIX + i];
+#pragma unroll
+          for (int ss = 0; ss < SPB; ++ss) a[ss] = a[ss] * bb[ss];
+        }
+      }
+      // ---- weights -> fixed point -> signed 8-bit digits
+      uint64_t xw[SPB], xu[SPB];
+#pragma unroll
+      for (int ss = 0; ss < SPB; ++ss) {
+        const double a2 = a[ss] * a[ss];
+        const double d = fma(a2, om2, v);                // dla_omega2 + noise variance  (process_qsos.m:194,198)
+        const double rd = fast_rcp(d);
+        const double r = fma(-a[ss], mu, y);             // y - dla_mu
+        const double t1 = r * rd;
+        const double wn = (a2 * rd) * cw;                // W'' in [0, CAP]
+        const double un = (a[ss] * t1) * cu;             // U'' in [-CAP, CAP]
+        xw[ss] = ((uint64_t)__double_as_longlong(__dadd_rn(wn, MAGIC)) + KADD) ^ BIAS;
+        xu[ss] = ((uint64_t)__double_as_longlong(__dadd_rn(un, MAGIC)) + KADD) ^ BIAS;
+        qacc[ss] = fma(r, t1, qacc[ss]);
+        ldm[ss] *= d;
+      }
+      // the stage is free once all four CTAs' MMAs have consumed its previous contents
+      mbar_wait_d(&bar_empty[stage], ((c / STAGES) & 1) ^ 1, xa.status, 1, xa.phase);
+      uint8_t* dW = wdst0 + stage * wstride + rowoff;
+      uint8_t* dU = udst0 + stage * ustride + rowoff;
+#pragma unroll
+      for (int ss = 0; ss < SPB; ++ss) {
+#pragma unroll
+        for (int j = 0; j < L; ++j) {
+          dW[ss * 16 + j * 256] = (uint8_t)(xw[ss] >> (8 * j));
+          dU[ss * 16 + j * 256] = (uint8_t)(xu[ss] >> (8 * j));
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic stores -> visible to the async proxy
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_rows[stage]);
+      if ((c & 7) == 7) {   // keep the running products of d in range: move their exponents to integers
+#pragma unroll
+        for (int ss = 0; ss < SPB; ++ss) {
+          const int hi = __double2hiint(ldm[ss]);
+          const int e2 = ((hi >> 20) & 0x7ff) - 1023;
+          lde[ss] += e2;
+          ldm[ss] = __hiloint2double(hi - (e2 << 20), __double2loint(ldm[ss]));
+        }
+      }
+    }
+    if (pr == 0) phase_add(2, clock64());   // producer main loop done
+#pragma unroll
+    for (int ss = 0; ss < SPB; ++ss) {   // per-sample scalars: sum r^2/d and sum log d
+      const double qs = warp_sum(qacc[ss]);
+      const double ld = warp_sum(log(ldm[ss]) + (double)lde[ss] * 0.693147180559945309417);
+      if (lane == 0) { s_q[row0 + ss] = qs; s_ld[row0 + ss] = ld; }
+    }
+  } else {
+    // =========================================================================== CONTROL WARPS
+    if (warp == 0 && lane == 0) {
+      // ---- MMA issuer: for every chunk, the L (L + 1) / 2 slice-pair products, one accumulator per diagonal
+      const uint32_t idesc = make_idesc(N);
+      for (int c = 0; c < nchunks; ++c) {
+        const int stage = c % STAGES, buf = c & 1;
+        mbar_wait_d(&bar_full[stage], (c / STAGES) & 1, xa.status, 2, xa.phase, 100);
+        mbar_wait_d(&bar_pfull[buf], (c >> 1) & 1, xa.status, 3, xa.phase);
+        asm volatile("tcgen05.fence::after_thread_sync;");
+        const uint32_t a0 = smem_u32(At + stage * Sh::A_TILE);
+        const uint32_t b0 = smem_u32(Bt + buf * Sh::B_BUF);
+#pragma unroll
+        for (int t = 0; t < L; ++t) {            // diagonal i + j = t + L - 1
+#pragma unroll
+          for (int i = t; i < L; ++i) {
+            const int j = t + L - 1 - i;
+            const uint64_t da = make_desc(a0 + i * 256, 128, Sh::SBO_A);
+            const uint64_t db = make_desc(b0 + j * N * KC, 128, 256);
+            mma_i8(tmem_base + (uint32_t)(t * N), da, db, idesc, (c > 0 || i > t) ? 1u : 0u);
+          }
+        }
+        mma_commit_multicast(&bar_empty[stage], (uint16_t)((1u << CLUSTER) - 1));   // frees the stage in all CTAs
+        mma_commit(&bar_pempty[buf]);
+      }
+      mma_commit(bar_acc);
+    } else if (warp == 1 && lane == 0) {
+      // ---- B-operand loader (1-D TMA bulk copies, double buffer)
+      for (int c = 0; c < nchunks; ++c) {
+        const int buf = c & 1;
+        if (c >= 2) mbar_wait_d(&bar_pempty[buf], ((c >> 1) - 1) & 1, xa.status, 4, xa.phase, 100);
+        mbar_expect_tx(&bar_pfull[buf], b_bytes);
+        tma_load_1d(Bt + buf * Sh::B_BUF, bsrc + (int64_t)c * Sh::CHUNK_BYTES, b_bytes, &bar_pfull[buf]);
+      }
+    } else if (warp == 2 && lane == 0) {
+      // ---- row-block sender: this CTA's 32 rows of W'' / U'' digits to the CTAs that contract them
+      for (int c = 0; c < nchunks; ++c) {
+        const int stage = c % STAGES;
+        mbar_wait_d(&bar_rows[stage], (c / STAGES) & 1, xa.status, 5, xa.phase, 100);
+        const uint32_t dst_off = smem_u32(At + stage * Sh::A_TILE) + rank * Sh::ROWBLOCK;   // same offset in every CTA
+        const uint32_t own_rows = dst_off;
+        const uint32_t other_rows = smem_u32(Sx + stage * Sh::ROWBLOCK);
+        const uint32_t fullbar = smem_u32(&bar_full[stage]);
+        for (uint32_t peer = 0; peer < (uint32_t)CLUSTER; ++peer) {
+          if (peer == rank) continue;
+          // W CTA -> W CTA: own rows; W CTA -> U CTA and U CTA -> W CTA: the rows kept in Sx
+          const uint32_t src = (rank < WCTAS && peer < WCTAS) ? own_rows : other_rows;
+          dsmem_bulk_copy(mapa(dst_off, peer), src, Sh::ROWBLOCK, mapa(fullbar, peer));
+        }
+        mbar_arrive_expect_tx(&bar_full[stage], (CLUSTER - 1) * Sh::ROWBLOCK);   // own rows are in place; 3 blocks inbound
+      }
+    }
+    __syncwarp();
+    // ---- epilogue part 1: recombine the diagonals, send every sample's entries to the CTA that produced it
+    if (lane == 0) mbar_wait_d(bar_acc, 0, xa.status, 6, xa.phase);
+    __syncwarp();
+    if (warp == 0) phase_add(3, clock64());   // accumulators final
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const double* cs = xa.colscale + (int64_t)q * Sh::NCOLTAB + rank * Sh::NMAX;
+    const uint32_t cs_remote = mapa(smem_u32(Cs), (uint32_t)warp) + (uint32_t)lane * 8;   // rows 32 warp.. belong to CTA `warp`
+    const uint32_t taddr0 = tmem_base + ((uint32_t)(warp * 32) << 16);
+    for (int c0 = 0; c0 < N; c0 += 8) {
+      uint32_t v[L][8];
+#pragma unroll
+      for (int t = 0; t < L; ++t) {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(v[t][0]), "=r"(v[t][1]), "=r"(v[t][2]), "=r"(v[t][3]), "=r"(v[t][4]), "=r"(v[t][5]), "=r"(v[t][6]),
+                       "=r"(v[t][7])
+                     : "r"(taddr0 + (uint32_t)(t * N + c0)));
+      }
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) {
+        const int idx = c_i8_stage[rank * 128 + c0 + jj];
+        if (idx >= 0) {
+          double acc = (double)(int32_t)v[L - 1][jj];
+#pragma unroll
+          for (int t = L - 2; t >= 0; --t) acc = fma(acc, 256.0, (double)(int32_t)v[t][jj]);
+          st_cluster_f64(cs_remote + (uint32_t)(idx * CSTR * 8), acc * cs[c0 + jj]);
+        }
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    if (warp == 0) phase_add(4, clock64());   // recombination done
+  }
+  cluster_sync_all();     // all Gram entries delivered; s_q, s_ld final; no remote access to this CTA after this
+  if (warp == 0) phase_add(5, clock64());     // cluster barrier passed
+  if (warp >= NCTRL) return;
+  asm volatile("tcgen05.fence::after_thread_sync;");
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
+  // ---- epilogue part 2 (K3): warp w factorises samples 8w .. 8w+7 of this CTA
+  factor_staged<K, CSTR>(Cs, s_q, s_ld, warp * 8, lane, meta, args, q, s0);
+  if (warp == 0) { phase_add(6, clock64()); if (xa.phase && lane == 0) atomicAdd(&xa.phase[7], 1ull); }
+}
+
+}  // namespace i8
+}  // namespace gpdla

@@ -469,6 +469,10 @@ __device__ __forceinline__ void dmma_k4_step(double (&acc)[NT][2], double aw, do
   }
 }
 
+template <int K, int CSTR>
+__device__ __forceinline__ void factor_staged(double* Cs, const double* s_q, const double* s_ld, int row0, int lane,
+                                              const QuasarMeta& meta, const LoglikArgs& args, int q, int64_t s0);
+
 // Epilogue shared by the fused kernels: stage one warp's 8 x NCOL accumulator tile through shared memory as
 // an augmented upper triangle and factorise it (K3).  `row0` = first sample row of this warp inside the CTA.
 template <int K, int NT, int CSTR>
@@ -485,10 +489,17 @@ __device__ __forceinline__ void stage_and_factor(double (&acc)[NT][2], double* C
     if (i1 >= 0) Cs[i1 * CSTR + row0 + gid] = acc[ni][1];
   }
   __syncwarp();
+  factor_staged<K, CSTR>(Cs, s_q, s_ld, row0, lane, meta, args, q, s0);
+}
 
-  // ---- K3: Cholesky of B = I + C (upper, R'R = B) with the projected vector g as column K (forward
-  // substitution for free), log-det, quadratic form.  Four lanes per sample; for row p the columns
-  // q = p+1 .. K are dealt round-robin to the quad.  Fully unrolled: every index is an immediate.
+// K3: Cholesky of B = I + C (upper, R'R = B) from the staged augmented triangle, with the projected vector
+// g as column K (forward substitution for free), log-det, quadratic form.  One warp factorises the 8 samples
+// row0..row0+7: four lanes per sample; for row p the columns q = p+1 .. K are dealt round-robin to the quad.
+// Fully unrolled: every index is an immediate.
+template <int K, int CSTR>
+__device__ __forceinline__ void factor_staged(double* Cs, const double* s_q, const double* s_ld, int row0, int lane,
+                                              const QuasarMeta& meta, const LoglikArgs& args, int q, int64_t s0) {
+  const int64_t S = args.S;
   {
     const int sl = row0 + (lane >> 2);          // sample handled by this lane quad
     const int l4 = lane & 3;

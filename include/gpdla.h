@@ -53,6 +53,13 @@ typedef struct {
   double pixel_spacing;         /* :60  1e-4 dex */
   int32_t num_lines;            /* :63  3 */
   int32_t batch_quasars;        /* quasars processed per launch group (workspace size); 0 = default */
+  int32_t gram_digits;          /* arithmetic of the Gram/projection contraction (log_mvnpdf_low_rank.m:22-28):
+                                 *  0 = default: exact-product INT8 tensor-core path with 6 signed 8-bit digits per
+                                 *      factor (47 fractional bits; k = 20 only -- other ranks use FP64 DMMA);
+                                 *      the environment variables GPDLA_GRAM=f64 / GPDLA_I8_DIGITS=5 change the default
+                                 * -1 = FP64 DMMA tensor cores
+                                 *  5, 6 = INT8 path with that many digits (5: 39 fractional bits, ~1e-11 relative) */
+  int32_t reserved;
 } gpdla_params;
 
 /* process_qsos.m:74-82,236-244 result variables; each array has Q entries unless noted.

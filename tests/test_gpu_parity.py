@@ -193,7 +193,8 @@ def test_batching_and_device_entry_agree_with_host_entry(api, synthetic_inputs):
     dev = proc.process_device(t["wavelengths"], t["flux"], t["noise_variance"], t["pixel_mask"], t["lengths"],
                               t["z_qsos"], return_sample_log_likelihoods=True)
     torch.cuda.synchronize()
-    assert proc.launch_count - n0 == 4 * 3            # 4 kernels per batch, 3 batches
+    # kernels per batch: prepare, [scales + digit operands | FP64 Gram operand], fused log-likelihood, evidence
+    assert proc.launch_count - n0 in (5 * 3, 4 * 3)   # 3 batches; 5 on the INT8 Gram path, 4 on the FP64 one
     for k in one:
         assert np.array_equal(one[k], dev[k].cpu().numpy(), equal_nan=True), k
 
@@ -305,6 +306,36 @@ def test_fuzz_extreme_inputs(api, synthetic_inputs):
     ok = ~np.isnan(ref["log_likelihoods_dla"])
     tie_free = np.array([np.sum(b[q] >= np.nanmax(b[q]) * (1 + 1e-12 * np.sign(-np.nanmax(b[q])))) == 1 if ok[q] else False for q in range(16)])
     assert np.array_equal(res["map_inds"][tie_free], ref["map_inds"][tie_free])
+
+
+def test_gram_paths_agree(api, synthetic_inputs):
+    """The exact-product INT8 tensor-core Gram (6 and 5 digits) against the FP64 DMMA Gram and the oracle at full
+    sample count: 6 digits are FP64-equivalent, 5 digits stay 100x inside the north-star tolerance (1e-8)."""
+    from gp_dla_detection_b200 import synthetic as syn
+    from oracle import process_qsos_oracle as O
+    si = synthetic_inputs
+    sp = syn.make_spectra(si["model"], 3, seed=5, dla_fraction=0.67)
+    res = {d: api.process_qsos(si["model"], si["samples"], sp, si["prior"], gram_digits=d) for d in (-1, 6, 5)}
+    ref = O.process_qsos(si["model"], si["samples"], sp, si["prior"], engine="c")
+    b = ref["sample_log_likelihoods_dla"]
+    for d, tol in ((-1, 1e-11), (6, 1e-11), (5, 1e-9)):
+        a = res[d]["sample_log_likelihoods_dla"]
+        assert np.max(np.abs(a - b) / np.abs(b)) < tol, (d, np.max(np.abs(a - b) / np.abs(b)))
+        assert np.allclose(res[d]["log_likelihoods_no_dla"], ref["log_likelihoods_no_dla"], rtol=tol, atol=0)
+        assert np.array_equal(res[d]["map_inds"], ref["map_inds"])
+        assert np.max(np.abs(res[d]["p_dlas"] - ref["p_dlas"])) < P_ATOL
+    a6, af = res[6]["sample_log_likelihoods_dla"], res[-1]["sample_log_likelihoods_dla"]
+    assert np.max(np.abs(a6 - af) / np.abs(af)) < 2e-12        # 47-bit digits vs FP64 accumulation
+    # ragged / masked / short spectra through both paths give the same NaN pattern and values
+    sp2 = syn.make_spectra(si["model"], 5, seed=9, dla_fraction=0.5)
+    sp2["all_pixel_mask"][1][:] = True
+    sp2["all_pixel_mask"][2][::2] = True
+    sub = {k: v[::40] for k, v in si["samples"].items()}
+    r6 = api.process_qsos(si["model"], sub, sp2, si["prior"], gram_digits=6)
+    rf = api.process_qsos(si["model"], sub, sp2, si["prior"], gram_digits=-1)
+    assert np.array_equal(np.isnan(r6["sample_log_likelihoods_dla"]), np.isnan(rf["sample_log_likelihoods_dla"]))
+    assert np.allclose(r6["sample_log_likelihoods_dla"], rf["sample_log_likelihoods_dla"], rtol=1e-11, atol=0, equal_nan=True)
+    assert np.allclose(r6["p_dlas"], rf["p_dlas"], rtol=0, atol=1e-9, equal_nan=True)
 
 
 def test_state_errors(api, synthetic_inputs):

@@ -193,3 +193,15 @@ def test_multi_oracle_engines_agree(synthetic_inputs):
     frac = np.count_nonzero(si["prior"]["dla_ind"][si["prior"]["z_qsos"] < sp["z_qsos"][0] + O.prior_z_qso_increase]) / \
         np.count_nonzero(si["prior"]["z_qsos"] < sp["z_qsos"][0] + O.prior_z_qso_increase)
     assert abs(lp.sum() - frac) < 1e-4
+
+
+def test_int8_digit_scheme_reproduces_fp64_gram():
+    """The exact-product scheme of the INT8 tensor-core Gram path (signed 8-bit digits, truncated slice pairs, s32
+    accumulators per diagonal) restated in integer NumPy: 6 digits are FP64-equivalent, 5 digits stay far inside
+    the north-star tolerance, on a synthetic quasar and on one with 10 decades of noise variance and outliers;
+    the s32 accumulators cannot overflow."""
+    from oracle.int8_gram_oracle import fuzzed_and_plain
+    plain, fuzz = fuzzed_and_plain(step=250, Ls=(5, 6))
+    for res in (plain, fuzz):
+        assert res[6][0] < 1e-12 and res[5][0] < 1e-10, res
+        assert res[6][1] < 27 and res[5][1] < 27, res

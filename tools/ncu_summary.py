@@ -10,6 +10,9 @@ want = ["Kernel Name", "Grid Size", "Block Size", "gpu__time_duration.sum", "dra
         "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
         "sm__pipe_shared_cycles_active.avg.pct_of_peak_sustained_active",
         "sm__inst_executed_pipe_tensor_subpipe_dmma.avg.pct_of_peak_sustained_active",
+        "sm__pipe_tensor_subpipe_imma_cycles_active_realtime.avg", "sm__cycles_active.avg",
+        "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed",
+        "sm__pipe_fp64_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed", "launch__cluster_dim_x",
         "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
         "launch__registers_per_thread", "launch__shared_mem_per_block_dynamic",
         "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
@@ -17,8 +20,9 @@ want = ["Kernel Name", "Grid Size", "Block Size", "gpu__time_duration.sum", "dra
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "smsp__inst_executed.sum"]
 d = {}
 for h, u, v in zip(hdr, units, vals):
-    if h in want:
-        d[h] = {"value": v, "unit": u}
+    for w in want:
+        if h == w or h.endswith("." + w):      # some metrics carry a section prefix (TPC.TriageCompute. ...)
+            d[w] = {"value": v, "unit": u}
 def num(k):
     return float(d[k]["value"].replace(",", ""))
 scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
