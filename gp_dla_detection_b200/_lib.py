@@ -31,6 +31,13 @@ RESULT_F64 = ["min_z_dlas", "max_z_dlas", "log_priors_no_dla", "log_priors_dla",
               "p_no_dlas", "p_dlas", "sample_log_likelihoods_dla", "map_z_dlas", "map_log_nhis"]
 
 
+class GpdlaPreloadParams(ctypes.Structure):
+    _fields_ = [("loading_min_lambda", ctypes.c_double), ("loading_max_lambda", ctypes.c_double),
+                ("normalization_min_lambda", ctypes.c_double), ("normalization_max_lambda", ctypes.c_double),
+                ("min_lambda", ctypes.c_double), ("max_lambda", ctypes.c_double),
+                ("min_num_pixels", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+
+
 class GpdlaResults(ctypes.Structure):
     _fields_ = [(n, ctypes.c_void_p) for n in RESULT_F64] + [("map_inds", ctypes.c_void_p)]
 
@@ -81,6 +88,11 @@ SYMBOLS = {
     "gpdla_voigt_batch_device": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p,
                                                 ctypes.c_int64, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p]),
     "gpdla_line_constants": (None, [c_double_p, c_double_p, c_double_p, c_double_p]),
+    "gpdla_default_preload_parameters": (None, [ctypes.POINTER(GpdlaPreloadParams)]),
+    "gpdla_preload_qsos": (ctypes.c_int, [ctypes.c_int64, ctypes.c_int64] + [ctypes.c_void_p] * 7
+                           + [ctypes.POINTER(GpdlaPreloadParams), ctypes.c_int64] + [ctypes.c_void_p] * 7),
+    "gpdla_preload_qsos_device": (ctypes.c_int, [ctypes.c_int64, ctypes.c_int64] + [ctypes.c_void_p] * 7
+                                  + [ctypes.POINTER(GpdlaPreloadParams), ctypes.c_int64] + [ctypes.c_void_p] * 8),
 }
 
 _lib = None

@@ -237,6 +237,93 @@ def process_qsos_multiple_dlas_meanflux(model: Dict, samples: Dict, spectra: Dic
         proc.close()
 
 
+def _pad_raw(raw: Dict) -> Dict[str, np.ndarray]:
+    F = raw["flux"]
+    Q = len(F)
+    lengths = np.array([len(f) for f in F], dtype=np.int32)
+    L = max(int(lengths.max()) if Q else 1, 1)
+    out = dict(flux=np.zeros((Q, L)), loglam=np.zeros((Q, L)), ivar=np.zeros((Q, L)),
+               and_mask=np.zeros((Q, L), dtype=np.int32), lengths=lengths)
+    for q in range(Q):
+        n = lengths[q]
+        out["flux"][q, :n] = raw["flux"][q]
+        out["loglam"][q, :n] = raw["loglam"][q]
+        out["ivar"][q, :n] = raw["ivar"][q]
+        out["and_mask"][q, :n] = np.asarray(raw["and_mask"][q]).astype(np.int64).astype(np.int32)
+    return out
+
+
+def preload_qsos(raw: Dict, z_qsos, filter_flags=None, params: Parameters = DEFAULT, device: int = 0,
+                 L_out: int = 0) -> Dict:
+    """Spectrum preprocessing on the GPU: read_spec.m:28-38 + preload_qsos.m:18-71.
+
+    ``raw`` holds the four columns of the SDSS speclite coadd table per quasar (ragged lists ``flux``, ``loglam``,
+    ``ivar``, ``and_mask``; read_spec.m:11-26).  Returns the variables preload_qsos.m:73-79 saves --
+    ``all_wavelengths``, ``all_flux``, ``all_noise_variance``, ``all_pixel_mask`` (ragged lists, empty for skipped
+    quasars), ``all_normalizers`` -- and the updated ``filter_flags``; the dict can be passed to ``process_qsos``
+    as ``spectra`` once ``z_qsos`` is added and the flagged quasars are dropped."""
+    import torch
+    lib = _lib.load()
+    pad = _pad_raw(raw)
+    Q, L_in = pad["flux"].shape
+    z = _f64(z_qsos)
+    if L_out <= 0:
+        # the loading window spans log10(1217 / 910) / 1e-4 = 1263 pixels of the BOSS grid, + 2 edge pixels
+        L_out = min(L_in, 1280)
+    p = _lib.GpdlaPreloadParams()
+    lib.gpdla_default_preload_parameters(ctypes.byref(p))
+    p.min_lambda, p.max_lambda = params.min_lambda, params.max_lambda
+    p.loading_min_lambda, p.loading_max_lambda = params.loading_min_lambda, params.loading_max_lambda
+    p.min_num_pixels = params.min_num_pixels
+    flags_in = None if filter_flags is None else np.ascontiguousarray(filter_flags, dtype=np.uint8)
+    out = dict(wavelengths=np.zeros((Q, L_out)), flux=np.zeros((Q, L_out)), noise_variance=np.zeros((Q, L_out)),
+               pixel_mask=np.zeros((Q, L_out), dtype=np.uint8), lengths=np.zeros(Q, dtype=np.int32),
+               normalizers=np.zeros(Q), filter_flags=np.zeros(Q, dtype=np.uint8))
+    vp = lambda a: None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+    with torch.cuda.device(device):
+        _lib.check(lib.gpdla_preload_qsos(Q, L_in, vp(pad["flux"]), vp(pad["loglam"]), vp(pad["ivar"]), vp(pad["and_mask"]),
+                                          vp(pad["lengths"]), vp(z), vp(flags_in), ctypes.byref(p), L_out,
+                                          vp(out["wavelengths"]), vp(out["flux"]), vp(out["noise_variance"]),
+                                          vp(out["pixel_mask"]), vp(out["lengths"]), vp(out["normalizers"]),
+                                          vp(out["filter_flags"])))
+    n = out["lengths"]
+    return dict(all_wavelengths=[out["wavelengths"][q, :n[q]].copy() for q in range(Q)],
+                all_flux=[out["flux"][q, :n[q]].copy() for q in range(Q)],
+                all_noise_variance=[out["noise_variance"][q, :n[q]].copy() for q in range(Q)],
+                all_pixel_mask=[out["pixel_mask"][q, :n[q]].astype(bool) for q in range(Q)],
+                all_normalizers=out["normalizers"], filter_flags=out["filter_flags"])
+
+
+def preload_qsos_device(flux, loglam, ivar, and_mask, lengths, z_qsos, filter_flags=None, params: Parameters = DEFAULT,
+                        L_out: int = 1280, stream: int = 0):
+    """Device-resident form: torch CUDA tensors in ([Q x L_in] planes), padded [Q x L_out] planes + lengths out --
+    exactly the arguments of ``DLAProcessor.process_device`` -- so real spectra never return to the host."""
+    import torch
+    lib = _lib.load()
+    Q, L_in = flux.shape
+    dev = flux.device
+    out = dict(wavelengths=torch.empty((Q, L_out), dtype=torch.float64, device=dev),
+               flux=torch.empty((Q, L_out), dtype=torch.float64, device=dev),
+               noise_variance=torch.empty((Q, L_out), dtype=torch.float64, device=dev),
+               pixel_mask=torch.empty((Q, L_out), dtype=torch.uint8, device=dev),
+               lengths=torch.empty(Q, dtype=torch.int32, device=dev),
+               normalizers=torch.empty(Q, dtype=torch.float64, device=dev),
+               filter_flags=torch.empty(Q, dtype=torch.uint8, device=dev))
+    p = _lib.GpdlaPreloadParams()
+    lib.gpdla_default_preload_parameters(ctypes.byref(p))
+    p.min_lambda, p.max_lambda = params.min_lambda, params.max_lambda
+    p.loading_min_lambda, p.loading_max_lambda = params.loading_min_lambda, params.loading_max_lambda
+    p.min_num_pixels = params.min_num_pixels
+    ptr = lambda t: None if t is None else ctypes.c_void_p(t.data_ptr())
+    with torch.cuda.device(dev):
+        _lib.check(lib.gpdla_preload_qsos_device(Q, L_in, ptr(flux), ptr(loglam), ptr(ivar), ptr(and_mask), ptr(lengths),
+                                                 ptr(z_qsos), ptr(filter_flags), ctypes.byref(p), L_out,
+                                                 ptr(out["wavelengths"]), ptr(out["flux"]), ptr(out["noise_variance"]),
+                                                 ptr(out["pixel_mask"]), ptr(out["lengths"]), ptr(out["normalizers"]),
+                                                 ptr(out["filter_flags"]), ctypes.c_void_p(stream)))
+    return out
+
+
 def matlab_default_rand(n: int) -> np.ndarray:
     """First ``n`` numbers of MATLAB's ``rng('default'); rand`` stream as the library generates them."""
     out = np.empty(int(n))

@@ -14,6 +14,7 @@
 #include "../../include/gpdla.h"
 #include "gpdla_kernels.cuh"
 #include "gpdla_i8_kernels.cuh"
+#include "gpdla_preload.cuh"
 
 using namespace gpdla;
 
@@ -1033,6 +1034,83 @@ int gpdla_voigt(const double* lambdas, int64_t num_points, double z, double N, i
     g_err = cudaGetErrorString(e1 != cudaSuccess ? e1 : e2);
   }
   cudaFree(d);
+  return rc;
+}
+
+void gpdla_default_preload_parameters(gpdla_preload_params* p) {
+  p->loading_min_lambda = 910.0; p->loading_max_lambda = 1217.0;                 // set_parameters.m:21-22
+  p->normalization_min_lambda = 1310.0; p->normalization_max_lambda = 1325.0;    // :29-30
+  p->min_lambda = 911.75; p->max_lambda = 1215.75;                               // :33-34
+  p->min_num_pixels = 200; p->reserved = 0;                                      // :26
+}
+
+int gpdla_preload_qsos_device(int64_t Q, int64_t L_in, const double* flux, const double* loglam, const double* ivar,
+                              const int32_t* and_mask, const int32_t* lengths_in, const double* z_qsos,
+                              const uint8_t* filter_flags_in, const gpdla_preload_params* p, int64_t L_out,
+                              double* wavelengths, double* out_flux, double* noise_variance, uint8_t* pixel_mask,
+                              int32_t* lengths, double* normalizers, uint8_t* filter_flags, void* stream) {
+  if (Q < 0 || L_in < 1 || L_out < 1 || !p ||
+      (Q > 0 && (!flux || !loglam || !ivar || !and_mask || !lengths_in || !z_qsos || !wavelengths || !out_flux ||
+                 !noise_variance || !pixel_mask || !lengths || !normalizers || !filter_flags))) {
+    g_err = "gpdla_preload_qsos_device: invalid arguments";
+    return GPDLA_ERR_INVALID;
+  }
+  if (Q == 0) return GPDLA_OK;
+  PreloadArgs a;
+  a.flux = flux; a.loglam = loglam; a.ivar = ivar; a.and_mask = and_mask; a.lengths_in = lengths_in; a.z_qsos = z_qsos;
+  a.filter_flags_in = filter_flags_in; a.L_in = L_in; a.L_out = L_out;
+  a.loading_min_lambda = p->loading_min_lambda; a.loading_max_lambda = p->loading_max_lambda;
+  a.normalization_min_lambda = p->normalization_min_lambda; a.normalization_max_lambda = p->normalization_max_lambda;
+  a.min_lambda = p->min_lambda; a.max_lambda = p->max_lambda; a.min_num_pixels = p->min_num_pixels;
+  a.wavelengths = wavelengths; a.out_flux = out_flux; a.noise_variance = noise_variance; a.pixel_mask = pixel_mask;
+  a.lengths = lengths; a.normalizers = normalizers; a.filter_flags = filter_flags;
+  preload_qsos_kernel<<<(unsigned)Q, PRE_THREADS, 0, (cudaStream_t)stream>>>(a);
+  CUDA_TRY(cudaGetLastError(), g_err);
+  return GPDLA_OK;
+}
+
+int gpdla_preload_qsos(int64_t Q, int64_t L_in, const double* flux, const double* loglam, const double* ivar,
+                       const int32_t* and_mask, const int32_t* lengths_in, const double* z_qsos,
+                       const uint8_t* filter_flags_in, const gpdla_preload_params* p, int64_t L_out,
+                       double* wavelengths, double* out_flux, double* noise_variance, uint8_t* pixel_mask,
+                       int32_t* lengths, double* normalizers, uint8_t* filter_flags) {
+  if (Q < 0 || L_in < 1 || L_out < 1 || !p) { g_err = "gpdla_preload_qsos: invalid arguments"; return GPDLA_ERR_INVALID; }
+  if (Q == 0) return GPDLA_OK;
+  const size_t QI = (size_t)Q * L_in, QO = (size_t)Q * L_out;
+  const size_t bytes = 3 * QI * 8 + QI * 4 + (size_t)Q * (4 + 8 + 1) + 3 * QO * 8 + QO + (size_t)Q * (4 + 8 + 1) + 256;
+  char* base = nullptr;
+  CUDA_TRY(cudaMalloc(&base, bytes), g_err);
+  char* ptr = base;
+  auto take = [&](size_t n) { char* r = ptr; ptr += (n + 15) / 16 * 16; return r; };
+  double* d_f = (double*)take(QI * 8); double* d_l = (double*)take(QI * 8); double* d_i = (double*)take(QI * 8);
+  double* d_z = (double*)take((size_t)Q * 8);
+  double* d_ow = (double*)take(QO * 8); double* d_of = (double*)take(QO * 8); double* d_ov = (double*)take(QO * 8);
+  double* d_norm = (double*)take((size_t)Q * 8);
+  int32_t* d_am = (int32_t*)take(QI * 4); int32_t* d_len = (int32_t*)take((size_t)Q * 4);
+  int32_t* d_olen = (int32_t*)take((size_t)Q * 4);
+  uint8_t* d_om = (uint8_t*)take(QO); uint8_t* d_fin = (uint8_t*)take((size_t)Q); uint8_t* d_fout = (uint8_t*)take((size_t)Q);
+  int rc = GPDLA_ERR_CUDA;
+  cudaError_t e = cudaSuccess;
+  auto up = [&](void* d, const void* h, size_t n) { if (e == cudaSuccess) e = cudaMemcpy(d, h, n, cudaMemcpyHostToDevice); };
+  auto down = [&](void* h, const void* d, size_t n) { if (e == cudaSuccess) e = cudaMemcpy(h, d, n, cudaMemcpyDeviceToHost); };
+  up(d_f, flux, QI * 8); up(d_l, loglam, QI * 8); up(d_i, ivar, QI * 8); up(d_am, and_mask, QI * 4);
+  up(d_len, lengths_in, (size_t)Q * 4); up(d_z, z_qsos, (size_t)Q * 8);
+  if (filter_flags_in) up(d_fin, filter_flags_in, (size_t)Q);
+  if (e == cudaSuccess) {
+    rc = gpdla_preload_qsos_device(Q, L_in, d_f, d_l, d_i, d_am, d_len, d_z, filter_flags_in ? d_fin : nullptr, p, L_out,
+                                   d_ow, d_of, d_ov, d_om, d_olen, d_norm, d_fout, 0);
+    if (rc == GPDLA_OK) {
+      down(wavelengths, d_ow, QO * 8); down(out_flux, d_of, QO * 8); down(noise_variance, d_ov, QO * 8);
+      down(pixel_mask, d_om, QO); down(lengths, d_olen, (size_t)Q * 4); down(normalizers, d_norm, (size_t)Q * 8);
+      down(filter_flags, d_fout, (size_t)Q);
+      if (e == cudaSuccess) {
+        for (int64_t q = 0; q < Q; ++q)
+          if (lengths[q] < 0) { g_err = "gpdla_preload_qsos: L_out too small (quasar " + std::to_string(q) + " needs " + std::to_string(-lengths[q]) + " pixels)"; rc = GPDLA_ERR_INVALID; break; }
+      }
+    }
+  }
+  if (e != cudaSuccess) { g_err = cudaGetErrorString(e); rc = GPDLA_ERR_CUDA; }
+  cudaFree(base);
   return rc;
 }
 

@@ -166,6 +166,36 @@ int gpdla_process_qsos_multi_device(gpdla_ctx* ctx, int64_t Q, int64_t L_max, co
 /* The uniform random stream the resampling consumes (MATLAB rng('default'); rand): n values. Pure host. */
 void gpdla_matlab_default_rand(double* out, int64_t n);
 
+/* ---- spectrum preprocessing on the device (the step before the path): read_spec.m:28-38 + preload_qsos.m:26-67 ----
+ * Inputs are the four columns of the SDSS speclite coadd table (read_spec.m:11-26: flux, loglam, ivar, and_mask)
+ * padded to [Q x L_in] with lengths_in[q] valid pixels, and the catalogue redshifts.  Outputs are the arrays
+ * all_wavelengths / all_flux / all_noise_variance / all_pixel_mask of preload_qsos.m:64-67 in the padded
+ * [Q x L_out] + lengths form gpdla_process_qsos(_device) reads, all_normalizers (:49) and the updated
+ * filter_flags (:36-39 bit 3 = 4: cannot normalise; :45-49 bit 4 = 8: fewer than min_num_pixels usable pixels;
+ * input flags > 0 skip the quasar, :19-21).  lengths[q] = 0 for skipped quasars, -(needed) if L_out is too small.
+ * Context-free; the _device entry is asynchronous on `stream` and works on the current device. */
+typedef struct {
+  double loading_min_lambda;         /* set_parameters.m:21  910  */
+  double loading_max_lambda;         /* :22  1217 */
+  double normalization_min_lambda;   /* :29  1310 */
+  double normalization_max_lambda;   /* :30  1325 */
+  double min_lambda;                 /* :33  911.75  */
+  double max_lambda;                 /* :34  1215.75 */
+  int32_t min_num_pixels;            /* :26  200 */
+  int32_t reserved;
+} gpdla_preload_params;
+void gpdla_default_preload_parameters(gpdla_preload_params* p);
+int gpdla_preload_qsos(int64_t Q, int64_t L_in, const double* flux, const double* loglam, const double* ivar,
+                       const int32_t* and_mask, const int32_t* lengths_in, const double* z_qsos,
+                       const uint8_t* filter_flags_in, const gpdla_preload_params* p, int64_t L_out,
+                       double* wavelengths, double* out_flux, double* noise_variance, uint8_t* pixel_mask,
+                       int32_t* lengths, double* normalizers, uint8_t* filter_flags);
+int gpdla_preload_qsos_device(int64_t Q, int64_t L_in, const double* flux, const double* loglam, const double* ivar,
+                              const int32_t* and_mask, const int32_t* lengths_in, const double* z_qsos,
+                              const uint8_t* filter_flags_in, const gpdla_preload_params* p, int64_t L_out,
+                              double* wavelengths, double* out_flux, double* noise_variance, uint8_t* pixel_mask,
+                              int32_t* lengths, double* normalizers, uint8_t* filter_flags, void* stream);
+
 /* voigt.c:253-304: profile has num_points - 6 entries.  Host buffers; runs on the current device. */
 int gpdla_voigt(const double* lambdas, int64_t num_points, double z, double N, int32_t num_lines, double* profile);
 /* Batched, device buffers: profile[s, :] = voigt(lambdas, z[s], N[s], num_lines), [S x (num_points-6)] */
