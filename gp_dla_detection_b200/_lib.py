@@ -88,6 +88,8 @@ SYMBOLS = {
     "gpdla_voigt_batch_device": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p,
                                                 ctypes.c_int64, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p]),
     "gpdla_line_constants": (None, [c_double_p, c_double_p, c_double_p, c_double_p]),
+    "gpdla_objective": (ctypes.c_int, [ctypes.c_int64, ctypes.c_int32, ctypes.c_int32] + [ctypes.c_void_p] * 6),
+    "gpdla_objective_device": (ctypes.c_int, [ctypes.c_int64, ctypes.c_int32, ctypes.c_int32] + [ctypes.c_void_p] * 7),
     "gpdla_default_preload_parameters": (None, [ctypes.POINTER(GpdlaPreloadParams)]),
     "gpdla_preload_qsos": (ctypes.c_int, [ctypes.c_int64, ctypes.c_int64] + [ctypes.c_void_p] * 7
                            + [ctypes.POINTER(GpdlaPreloadParams), ctypes.c_int64] + [ctypes.c_void_p] * 7),

@@ -324,6 +324,75 @@ def preload_qsos_device(flux, loglam, ivar, and_mask, lengths, z_qsos, filter_fl
     return out
 
 
+def objective(x, centered_rest_fluxes, lya_1pzs, rest_noise_variances, device: int = 0):
+    """``[f, g] = objective(x, centered_rest_fluxes, lya_1pzs, rest_noise_variances)`` of objective.m:12-73 on the
+    GPU: negative log-likelihood of the training set and its gradient, ``x = [M(:); log_omega; log c_0; log tau_0;
+    log beta]`` (M column-major as in MATLAB).  Host arrays in, ``(float, ndarray)`` out."""
+    import torch
+    lib = _lib.load()
+    y, z1, nv, xx = _f64(centered_rest_fluxes), _f64(lya_1pzs), _f64(rest_noise_variances), _f64(x)
+    N, P = y.shape
+    k = (xx.size - 3) // P - 1                                            # objective.m:17
+    if xx.size != P * (k + 1) + 3 or z1.shape != y.shape or nv.shape != y.shape:
+        raise ValueError("x must have num_pixels * (k + 1) + 3 entries and the three data matrices one shape")
+    f = np.zeros(1); g = np.zeros(xx.size)
+    vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    with torch.cuda.device(device):
+        _lib.check(lib.gpdla_objective(N, P, k, vp(y), vp(z1), vp(nv), vp(xx), vp(f), vp(g)))
+    return float(f[0]), g
+
+
+class TrainingObjective:
+    """The training matrices of learn_qso_model.m:36-75 resident on one GPU; ``ev(x) -> (f, g)`` evaluates
+    objective.m for a parameter vector (what minFunc calls at learn_qso_model.m:97-99), uploading only ``x``."""
+
+    def __init__(self, centered_rest_fluxes, lya_1pzs, rest_noise_variances, k: int, device: int = 0):
+        import torch
+        self._lib = _lib.load()
+        self._torch = torch
+        self.dev = torch.device("cuda", device)
+        self.N, self.P = np.shape(centered_rest_fluxes)
+        self.k = int(k)
+        up = lambda a: torch.from_numpy(_f64(a)).to(self.dev)
+        self.y, self.z1, self.nv = up(centered_rest_fluxes), up(lya_1pzs), up(rest_noise_variances)
+        self.nx = self.P * (self.k + 1) + 3
+        self.x = torch.empty(self.nx, dtype=torch.float64, device=self.dev)
+        self.g = torch.empty(self.nx, dtype=torch.float64, device=self.dev)
+        self.f = torch.empty(1, dtype=torch.float64, device=self.dev)
+
+    def evaluate_device(self, x_dev, stream: int = 0):
+        """x on the device -> (f, g) device tensors (asynchronous)."""
+        ptr = lambda t: ctypes.c_void_p(t.data_ptr())
+        with self._torch.cuda.device(self.dev):
+            _lib.check(self._lib.gpdla_objective_device(self.N, self.P, self.k, ptr(self.y), ptr(self.z1), ptr(self.nv),
+                                                        ptr(x_dev), ptr(self.f), ptr(self.g), ctypes.c_void_p(stream)))
+        return self.f, self.g
+
+    def __call__(self, x):
+        xx = _f64(x)
+        if xx.size != self.nx:
+            raise ValueError("x must have %d entries" % self.nx)
+        self.x.copy_(self._torch.from_numpy(xx))
+        f, g = self.evaluate_device(self.x)
+        return float(f.item()), g.cpu().numpy()
+
+    def close(self):
+        self.y = self.z1 = self.nv = self.x = self.g = self.f = None
+
+
+def learn_qso_model(centered_rest_fluxes, lya_1pzs, rest_noise_variances, initial_x, k: int, max_iter: int = 2000,
+                    device: int = 0):
+    """The optimisation of learn_qso_model.m:97-99 (minFunc L-BFGS there, SciPy's L-BFGS-B here) with the objective and
+    gradient evaluated on the GPU.  Returns ``(x, f, scipy_result)``; M = x[:P k].reshape(k, P).T etc. (:101-110)."""
+    from scipy.optimize import minimize
+    ev = TrainingObjective(centered_rest_fluxes, lya_1pzs, rest_noise_variances, k, device)
+    try:
+        res = minimize(lambda v: ev(v), _f64(initial_x), jac=True, method="L-BFGS-B", options={"maxiter": max_iter})
+    finally:
+        ev.close()
+    return res.x, float(res.fun), res
+
+
 def matlab_default_rand(n: int) -> np.ndarray:
     """First ``n`` numbers of MATLAB's ``rng('default'); rand`` stream as the library generates them."""
     out = np.empty(int(n))

@@ -15,6 +15,7 @@
 #include "gpdla_kernels.cuh"
 #include "gpdla_i8_kernels.cuh"
 #include "gpdla_preload.cuh"
+#include "gpdla_objective.cuh"
 
 using namespace gpdla;
 
@@ -464,6 +465,14 @@ static int launch_mode(gpdla_ctx* c, const LoglikArgs& la, int nq, cudaStream_t 
   if (c->params.num_lines == 3) { GPDLA_FOR_RANK(c->k, (rc = launch_loglik<K, 3, MODE, NSPLIT>(c, la, nq, st))); }
   else { GPDLA_FOR_RANK(c->k, (rc = launch_loglik<K, 0, MODE, NSPLIT>(c, la, nq, st))); }
   return rc;
+}
+
+template <int K>
+static int launch_objective(const ObjectiveArgs& a, cudaStream_t st) {
+  const size_t smem = objective_smem_bytes<K>(a.P);
+  CUDA_TRY(cudaFuncSetAttribute(objective_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), g_err);
+  objective_kernel<K><<<(unsigned)a.N, OBJ_THREADS, smem, st>>>(a);
+  return GPDLA_OK;
 }
 
 template <int MODE>
@@ -1107,6 +1116,59 @@ int gpdla_preload_qsos(int64_t Q, int64_t L_in, const double* flux, const double
         for (int64_t q = 0; q < Q; ++q)
           if (lengths[q] < 0) { g_err = "gpdla_preload_qsos: L_out too small (quasar " + std::to_string(q) + " needs " + std::to_string(-lengths[q]) + " pixels)"; rc = GPDLA_ERR_INVALID; break; }
       }
+    }
+  }
+  if (e != cudaSuccess) { g_err = cudaGetErrorString(e); rc = GPDLA_ERR_CUDA; }
+  cudaFree(base);
+  return rc;
+}
+
+int gpdla_objective_device(int64_t num_quasars, int32_t num_pixels, int32_t k, const double* centered_rest_fluxes,
+                           const double* lya_1pzs, const double* rest_noise_variances, const double* x, double* f,
+                           double* g, void* stream) {
+  if (num_quasars < 0 || num_pixels < 1 || !x || !f || !g ||
+      (num_quasars > 0 && (!centered_rest_fluxes || !lya_1pzs || !rest_noise_variances))) {
+    g_err = "gpdla_objective_device: invalid arguments";
+    return GPDLA_ERR_INVALID;
+  }
+  if (!rank_supported(k)) {
+    g_err = "gpdla_objective_device: rank k=" + std::to_string(k) + " not compiled in (available: 10, 20, 40)";
+    return GPDLA_ERR_UNSUPPORTED;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t nx = (int64_t)num_pixels * (k + 1) + 3;
+  CUDA_TRY(cudaMemsetAsync(f, 0, sizeof(double), st), g_err);
+  CUDA_TRY(cudaMemsetAsync(g, 0, nx * sizeof(double), st), g_err);
+  ObjectiveArgs a;
+  a.y = centered_rest_fluxes; a.lya_1pz = lya_1pzs; a.nv = rest_noise_variances; a.x = x; a.f = f; a.g = g;
+  a.N = num_quasars; a.P = num_pixels;
+  if (num_quasars > 0) {
+    int rc = GPDLA_OK;
+    GPDLA_FOR_RANK(k, (rc = launch_objective<K>(a, st)));
+    if (rc) return rc;
+    CUDA_TRY(cudaGetLastError(), g_err);
+  }
+  objective_prior_kernel<<<1, 1, 0, st>>>(x, g, (int64_t)num_pixels * (k + 1));
+  CUDA_TRY(cudaGetLastError(), g_err);
+  return GPDLA_OK;
+}
+
+int gpdla_objective(int64_t num_quasars, int32_t num_pixels, int32_t k, const double* centered_rest_fluxes,
+                    const double* lya_1pzs, const double* rest_noise_variances, const double* x, double* f, double* g) {
+  if (num_quasars < 0 || num_pixels < 1 || k < 1 || !x || !f || !g) { g_err = "gpdla_objective: invalid arguments"; return GPDLA_ERR_INVALID; }
+  const size_t NP = (size_t)num_quasars * num_pixels, nx = (size_t)num_pixels * (k + 1) + 3;
+  double* base = nullptr;
+  CUDA_TRY(cudaMalloc(&base, (3 * NP + 2 * nx + 2) * sizeof(double)), g_err);
+  double *d_y = base, *d_z = base + NP, *d_v = base + 2 * NP, *d_x = base + 3 * NP, *d_g = d_x + nx, *d_f = d_g + nx;
+  cudaError_t e = cudaSuccess;
+  auto up = [&](void* d, const void* h, size_t n) { if (e == cudaSuccess && n) e = cudaMemcpy(d, h, n, cudaMemcpyHostToDevice); };
+  up(d_y, centered_rest_fluxes, NP * 8); up(d_z, lya_1pzs, NP * 8); up(d_v, rest_noise_variances, NP * 8); up(d_x, x, nx * 8);
+  int rc = GPDLA_ERR_CUDA;
+  if (e == cudaSuccess) {
+    rc = gpdla_objective_device(num_quasars, num_pixels, k, d_y, d_z, d_v, d_x, d_f, d_g, 0);
+    if (rc == GPDLA_OK) {
+      e = cudaMemcpy(f, d_f, 8, cudaMemcpyDeviceToHost);
+      if (e == cudaSuccess) e = cudaMemcpy(g, d_g, nx * 8, cudaMemcpyDeviceToHost);
     }
   }
   if (e != cudaSuccess) { g_err = cudaGetErrorString(e); rc = GPDLA_ERR_CUDA; }

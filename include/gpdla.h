@@ -196,6 +196,19 @@ int gpdla_preload_qsos_device(int64_t Q, int64_t L_in, const double* flux, const
                               double* wavelengths, double* out_flux, double* noise_variance, uint8_t* pixel_mask,
                               int32_t* lengths, double* normalizers, uint8_t* filter_flags, void* stream);
 
+/* ---- GP training objective on the device: objective.m:12-73 + spectrum_loss.m:14-74 ----
+ * f(x) = -sum_i log N(y_i; 0, M M' + diag(sigma_i^2 + omega^2 (c_0 + 1 - exp(-tau_0 (1+z)^beta))^2)) and g = df/dx for
+ *   x = [vec M (column-major num_pixels x k, as MATLAB's M(:)); log omega (num_pixels); log c_0; log tau_0; log beta]
+ * (objective.m:3-6), including the Kim et al. priors on tau_0 and beta (:59-71).  The three data matrices are
+ * centered_rest_fluxes, lya_1pzs, rest_noise_variances of learn_qso_model.m:36-75, [num_quasars x num_pixels]
+ * row-major, NaN in centered_rest_fluxes = pixel not observed (objective.m:42).  g has the layout of x.
+ * Context-free; the _device entry (device pointers for data, x, f, g) is asynchronous on `stream`. */
+int gpdla_objective(int64_t num_quasars, int32_t num_pixels, int32_t k, const double* centered_rest_fluxes,
+                    const double* lya_1pzs, const double* rest_noise_variances, const double* x, double* f, double* g);
+int gpdla_objective_device(int64_t num_quasars, int32_t num_pixels, int32_t k, const double* centered_rest_fluxes,
+                           const double* lya_1pzs, const double* rest_noise_variances, const double* x, double* f,
+                           double* g, void* stream);
+
 /* voigt.c:253-304: profile has num_points - 6 entries.  Host buffers; runs on the current device. */
 int gpdla_voigt(const double* lambdas, int64_t num_points, double z, double N, int32_t num_lines, double* profile);
 /* Batched, device buffers: profile[s, :] = voigt(lambdas, z[s], N[s], num_lines), [S x (num_points-6)] */
