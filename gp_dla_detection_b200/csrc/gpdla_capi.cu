@@ -374,6 +374,8 @@ static i8::I8Args i8_args(gpdla_ctx* c) {
                       h[7], h[0] / h[7], h[1] / h[7], h[2] / h[7], h[3] / h[7], h[4] / h[7], h[5] / h[7], h[6] / h[7]);
     if (h[7]) fprintf(stderr, "[i8 waits, mean cycles per CTA] producers: A-stage empty (per thread) %llu | mma: A full %llu | mma: B full %llu | loader: B empty %llu | sender: rows %llu | epilogue: accumulators %llu\n",
                       h[9] / h[7] / 256, h[10] / h[7], h[11] / h[7], h[12] / h[7], h[13] / h[7], h[14] / h[7] / 4);
+    if (h[7]) fprintf(stderr, "[i8 persistent waits, mean cycles per tile] producer: stage empty (per thread) %llu | mma: A full %llu, B full %llu, TMEM drained %llu | loader %llu | sender %llu | epilogue (per warp): acc final %llu, triangle free %llu, triangle full %llu, scalars %llu\n",
+                      h[9] / h[7] / 256, h[10] / h[7], h[11] / h[7], h[21] / h[7], h[12] / h[7], h[13] / h[7], h[14] / h[7] / 4, h[18] / h[7] / 4, h[19] / h[7] / 4, h[20] / h[7] / 4);
     cudaMemset(d_phase, 0, sizeof h);
     xa.phase = d_phase;
   }
@@ -405,26 +407,65 @@ static int build_i8_operands(gpdla_ctx* c, int nq, int npix, cudaStream_t st) {
   return i8_digits(c) == 5 ? build_i8_operands_L<5>(c, nq, npix, st) : build_i8_operands_L<6>(c, nq, npix, st);
 }
 
+// resident 4-CTA clusters of the persistent kernel on this device (0 = query failed)
+template <class Kern>
+static int max_resident_clusters(Kern kern, size_t smem, int threads) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(i8::CLUSTER * 148, 1, 1); cfg.blockDim = dim3(threads, 1, 1); cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = i8::CLUSTER; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+// GPDLA_I8_PERSISTENT=0 selects the one-tile-per-cluster kernel (development comparison)
+static bool i8_persistent() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("GPDLA_I8_PERSISTENT"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
+
 template <int L, int NL, int MODE>
 static int launch_loglik_i8(gpdla_ctx* c, const LoglikArgs& la, int nq, cudaStream_t st) {
   using Sh = i8::Shape<I8_K, L>;
-  auto kern = i8::dla_loglik_i8_kernel<I8_K, L, NL, MODE>;
-  const size_t smem = Sh::smem_bytes(la.num_lines);
-  static size_t configured[64] = {};
   const int dev = c->device & 63;
-  if (configured[dev] < smem) {
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), c->err);
-    configured[dev] = smem;
-  }
   const unsigned clusters = (unsigned)((la.S + (la.log_likelihoods_no_dla ? 1 : 0) + i8::TM - 1) / i8::TM);
-  dim3 grid(clusters * i8::CLUSTER, (unsigned)nq, 1);
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (c->profiling) {
     CUDA_TRY(cudaEventCreate(&e0), c->err);
     CUDA_TRY(cudaEventCreate(&e1), c->err);
     CUDA_TRY(cudaEventRecord(e0, st), c->err);
   }
-  kern<<<grid, i8::THREADS, smem, st>>>(la, i8_args(c));
+  if (i8_persistent()) {
+    auto kern = i8::dla_loglik_i8p_kernel<I8_K, L, NL, MODE>;
+    const size_t smem = i8::PShape<I8_K, L>::smem_bytes(la.num_lines);
+    static size_t configured[64] = {};
+    static int resident[64] = {};
+    if (configured[dev] < smem) {
+      CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), c->err);
+      configured[dev] = smem;
+      int n = max_resident_clusters(kern, smem, i8::P_THREADS);
+      const char* e = getenv("GPDLA_I8_CLUSTERS");
+      if (e) n = atoi(e);
+      if (getenv("GPDLA_I8_VERBOSE")) fprintf(stderr, "[i8] resident clusters: query %d, using %d\n", max_resident_clusters(kern, smem, i8::P_THREADS), n > 0 ? n : 32);
+      resident[dev] = n > 0 ? n : 32;
+    }
+    const long long tiles = (long long)nq * clusters;
+    const unsigned ncl = (unsigned)std::min<long long>(resident[dev], tiles);
+    kern<<<dim3(ncl * i8::CLUSTER, 1, 1), i8::P_THREADS, smem, st>>>(la, i8_args(c), nq, (int)clusters);
+  } else {
+    auto kern = i8::dla_loglik_i8_kernel<I8_K, L, NL, MODE>;
+    const size_t smem = Sh::smem_bytes(la.num_lines);
+    static size_t configured[64] = {};
+    if (configured[dev] < smem) {
+      CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), c->err);
+      configured[dev] = smem;
+    }
+    kern<<<dim3(clusters * i8::CLUSTER, (unsigned)nq, 1), i8::THREADS, smem, st>>>(la, i8_args(c));
+  }
   c->launches++;
   CUDA_TRY(cudaGetLastError(), c->err);
   if (c->profiling) {

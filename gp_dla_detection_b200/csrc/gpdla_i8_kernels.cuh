@@ -180,35 +180,59 @@ __global__ void __launch_bounds__(NTHREADS) i8_scales_kernel(const QuasarMeta* _
     p2[i * 2 + 0] = cw; p2[i * 2 + 1] = cu;
   }
   __syncthreads();
+  // column maxima of |P''| and |M''| over the pixels, tiled through shared memory (M rows and 1/cw, 1/cu of 32 pixels)
   const int n_u = meta[q].n_u;
   const double* mq = Mq + (int64_t)q * NPIX * K;
-  for (int idx = tid; idx < Sh::NCOLTAB; idx += NTHREADS) {
+  __shared__ double sM[KC][K + 1];
+  __shared__ double sr[KC][2];
+  static_assert(Sh::NCOLTAB <= 2 * NTHREADS, "column table entries per thread");
+  int cp[2] = {-1, -1}, cq[2] = {0, 0}, crank[2] = {0, 0};
+  double mx2[2] = {0.0, 0.0};
+#pragma unroll
+  for (int m = 0; m < 2; ++m) {
+    const int idx = tid + m * NTHREADS;
+    if (idx >= Sh::NCOLTAB) continue;
     const int rank = idx / Sh::NMAX, n = idx % Sh::NMAX;
-    int p = -1, qq = 0;
+    crank[m] = rank;
     if (rank < WCTAS) {
       const int c = rank * Sh::WCOLS + n;
       if (n < Sh::WCOLS && c < G::NPAIR) {
-        p = 0;
+        int p = 0;
         while (p + 1 < K && G::pair_index(p + 1, p + 1) <= c) ++p;
-        qq = p + (c - G::pair_index(p, p));
+        cp[m] = p; cq[m] = p + (c - G::pair_index(p, p));
       }
     } else if (n < K) {
-      p = n;
+      cp[m] = n;
     }
-    double mx = 0.0;
-    if (p >= 0) {
-      for (int i = 0; i < n_u; ++i) {
-        double x;
-        if (rank < WCTAS) { const double cw = p2[i * 2]; x = cw > 0.0 ? __ddiv_rn(__dmul_rn(mq[i * K + p], mq[i * K + qq]), cw) : 0.0; }
-        else { const double cu = p2[i * 2 + 1]; x = cu > 0.0 ? __ddiv_rn(mq[i * K + p], cu) : 0.0; }
-        mx = fmax(mx, fabs(x));
+  }
+  for (int i0 = 0; i0 < n_u; i0 += KC) {
+    for (int t = tid; t < KC * K; t += NTHREADS) sM[t / K][t % K] = mq[(int64_t)i0 * K + t];
+    if (tid < KC * 2) {
+      const double c = p2[(i0 + tid / 2) * 2 + (tid & 1)];
+      sr[tid / 2][tid & 1] = c > 0.0 ? 1.0 / c : 0.0;       // the operand builder multiplies by the same reciprocals
+    }
+    __syncthreads();
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+      if (cp[m] < 0) continue;
+      for (int r = 0; r < KC; ++r) {
+        const double x = (crank[m] < WCTAS) ? __dmul_rn(__dmul_rn(sM[r][cp[m]], sM[r][cq[m]]), sr[r][0])
+                                            : __dmul_rn(sM[r][cp[m]], sr[r][1]);
+        mx2[m] = fmax(mx2[m], fabs(x));
       }
     }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int m = 0; m < 2; ++m) {
+    const int idx = tid + m * NTHREADS;
+    if (idx >= Sh::NCOLTAB) continue;
+    const double mx = mx2[m];
     int e = 0;
     if (mx > 0.0 && isfinite(mx)) {
       int ex;
-      const double m = frexp(mx, &ex);        // mx = m 2^ex, m in [0.5, 1)
-      e = (m <= CAP) ? ex : ex + 1;
+      const double mant = frexp(mx, &ex);     // mx = mant 2^ex, mant in [0.5, 1)
+      e = (mant <= CAP) ? ex : ex + 1;
     }
     xa.colscale[(int64_t)q * Sh::NCOLTAB + idx] = ldexp(1.0, e - 2 * Sh::F + 8 * (L - 1));
     xa.colinv[(int64_t)q * Sh::NCOLTAB + idx] = ldexp(1.0, -e);
@@ -227,7 +251,10 @@ __global__ void __launch_bounds__(NTHREADS) i8_build_operand_kernel(const Quasar
   __shared__ double sc[KC][2];
   const double* src = Mq + ((int64_t)q * NPIX + (int64_t)chunk * KC) * K;
   for (int t = threadIdx.x; t < KC * K; t += NTHREADS) sM[t / K][t % K] = src[t];
-  for (int t = threadIdx.x; t < KC * 2; t += NTHREADS) sc[t / 2][t % 2] = xa.pix2[((int64_t)q * NPIX + (int64_t)chunk * KC) * 2 + t];
+  for (int t = threadIdx.x; t < KC * 2; t += NTHREADS) {   // 1/cw, 1/cu: the same reciprocals as in i8_scales_kernel
+    const double c = xa.pix2[((int64_t)q * NPIX + (int64_t)chunk * KC) * 2 + t];
+    sc[t / 2][t % 2] = c > 0.0 ? 1.0 / c : 0.0;
+  }
   __syncthreads();
   uint8_t* dst = xa.bop + ((int64_t)q * (NPIX / KC) + chunk) * Sh::CHUNK_BYTES;
   const double* cinv = xa.colinv + (int64_t)q * Sh::NCOLTAB;
@@ -244,12 +271,10 @@ __global__ void __launch_bounds__(NTHREADS) i8_build_operand_kernel(const Quasar
         int p = 0;
         while (p + 1 < K && G::pair_index(p + 1, p + 1) <= c) ++p;
         const int qq = p + (c - G::pair_index(p, p));
-        const double cw = sc[k][0];
-        x = cw > 0.0 ? __ddiv_rn(__dmul_rn(sM[k][p], sM[k][qq]), cw) : 0.0;
+        x = __dmul_rn(__dmul_rn(sM[k][p], sM[k][qq]), sc[k][0]);
       }
     } else if (n < K) {
-      const double cu = sc[k][1];
-      x = cu > 0.0 ? __ddiv_rn(sM[k][n], cu) : 0.0;
+      x = __dmul_rn(sM[k][n], sc[k][1]);
     }
     x = x * cinv[rank * Sh::NMAX + n];                       // exact: power of two
     const long long X = __double2ll_rn(ldexp(x, Sh::F));     // |X| <= CAP 2^F
@@ -603,6 +628,448 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(THREADS, 1) dl
   // ---- epilogue part 2 (K3): warp w factorises samples 8w .. 8w+7 of this CTA
   factor_staged<K, CSTR>(Cs, s_q, s_ld, warp * 8, lane, meta, args, q, s0);
   if (warp == 0) { phase_add(6, clock64()); if (xa.phase && lane == 0) atomicAdd(&xa.phase[7], 1ull); }
+}
+
+// ------------------------------------------------------------------------------------------
+// Persistent variant (shipped).  The grid holds as many 4-CTA clusters as the GPU can keep resident; each cluster
+// walks the (quasar, 128-sample tile) list with stride = number of clusters.  A CTA has 16 warps in four
+// warpgroups with their own register budgets (setmaxnreg): control (MMA issuer, B loader, row-block sender; 48
+// registers), two producer warpgroups (168) and an EPILOGUE warpgroup (128) that recombines the TMEM accumulators
+// and runs the Cholesky of tile t while the producers and the tensor pipe are already working on tile t + 1.
+// Hand-overs: accumulators final (tcgen05.commit -> bar_acc), TMEM drained (bar_tfree), staging triangle delivered
+// (remote arrivals on the owner's bar_csfull) and free again (remote arrivals on every writer's bar_csfree[owner]),
+// per-sample scalars (bar_sq, double-buffered).  All main-loop barriers run on a chunk counter that spans tiles.
+constexpr int P_THREADS = 32 * (NCTRL + NPROD + 4);
+constexpr int REG_CTRL = 48, REG_PROD = 168, REG_EPI = 128;
+static_assert(REG_CTRL * 128 + REG_PROD * 256 + REG_EPI * 128 <= 65536, "register budgets exceed the register file");
+
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t remote_bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote_bar) : "memory");
+}
+// wait with cluster-scope acquire (the data was written by other CTAs of the cluster)
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity, int* status, int code,
+                                                  unsigned long long* phase = nullptr) {
+  const uint32_t a = smem_u32(bar);
+  const long long t0 = phase ? clock64() : 0;
+  for (uint32_t spins = 0;; ++spins) {
+    uint32_t ok;
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+    if (ok) break;
+    if (spins > 20000000u) {
+      if (status) atomicExch(status, code + 100 * (int)(cluster_ctarank() + 1));
+      __threadfence_system();
+      asm volatile("trap;");
+    }
+  }
+  if (phase) atomicAdd(&phase[8 + code], (unsigned long long)(clock64() - t0));
+}
+
+template <int K, int L>
+struct PShape {
+  using Sh = Shape<K, L>;
+  static constexpr size_t OFF_MISC = Sh::OFF_MISC;
+  __host__ __device__ static constexpr size_t smem_bytes(int num_lines) {
+    // per-sample arrays: nhi, q[2], ld[2], mult[num_lines + 1]; 64 barriers; partner indices
+    return OFF_MISC + (size_t)TS * (num_lines + 6) * 8 + 64 * 8 + 3 * TS * 4 + 64;
+  }
+};
+
+template <int K, int L, int NL, int MODE>
+__global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(P_THREADS, 1)
+dla_loglik_i8p_kernel(LoglikArgs args, I8Args xa, int num_quasars, int tiles_per_quasar) {
+  using Sh = Shape<K, L>;
+  constexpr int CSTR = Sh::CSTR;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int64_t S = args.S;
+  const int cluster_id = blockIdx.x / CLUSTER, num_clusters = gridDim.x / CLUSTER;
+  const int num_tiles = num_quasars * tiles_per_quasar;
+
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  uint8_t* At = smem_raw + Sh::OFF_A;
+  uint8_t* Sx = smem_raw + Sh::OFF_SX;
+  uint8_t* Bt = smem_raw + Sh::OFF_B;
+  double* Cs = reinterpret_cast<double*>(smem_raw + Sh::OFF_CS);
+  double* rawbuf = reinterpret_cast<double*>(smem_raw + Sh::OFF_RAW);
+  double* s_nhi = reinterpret_cast<double*>(smem_raw + Sh::OFF_MISC);      // [TS]
+  double* s_q = s_nhi + TS;                                                // [2][TS]  sum r^2/d, by tile parity
+  double* s_ld = s_q + 2 * TS;                                             // [2][TS]  sum log d
+  double* s_mult = s_ld + 2 * TS;                                          // [num_lines][TS]
+  const int num_lines = (NL > 0) ? NL : args.num_lines;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_mult + (size_t)TS * num_lines + TS);
+  uint64_t* bar_full = bars;                    // [STAGES]
+  uint64_t* bar_empty = bar_full + STAGES;      // [STAGES]
+  uint64_t* bar_rows = bar_empty + STAGES;      // [STAGES]
+  uint64_t* bar_pfull = bar_rows + STAGES;      // [2]
+  uint64_t* bar_pempty = bar_pfull + 2;         // [2]
+  uint64_t* bar_acc = bar_pempty + 2;           // accumulators of the tile final
+  uint64_t* bar_tfree = bar_acc + 1;            // TMEM drained by the epilogue warps
+  uint64_t* bar_sq = bar_tfree + 1;             // [2] per-sample scalars of the tile written
+  uint64_t* bar_csfull = bar_sq + 2;            // this CTA's staging triangle is complete
+  uint64_t* bar_csfree = bar_csfull + 1;        // [CLUSTER] CTA w has finished factorising: its triangle may be rewritten
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 32);
+  int* s_part = reinterpret_cast<int*>(bars + 64);                         // [3][TS]
+
+  if (tid == 0) {
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], CLUSTER); mbar_init(&bar_rows[i], NPROD); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&bar_pfull[i], 1); mbar_init(&bar_pempty[i], 1); mbar_init(&bar_sq[i], NPROD); }
+    mbar_init(bar_acc, 1); mbar_init(bar_tfree, 4); mbar_init(bar_csfull, CLUSTER);
+    for (int i = 0; i < CLUSTER; ++i) mbar_init(&bar_csfree[i], 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "n"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;");
+  const uint32_t tmem_base = *s_tmem;
+  cluster_sync_all();
+
+  const int N = rank < WCTAS ? Sh::NW : Sh::NU;
+  const uint32_t b_bytes = (uint32_t)Sh::b_bytes(rank);
+  // a tile is skipped by every role alike when its quasar has no usable pixel or is inactive
+  auto tile_quasar = [&](int t) { return t / tiles_per_quasar; };
+  auto tile_live = [&](int q, const QuasarMeta& m) { return m.nchunks > 0 && !(args.active != nullptr && args.active[q] == 0); };
+
+  if (warp >= NCTRL + NPROD) {
+    // =========================================================================== EPILOGUE WARPGROUP
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REG_EPI));
+    const int e = warp - NCTRL - NPROD;              // TMEM lane quarter = samples 32 e .. 32 e + 31 = CTA e's samples
+    const uint32_t cs_remote = mapa(smem_u32(Cs), (uint32_t)e) + (uint32_t)lane * 8;
+    const uint32_t csfull_remote = mapa(smem_u32(bar_csfull), (uint32_t)e);
+    const uint32_t taddr0 = tmem_base + ((uint32_t)(e * 32) << 16);
+    int it = 0;
+    for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+      const int q = tile_quasar(t);
+      const QuasarMeta meta = args.meta[q];
+      const int64_t s0 = (int64_t)(t % tiles_per_quasar) * TM + (int64_t)rank * TS;
+      if (!tile_live(q, meta)) {
+        if (lane < 8) {
+          const int64_t s = s0 + e * 8 + lane;
+          if (s < S) args.sample_log_likelihoods[(int64_t)q * args.sll_stride + s] = NAN;
+          else if (s == S && args.log_likelihoods_no_dla) args.log_likelihoods_no_dla[q] = NAN;
+        }
+        continue;
+      }
+      if (lane == 0) {
+        mbar_wait_d(bar_acc, it & 1, xa.status, 6, xa.phase, 500);   // latency-insensitive: poll rarely
+        if (it > 0) mbar_wait_cluster(&bar_csfree[e], (it - 1) & 1, xa.status, 10, xa.phase);   // CTA e is done with its previous triangle
+      }
+      __syncwarp();
+      asm volatile("tcgen05.fence::after_thread_sync;");
+      const double* cs = xa.colscale + (int64_t)q * Sh::NCOLTAB + rank * Sh::NMAX;
+      for (int c0 = 0; c0 < N; c0 += 8) {
+        uint32_t v[L][8];
+#pragma unroll
+        for (int tt = 0; tt < L; ++tt) {
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                       : "=r"(v[tt][0]), "=r"(v[tt][1]), "=r"(v[tt][2]), "=r"(v[tt][3]), "=r"(v[tt][4]), "=r"(v[tt][5]),
+                         "=r"(v[tt][6]), "=r"(v[tt][7])
+                       : "r"(taddr0 + (uint32_t)(tt * N + c0)));
+        }
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+          const int idx = c_i8_stage[rank * 128 + c0 + jj];
+          if (idx >= 0) {
+            double acc = (double)(int32_t)v[L - 1][jj];
+#pragma unroll
+            for (int tt = L - 2; tt >= 0; --tt) acc = fma(acc, 256.0, (double)(int32_t)v[tt][jj]);
+            st_cluster_f64(cs_remote + (uint32_t)(idx * CSTR * 8), acc * cs[c0 + jj]);
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;");
+      asm volatile("fence.acq_rel.cluster;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(bar_tfree);                      // the MMA issuer may overwrite the accumulators
+        mbar_arrive_cluster(csfull_remote);          // this CTA's share of CTA e's triangle is in place
+        mbar_wait_cluster(bar_csfull, it & 1, xa.status, 11, xa.phase);                 // all four shares of my triangle
+        mbar_wait_d(&bar_sq[it & 1], (it >> 1) & 1, xa.status, 12, xa.phase, 200);            // my producers' scalars
+      }
+      __syncwarp();
+      factor_staged<K, CSTR>(Cs, s_q + (it & 1) * TS, s_ld + (it & 1) * TS, e * 8, lane, meta, args, q, s0);
+      __syncwarp();
+      if (lane == 0) {
+        const uint32_t freebar = smem_u32(&bar_csfree[rank]);
+        for (uint32_t peer = 0; peer < (uint32_t)CLUSTER; ++peer) mbar_arrive_cluster(mapa(freebar, peer));
+      }
+      ++it;
+    }
+  } else if (warp >= NCTRL) {
+    // =========================================================================== PRODUCERS
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REG_PROD));
+    const int pr = warp - NCTRL;
+    const int row0 = pr * SPB;
+    const uint32_t own_block = rank * Sh::ROWBLOCK;
+    uint8_t* const wdst0 = (rank < WCTAS) ? At + own_block : Sx;
+    uint8_t* const udst0 = (rank < WCTAS) ? Sx : At + own_block;
+    const uint32_t wstride = (rank < WCTAS) ? Sh::A_TILE : Sh::ROWBLOCK;
+    const uint32_t ustride = (rank < WCTAS) ? Sh::ROWBLOCK : Sh::A_TILE;
+    const uint32_t rowoff = (row0 / 8) * Sh::SBO_A + (row0 % 8) * 16 + (lane / 16) * 128 + (lane % 16);
+    constexpr uint64_t BIAS = Sh::digit_bias();
+    const double MAGIC = Sh::magic();
+    const uint64_t KADD = BIAS - (uint64_t)__double_as_longlong(MAGIC);
+    double* myraw = rawbuf + row0 * RAWS;
+    int gc = 0, it = 0;                               // chunk counter across tiles, live-tile counter
+    for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+      const int q = tile_quasar(t);
+      const QuasarMeta meta = args.meta[q];
+      if (!tile_live(q, meta)) continue;
+      const int64_t s0 = (int64_t)(t % tiles_per_quasar) * TM + (int64_t)rank * TS;
+      const int nchunks = meta.nchunks;
+      // per-sample parameters of this warp's four samples (rows private to the warp)
+      __syncwarp();
+      if (lane < SPB) {
+        const int i = row0 + lane;
+        const int64_t s = s0 + i;
+        const bool is_null = s >= S;
+        const double z = is_null ? 0.0
+                                 : __dadd_rn(meta.min_z_dla, __dmul_rn(meta.max_z_dla - meta.min_z_dla, args.offset_samples[s]));
+        s_nhi[i] = is_null ? -1.0 : args.nhi_samples[s];
+        for (int j = 0; j < num_lines; ++j) s_mult[j * TS + i] = line_multiplier(j, z);
+        if (MODE == 2) {
+          for (int j = 0; j < args.num_partners; ++j)
+            s_part[j * TS + i] = is_null ? 0 : args.partners[((int64_t)q * 3 + j) * S + s];
+        }
+      }
+      __syncwarp();
+      const double* lam = args.lam_pad + (int64_t)q * (args.NPIX + 8);
+      const double* pix = args.pix + (int64_t)q * args.NPIX * 4;
+      const double* pix2 = xa.pix2 + (int64_t)q * args.NPIX * 2;
+      double* const cache_q = (MODE != 0) ? args.acache + (int64_t)q * S * args.NPIX : nullptr;
+
+      auto eval_raw = [&](double lambda, double (&e)[SPB]) {        // voigt.c:282-292, 4 samples at one wavelength
+        const double* mymult = s_mult + row0;
+        const double* mynhi = s_nhi + row0;
+        double tau[SPB];
+        if (NL == 3) {
+          unsigned coremask = 0;
+#pragma unroll
+          for (int ss = 0; ss < SPB; ++ss) {
+            bool core;
+            tau[ss] = tau_sum_3_wing(lambda, mymult[ss], mymult[TS + ss], mymult[2 * TS + ss], core);
+            coremask |= core ? (1u << ss) : 0u;
+          }
+          if (coremask) {
+#pragma unroll
+            for (int ss = 0; ss < SPB; ++ss)
+              if (coremask & (1u << ss)) tau[ss] = tau_sum_3_exact(lambda, mymult[ss], mymult[TS + ss], mymult[2 * TS + ss]);
+          }
+        } else {
+#pragma unroll
+          for (int ss = 0; ss < SPB; ++ss) tau[ss] = tau_sum_generic(lambda, mymult + ss, TS, num_lines);
+        }
+#pragma unroll
+        for (int ss = 0; ss < SPB; ++ss) e[ss] = -mynhi[ss] * tau[ss];
+#pragma unroll
+        for (int ss = 0; ss < SPB; ++ss) e[ss] = exp_nonpos(e[ss]);                  // voigt.c:291
+      };
+      if (MODE != 2) {   // leading pad pixels p = 0..5
+        double e[SPB];
+        eval_raw(lam[lane < 6 ? lane : 5], e);
+        if (lane < 6) {
+#pragma unroll
+          for (int ss = 0; ss < SPB; ++ss) myraw[ss * RAWS + lane] = e[ss];
+        }
+      }
+      double qacc[SPB], ldm[SPB];
+      int lde[SPB];
+#pragma unroll
+      for (int ss = 0; ss < SPB; ++ss) { qacc[ss] = 0.0; ldm[ss] = 1.0; lde[ss] = 0; }
+      double lambda_n = lam[6 + lane];
+      double2 p01n = *reinterpret_cast<const double2*>(pix + (int64_t)lane * 4);
+      double2 p23n = *reinterpret_cast<const double2*>(pix + (int64_t)lane * 4 + 2);
+      double2 p45n = *reinterpret_cast<const double2*>(pix2 + (int64_t)lane * 2);
+      for (int c = 0; c < nchunks; ++c, ++gc) {
+        const int stage = gc % STAGES;
+        const int i = c * KC + lane;
+        const double lambda = lambda_n;
+        const double y = p01n.x, v = p01n.y, mu = p23n.x, om2 = p23n.y, cw = p45n.x, cu = p45n.y;
+        if (c + 1 < nchunks) {
+          lambda_n = lam[i + KC + 6];
+          p01n = *reinterpret_cast<const double2*>(pix + (int64_t)(i + KC) * 4);
+          p23n = *reinterpret_cast<const double2*>(pix + (int64_t)(i + KC) * 4 + 2);
+          p45n = *reinterpret_cast<const double2*>(pix2 + (int64_t)(i + KC) * 2);
+        }
+        double a[SPB];
+        if (MODE != 2) {
+          double e[SPB];
+          eval_raw(lambda, e);
+#pragma unroll
+          for (int ss = 0; ss < SPB; ++ss) myraw[ss * RAWS + 6 + lane] = e[ss];
+          __syncwarp();
+          double carry[SPB];
+#pragma unroll
+          for (int ss = 0; ss < SPB; ++ss) {
+            const double* rb = myraw + ss * RAWS;
+            double acc_a = 0.0;
+#pragma unroll
+            for (int tt = 0; tt < 7; ++tt) acc_a = fma(rb[lane + tt], c_lines.ip[tt], acc_a);   // voigt.c:297-299
+            carry[ss] = rb[KC + (lane < 6 ? lane : 0)];
+            a[ss] = (__double2hiint(s_nhi[row0 + ss]) < 0) ? 1.0 : acc_a;   // null model (N marked negative)
+          }
+          __syncwarp();
+          if (lane < 6) {
+#pragma unroll
+            for (int ss = 0; ss < SPB; ++ss) myraw[ss * RAWS + lane] = carry[ss];
+          }
+          if (MODE == 1) {
+#pragma unroll
+            for (int ss = 0; ss < SPB; ++ss) {
+              const int64_t smp = s0 + row0 + ss;
+              if (smp < S) cache_q[smp * args.NPIX + i] = a[ss];
+            }
+          }
+        } else {
+#pragma unroll
+          for (int ss = 0; ss < SPB; ++ss) {
+            const int64_t smp = min(s0 + row0 + ss, S - 1);
+            a[ss] = cache_q[smp * args.NPIX + i];
+          }
+          for (int j = 0; j < args.num_partners; ++j) {
+            double bb[SPB];
+#pragma unroll
+            for (int ss = 0; ss < SPB; ++ss) bb[ss] = cache_q[(int64_t)s_part[j * TS + row0 + ss] * args.NPIX + i];
+#pragma unroll
+            for (int ss = 0; ss < SPB; ++ss) a[ss] = a[ss] * bb[ss];
+          }
+        }
+        uint64_t xw[SPB], xu[SPB];
+#pragma unroll
+        for (int ss = 0; ss < SPB; ++ss) {
+          const double a2 = a[ss] * a[ss];
+          const double d = fma(a2, om2, v);                // process_qsos.m:194,198
+          const double rd = fast_rcp(d);
+          const double r = fma(-a[ss], mu, y);
+          const double t1 = r * rd;
+          const double wn = (a2 * rd) * cw;
+          const double un = (a[ss] * t1) * cu;
+          xw[ss] = ((uint64_t)__double_as_longlong(__dadd_rn(wn, MAGIC)) + KADD) ^ BIAS;
+          xu[ss] = ((uint64_t)__double_as_longlong(__dadd_rn(un, MAGIC)) + KADD) ^ BIAS;
+          qacc[ss] = fma(r, t1, qacc[ss]);
+          ldm[ss] *= d;
+        }
+        mbar_wait_d(&bar_empty[stage], ((gc / STAGES) & 1) ^ 1, xa.status, 1, xa.phase);
+        uint8_t* dW = wdst0 + stage * wstride + rowoff;
+        uint8_t* dU = udst0 + stage * ustride + rowoff;
+#pragma unroll
+        for (int ss = 0; ss < SPB; ++ss) {
+#pragma unroll
+          for (int j = 0; j < L; ++j) {
+            dW[ss * 16 + j * 256] = (uint8_t)(xw[ss] >> (8 * j));
+            dU[ss * 16 + j * 256] = (uint8_t)(xu[ss] >> (8 * j));
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_rows[stage]);
+        if ((c & 7) == 7) {
+#pragma unroll
+          for (int ss = 0; ss < SPB; ++ss) {
+            const int hi = __double2hiint(ldm[ss]);
+            const int e2 = ((hi >> 20) & 0x7ff) - 1023;
+            lde[ss] += e2;
+            ldm[ss] = __hiloint2double(hi - (e2 << 20), __double2loint(ldm[ss]));
+          }
+        }
+      }
+      // per-sample scalars into the buffer of this tile's parity (the epilogue of tile it - 2 has long finished:
+      // the MMAs of tile it needed the TMEM drain of tile it - 1, which follows the factorisation of tile it - 2)
+#pragma unroll
+      for (int ss = 0; ss < SPB; ++ss) {
+        const double qs = warp_sum(qacc[ss]);
+        const double ld = warp_sum(log(ldm[ss]) + (double)lde[ss] * 0.693147180559945309417);
+        if (lane == 0) { s_q[(it & 1) * TS + row0 + ss] = qs; s_ld[(it & 1) * TS + row0 + ss] = ld; }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_sq[it & 1]);
+      if (xa.phase && pr == 0 && lane == 0) atomicAdd(&xa.phase[7], 1ull);
+      ++it;
+    }
+  } else {
+    // =========================================================================== CONTROL WARPGROUP
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REG_CTRL));
+    if (warp == 0 && lane == 0) {
+      // ---- MMA issuer
+      const uint32_t idesc = make_idesc(N);
+      int gc = 0, it = 0;
+      for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+        const int q = tile_quasar(t);
+        const QuasarMeta meta = args.meta[q];
+        if (!tile_live(q, meta)) continue;
+        if (it > 0) mbar_wait_d(bar_tfree, (it - 1) & 1, xa.status, 13, xa.phase, 100);   // accumulators of the previous tile read out
+        for (int c = 0; c < meta.nchunks; ++c, ++gc) {
+          const int stage = gc % STAGES, buf = gc & 1;
+          mbar_wait_d(&bar_full[stage], (gc / STAGES) & 1, xa.status, 2, xa.phase, 100);
+          mbar_wait_d(&bar_pfull[buf], (gc >> 1) & 1, xa.status, 3, xa.phase);
+          asm volatile("tcgen05.fence::after_thread_sync;");
+          const uint32_t a0 = smem_u32(At + stage * Sh::A_TILE);
+          const uint32_t b0 = smem_u32(Bt + buf * Sh::B_BUF);
+#pragma unroll
+          for (int tt = 0; tt < L; ++tt) {
+#pragma unroll
+            for (int i = tt; i < L; ++i) {
+              const int j = tt + L - 1 - i;
+              const uint64_t da = make_desc(a0 + i * 256, 128, Sh::SBO_A);
+              const uint64_t db = make_desc(b0 + j * N * KC, 128, 256);
+              mma_i8(tmem_base + (uint32_t)(tt * N), da, db, idesc, (c > 0 || i > tt) ? 1u : 0u);
+            }
+          }
+          mma_commit_multicast(&bar_empty[stage], (uint16_t)((1u << CLUSTER) - 1));
+          mma_commit(&bar_pempty[buf]);
+        }
+        mma_commit(bar_acc);
+        ++it;
+      }
+    } else if (warp == 1 && lane == 0) {
+      // ---- B-operand loader
+      int gc = 0;
+      for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+        const int q = tile_quasar(t);
+        const QuasarMeta meta = args.meta[q];
+        if (!tile_live(q, meta)) continue;
+        const uint8_t* bsrc = xa.bop + (int64_t)q * (args.NPIX / KC) * Sh::CHUNK_BYTES + Sh::b_offset(rank);
+        for (int c = 0; c < meta.nchunks; ++c, ++gc) {
+          const int buf = gc & 1;
+          if (gc >= 2) mbar_wait_d(&bar_pempty[buf], ((gc >> 1) - 1) & 1, xa.status, 4, xa.phase, 100);
+          mbar_expect_tx(&bar_pfull[buf], b_bytes);
+          tma_load_1d(Bt + buf * Sh::B_BUF, bsrc + (int64_t)c * Sh::CHUNK_BYTES, b_bytes, &bar_pfull[buf]);
+        }
+      }
+    } else if (warp == 2 && lane == 0) {
+      // ---- row-block sender
+      int gc = 0;
+      for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+        const int q = tile_quasar(t);
+        const QuasarMeta meta = args.meta[q];
+        if (!tile_live(q, meta)) continue;
+        for (int c = 0; c < meta.nchunks; ++c, ++gc) {
+          const int stage = gc % STAGES;
+          mbar_wait_d(&bar_rows[stage], (gc / STAGES) & 1, xa.status, 5, xa.phase, 100);
+          const uint32_t dst_off = smem_u32(At + stage * Sh::A_TILE) + rank * Sh::ROWBLOCK;
+          const uint32_t other_rows = smem_u32(Sx + stage * Sh::ROWBLOCK);
+          const uint32_t fullbar = smem_u32(&bar_full[stage]);
+          for (uint32_t peer = 0; peer < (uint32_t)CLUSTER; ++peer) {
+            if (peer == rank) continue;
+            const uint32_t src = (rank < WCTAS && peer < WCTAS) ? dst_off : other_rows;
+            dsmem_bulk_copy(mapa(dst_off, peer), src, Sh::ROWBLOCK, mapa(fullbar, peer));
+          }
+          mbar_arrive_expect_tx(&bar_full[stage], (CLUSTER - 1) * Sh::ROWBLOCK);
+        }
+      }
+    }
+    __syncwarp();
+  }
+  // nobody leaves while a peer may still address this CTA's shared memory or barriers
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  cluster_sync_all();
+  asm volatile("tcgen05.fence::after_thread_sync;");
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
 }
 
 }  // namespace i8
