@@ -1,0 +1,317 @@
+// How does the producers' part of the INT8 fused kernel (Voigt profile -> convolution -> weights -> digits, no
+// barriers, no MMA, no DSMEM) scale with the number of warps per SM?  One CTA per SM, NW warps, each warp does
+// 4 samples x 32 pixels per chunk exactly as dla_loglik_i8_kernel's producers (digits stored to its own smem).
+// Prints cycles per chunk-of-32-samples-equivalent.   nvcc -DNW=8|12|16 ...
+#include <cstdio>
+#include <cstdlib>
+#include <cstdint>
+#include <vector>
+#include <cuda_runtime.h>
+#include "../gp_dla_detection_b200/csrc/gpdla_kernels.cuh"
+using namespace gpdla;
+#ifndef NW
+#define NW 8
+#endif
+#ifndef MAXREG_BLOCKS
+#define MAXREG_BLOCKS 1
+#endif
+constexpr int SPB = 4, L = 6;
+#ifndef LBO
+#define LBO 128
+#endif
+constexpr int PSLOT = (LBO == 128) ? 256 : 288;   // bytes per (8-row group, digit plane): two 128-byte core matrices LBO apart
+constexpr int TSX = NW * SPB;          // samples per CTA in this benchmark
+
+__global__ void __launch_bounds__(NW * 32, MAXREG_BLOCKS) k_prod(const double* __restrict__ lam, const double* __restrict__ pix,
+                                                                 const double* __restrict__ pix2, const double* __restrict__ zs,
+                                                                 const double* __restrict__ nhis, int nchunks, double* out,
+                                                                 long long* cycles) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  double* rawbuf = reinterpret_cast<double*>(smem);                  // [TSX][RAWS]
+  double* s_mult = rawbuf + TSX * RAWS;                              // [3][TSX]
+  double* s_nhi = s_mult + 3 * TSX;                                  // [TSX]
+  uint8_t* dig = reinterpret_cast<uint8_t*>(s_nhi + TSX);            // [TSX/8][L][2][256] W then U, same layout idea
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < TSX; i += NW * 32) {
+    const double z = zs[(blockIdx.x * TSX + i) % 4096];
+    s_nhi[i] = nhis[(blockIdx.x * TSX + i) % 4096];
+    for (int j = 0; j < 3; ++j) s_mult[j * TSX + i] = line_multiplier(j, z);
+  }
+  __syncthreads();
+  const int row0 = warp * SPB;
+  auto eval_raw = [&](double lambda, double (&e)[SPB]) {
+    const double* mymult = s_mult + row0;
+    const double* mynhi = s_nhi + row0;
+    double tau[SPB];
+    unsigned coremask = 0;
+#pragma unroll
+    for (int ss = 0; ss < SPB; ++ss) {
+      bool core;
+      tau[ss] = tau_sum_3_wing(lambda, mymult[ss], mymult[TSX + ss], mymult[2 * TSX + ss], core);
+      coremask |= core ? (1u << ss) : 0u;
+    }
+    if (coremask) {
+#pragma unroll
+      for (int ss = 0; ss < SPB; ++ss)
+        if (coremask & (1u << ss)) tau[ss] = tau_sum_3_exact(lambda, mymult[ss], mymult[TSX + ss], mymult[2 * TSX + ss]);
+    }
+#pragma unroll
+    for (int ss = 0; ss < SPB; ++ss) e[ss] = -mynhi[ss] * tau[ss];
+#pragma unroll
+    for (int ss = 0; ss < SPB; ++ss) e[ss] = exp_nonpos(e[ss]);
+  };
+  double* myraw = rawbuf + row0 * RAWS;
+  {
+    double e[SPB];
+    eval_raw(lam[lane < 6 ? lane : 5], e);
+    if (lane < 6) for (int ss = 0; ss < SPB; ++ss) myraw[ss * RAWS + lane] = e[ss];
+  }
+  double qacc[SPB], ldm[SPB]; int lde[SPB];
+  for (int ss = 0; ss < SPB; ++ss) { qacc[ss] = 0.0; ldm[ss] = 1.0; lde[ss] = 0; }
+  const uint64_t BIAS = 0x808080808080ull;
+  const double MAGIC = 48.0;
+  const uint64_t KADD = BIAS - (uint64_t)__double_as_longlong(MAGIC);
+  const uint32_t rowoff = (row0 / 8) * (2 * L * PSLOT) + (row0 % 8) * 16 + (lane / 16) * LBO + (lane % 16);
+  double lambda_n = lam[6 + lane];
+  double2 p01n = *reinterpret_cast<const double2*>(pix + (int64_t)lane * 4);
+  double2 p23n = *reinterpret_cast<const double2*>(pix + (int64_t)lane * 4 + 2);
+  double2 p45n = *reinterpret_cast<const double2*>(pix2 + (int64_t)lane * 2);
+  const long long t0 = clock64();
+  for (int c = 0; c < nchunks; ++c) {
+    const int i = c * KC + lane;
+    const double lambda = lambda_n;
+    const double y = p01n.x, v = p01n.y, mu = p23n.x, om2 = p23n.y, cw = p45n.x, cu = p45n.y;
+    if (c + 1 < nchunks) {
+      lambda_n = lam[i + KC + 6];
+      p01n = *reinterpret_cast<const double2*>(pix + (int64_t)(i + KC) * 4);
+      p23n = *reinterpret_cast<const double2*>(pix + (int64_t)(i + KC) * 4 + 2);
+      p45n = *reinterpret_cast<const double2*>(pix2 + (int64_t)(i + KC) * 2);
+    }
+#ifdef VARIANT_SG
+    // lane = pixel for the raw profile; lane = (sample sl = lane / 8, pixel quad g = lane % 8) afterwards
+    const int sl = lane >> 3, g = lane & 7;
+    if (lane < 12) {   // next chunk's pixel block into L1 (12 lines of 128 B)
+      const char* pf = (lane < 8) ? (const char*)(pix + (int64_t)(c + 1) * KC * 4) + lane * 128 : (const char*)(pix2 + (int64_t)(c + 1) * KC * 2) + (lane - 8) * 128;
+      if (c + 1 < nchunks) asm volatile("prefetch.global.L1 [%0];" ::"l"(pf));
+    }
+    double e[SPB];
+    eval_raw(lambda, e);
+#pragma unroll
+    for (int ss = 0; ss < SPB; ++ss) myraw[ss * RAWS + 6 + lane] = e[ss];
+    const int i0 = c * KC + 4 * g;
+    double2 q01[4], q23[4], q45[4];
+#if defined(SG_NOPIX)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { q01[j] = make_double2(1.0 + 1e-3 * lambda, 0.05); q23[j] = make_double2(1.0, 0.01); q45[j] = make_double2(0.0597, 0.01); }
+#elif defined(SG_SOA)
+    {   // per-chunk structure-of-arrays block [6][KC]: (y, v, mu, om2, cw, cu); here read from `pix` as if laid out that way
+      const double* pb = pix + (int64_t)c * KC * 4 + 4 * g;
+      auto ld4 = [](const double* p, double2& u, double2& w) { u = *reinterpret_cast<const double2*>(p); w = *reinterpret_cast<const double2*>(p + 2); };
+      double2 y01, y23, v01, v23, m01, m23;
+      ld4(pb, y01, y23); ld4(pb + KC, v01, v23); ld4(pb + 2 * KC, m01, m23);
+      q01[0] = make_double2(y01.x, 0.05 + 1e-9 * v01.x); q01[1] = make_double2(y01.y, 0.05 + 1e-9 * v01.y); q01[2] = make_double2(y23.x, 0.05 + 1e-9 * v23.x); q01[3] = make_double2(y23.y, 0.05 + 1e-9 * v23.y);
+      const double* pc = pix2 + (int64_t)c * KC * 2 + 4 * g;
+      double2 o01, o23, c01, c23, u01, u23;
+      ld4(pb + 3 * KC, o01, o23); ld4(pc, c01, c23); ld4(pc + KC, u01, u23);
+      q23[0] = make_double2(1.0 + 1e-9 * m01.x, 0.01 + 1e-9 * o01.x); q23[1] = make_double2(1.0 + 1e-9 * m01.y, 0.01 + 1e-9 * o01.y);
+      q23[2] = make_double2(1.0 + 1e-9 * m23.x, 0.01 + 1e-9 * o23.x); q23[3] = make_double2(1.0 + 1e-9 * m23.y, 0.01 + 1e-9 * o23.y);
+      q45[0] = make_double2(0.0597 + 1e-9 * c01.x, 0.01 + 1e-9 * u01.x); q45[1] = make_double2(0.0597 + 1e-9 * c01.y, 0.01 + 1e-9 * u01.y);
+      q45[2] = make_double2(0.0597 + 1e-9 * c23.x, 0.01 + 1e-9 * u23.x); q45[3] = make_double2(0.0597 + 1e-9 * c23.y, 0.01 + 1e-9 * u23.y);
+    }
+#else
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      q01[j] = *reinterpret_cast<const double2*>(pix + (int64_t)(i0 + j) * 4);
+      q23[j] = *reinterpret_cast<const double2*>(pix + (int64_t)(i0 + j) * 4 + 2);
+      q45[j] = *reinterpret_cast<const double2*>(pix2 + (int64_t)(i0 + j) * 2);
+    }
+#endif
+    __syncwarp();
+    const double* rb = myraw + sl * RAWS + 4 * g;
+    double r[10];
+#pragma unroll
+    for (int j = 0; j < 5; ++j) { const double2 t = *reinterpret_cast<const double2*>(rb + 2 * j); r[2 * j] = t.x; r[2 * j + 1] = t.y; }
+    const bool null_slot = __double2hiint(s_nhi[row0 + sl]) < 0;
+    double a[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      double acc_a = 0.0;
+#pragma unroll
+      for (int t = 0; t < 7; ++t) acc_a = fma(r[j + t], c_lines.ip[t], acc_a);
+      a[j] = null_slot ? 1.0 : acc_a;
+    }
+    __syncwarp();
+    if (g == 7) {
+      double* front = myraw + sl * RAWS;
+#pragma unroll
+      for (int j = 0; j < 3; ++j) *reinterpret_cast<double2*>(front + 2 * j) = make_double2(r[4 + 2 * j], r[5 + 2 * j]);
+    }
+    uint64_t xw[4], xu[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const double a2 = a[j] * a[j];
+      const double d = fma(a2, q23[j].y, q01[j].y);
+      const double rd = fast_rcp(d);
+      const double rr = fma(-a[j], q23[j].x, q01[j].x);
+      const double t1 = rr * rd;
+      const double wn = (a2 * rd) * q45[j].x;
+      const double un = (a[j] * t1) * q45[j].y;
+      xw[j] = ((uint64_t)__double_as_longlong(__dadd_rn(wn, MAGIC)) + KADD) ^ BIAS;
+      xu[j] = ((uint64_t)__double_as_longlong(__dadd_rn(un, MAGIC)) + KADD) ^ BIAS;
+      qacc[0] = fma(rr, t1, qacc[0]);
+      ldm[0] *= d;
+    }
+    uint32_t ww[8], wu[8];
+    auto planes = [](const uint64_t (&x)[4], uint32_t (&w)[8]) {
+      const uint32_t l0 = (uint32_t)x[0], l1 = (uint32_t)x[1], l2 = (uint32_t)x[2], l3 = (uint32_t)x[3];
+      const uint32_t h0 = (uint32_t)(x[0] >> 32), h1 = (uint32_t)(x[1] >> 32), h2 = (uint32_t)(x[2] >> 32), h3 = (uint32_t)(x[3] >> 32);
+      const uint32_t a01 = __byte_perm(l0, l1, 0x5140), b01 = __byte_perm(l0, l1, 0x7362);
+      const uint32_t a23 = __byte_perm(l2, l3, 0x5140), b23 = __byte_perm(l2, l3, 0x7362);
+      w[0] = __byte_perm(a01, a23, 0x5410); w[1] = __byte_perm(a01, a23, 0x7632);
+      w[2] = __byte_perm(b01, b23, 0x5410); w[3] = __byte_perm(b01, b23, 0x7632);
+      const uint32_t c01 = __byte_perm(h0, h1, 0x5140), c23 = __byte_perm(h2, h3, 0x5140);
+      w[4] = __byte_perm(c01, c23, 0x5410); w[5] = __byte_perm(c01, c23, 0x7632);
+      w[6] = 0; w[7] = 0;
+    };
+    planes(xw, ww); planes(xu, wu);
+    {
+      const int myrow = row0 + sl;
+      uint8_t* dW = dig + (myrow / 8) * (L * 512) + (myrow % 8) * 16 + (g >> 2) * 128 + (g & 3) * 4;
+      uint8_t* dU = dW + L * 256;
+#pragma unroll
+      for (int j = 0; j < L; ++j) {
+        *reinterpret_cast<uint32_t*>(dW + j * 256) = ww[j];
+        *reinterpret_cast<uint32_t*>(dU + j * 256) = wu[j];
+      }
+    }
+    __syncwarp();
+#else
+    double a[SPB];
+#ifndef SKIP_EVAL
+    double e[SPB];
+    eval_raw(lambda, e);
+#else
+    double e[SPB];
+    for (int ss = 0; ss < SPB; ++ss) e[ss] = 0.5 + 1e-3 * lambda;
+#endif
+#pragma unroll
+    for (int ss = 0; ss < SPB; ++ss) myraw[ss * RAWS + 6 + lane] = e[ss];
+    __syncwarp();
+    double carry[SPB];
+#pragma unroll
+    for (int ss = 0; ss < SPB; ++ss) {
+      const double* rb = myraw + ss * RAWS;
+      double acc_a = 0.0;
+#pragma unroll
+      for (int t = 0; t < 7; ++t) acc_a = fma(rb[lane + t], c_lines.ip[t], acc_a);
+      carry[ss] = rb[KC + (lane < 6 ? lane : 0)];
+      a[ss] = (__double2hiint(s_nhi[row0 + ss]) < 0) ? 1.0 : acc_a;
+    }
+    __syncwarp();
+    if (lane < 6) {
+#pragma unroll
+      for (int ss = 0; ss < SPB; ++ss) myraw[ss * RAWS + lane] = carry[ss];
+    }
+#ifndef SKIP_WEIGHTS
+    uint64_t xw[SPB], xu[SPB];
+#pragma unroll
+    for (int ss = 0; ss < SPB; ++ss) {
+      const double a2 = a[ss] * a[ss];
+      const double d = fma(a2, om2, v);
+      const double rd = fast_rcp(d);
+      const double r = fma(-a[ss], mu, y);
+      const double t1 = r * rd;
+      const double wn = (a2 * rd) * cw;
+      const double un = (a[ss] * t1) * cu;
+      xw[ss] = ((uint64_t)__double_as_longlong(__dadd_rn(wn, MAGIC)) + KADD) ^ BIAS;
+      xu[ss] = ((uint64_t)__double_as_longlong(__dadd_rn(un, MAGIC)) + KADD) ^ BIAS;
+      qacc[ss] = fma(r, t1, qacc[ss]);
+      ldm[ss] *= d;
+    }
+    uint8_t* dW = dig + rowoff;
+    uint8_t* dU = dig + rowoff + L * PSLOT;
+#pragma unroll
+    for (int ss = 0; ss < SPB; ++ss) {
+#pragma unroll
+      for (int j = 0; j < L; ++j) {
+        dW[ss * 16 + j * PSLOT] = (uint8_t)(xw[ss] >> (8 * j));
+        dU[ss * 16 + j * PSLOT] = (uint8_t)(xu[ss] >> (8 * j));
+      }
+    }
+#ifdef WITH_FENCE
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#endif
+    __syncwarp();
+#else
+    for (int ss = 0; ss < SPB; ++ss) qacc[ss] += a[ss];
+#endif
+#endif
+    if ((c & 7) == 7) {
+#pragma unroll
+      for (int ss = 0; ss < SPB; ++ss) {
+        const int hi = __double2hiint(ldm[ss]);
+        const int e2 = ((hi >> 20) & 0x7ff) - 1023;
+        lde[ss] += e2;
+        ldm[ss] = __hiloint2double(hi - (e2 << 20), __double2loint(ldm[ss]));
+      }
+    }
+  }
+  const long long t1 = clock64();
+  double sres = 0.0;
+  for (int ss = 0; ss < SPB; ++ss) sres += qacc[ss] + ldm[ss] + lde[ss];
+  out[blockIdx.x * NW * 32 + tid] = sres + dig[tid];
+  if (tid == 0) cycles[blockIdx.x] = t1 - t0;
+}
+
+int main() {
+  const int nchunks = 40, NPIX = nchunks * KC;
+  // line constants as the library computes them (only what the wing path needs is exact enough for timing)
+  LineConstants lc = {};
+  const double tw[3] = {1.2156701e-5, 1.0257223e-5, 0.97253680e-5}, osc[3] = {0.4164, 0.07912, 0.02901}, gam[3] = {6.265e8, 1.897e8, 8.127e7};
+  const double sigma = 9.08537121627923800e5, c = 2.99792458e10;
+  for (int j = 0; j < 3; ++j) {
+    lc.tw[j] = tw[j]; lc.lc[j] = 2.654e-2 * osc[j] * tw[j]; lc.gam[j] = gam[j] * tw[j] / (4 * M_PI);
+    lc.y[j] = lc.gam[j] / (sqrt(2.0) * sigma); lc.y2[j] = lc.y[j] * lc.y[j];
+    lc.kcore[j] = lc.lc[j] / (sqrt(2 * M_PI) * sigma); lc.kwing[j] = lc.kcore[j] * lc.y[j] / sqrt(M_PI);
+  }
+  const double ip[7] = {2.171e-3, 4.5e-2, 0.24, 0.4256, 0.24, 4.5e-2, 2.171e-3};
+  for (int t = 0; t < 7; ++t) lc.ip[t] = ip[t];
+  lc.c = c; lc.inv_s2s = 1.0 / (sqrt(2.0) * sigma);
+  cudaMemcpyToSymbol(c_lines, &lc, sizeof lc);
+  {
+    const double wa[GPDLA_VOIGT_DEG_A + 1] = GPDLA_VOIGT_WING_A;
+    const double wb[GPDLA_VOIGT_DEG_B + 1] = GPDLA_VOIGT_WING_B;
+    const double two_s2 = 2.0 * sigma * sigma;
+    Wing3 w3;
+    for (int j = 0; j < 3; ++j) {
+      double sc = two_s2 * lc.kwing[j];
+      for (int i = 0; i <= GPDLA_VOIGT_DEG_A; ++i) { w3.a[j][i] = sc * wa[i]; sc *= two_s2; }
+      w3.yy[j] = two_s2 * lc.kwing[j] * lc.y2[j] * two_s2 * wb[0];
+    }
+    w3.b1 = wb[1] / wb[0] * two_s2;
+    w3.v2min = GPDLA_VOIGT_X0 * GPDLA_VOIGT_X0 * two_s2;
+    cudaMemcpyToSymbol(c_wing3, &w3, sizeof w3);
+  }
+  std::vector<double> lam(NPIX + 8), pix(NPIX * 4), pix2(NPIX * 2), zs(4096), nh(4096);
+  const double zq = 3.0;
+  for (int i = 0; i < NPIX + 8; ++i) lam[i] = 911.75 * (1 + zq) * pow(10.0, 1e-4 * (i - 3));
+  srand(1);
+  for (int i = 0; i < NPIX; ++i) { pix[4 * i] = 1.0 + 0.1 * (rand() % 100) / 100.0; pix[4 * i + 1] = 0.05; pix[4 * i + 2] = 1.0; pix[4 * i + 3] = 0.01; pix2[2 * i] = 0.996 * 0.06; pix2[2 * i + 1] = 0.01; }
+  for (int i = 0; i < 4096; ++i) { zs[i] = 2.0 + 1.0 * (rand() % 10000) / 10000.0; nh[i] = pow(10.0, 20.0 + 2.0 * (rand() % 1000) / 1000.0); }
+  double *dl, *dp, *dp2, *dz, *dn, *dout; long long* dcyc;
+  cudaMalloc(&dl, lam.size() * 8); cudaMalloc(&dp, pix.size() * 8); cudaMalloc(&dp2, pix2.size() * 8);
+  cudaMalloc(&dz, 4096 * 8); cudaMalloc(&dn, 4096 * 8); cudaMalloc(&dout, 148 * NW * 32 * 8); cudaMalloc(&dcyc, 148 * 8);
+  cudaMemcpy(dl, lam.data(), lam.size() * 8, cudaMemcpyHostToDevice); cudaMemcpy(dp, pix.data(), pix.size() * 8, cudaMemcpyHostToDevice);
+  cudaMemcpy(dp2, pix2.data(), pix2.size() * 8, cudaMemcpyHostToDevice); cudaMemcpy(dz, zs.data(), 4096 * 8, cudaMemcpyHostToDevice);
+  cudaMemcpy(dn, nh.data(), 4096 * 8, cudaMemcpyHostToDevice);
+  const size_t smem = (size_t)TSX * RAWS * 8 + 4 * TSX * 8 + (size_t)(TSX / 8 + 1) * L * 2 * 288 + 1024;
+  cudaFuncSetAttribute(k_prod, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, k_prod);
+  for (int rep = 0; rep < 2; ++rep) k_prod<<<148, NW * 32, smem>>>(dl, dp, dp2, dz, dn, nchunks, dout, dcyc);
+  cudaError_t e = cudaDeviceSynchronize();
+  std::vector<long long> cyc(148); cudaMemcpy(cyc.data(), dcyc, 148 * 8, cudaMemcpyDeviceToHost);
+  double mean = 0; for (auto x : cyc) mean += x; mean /= 148;
+  printf("{\"warps\": %d, \"regs\": %d, \"local_bytes\": %zu, \"status\": \"%s\", \"cycles_per_chunk_per_warp_iteration\": %.0f, \"cycles_per_32_samples_chunk\": %.0f}\n",
+         NW, fa.numRegs, (size_t)fa.localSizeBytes, cudaGetErrorString(e), mean / nchunks, mean / nchunks * 32.0 / TSX);
+  return 0;
+}

@@ -365,6 +365,7 @@ static i8::I8Args i8_args(gpdla_ctx* c) {
   i8::I8Args xa;
   xa.pix2 = c->d_pix2; xa.bop = c->d_bop; xa.colscale = c->d_colscale; xa.colinv = c->d_colinv; xa.status = c->d_status;
   xa.phase = nullptr;
+  { static int dbg = -1; if (dbg < 0) { const char* e = getenv("GPDLA_I8_DEBUG"); dbg = e ? atoi(e) : 0; } xa.debug = dbg; }
   if (getenv("GPDLA_I8_PHASES")) {
     static unsigned long long* d_phase = nullptr;
     if (!d_phase) { cudaMalloc(&d_phase, 24 * sizeof(unsigned long long)); cudaMemset(d_phase, 0, 24 * sizeof(unsigned long long)); }

@@ -36,6 +36,9 @@ constexpr int THREADS = 32 * (NCTRL + NPROD);
 constexpr int STAGES = 3;           // A-operand stages
 constexpr double CAP = 0.996;       // |x| <= CAP keeps the top signed digit within [-128, 127]
 constexpr int TMEM_COLS = 512;
+#ifndef GPDLA_I8_TSA
+#define GPDLA_I8_TSA 0      // 1: the most-used digit planes of A are copied to TMEM once per chunk (tcgen05.cp) and read from there; exact, but measured 2-4 % slower
+#endif
 
 template <int K, int L>
 struct Shape {
@@ -45,9 +48,16 @@ struct Shape {
   static constexpr int NU = (K + 15) / 16 * 16;                   // MMA N of the U CTA (32)
   static constexpr int NMAX = NW > NU ? NW : NU;
   static constexpr int F = 8 * L - 1;                             // fractional bits
-  // A tile (128 samples x 32 pixels x L digits), K-major, no swizzle: 8-row x 16-byte core matrices,
-  // 128 B apart along K (LBO), the L digit planes of an 8-row group side by side, groups SBO apart
-  static constexpr int SBO_A = 256 * L;
+  // A tile (128 samples x 32 pixels x L digits), K-major, no swizzle: 8-row x 16-byte core matrices, the two K
+  // halves LBO_A apart, the L digit planes of an 8-row group side by side (PLANE_A apart), groups SBO_A apart.
+  // LBO_A = 144 instead of the dense 128 shifts the second K half by 4 banks, so that a producer warp's byte
+  // stores (lanes 0-15 / 16-31 = the two halves of one row) do not collide.
+#ifndef GPDLA_I8_LBO_A
+#define GPDLA_I8_LBO_A 144
+#endif
+  static constexpr int LBO_A = GPDLA_I8_LBO_A;
+  static constexpr int PLANE_A = (LBO_A == 128) ? 256 : 288;
+  static constexpr int SBO_A = PLANE_A * L;
   static constexpr int ROWBLOCK = (TS / 8) * SBO_A;               // one CTA's 32 rows, all digit planes: contiguous
   static constexpr int A_TILE = (TM / 8) * SBO_A;
   static constexpr int BW_PLANE = NW * KC, BU_PLANE = NU * KC;    // bytes of one digit plane of the B operand
@@ -58,6 +68,9 @@ struct Shape {
   static constexpr int CSTR = TS + 4;
   static constexpr int NENT = (K + 1) * (K + 2) / 2;
   static_assert(L * NW <= TMEM_COLS, "diagonal accumulators must fit in TMEM");
+  // digit planes of A kept in TMEM (8 columns each) next to the accumulators: the highest planes are used most
+  static constexpr int TS_PLANES = GPDLA_I8_TSA ? ((TMEM_COLS - L * NW) / 8 < L ? (TMEM_COLS - L * NW) / 8 : L) : 0;
+  static constexpr int TS_FIRST = L - TS_PLANES;     // planes TS_FIRST .. L-1 come from TMEM
   static_assert(L >= 2 && L <= 7, "digit count");
   __host__ __device__ static constexpr int b_offset(int rank) { return rank * L * BW_PLANE; }
   __host__ __device__ static constexpr int b_bytes(int rank) { return L * (rank < WCTAS ? BW_PLANE : BU_PLANE); }
@@ -91,6 +104,7 @@ struct I8Args {
   double* colscale;        // [Q x 4 x NMAX]  2^(e_c - 2F + 8(L-1)): accumulator -> Gram entry
   double* colinv;          // [Q x 4 x NMAX]  2^-e_c
   int* status;             // != 0: a barrier wait timed out (kernel traps)
+  int debug;               // timing experiments (GPDLA_I8_DEBUG, one-tile-per-cluster kernel only): 2 skip MMA issue, 4 skip row-block copies
   unsigned long long* phase;   // nullable: [16] summed cycles per phase (GPDLA_I8_PHASES)
 };
 
@@ -149,6 +163,18 @@ __device__ __forceinline__ void mma_i8(uint32_t tmem_d, uint64_t da, uint64_t db
       "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n}\n" ::"r"(tmem_d),
       "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(0u)
       : "memory");
+}
+// A operand from TMEM (128 lanes x 8 columns per digit plane, staged by tcgen05.cp): no shared-memory read of A
+__device__ __forceinline__ void mma_i8_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate), "r"(0u)
+      : "memory");
+}
+// shared memory (matrix descriptor, 128 rows x 256 bits) -> TMEM, ordered with the MMAs of the issuing thread
+__device__ __forceinline__ void tmem_cp_128x256b(uint32_t tmem_dst, uint64_t sdesc) {
+  asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(tmem_dst), "l"(sdesc) : "memory");
 }
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -380,7 +406,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(THREADS, 1) dl
     uint8_t* const udst0 = (rank < WCTAS) ? Sx : At + own_block;
     const uint32_t wstride = (rank < WCTAS) ? Sh::A_TILE : Sh::ROWBLOCK;   // bytes between stages
     const uint32_t ustride = (rank < WCTAS) ? Sh::ROWBLOCK : Sh::A_TILE;
-    const uint32_t rowoff = (row0 / 8) * Sh::SBO_A + (row0 % 8) * 16 + (lane / 16) * 128 + (lane % 16);
+    const uint32_t rowoff = (row0 / 8) * Sh::SBO_A + (row0 % 8) * 16 + (lane / 16) * Sh::LBO_A + (lane % 16);
 
     auto eval_raw = [&](double lambda, double (&e)[SPB]) {        // voigt.c:282-292, 4 samples at one wavelength
       const double* mymult = s_mult + row0;
@@ -511,8 +537,8 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(THREADS, 1) dl
       for (int ss = 0; ss < SPB; ++ss) {
 #pragma unroll
         for (int j = 0; j < L; ++j) {
-          dW[ss * 16 + j * 256] = (uint8_t)(xw[ss] >> (8 * j));
-          dU[ss * 16 + j * 256] = (uint8_t)(xu[ss] >> (8 * j));
+          dW[ss * 16 + j * Sh::PLANE_A] = (uint8_t)(xw[ss] >> (8 * j));
+          dU[ss * 16 + j * Sh::PLANE_A] = (uint8_t)(xu[ss] >> (8 * j));
         }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic stores -> visible to the async proxy
@@ -547,15 +573,22 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(THREADS, 1) dl
         asm volatile("tcgen05.fence::after_thread_sync;");
         const uint32_t a0 = smem_u32(At + stage * Sh::A_TILE);
         const uint32_t b0 = smem_u32(Bt + buf * Sh::B_BUF);
+        if (!(xa.debug & 2)) {
+        const uint32_t tmem_a0 = tmem_base + (uint32_t)(L * Sh::NW);      // A planes behind the accumulators
+#pragma unroll
+        for (int i = Sh::TS_FIRST; i < L; ++i)
+          tmem_cp_128x256b(tmem_a0 + (uint32_t)((i - Sh::TS_FIRST) * 8), make_desc(a0 + i * Sh::PLANE_A, Sh::LBO_A, Sh::SBO_A));
 #pragma unroll
         for (int t = 0; t < L; ++t) {            // diagonal i + j = t + L - 1
 #pragma unroll
           for (int i = t; i < L; ++i) {
             const int j = t + L - 1 - i;
-            const uint64_t da = make_desc(a0 + i * 256, 128, Sh::SBO_A);
             const uint64_t db = make_desc(b0 + j * N * KC, 128, 256);
-            mma_i8(tmem_base + (uint32_t)(t * N), da, db, idesc, (c > 0 || i > t) ? 1u : 0u);
+            const uint32_t acc = (c > 0 || i > t) ? 1u : 0u;
+            if (i >= Sh::TS_FIRST) mma_i8_ts(tmem_base + (uint32_t)(t * N), tmem_a0 + (uint32_t)((i - Sh::TS_FIRST) * 8), db, idesc, acc);
+            else mma_i8(tmem_base + (uint32_t)(t * N), make_desc(a0 + i * Sh::PLANE_A, Sh::LBO_A, Sh::SBO_A), db, idesc, acc);
           }
+        }
         }
         mma_commit_multicast(&bar_empty[stage], (uint16_t)((1u << CLUSTER) - 1));   // frees the stage in all CTAs
         mma_commit(&bar_pempty[buf]);
@@ -579,12 +612,12 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(THREADS, 1) dl
         const uint32_t other_rows = smem_u32(Sx + stage * Sh::ROWBLOCK);
         const uint32_t fullbar = smem_u32(&bar_full[stage]);
         for (uint32_t peer = 0; peer < (uint32_t)CLUSTER; ++peer) {
-          if (peer == rank) continue;
+          if (peer == rank || (xa.debug & 4)) continue;
           // W CTA -> W CTA: own rows; W CTA -> U CTA and U CTA -> W CTA: the rows kept in Sx
           const uint32_t src = (rank < WCTAS && peer < WCTAS) ? own_rows : other_rows;
           dsmem_bulk_copy(mapa(dst_off, peer), src, Sh::ROWBLOCK, mapa(fullbar, peer));
         }
-        mbar_arrive_expect_tx(&bar_full[stage], (CLUSTER - 1) * Sh::ROWBLOCK);   // own rows are in place; 3 blocks inbound
+        mbar_arrive_expect_tx(&bar_full[stage], (xa.debug & 4) ? 0u : (uint32_t)((CLUSTER - 1) * Sh::ROWBLOCK));   // own rows are in place; 3 blocks inbound
       }
     }
     __syncwarp();
@@ -810,7 +843,7 @@ dla_loglik_i8p_kernel(LoglikArgs args, I8Args xa, int num_quasars, int tiles_per
     uint8_t* const udst0 = (rank < WCTAS) ? Sx : At + own_block;
     const uint32_t wstride = (rank < WCTAS) ? Sh::A_TILE : Sh::ROWBLOCK;
     const uint32_t ustride = (rank < WCTAS) ? Sh::ROWBLOCK : Sh::A_TILE;
-    const uint32_t rowoff = (row0 / 8) * Sh::SBO_A + (row0 % 8) * 16 + (lane / 16) * 128 + (lane % 16);
+    const uint32_t rowoff = (row0 / 8) * Sh::SBO_A + (row0 % 8) * 16 + (lane / 16) * Sh::LBO_A + (lane % 16);
     constexpr uint64_t BIAS = Sh::digit_bias();
     const double MAGIC = Sh::magic();
     const uint64_t KADD = BIAS - (uint64_t)__double_as_longlong(MAGIC);
@@ -961,8 +994,8 @@ dla_loglik_i8p_kernel(LoglikArgs args, I8Args xa, int num_quasars, int tiles_per
         for (int ss = 0; ss < SPB; ++ss) {
 #pragma unroll
           for (int j = 0; j < L; ++j) {
-            dW[ss * 16 + j * 256] = (uint8_t)(xw[ss] >> (8 * j));
-            dU[ss * 16 + j * 256] = (uint8_t)(xu[ss] >> (8 * j));
+            dW[ss * 16 + j * Sh::PLANE_A] = (uint8_t)(xw[ss] >> (8 * j));
+            dU[ss * 16 + j * Sh::PLANE_A] = (uint8_t)(xu[ss] >> (8 * j));
           }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -1010,14 +1043,19 @@ dla_loglik_i8p_kernel(LoglikArgs args, I8Args xa, int num_quasars, int tiles_per
           asm volatile("tcgen05.fence::after_thread_sync;");
           const uint32_t a0 = smem_u32(At + stage * Sh::A_TILE);
           const uint32_t b0 = smem_u32(Bt + buf * Sh::B_BUF);
+          const uint32_t tmem_a0 = tmem_base + (uint32_t)(L * Sh::NW);    // A planes behind the accumulators
+#pragma unroll
+          for (int i = Sh::TS_FIRST; i < L; ++i)
+            tmem_cp_128x256b(tmem_a0 + (uint32_t)((i - Sh::TS_FIRST) * 8), make_desc(a0 + i * Sh::PLANE_A, Sh::LBO_A, Sh::SBO_A));
 #pragma unroll
           for (int tt = 0; tt < L; ++tt) {
 #pragma unroll
             for (int i = tt; i < L; ++i) {
               const int j = tt + L - 1 - i;
-              const uint64_t da = make_desc(a0 + i * 256, 128, Sh::SBO_A);
               const uint64_t db = make_desc(b0 + j * N * KC, 128, 256);
-              mma_i8(tmem_base + (uint32_t)(tt * N), da, db, idesc, (c > 0 || i > tt) ? 1u : 0u);
+              const uint32_t acc = (c > 0 || i > tt) ? 1u : 0u;
+              if (i >= Sh::TS_FIRST) mma_i8_ts(tmem_base + (uint32_t)(tt * N), tmem_a0 + (uint32_t)((i - Sh::TS_FIRST) * 8), db, idesc, acc);
+              else mma_i8(tmem_base + (uint32_t)(tt * N), make_desc(a0 + i * Sh::PLANE_A, Sh::LBO_A, Sh::SBO_A), db, idesc, acc);
             }
           }
           mma_commit_multicast(&bar_empty[stage], (uint16_t)((1u << CLUSTER) - 1));
