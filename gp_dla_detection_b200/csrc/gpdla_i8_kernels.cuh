@@ -186,6 +186,25 @@ __device__ __forceinline__ void mma_commit_multicast(uint64_t* bar, uint16_t mas
                : "memory");
 }
 
+// The L (L + 1) / 2 slice-pair products of one chunk.  Digit plane i of A pairs with the B planes j = L-1-i .. L-1,
+// which are consecutive in shared memory, into the diagonals t = i + j - (L-1) = 0 .. i, which are consecutive in
+// TMEM: up to 256 / n accumulator blocks are therefore covered by ONE tcgen05.mma whose N spans several planes.
+// 6 digits: 9 instructions instead of 21 (5 digits: 7 instead of 15).  What the instruction count buys is measured
+// in DESIGN.md 4.3: every tcgen05.mma slows the producers by the same amount regardless of its size.
+template <class Sh, int L>
+__device__ __forceinline__ void issue_chunk_mmas(uint32_t tmem_base, uint32_t a0, uint32_t b0, int n, bool accumulate) {
+  const int group = 256 / n;                       // diagonals per instruction (3 for N = 80, 8 for N = 32)
+#pragma unroll
+  for (int i = L - 1; i >= 0; --i) {               // plane L-1 first: it reaches every diagonal, so it may overwrite
+    const uint64_t da = make_desc(a0 + i * Sh::PLANE_A, Sh::LBO_A, Sh::SBO_A);
+    for (int t0 = 0; t0 <= i; t0 += group) {
+      const int nt = min(group, i + 1 - t0);
+      const uint64_t db = make_desc(b0 + (L - 1 - i + t0) * n * KC, 128, 256);
+      mma_i8(tmem_base + (uint32_t)(t0 * n), da, db, make_idesc(nt * n), (accumulate || i < L - 1) ? 1u : 0u);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // K0c: per-pixel scales (cw, cu) and per-column exponents of the digit operands.  One CTA per quasar.
 template <int K, int L>
@@ -565,7 +584,6 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(THREADS, 1) dl
     // =========================================================================== CONTROL WARPS
     if (warp == 0 && lane == 0) {
       // ---- MMA issuer: for every chunk, the L (L + 1) / 2 slice-pair products, one accumulator per diagonal
-      const uint32_t idesc = make_idesc(N);
       for (int c = 0; c < nchunks; ++c) {
         const int stage = c % STAGES, buf = c & 1;
         mbar_wait_d(&bar_full[stage], (c / STAGES) & 1, xa.status, 2, xa.phase, 100);
@@ -573,23 +591,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(THREADS, 1) dl
         asm volatile("tcgen05.fence::after_thread_sync;");
         const uint32_t a0 = smem_u32(At + stage * Sh::A_TILE);
         const uint32_t b0 = smem_u32(Bt + buf * Sh::B_BUF);
-        if (!(xa.debug & 2)) {
-        const uint32_t tmem_a0 = tmem_base + (uint32_t)(L * Sh::NW);      // A planes behind the accumulators
-#pragma unroll
-        for (int i = Sh::TS_FIRST; i < L; ++i)
-          tmem_cp_128x256b(tmem_a0 + (uint32_t)((i - Sh::TS_FIRST) * 8), make_desc(a0 + i * Sh::PLANE_A, Sh::LBO_A, Sh::SBO_A));
-#pragma unroll
-        for (int t = 0; t < L; ++t) {            // diagonal i + j = t + L - 1
-#pragma unroll
-          for (int i = t; i < L; ++i) {
-            const int j = t + L - 1 - i;
-            const uint64_t db = make_desc(b0 + j * N * KC, 128, 256);
-            const uint32_t acc = (c > 0 || i > t) ? 1u : 0u;
-            if (i >= Sh::TS_FIRST) mma_i8_ts(tmem_base + (uint32_t)(t * N), tmem_a0 + (uint32_t)((i - Sh::TS_FIRST) * 8), db, idesc, acc);
-            else mma_i8(tmem_base + (uint32_t)(t * N), make_desc(a0 + i * Sh::PLANE_A, Sh::LBO_A, Sh::SBO_A), db, idesc, acc);
-          }
-        }
-        }
+        if (!(xa.debug & 2)) issue_chunk_mmas<Sh, L>(tmem_base, a0, b0, N, c > 0);
         mma_commit_multicast(&bar_empty[stage], (uint16_t)((1u << CLUSTER) - 1));   // frees the stage in all CTAs
         mma_commit(&bar_pempty[buf]);
       }
@@ -1029,7 +1031,6 @@ dla_loglik_i8p_kernel(LoglikArgs args, I8Args xa, int num_quasars, int tiles_per
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REG_CTRL));
     if (warp == 0 && lane == 0) {
       // ---- MMA issuer
-      const uint32_t idesc = make_idesc(N);
       int gc = 0, it = 0;
       for (int t = cluster_id; t < num_tiles; t += num_clusters) {
         const int q = tile_quasar(t);
@@ -1043,21 +1044,7 @@ dla_loglik_i8p_kernel(LoglikArgs args, I8Args xa, int num_quasars, int tiles_per
           asm volatile("tcgen05.fence::after_thread_sync;");
           const uint32_t a0 = smem_u32(At + stage * Sh::A_TILE);
           const uint32_t b0 = smem_u32(Bt + buf * Sh::B_BUF);
-          const uint32_t tmem_a0 = tmem_base + (uint32_t)(L * Sh::NW);    // A planes behind the accumulators
-#pragma unroll
-          for (int i = Sh::TS_FIRST; i < L; ++i)
-            tmem_cp_128x256b(tmem_a0 + (uint32_t)((i - Sh::TS_FIRST) * 8), make_desc(a0 + i * Sh::PLANE_A, Sh::LBO_A, Sh::SBO_A));
-#pragma unroll
-          for (int tt = 0; tt < L; ++tt) {
-#pragma unroll
-            for (int i = tt; i < L; ++i) {
-              const int j = tt + L - 1 - i;
-              const uint64_t db = make_desc(b0 + j * N * KC, 128, 256);
-              const uint32_t acc = (c > 0 || i > tt) ? 1u : 0u;
-              if (i >= Sh::TS_FIRST) mma_i8_ts(tmem_base + (uint32_t)(tt * N), tmem_a0 + (uint32_t)((i - Sh::TS_FIRST) * 8), db, idesc, acc);
-              else mma_i8(tmem_base + (uint32_t)(tt * N), make_desc(a0 + i * Sh::PLANE_A, Sh::LBO_A, Sh::SBO_A), db, idesc, acc);
-            }
-          }
+          issue_chunk_mmas<Sh, L>(tmem_base, a0, b0, N, c > 0);
           mma_commit_multicast(&bar_empty[stage], (uint16_t)((1u << CLUSTER) - 1));
           mma_commit(&bar_pempty[buf]);
         }
