@@ -264,13 +264,15 @@ def main():
             clusters = (NUM_SAMPLES + 1 + 127) // 128
             int8_ops = float(chunks) * clusters * pairs * 2.0 * 128 * 32 * (3 * 80 + 32)
             roof.update({
-                "kernel": "dla_loglik_i8_kernel (fused Voigt + exact-product INT8 tcgen05 Gram, %d signed 8-bit digits per "
-                          "factor, s32 TMEM accumulators + Cholesky; 4-CTA clusters, DSMEM row-block exchange)" % digits,
+                "kernel": "dla_loglik_i8p_kernel (fused Voigt + exact-product INT8 tcgen05 Gram, %d signed 8-bit digits per "
+                          "factor, s32 TMEM accumulators + Cholesky; persistent 4-CTA clusters, DSMEM row-block exchange, "
+                          "epilogue warpgroup, merged slice-pair MMAs)" % digits,
                 "note": "achieved/peak = FP64-equivalent Gram rate (S n k(k+3) per quasar, SURVEY 8(d)) over the measured "
                         "FP64 DMMA peak; the contraction itself runs as exact INT8 slice products on the tcgen05 tensor "
-                        "pipe, which leaves the FP64 pipe to the Voigt/weight arithmetic -- the stage that now bounds "
-                        "the kernel (ncu: FP64 pipe ~26 % busy, tensor pipe ~50 %, the producers' dependent-issue "
-                        "latency limits both; DESIGN.md 4.3)",
+                        "pipe, which leaves the FP64 pipe to the Voigt/weight arithmetic -- the stage that bounds the "
+                        "kernel (ncu: IMMA sub-pipe 67 % of SM-active cycles, FP64 pipe 36 %, issue slots 47 %; the "
+                        "producers alone need 2 460 of the 3 830 cycles per 32-pixel chunk; DESIGN.md 4.3). 132 of the "
+                        "148 SMs host clusters (4-CTA cluster placement)",
                 "int8_tensor": {"achieved_tops": int8_ops * args.steps / (k_ms * 1e-3) * 1e-12 if k_ms > 0 else None,
                                 "peak_tops": 4283.0, "peak_source": "profiles/r01_tcgen05_i8.txt (this pool's B200, N = 240)"},
             })
