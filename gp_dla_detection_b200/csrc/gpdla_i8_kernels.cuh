@@ -16,9 +16,15 @@
 // digits -- the FP64 work that remains) and ships its 32-row block to the peers that contract it with one bulk
 // shared-memory-to-shared-memory copy each (DSMEM, completion on the receiver's mbarrier).  CTAs 0..2
 // contract W'' with a third of the Gram columns each (N = 80), CTA 3 contracts U'' with M'' (N = 32): TMEM
-// holds L diagonals x N columns per CTA.  The P''/M'' digit chunk arrives by 1-D TMA.  After the last chunk
-// the accumulators are recombined, sent to the CTA that produced the sample (DSMEM stores) and factorised
-// there (factor_staged, the same Cholesky as the FP64 kernels).
+// holds L diagonals x N columns per CTA.  The P''/M'' digit chunk arrives by 1-D TMA.  One tcgen05.mma spans up
+// to three consecutive digit planes / diagonals (issue_chunk_mmas: 9 instructions for the 21 slice pairs).  After
+// the last chunk the accumulators are recombined, sent to the CTA that produced the sample (DSMEM stores) and
+// factorised there (factor_staged, the same Cholesky as the FP64 kernels).
+//
+// Two kernels share this scheme: dla_loglik_i8p_kernel (shipped) keeps the clusters resident and overlaps the
+// epilogue of a tile with the main loop of the next one (own warpgroup, setmaxnreg); dla_loglik_i8_kernel runs one
+// tile per cluster and carries the development instrumentation (GPDLA_I8_PERSISTENT=0, GPDLA_I8_PHASES,
+// GPDLA_I8_DEBUG).  Measurements, failed variants and the interference probes: DESIGN.md 4.3.
 #pragma once
 #include "gpdla_kernels.cuh"
 
@@ -36,9 +42,6 @@ constexpr int THREADS = 32 * (NCTRL + NPROD);
 constexpr int STAGES = 3;           // A-operand stages
 constexpr double CAP = 0.996;       // |x| <= CAP keeps the top signed digit within [-128, 127]
 constexpr int TMEM_COLS = 512;
-#ifndef GPDLA_I8_TSA
-#define GPDLA_I8_TSA 0      // 1: the most-used digit planes of A are copied to TMEM once per chunk (tcgen05.cp) and read from there; exact, but measured 2-4 % slower
-#endif
 
 template <int K, int L>
 struct Shape {
@@ -68,9 +71,6 @@ struct Shape {
   static constexpr int CSTR = TS + 4;
   static constexpr int NENT = (K + 1) * (K + 2) / 2;
   static_assert(L * NW <= TMEM_COLS, "diagonal accumulators must fit in TMEM");
-  // digit planes of A kept in TMEM (8 columns each) next to the accumulators: the highest planes are used most
-  static constexpr int TS_PLANES = GPDLA_I8_TSA ? ((TMEM_COLS - L * NW) / 8 < L ? (TMEM_COLS - L * NW) / 8 : L) : 0;
-  static constexpr int TS_FIRST = L - TS_PLANES;     // planes TS_FIRST .. L-1 come from TMEM
   static_assert(L >= 2 && L <= 7, "digit count");
   __host__ __device__ static constexpr int b_offset(int rank) { return rank * L * BW_PLANE; }
   __host__ __device__ static constexpr int b_bytes(int rank) { return L * (rank < WCTAS ? BW_PLANE : BU_PLANE); }
@@ -164,7 +164,9 @@ __device__ __forceinline__ void mma_i8(uint32_t tmem_d, uint64_t da, uint64_t db
       "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(0u)
       : "memory");
 }
-// A operand from TMEM (128 lanes x 8 columns per digit plane, staged by tcgen05.cp): no shared-memory read of A
+// A operand from TMEM (128 lanes x 8 columns per digit plane, staged by tcgen05.cp.128x256b with the same matrix
+// descriptor as the shared-memory A operand).  Validated (exact results) but measured slower than reading A from
+// shared memory; kept for reference, not used by the shipped kernels.
 __device__ __forceinline__ void mma_i8_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
