@@ -17,11 +17,19 @@
 constexpr int M = 128, N = NN, KMMA = 32;
 constexpr int A_SLAB = M * KMMA, B_SLAB = N * KMMA;    // bytes per k-step
 constexpr uint32_t LBO = 128, SBO = 256;
+#ifndef A_LBO
+#define A_LBO 128
+#endif
+#ifndef A_SBO
+#define A_SBO 256
+#endif
+// A operand layout as in the fused kernel: K halves A_LBO apart, 8-row groups A_SBO apart (digit planes interleaved)
+constexpr int A_SLAB_BYTES = (M / 8) * A_SBO;
 constexpr int TMEM_COLS = N <= 32 ? 32 : N <= 64 ? 64 : N <= 128 ? 128 : 256;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
-  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((LBO >> 4) & 0x3FFF) << 16) | ((uint64_t)((SBO >> 4) & 0x3FFF) << 32) |
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo = LBO, uint32_t sbo = SBO) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) |
          (1ull << 46);   // version 1 (Blackwell), base offset 0, SWIZZLE_NONE
 }
 // kind::i8 instruction descriptor: D = s32, A = B = signed 8-bit, both K-major, N >> 3, M >> 4
@@ -44,14 +52,14 @@ __global__ void __launch_bounds__(128, 1) k_i8(const int8_t* __restrict__ A, con
   extern __shared__ __align__(1024) uint8_t smem[];
   const int ksteps = K / KMMA;
   uint8_t* sA = smem;
-  uint8_t* sB = smem + (size_t)ksteps * A_SLAB;
+  uint8_t* sB = smem + (size_t)ksteps * A_SLAB_BYTES;
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // stage operands in the canonical layout (16-byte granules)
   for (int g = tid; g < ksteps * M * 2; g += 128) {          // A: granule = (kstep, row, half)
     int s = g / (M * 2), r = (g / 2) % M, h = g % 2;
-    *reinterpret_cast<int4*>(sA + (size_t)s * A_SLAB + (r / 8) * SBO + h * LBO + (r % 8) * 16) =
+    *reinterpret_cast<int4*>(sA + (size_t)s * A_SLAB_BYTES + (r / 8) * A_SBO + h * A_LBO + (r % 8) * 16) =
         *reinterpret_cast<const int4*>(A + (size_t)r * K + s * KMMA + h * 16);
   }
   for (int g = tid; g < ksteps * N * 2; g += 128) {
@@ -80,7 +88,7 @@ __global__ void __launch_bounds__(128, 1) k_i8(const int8_t* __restrict__ A, con
       const uint32_t idesc = make_idesc();
       for (int rep = 0; rep < reps; ++rep) {
         for (int s = 0; s < ksteps; ++s) {
-          const uint64_t da = make_desc(smem_u32(sA + (size_t)s * A_SLAB));
+          const uint64_t da = make_desc(smem_u32(sA + (size_t)s * A_SLAB_BYTES), A_LBO, A_SBO);
           const uint64_t db = make_desc(smem_u32(sB + (size_t)s * B_SLAB));
           const uint32_t accumulate = (s > 0) ? 1u : 0u;
           asm volatile(
@@ -118,7 +126,10 @@ __global__ void __launch_bounds__(128, 1) k_i8(const int8_t* __restrict__ A, con
 }
 
 int main() {
-  const int K = 512;    // 16 k-steps staged in shared memory (188 KB)
+#ifndef KTOT
+#define KTOT 512
+#endif
+  const int K = KTOT;   // k-steps staged in shared memory
   std::vector<int8_t> hA((size_t)M * K), hB((size_t)N * K);
   srand(7);
   for (auto& x : hA) x = (int8_t)(rand() % 128 - 64);
@@ -127,7 +138,7 @@ int main() {
   CK(cudaMalloc(&dA, hA.size())); CK(cudaMalloc(&dB, hB.size())); CK(cudaMalloc(&dD, (size_t)M * N * 4));
   CK(cudaMalloc(&dcyc, 148 * 8)); CK(cudaMalloc(&dst, 4)); CK(cudaMemset(dst, 0, 4));
   CK(cudaMemcpy(dA, hA.data(), hA.size(), cudaMemcpyHostToDevice)); CK(cudaMemcpy(dB, hB.data(), hB.size(), cudaMemcpyHostToDevice));
-  const size_t smem = (size_t)(K / KMMA) * (A_SLAB + B_SLAB) + 1024;
+  const size_t smem = (size_t)(K / KMMA) * (A_SLAB_BYTES + B_SLAB) + 1024;
   CK(cudaFuncSetAttribute(k_i8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // ---- correctness: one CTA
   k_i8<<<1, 128, smem>>>(dA, dB, K, dD, 1, dcyc, dst);
