@@ -67,6 +67,7 @@ __global__ void __launch_bounds__(NW * 32, MAXREG_BLOCKS) k_prod(const double* _
     if (lane < 6) for (int ss = 0; ss < SPB; ++ss) myraw[ss * RAWS + lane] = e[ss];
   }
   double qacc[SPB], ldm[SPB]; int lde[SPB];
+  double eprev[SPB] = {1.0, 1.0, 1.0, 1.0};
   for (int ss = 0; ss < SPB; ++ss) { qacc[ss] = 0.0; ldm[ss] = 1.0; lde[ss] = 0; }
   const uint64_t BIAS = 0x808080808080ull;
   const double MAGIC = 48.0;
@@ -194,6 +195,26 @@ __global__ void __launch_bounds__(NW * 32, MAXREG_BLOCKS) k_prod(const double* _
     double e[SPB];
     for (int ss = 0; ss < SPB; ++ss) e[ss] = 0.5 + 1e-3 * lambda;
 #endif
+#if defined(SKIP_CONV)
+#pragma unroll
+    for (int ss = 0; ss < SPB; ++ss) a[ss] = e[ss];
+#elif defined(CONV_SHFL)
+    // convolution through shuffles: tap t of pixel `lane` is the raw value of lane - 6 + t, of this chunk (src >= 0)
+    // or of the previous chunk (kept in eprev)
+#pragma unroll
+    for (int ss = 0; ss < SPB; ++ss) {
+      double acc_a = 0.0;
+#pragma unroll
+      for (int t = 0; t < 7; ++t) {
+        const int src = lane - 6 + t;
+        const double cur = __shfl_sync(0xffffffffu, e[ss], src & 31);
+        const double prv = __shfl_sync(0xffffffffu, eprev[ss], src & 31);
+        acc_a = fma(src >= 0 ? cur : prv, c_lines.ip[t], acc_a);
+      }
+      a[ss] = (__double2hiint(s_nhi[row0 + ss]) < 0) ? 1.0 : acc_a;
+      eprev[ss] = e[ss];
+    }
+#else
 #pragma unroll
     for (int ss = 0; ss < SPB; ++ss) myraw[ss * RAWS + 6 + lane] = e[ss];
     __syncwarp();
@@ -212,6 +233,7 @@ __global__ void __launch_bounds__(NW * 32, MAXREG_BLOCKS) k_prod(const double* _
 #pragma unroll
       for (int ss = 0; ss < SPB; ++ss) myraw[ss * RAWS + lane] = carry[ss];
     }
+#endif
 #ifndef SKIP_WEIGHTS
     uint64_t xw[SPB], xu[SPB];
 #pragma unroll

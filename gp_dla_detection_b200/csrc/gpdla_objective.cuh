@@ -177,22 +177,38 @@ __global__ void __launch_bounds__(OBJ_THREADS, (K <= 20) ? 2 : 1) objective_kern
   for (int p = 0; p < K; ++p) logdetB += log(B[p * (K + 1) + p]);   // sum log diag L (:48)
   __syncthreads();
 
-  // ---- pass 1 over pixels: K^-1 y, K^-1 M = D^-1 M B^-1, diag K^-1, all gradients except the rank-one part of dM
-  double quad = 0.0, g_c0 = 0.0, g_tau = 0.0, g_beta = 0.0;
+  // ---- pass 1 over pixels: K^-1 y (needs only v1), then w = (K^-1 y)' M
+  double quad = 0.0;
+  for (int t = tid; t < n; t += OBJ_THREADS) {
+    const int i = idx[t];
+    const double di = dinv[t], yi = y[i];
+    double dot_v1 = 0.0;
+#pragma unroll
+    for (int j = 0; j < K; ++j) dot_v1 = fma(di * M[(int64_t)j * P + i], v1[j], dot_v1);
+    const double ky = di * yi - dot_v1;                                                    // K^-1 y (:46)
+    kiy[t] = ky;
+    quad = fma(yi, ky, quad);
+  }
+  __syncthreads();
+  for (int j = warp; j < K; j += OBJ_THREADS / 32) {      // w = (K^-1 y)' M, one warp per column
+    double t = 0.0;
+    for (int u = lane; u < n; u += 32) t = fma(kiy[u], M[(int64_t)j * P + idx[u]], t);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (lane == 0) wv[j] = t;
+  }
+  __syncthreads();
+  // ---- pass 2: K^-1 M = D^-1 M B^-1, diag K^-1, every gradient; one atomic per entry of dM:
+  //      dM(i, :) = K^-1 M (i, :) - K^-1 y (i) w   (:54-55)
+  double g_c0 = 0.0, g_tau = 0.0, g_beta = 0.0;
   double* gM = a.g;
   double* gom = a.g + (int64_t)P * K;
   for (int t = tid; t < n; t += OBJ_THREADS) {
     const int i = idx[t];
-    const double di = dinv[t], yi = y[i];
+    const double di = dinv[t], ky = kiy[t];
     double r[K];
 #pragma unroll
     for (int j = 0; j < K; ++j) r[j] = di * M[(int64_t)j * P + i];                       // D^-1 M row (:33)
-    double dot_v1 = 0.0;
-#pragma unroll
-    for (int j = 0; j < K; ++j) dot_v1 = fma(r[j], v1[j], dot_v1);
-    const double ky = di * yi - dot_v1;                                                    // K^-1 y (:46)
-    kiy[t] = ky;
-    quad = fma(yi, ky, quad);
     double diagk = di;
 #pragma unroll 4
     for (int j = 0; j < K; ++j) {
@@ -200,7 +216,7 @@ __global__ void __launch_bounds__(OBJ_THREADS, (K <= 20) ? 2 : 1) objective_kern
 #pragma unroll
       for (int c = 0; c < K; ++c) tj = fma(r[c], Binv[c * (K + 1) + j], tj);
       diagk = fma(-tj, r[j], diagk);                                                       // diag K^-1 (:58)
-      atomicAdd(&gM[(int64_t)j * P + i], tj);                                              // + K^-1 M part of dM (:54-55)
+      atomicAdd(&gM[(int64_t)j * P + i], fma(-ky, wv[j], tj));
     }
     double od, ab, sf, an;
     noise_terms(i, od, ab, sf, an);
@@ -214,7 +230,6 @@ __global__ void __launch_bounds__(OBJ_THREADS, (K <= 20) ? 2 : 1) objective_kern
     da = da * log(z1[i]) * beta;                                                           // (:72-73)
     g_beta -= da * kk;
   }
-  // block reductions: w = (K^-1 y)' M, scalars
   auto block_reduce = [&](double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -225,24 +240,8 @@ __global__ void __launch_bounds__(OBJ_THREADS, (K <= 20) ? 2 : 1) objective_kern
     for (int w = 0; w < OBJ_THREADS / 32; ++w) tsum += red[w];
     return tsum;
   };
-  __syncthreads();
-  for (int j = warp; j < K; j += OBJ_THREADS / 32) {      // w = (K^-1 y)' M, one warp per column
-    double t = 0.0;
-    for (int u = lane; u < n; u += 32) t = fma(kiy[u], M[(int64_t)j * P + idx[u]], t);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-    if (lane == 0) wv[j] = t;
-  }
   quad = block_reduce(quad); ld = block_reduce(ld);
   g_c0 = block_reduce(g_c0); g_tau = block_reduce(g_tau); g_beta = block_reduce(g_beta);
-  __syncthreads();
-  // ---- pass 2: dM(i, :) -= K^-1 y (i) * w   (:54-55)
-  for (int t = tid; t < n; t += OBJ_THREADS) {
-    const int i = idx[t];
-    const double ky = kiy[t];
-#pragma unroll 4
-    for (int j = 0; j < K; ++j) atomicAdd(&gM[(int64_t)j * P + i], -ky * wv[j]);
-  }
   if (tid == 0) {
     const double log_2pi = 1.83787706640934534;                                            // (:17)
     atomicAdd(a.f, 0.5 * (quad + (ld + 2.0 * logdetB) + n * log_2pi));                     // (:48-52)

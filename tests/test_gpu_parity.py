@@ -347,3 +347,33 @@ def test_state_errors(api, synthetic_inputs):
     empty = dict(all_wavelengths=[], all_flux=[], all_noise_variance=[], all_pixel_mask=[], z_qsos=np.zeros(0))
     res = api.process_qsos(si["model"], si["samples"], empty, si["prior"])
     assert res["p_dlas"].shape == (0,)
+
+
+def test_persistent_and_one_tile_kernels_are_bit_identical(api, synthetic_inputs, tmp_path):
+    """The shipped persistent INT8 kernel and the one-tile-per-cluster development kernel (GPDLA_I8_PERSISTENT=0,
+    read once per process, hence the subprocess) produce identical bits: integer slice products are exact and the
+    recombination / Cholesky code is shared."""
+    import os, subprocess, sys
+    from gp_dla_detection_b200 import synthetic as syn
+    si = synthetic_inputs
+    sp = syn.make_spectra(si["model"], 5, seed=31, dla_fraction=0.6)
+    sp["all_pixel_mask"][3][:] = True          # an empty quasar among live ones
+    sub = {k: v[::7] for k, v in si["samples"].items()}
+    here = api.process_qsos(si["model"], sub, sp, si["prior"], gram_digits=6)
+    script = tmp_path / "one_tile.py"
+    out = tmp_path / "one_tile.npz"
+    script.write_text(
+        "import sys, numpy as np\n"
+        "sys.path.insert(0, %r)\n"
+        "from gp_dla_detection_b200 import api, synthetic as syn\n"
+        "model, samples, prior = syn.make_model(), syn.make_samples(10000), syn.make_prior()\n"
+        "sp = syn.make_spectra(model, 5, seed=31, dla_fraction=0.6)\n"
+        "sp['all_pixel_mask'][3][:] = True\n"
+        "sub = {k: v[::7] for k, v in samples.items()}\n"
+        "r = api.process_qsos(model, sub, sp, prior, gram_digits=6)\n"
+        "np.savez(%r, **r)\n" % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), str(out)))
+    env = dict(os.environ, GPDLA_I8_PERSISTENT="0")
+    subprocess.run([sys.executable, str(script)], check=True, env=env, timeout=600)
+    other = np.load(out)
+    for k in here:
+        assert np.array_equal(here[k], other[k], equal_nan=True), k
