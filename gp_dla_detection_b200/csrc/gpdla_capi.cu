@@ -770,7 +770,8 @@ int gpdla_process_qsos(gpdla_ctx* c, int64_t Q, int64_t L_max, const double* wav
   const bool want_sll = out->sample_log_likelihoods_dla != nullptr;
   // one device staging block: 3 double planes + lengths/z + mask + 14 result columns (+ Q x S)
   const size_t n_res = 14;
-  size_t bytes = 3 * QL * 8 + (size_t)Q * 8 + (n_res + 1) * Q * 8 + (size_t)Q * 8 + (size_t)Q * 4 + QL + 64 +
+  // (+ 16 bytes of rounding slack for each of the 9 sub-blocks carved out below)
+  size_t bytes = 3 * QL * 8 + (size_t)Q * 8 + (n_res + 1) * Q * 8 + (size_t)Q * 8 + (size_t)Q * 4 + QL + 9 * 16 +
                  (want_sll ? (size_t)Q * c->S * 8 : 0);
   if (c->st_bytes < bytes) {
     cudaFree(c->d_stage); c->d_stage = nullptr; c->st_bytes = 0;
