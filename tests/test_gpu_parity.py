@@ -349,10 +349,11 @@ def test_state_errors(api, synthetic_inputs):
     assert res["p_dlas"].shape == (0,)
 
 
-def test_persistent_and_one_tile_kernels_are_bit_identical(api, synthetic_inputs, tmp_path):
+def test_persistent_and_one_tile_kernels_agree(api, synthetic_inputs, tmp_path):
     """The shipped persistent INT8 kernel and the one-tile-per-cluster development kernel (GPDLA_I8_PERSISTENT=0,
-    read once per process, hence the subprocess) produce identical bits: integer slice products are exact and the
-    recombination / Cholesky code is shared."""
+    read once per process, hence the subprocess) agree to rounding: the integer slice products are exact and the
+    recombination / Cholesky code is shared; only the compiler's FMA contraction of the FP64 producer arithmetic
+    differs between the two kernels (measured on a B200: not bit-identical), so the comparison is at 1e-12."""
     import os, subprocess, sys
     from gp_dla_detection_b200 import synthetic as syn
     si = synthetic_inputs
@@ -376,4 +377,10 @@ def test_persistent_and_one_tile_kernels_are_bit_identical(api, synthetic_inputs
     subprocess.run([sys.executable, str(script)], check=True, env=env, timeout=600)
     other = np.load(out)
     for k in here:
-        assert np.array_equal(here[k], other[k], equal_nan=True), k
+        a, b = np.asarray(here[k], dtype=np.float64), np.asarray(other[k], dtype=np.float64)
+        assert np.array_equal(np.isnan(a), np.isnan(b)), k
+        if k in ("map_inds", "map_z_dlas", "map_log_nhis", "min_z_dlas", "max_z_dlas", "log_priors_dla", "log_priors_no_dla"):
+            assert np.array_equal(a, b, equal_nan=True), k
+        else:
+            ok = ~np.isnan(a)
+            assert np.all(np.abs(a[ok] - b[ok]) <= 1e-12 * np.maximum(1.0, np.abs(b[ok]))), k
