@@ -207,6 +207,25 @@ __device__ __forceinline__ void issue_chunk_mmas(uint32_t tmem_base, uint32_t a0
   }
 }
 
+// The same instruction list with every descriptor offset an immediate (N is a template parameter): the issuing
+// thread shares an SM sub-partition with two producer warps, and each instruction it spends on descriptor
+// arithmetic is an issue slot taken from them (the cost of an MMA does not depend on its size).
+// da0 / db0 are the descriptors of digit plane 0 of the A stage / B buffer.
+template <class Sh, int L, int N>
+__device__ __forceinline__ void issue_chunk_mmas_fixed(uint32_t tmem_base, uint64_t da0, uint64_t db0, bool accumulate) {
+  constexpr int group = 256 / N;
+#pragma unroll
+  for (int i = L - 1; i >= 0; --i) {
+    const uint64_t da = da0 + (uint64_t)((i * Sh::PLANE_A) >> 4);
+#pragma unroll
+    for (int t0 = 0; t0 <= i; t0 += group) {
+      const int nt = (group < i + 1 - t0) ? group : i + 1 - t0;
+      const uint64_t db = db0 + (uint64_t)(((L - 1 - i + t0) * N * KC) >> 4);
+      mma_i8(tmem_base + (uint32_t)(t0 * N), da, db, make_idesc(nt * N), (accumulate || i < L - 1) ? 1u : 0u);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // K0c: per-pixel scales (cw, cu) and per-column exponents of the digit operands.  One CTA per quasar.
 template <int K, int L>
@@ -1033,6 +1052,9 @@ dla_loglik_i8p_kernel(LoglikArgs args, I8Args xa, int num_quasars, int tiles_per
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REG_CTRL));
     if (warp == 0 && lane == 0) {
       // ---- MMA issuer
+      static_assert(Sh::A_TILE % 16 == 0 && Sh::B_BUF % 16 == 0 && Sh::PLANE_A % 16 == 0, "descriptor offsets are in 16-byte units");
+      const uint64_t da_stage0 = make_desc(smem_u32(At), Sh::LBO_A, Sh::SBO_A);
+      const uint64_t db_buf0 = make_desc(smem_u32(Bt), 128, 256);
       int gc = 0, it = 0;
       for (int t = cluster_id; t < num_tiles; t += num_clusters) {
         const int q = tile_quasar(t);
@@ -1044,9 +1066,10 @@ dla_loglik_i8p_kernel(LoglikArgs args, I8Args xa, int num_quasars, int tiles_per
           mbar_wait_d(&bar_full[stage], (gc / STAGES) & 1, xa.status, 2, xa.phase, 100);
           mbar_wait_d(&bar_pfull[buf], (gc >> 1) & 1, xa.status, 3, xa.phase);
           asm volatile("tcgen05.fence::after_thread_sync;");
-          const uint32_t a0 = smem_u32(At + stage * Sh::A_TILE);
-          const uint32_t b0 = smem_u32(Bt + buf * Sh::B_BUF);
-          issue_chunk_mmas<Sh, L>(tmem_base, a0, b0, N, c > 0);
+          const uint64_t da0 = da_stage0 + (uint64_t)(uint32_t)(stage * (Sh::A_TILE >> 4));
+          const uint64_t db0 = db_buf0 + (uint64_t)(uint32_t)(buf * (Sh::B_BUF >> 4));
+          if (rank < WCTAS) issue_chunk_mmas_fixed<Sh, L, Sh::NW>(tmem_base, da0, db0, c > 0);
+          else issue_chunk_mmas_fixed<Sh, L, Sh::NU>(tmem_base, da0, db0, c > 0);
           mma_commit_multicast(&bar_empty[stage], (uint16_t)((1u << CLUSTER) - 1));
           mma_commit(&bar_pempty[buf]);
         }

@@ -141,11 +141,11 @@ __device__ __forceinline__ double tau_wing3_line(int j, double q) {
 
 __device__ __forceinline__ double tau_sum_3_wing(double lambda, double m0, double m1, double m2, bool& core) {
   const double v0 = fma(lambda, m0, -c_lines.c), v1 = fma(lambda, m1, -c_lines.c), v2 = fma(lambda, m2, -c_lines.c);
-  double s0 = v0 * v0, s1 = v1 * v1, s2 = v2 * v2;
+  const double s0 = v0 * v0, s1 = v1 * v1, s2 = v2 * v2;
   const double lim = c_wing3.v2min;
-  const bool k0 = hi_less(s0, lim), k1 = hi_less(s1, lim), k2 = hi_less(s2, lim);
-  core = k0 | k1 | k2;
-  s0 = k0 ? lim : s0; s1 = k1 ? lim : s1; s2 = k2 ? lim : s2;
+  // a lane inside a line core is re-evaluated by the caller, so its wing value may be anything (inf / NaN when
+  // v = 0): no clamp of s before the reciprocal
+  core = hi_less(s0, lim) | hi_less(s1, lim) | hi_less(s2, lim);
   const double q0 = fast_rcp(s0), q1 = fast_rcp(s1), q2 = fast_rcp(s2);
   return (tau_wing3_line(0, q0) + tau_wing3_line(1, q1)) + tau_wing3_line(2, q2);
 }
@@ -165,8 +165,7 @@ __device__ __noinline__ double tau_sum_3_exact(double lambda, double m0, double 
 }
 
 // exp(x) for x <= 0 (and small positive x), branch-free: Cody-Waite reduction, degree-11 polynomial
-// (tools/gen_voigt_tables.py), exponent assembled in integer registers.  Returns 0 below -708
-// (the reference's libm would return values < 2.3e-308 there).
+// (tools/gen_voigt_tables.py), exponent assembled in integer registers.  The argument is clamped at -708.
 __constant__ double c_exp_poly[12] = GPDLA_EXP_POLY;
 __device__ __forceinline__ double exp_nonpos(double x) {
   const double SHIFT = 6755399441055744.0;   // 1.5 * 2^52
@@ -181,8 +180,8 @@ __device__ __forceinline__ double exp_nonpos(double x) {
   double p = c_exp_poly[11];
 #pragma unroll
   for (int i = 10; i >= 0; --i) p = fma(p, r, c_exp_poly[i]);
-  const double res = __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
-  return tiny ? 0.0 : res;
+  // below -708 the result is exp(-708) = 3.3e-308 instead of the reference's libm value in [0, 2.3e-308]
+  return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
 }
 
 }  // namespace gpdla
