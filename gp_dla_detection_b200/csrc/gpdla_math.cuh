@@ -70,22 +70,47 @@ __device__ __forceinline__ double tau_wing(int j, double u) {
   return c_lines.kwing[j] * u * fma(-t, b, a);
 }
 
-// tau_j / N for |x| < X0 (rare: <= 7 pixels per line per sample).
+// exp(x) for x <= 0 (and small positive x), branch-free: Cody-Waite reduction, degree-11 polynomial
+// (tools/gen_voigt_tables.py), exponent assembled in integer registers.  The argument is clamped at -708.
+__constant__ double c_exp_poly[12] = GPDLA_EXP_POLY;
+__device__ __forceinline__ double exp_nonpos(double x) {
+  const double SHIFT = 6755399441055744.0;   // 1.5 * 2^52
+  // x <= 0 (or tiny positive): "below -708" is an unsigned compare of the high word (integer pipe)
+  const bool tiny = (unsigned)__double2hiint(x) > 0xC0862000u;   // x < -708 (hi word of -708.0 is 0xC0862000)
+  const double xc = tiny ? -708.0 : x;
+  double kd = fma(xc, 1.4426950408889634074, SHIFT);
+  const int k = __double2loint(kd);
+  kd -= SHIFT;
+  double r = fma(kd, -6.93147180369123816490e-01, xc);
+  r = fma(kd, -1.90821492927058770002e-10, r);
+  double p = c_exp_poly[11];
+#pragma unroll
+  for (int i = 10; i >= 0; --i) p = fma(p, r, c_exp_poly[i]);
+  // below -708 the result is exp(-708) = 3.3e-308 instead of the reference's libm value in [0, 2.3e-308]
+  return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+}
+
+// tau_j / N for |x| < X0 (rare: <= 7 pixels per line per sample).  The warp that lands here delays its whole
+// cluster (the chunk hand-over is lock-step), so the dependency chains are kept short: H1 as even + odd halves,
+// H3 and the exponential as independent chains.
 __device__ __noinline__ double tau_core(int j, double x) {
   double ax = fabs(x);
   int idx = (int)(ax * GPDLA_VOIGT_INV_H);
   idx = idx < GPDLA_VOIGT_NINT ? idx : GPDLA_VOIGT_NINT - 1;
   double t = fma(ax, 2.0 * GPDLA_VOIGT_INV_H, -(2.0 * idx + 1.0));   // (ax - centre)/(H/2)
+  const double t2 = t * t;
   const double* tab = g_core_table + idx * GPDLA_VOIGT_CORE_STRIDE;
-  double h1 = tab[GPDLA_VOIGT_DEG_H1];
+  static_assert(GPDLA_VOIGT_DEG_H1 % 2 == 1, "even/odd split of H1");
+  double h1e = tab[GPDLA_VOIGT_DEG_H1 - 1], h1o = tab[GPDLA_VOIGT_DEG_H1];
 #pragma unroll
-  for (int i = GPDLA_VOIGT_DEG_H1 - 1; i >= 0; --i) h1 = fma(h1, t, tab[i]);
+  for (int i = GPDLA_VOIGT_DEG_H1 - 3; i >= 0; i -= 2) { h1e = fma(h1e, t2, tab[i]); h1o = fma(h1o, t2, tab[i + 1]); }
+  const double h1 = fma(h1o, t, h1e);
   const double* tab3 = tab + GPDLA_VOIGT_DEG_H1 + 1;
   double h3 = tab3[GPDLA_VOIGT_DEG_H3];
 #pragma unroll
   for (int i = GPDLA_VOIGT_DEG_H3 - 1; i >= 0; --i) h3 = fma(h3, t, tab3[i]);
   double x2 = x * x;
-  double e = exp(-x2);
+  double e = exp_nonpos(-x2);
   double y = c_lines.y[j], y2 = c_lines.y2[j];
   double p4 = fma(x2, fma(x2, 4.0, -12.0), 3.0) * (1.0 / 6.0);
   double even = fma(y2, fma(y2, p4, fma(-2.0, x2, 1.0)), 1.0);   // 1 + y^2 (1-2x^2) + y^4 p4
@@ -150,38 +175,20 @@ __device__ __forceinline__ double tau_sum_3_wing(double lambda, double m0, doubl
   return (tau_wing3_line(0, q0) + tau_wing3_line(1, q1)) + tau_wing3_line(2, q2);
 }
 
-// Exact three-line sum including core pixels (rare path; same summation order as voigt.c:285-290).
+// Three-line sum for lanes with a line core in reach (rare path; same summation order as voigt.c:285-290).  The wing
+// terms of all three lines are evaluated first, branch-free (three independent chains, same formula as the fast
+// path); then only the lines that are within X0 Doppler widths -- normally one, the same for every lane of the warp
+// -- are replaced by the core evaluation, with voigt.c:287's exact rounding of the velocity.
 __device__ __noinline__ double tau_sum_3_exact(double lambda, double m0, double m1, double m2) {
-  const double X02 = GPDLA_VOIGT_X0 * GPDLA_VOIGT_X0;
-  double m[3] = {m0, m1, m2};
-  double t[3];
-#pragma unroll
-  for (int j = 0; j < 3; ++j) {
-    double x = __dsub_rn(__dmul_rn(lambda, m[j]), c_lines.c) * c_lines.inv_s2s;
-    double s = x * x;
-    t[j] = (s < X02) ? tau_core(j, x) : tau_wing(j, fast_rcp(s));
-  }
-  return (t[0] + t[1]) + t[2];
-}
-
-// exp(x) for x <= 0 (and small positive x), branch-free: Cody-Waite reduction, degree-11 polynomial
-// (tools/gen_voigt_tables.py), exponent assembled in integer registers.  The argument is clamped at -708.
-__constant__ double c_exp_poly[12] = GPDLA_EXP_POLY;
-__device__ __forceinline__ double exp_nonpos(double x) {
-  const double SHIFT = 6755399441055744.0;   // 1.5 * 2^52
-  // x <= 0 (or tiny positive): "below -708" is an unsigned compare of the high word (integer pipe)
-  const bool tiny = (unsigned)__double2hiint(x) > 0xC0862000u;   // x < -708 (hi word of -708.0 is 0xC0862000)
-  const double xc = tiny ? -708.0 : x;
-  double kd = fma(xc, 1.4426950408889634074, SHIFT);
-  const int k = __double2loint(kd);
-  kd -= SHIFT;
-  double r = fma(kd, -6.93147180369123816490e-01, xc);
-  r = fma(kd, -1.90821492927058770002e-10, r);
-  double p = c_exp_poly[11];
-#pragma unroll
-  for (int i = 10; i >= 0; --i) p = fma(p, r, c_exp_poly[i]);
-  // below -708 the result is exp(-708) = 3.3e-308 instead of the reference's libm value in [0, 2.3e-308]
-  return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+  const double v0 = fma(lambda, m0, -c_lines.c), v1 = fma(lambda, m1, -c_lines.c), v2 = fma(lambda, m2, -c_lines.c);
+  const double s0 = v0 * v0, s1 = v1 * v1, s2 = v2 * v2;
+  const double lim = c_wing3.v2min;
+  const bool k0 = hi_less(s0, lim), k1 = hi_less(s1, lim), k2 = hi_less(s2, lim);
+  double t0 = tau_wing3_line(0, fast_rcp(s0)), t1 = tau_wing3_line(1, fast_rcp(s1)), t2 = tau_wing3_line(2, fast_rcp(s2));
+  if (k0) t0 = tau_core(0, __dsub_rn(__dmul_rn(lambda, m0), c_lines.c) * c_lines.inv_s2s);
+  if (k1) t1 = tau_core(1, __dsub_rn(__dmul_rn(lambda, m1), c_lines.c) * c_lines.inv_s2s);
+  if (k2) t2 = tau_core(2, __dsub_rn(__dmul_rn(lambda, m2), c_lines.c) * c_lines.inv_s2s);
+  return (t0 + t1) + t2;
 }
 
 }  // namespace gpdla

@@ -94,3 +94,50 @@ def generate_dla_samples(num_dla_samples: int = 10000, catalog_log_nhis: Optiona
         log_nhi_samples[i] = brentq(g, lo, hi) if g(lo) * g(hi) < 0 else (lo if abs(g(lo)) < abs(g(hi)) else hi)
     return dict(offset_samples=offset_samples, log_nhi_samples=log_nhi_samples,
                 nhi_samples=10.0 ** log_nhi_samples, log_pdf_poly=f, alpha=alpha)
+
+
+def generate_lls_samples(num_dla_samples: int = 10000, catalog_log_nhis: Optional[Sequence[float]] = None,
+                         log_pdf_poly: Optional[Sequence[float]] = None, alpha: float = 0.97,
+                         min_lls_log_nhi: float = 19.5, uniform_min_log_nhi: float = 19.5,
+                         uniform_max_log_nhi: float = 23.0, fit_min_log_nhi: float = 20.0,
+                         fit_max_log_nhi: float = 22.0, extrapolate_min_log_nhi: float = 19.5,
+                         peak_log_nhi: float = 20.03269) -> Dict[str, np.ndarray]:
+    """``multi_dlas/set_lls_parameters.m:5-71``: the sub-DLA (Lyman-limit system) column-density samples and the
+    partition functions ``Z_lls`` / ``Z_dla`` of the multi-DLA model (``gpdla_set_lls_samples``).
+
+    Dimension 3 of the 3-D RR2-scrambled Halton sequence is mapped uniformly onto
+    ``[min_lls_log_nhi, fit_min_log_nhi)`` (:55-63).  The column-density density is the quadratic fit of
+    ``generate_dla_samples``, held constant at its value at ``peak_log_nhi`` below that point (:42-45), normalised
+    on ``[extrapolate_min_log_nhi, 25]`` (:46) and mixed with a uniform on ``[uniform_min, uniform_max]`` (:50-52);
+    ``Z_lls`` integrates the mixture over ``[min_lls_log_nhi, fit_min_log_nhi]``, ``Z_dla`` over
+    ``[fit_min_log_nhi, uniform_max_log_nhi]`` (:68-71).  Parity status: unpinned, like ``generate_dla_samples``.
+    """
+    from scipy.integrate import quad
+    seq = halton_rr2(num_dla_samples, 3)                                             # :15
+    if log_pdf_poly is None:
+        if catalog_log_nhis is None:
+            raise ValueError("need catalog_log_nhis or log_pdf_poly")
+        x = np.linspace(fit_min_log_nhi, fit_max_log_nhi, 1000)                      # :38
+        log_pdf_poly = np.polyfit(x, np.log(ksdensity_normal(catalog_log_nhis, x)), 2)   # :39-40
+    f = np.asarray(log_pdf_poly, dtype=np.float64)
+    plateau = float(np.exp(np.polyval(f, peak_log_nhi)))
+
+    def unnormalized_pdf(nhi):                                                       # :43-45 (heaviside(0) = 1/2)
+        nhi = np.asarray(nhi, dtype=np.float64)
+        h = np.where(nhi > peak_log_nhi, 1.0, np.where(nhi < peak_log_nhi, 0.0, 0.5))
+        return np.exp(np.polyval(f, nhi)) * h + plateau * (1.0 - h)
+
+    Z = quad(unnormalized_pdf, extrapolate_min_log_nhi, 25.0, points=[peak_log_nhi], limit=200)[0]   # :46
+    width = uniform_max_log_nhi - uniform_min_log_nhi
+
+    def normalized_pdf(nhi):                                                         # :50-52
+        u = ((nhi >= uniform_min_log_nhi) & (nhi <= uniform_max_log_nhi)) / width
+        return alpha * unnormalized_pdf(nhi) / Z + (1 - alpha) * u
+
+    lls_offset_samples = seq[:, 2]                                                   # :55
+    lls_log_nhi_samples = min_lls_log_nhi + (fit_min_log_nhi - min_lls_log_nhi) * lls_offset_samples   # :58-60
+    Z_lls = quad(normalized_pdf, min_lls_log_nhi, fit_min_log_nhi, limit=200)[0]     # :70
+    Z_dla = quad(normalized_pdf, fit_min_log_nhi, uniform_max_log_nhi, points=[peak_log_nhi], limit=200)[0]   # :71
+    return dict(offset_samples=seq[:, 0], lls_offset_samples=lls_offset_samples,
+                lls_log_nhi_samples=lls_log_nhi_samples, lls_nhi_samples=10.0 ** lls_log_nhi_samples,
+                Z_lls=float(Z_lls), Z_dla=float(Z_dla), log_pdf_poly=f, alpha=alpha)
