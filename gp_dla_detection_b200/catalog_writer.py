@@ -48,3 +48,65 @@ def write_results(path: str, results: Dict[str, np.ndarray], thing_ids: Sequence
                 results["log_priors_dla"][i], results["log_likelihoods_no_dla"][i],
                 results["log_likelihoods_dla"][i], _exp3(mp[i, 0]), _exp3(mp[i, 1])))
             f.write("%06.4f %07.4f\n" % (map_z[i], map_n[i]))
+
+
+def _item(x):
+    """numpy scalar -> Python scalar (``.item()`` in the reference), so that ``json`` can serialise it."""
+    return x.item() if hasattr(x, "item") else x
+
+
+def write_json_catalogue(path: str, results: Dict[str, np.ndarray], info: Dict[str, Sequence], sub_dla: bool = True):
+    """``predictions_multi_DLAs.json`` (CDDF_analysis/qso_loader.py:1927-2033, ``generate_json_catalogue``), the
+    Parks-et-al.-style catalogue of the multi-DLA run: one record per quasar with ``p_dla``, ``p_no_dla``, the
+    largest model posterior, the number of DLAs of the most probable model and their MAP ``(z_dla, log_nhi)``.
+
+    ``results`` is what ``process_qsos_multiple_dlas_meanflux`` returns (``model_posteriors`` with columns
+    [no DLA, sub-DLA, 1..max DLAs], ``MAP_z_dlas`` / ``MAP_log_nhis`` ``[Q, max_dlas, max_dlas]``, ``p_dlas``,
+    ``p_no_dlas``, ``min_z_dlas``, ``max_z_dlas``); ``info`` carries the per-quasar catalogue columns ``thing_ids,
+    z_qsos, snrs, ras, decs, plates, mjds, fiber_ids``.  As in the reference, a quasar whose most probable model is
+    the null or the sub-DLA model reports ``p_no_dla`` as its ``max_model_posterior`` and zero DLAs (:1970-1979).
+    Returns the list that was written."""
+    import json
+    mp = np.asarray(results["model_posteriors"])
+    model_index = np.array([int(np.argmax(r)) if not np.all(np.isnan(r)) else 0 for r in mp])
+    max_mp = np.array([r[i] for r, i in zip(mp, model_index)], dtype=np.float64)
+    off = 1 if sub_dla else 0
+    if sub_dla:
+        inds = model_index < 1 + off
+        max_mp[inds] = np.asarray(results["p_no_dlas"])[inds]
+    num_dlas = np.maximum(model_index - off, 0)
+    out = []
+    for i, thing_id in enumerate(info["thing_ids"]):
+        n = int(num_dlas[i])
+        spec = {
+            "p_dla": _item(results["p_dlas"][i]), "p_no_dla": _item(results["p_no_dlas"][i]),
+            "max_model_posterior": float(max_mp[i]), "num_dlas": n,
+            "min_z_dla": _item(results["min_z_dlas"][i]), "max_z_dla": _item(results["max_z_dlas"][i]),
+            "snr": _item(info["snrs"][i]), "ra": _item(info["ras"][i]), "dec": _item(info["decs"][i]),
+            "plate": _item(info["plates"][i]), "mjd": _item(info["mjds"][i]), "fiber_id": _item(info["fiber_ids"][i]),
+            "thing_id": _item(thing_id), "z_qso": _item(info["z_qsos"][i]),
+        }
+        spec["dlas"] = [{"log_nhi": float(results["MAP_log_nhis"][i, n - 1, j]),
+                         "z_dla": float(results["MAP_z_dlas"][i, n - 1, j])} for j in range(n)]
+        out.append(spec)
+    with open(path, "w") as f:
+        json.dump(out, f, indent=2)
+    return out
+
+
+def write_sub_dla_catalogue(path: str, results: Dict[str, np.ndarray], info: Dict[str, Sequence]):
+    """``predictions_sub_DLA_candidates.json`` (CDDF_analysis/qso_loader.py:2035-2090): the quasars whose most
+    probable model is the sub-DLA model (column 1 of ``model_posteriors``), with that posterior as ``p_sub_dla``."""
+    import json
+    mp = np.asarray(results["model_posteriors"])
+    out = []
+    for i in range(mp.shape[0]):
+        if np.all(np.isnan(mp[i])) or int(np.argmax(mp[i])) != 1:
+            continue
+        out.append({"p_sub_dla": float(mp[i, 1]), "ra": _item(info["ras"][i]), "snr": _item(info["snrs"][i]),
+                    "dec": _item(info["decs"][i]), "plate": _item(info["plates"][i]), "mjd": _item(info["mjds"][i]),
+                    "fiber_id": _item(info["fiber_ids"][i]), "thing_id": _item(info["thing_ids"][i]),
+                    "z_qso": _item(info["z_qsos"][i])})
+    with open(path, "w") as f:
+        json.dump(out, f, indent=2)
+    return out

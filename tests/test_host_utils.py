@@ -56,3 +56,30 @@ def test_lls_samples_and_partition_functions():
     z_dla = np.trapezoid(pdf[sel], grid[sel])
     assert abs(s["Z_lls"] - z_lls) < 1e-5 and abs(s["Z_dla"] - z_dla) < 1e-5
     assert 0.0 < s["Z_lls"] < s["Z_dla"] < 1.0 and s["Z_lls"] + s["Z_dla"] < 1.0
+
+
+def test_json_catalogues(tmp_path):
+    """qso_loader.py:1927-2090: record layout, num_dlas from the arg-max model, sub-DLA / null folded into p_no_dla."""
+    import json
+    from gp_dla_detection_b200 import catalog_writer as cw
+    mp = np.array([[0.7, 0.1, 0.15, 0.05], [0.1, 0.6, 0.2, 0.1], [0.05, 0.05, 0.2, 0.7], [0.1, 0.1, 0.6, 0.2]])
+    MAPz = np.arange(4 * 2 * 2, dtype=float).reshape(4, 2, 2) / 10 + 2.0
+    MAPn = np.arange(4 * 2 * 2, dtype=float).reshape(4, 2, 2) / 10 + 20.0
+    res = dict(model_posteriors=mp, p_no_dlas=mp[:, 0] + mp[:, 1], p_dlas=1 - mp[:, 0] - mp[:, 1],
+               min_z_dlas=np.full(4, 2.0), max_z_dlas=np.full(4, 3.0), MAP_z_dlas=MAPz, MAP_log_nhis=MAPn)
+    info = dict(thing_ids=np.array([11, 22, 33, 44]), z_qsos=np.full(4, 3.1), snrs=np.full(4, 5.0),
+                ras=np.arange(4.0), decs=-np.arange(4.0), plates=np.array([1, 2, 3, 4]), mjds=np.array([5, 6, 7, 8]),
+                fiber_ids=np.array([9, 10, 11, 12]))
+    out = cw.write_json_catalogue(str(tmp_path / "p.json"), res, info)
+    back = json.load(open(tmp_path / "p.json"))
+    assert back == out and [r["num_dlas"] for r in back] == [0, 0, 2, 1]
+    assert back[0]["max_model_posterior"] == 0.8 or abs(back[0]["max_model_posterior"] - 0.8) < 1e-15
+    assert abs(back[1]["max_model_posterior"] - 0.7) < 1e-15 and back[2]["max_model_posterior"] == 0.7
+    assert back[2]["dlas"] == [{"log_nhi": MAPn[2, 1, 0], "z_dla": MAPz[2, 1, 0]},
+                               {"log_nhi": MAPn[2, 1, 1], "z_dla": MAPz[2, 1, 1]}]
+    assert back[3]["dlas"] == [{"log_nhi": MAPn[3, 0, 0], "z_dla": MAPz[3, 0, 0]}] and back[0]["dlas"] == []
+    assert set(back[0]) == {"p_dla", "p_no_dla", "max_model_posterior", "num_dlas", "dlas", "min_z_dla", "max_z_dla",
+                            "ra", "snr", "dec", "plate", "mjd", "fiber_id", "thing_id", "z_qso"}
+    sub = cw.write_sub_dla_catalogue(str(tmp_path / "s.json"), res, info)
+    assert [r["thing_id"] for r in sub] == [22] and sub[0]["p_sub_dla"] == 0.6
+    assert json.load(open(tmp_path / "s.json")) == sub
