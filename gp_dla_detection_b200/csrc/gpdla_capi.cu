@@ -200,9 +200,6 @@ struct gpdla_ctx {
   double c_0 = 0, tau_0 = 0, beta = 0;
   // DLA samples
   double *d_offset = nullptr, *d_log_nhi = nullptr, *d_nhi = nullptr;
-  // the same samples in processing order (ascending redshift offset) and the column each one's result belongs to
-  double *d_offset_sorted = nullptr, *d_nhi_sorted = nullptr;
-  int32_t* d_sample_perm = nullptr;
   int64_t S = 0;
   // prior catalogue
   double* d_prior_z = nullptr;
@@ -578,7 +575,6 @@ void gpdla_destroy(gpdla_ctx* c) {
   free_workspace(c);
   cudaFree(c->d_rest); cudaFree(c->d_mu); cudaFree(c->d_M); cudaFree(c->d_log_omega);
   cudaFree(c->d_offset); cudaFree(c->d_log_nhi); cudaFree(c->d_nhi);
-  cudaFree(c->d_offset_sorted); cudaFree(c->d_nhi_sorted); cudaFree(c->d_sample_perm);
   cudaFree(c->d_prior_z); cudaFree(c->d_prior_dla); cudaFree(c->d_stage);
   cudaFree(c->d_pix2); cudaFree(c->d_colscale); cudaFree(c->d_colinv); cudaFree(c->d_bop); cudaFree(c->d_status);
   cudaFree(c->d_lls_nhi); cudaFree(c->d_uniforms); cudaFree(c->d_acache); cudaFree(c->d_msll); cudaFree(c->d_mlls);
@@ -654,21 +650,6 @@ int gpdla_set_samples(gpdla_ctx* c, const double* offset, const double* log_nhi,
   if ((rc = dev_upload(&c->d_log_nhi, log_nhi, S, c->err))) return rc;
   if ((rc = dev_upload(&c->d_nhi, nhi, S, c->err))) return rc;
   c->S = S;
-  // processing order of the single-DLA path (LoglikArgs::sample_perm); GPDLA_SORT_SAMPLES=0 keeps the caller's order
-  cudaFree(c->d_offset_sorted); cudaFree(c->d_nhi_sorted); cudaFree(c->d_sample_perm);
-  c->d_offset_sorted = c->d_nhi_sorted = nullptr; c->d_sample_perm = nullptr;
-  const char* env = getenv("GPDLA_SORT_SAMPLES");
-  if (S <= 2147483647LL && !(env && atoi(env) == 0)) {
-    std::vector<int32_t> perm((size_t)S);
-    for (int64_t i = 0; i < S; ++i) perm[(size_t)i] = (int32_t)i;
-    std::stable_sort(perm.begin(), perm.end(), [&](int32_t a, int32_t b) { return offset[a] < offset[b]; });
-    std::vector<double> so((size_t)S), sn((size_t)S);
-    for (int64_t i = 0; i < S; ++i) { so[(size_t)i] = offset[perm[(size_t)i]]; sn[(size_t)i] = nhi[perm[(size_t)i]]; }
-    if ((rc = dev_upload(&c->d_offset_sorted, so.data(), S, c->err))) return rc;
-    if ((rc = dev_upload(&c->d_nhi_sorted, sn.data(), S, c->err))) return rc;
-    CUDA_TRY(cudaMalloc(&c->d_sample_perm, (size_t)S * sizeof(int32_t)), c->err);
-    CUDA_TRY(cudaMemcpy(c->d_sample_perm, perm.data(), (size_t)S * sizeof(int32_t), cudaMemcpyHostToDevice), c->err);
-  }
   return GPDLA_OK;
 }
 
@@ -735,9 +716,6 @@ int gpdla_process_qsos_device(gpdla_ctx* c, int64_t Q, int64_t L_max, const doub
     LoglikArgs la;
     la.meta = c->d_meta; la.lam_pad = c->d_lam; la.pix = c->d_pix; la.P = c->d_P;
     la.offset_samples = c->d_offset; la.nhi_samples = c->d_nhi; la.S = c->S;
-    if (c->d_sample_perm && rank_splits(c->k) == 1) {   // (the column-split rank's Cholesky kernel writes by row)
-      la.offset_samples = c->d_offset_sorted; la.nhi_samples = c->d_nhi_sorted; la.sample_perm = c->d_sample_perm;
-    }
     la.num_lines = c->params.num_lines; la.NPIX = npix;
     la.sample_log_likelihoods = sll; la.log_likelihoods_no_dla = llno;
     la.sll_stride = c->S; la.acache = nullptr; la.partners = nullptr; la.num_partners = 0; la.active = nullptr;

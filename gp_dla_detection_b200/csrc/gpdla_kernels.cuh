@@ -401,11 +401,6 @@ struct LoglikArgs {
   double* sample_log_likelihoods;   // [Q x S] (row stride sll_stride)
   double* log_likelihoods_no_dla;   // [Q]; nullptr: no null-model slot (tiles cover S samples only)
   int64_t sll_stride;               // elements between consecutive quasars' rows of sample_log_likelihoods
-  // processing order: tile position p holds the sample parameters offset_samples[p], nhi_samples[p] and its result
-  // goes to column sample_perm[p] (nullptr: identity).  The host sorts the samples by redshift offset so that the
-  // 128 samples of a tile cross the line cores in the same pixel chunks (the rare core path then delays all
-  // warps of a cluster together instead of a different warp in every chunk)
-  const int32_t* sample_perm = nullptr;
   // multi-DLA levels (...meanflux.m:337-381): the convolved absorption of every sample is cached at level 1
   // (MODE 1) and levels >= 2 (MODE 2) multiply cached rows instead of re-evaluating Voigt profiles
   double* acache;                   // [Q x S x NPIX]
@@ -541,7 +536,7 @@ __device__ __forceinline__ void factor_staged(double* Cs, const double* s_q, con
       const double logdet = s_ld[sl] + log(prod0) + log(prod1);             //                           :30
       const double lp = -0.5 * (quad + logdet + (double)meta.n * LOG_2PI);  //                           :32
       const int64_t s = s0 + sl;
-      if (s < S) args.sample_log_likelihoods[(int64_t)q * args.sll_stride + (args.sample_perm ? args.sample_perm[s] : s)] = lp;
+      if (s < S) args.sample_log_likelihoods[(int64_t)q * args.sll_stride + s] = lp;
       else if (s == S && args.log_likelihoods_no_dla) args.log_likelihoods_no_dla[q] = lp;
     }
   }

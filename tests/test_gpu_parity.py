@@ -385,23 +385,3 @@ def test_persistent_and_one_tile_kernels_agree(api, synthetic_inputs, tmp_path):
             ok = ~np.isnan(a)
             assert np.all(np.abs(a[ok] - b[ok]) <= 1e-12 * np.maximum(1.0, np.abs(b[ok]))), k
 
-
-def test_processing_order_does_not_change_results(api, synthetic_inputs):
-    """The library walks the samples in ascending redshift offset (gpdla_set_samples sorts; LoglikArgs::sample_perm
-    routes every result back to its column).  A sample's arithmetic does not depend on its tile, so the results are
-    bit-identical to the caller's order (GPDLA_SORT_SAMPLES=0), for both Gram arithmetics."""
-    import os
-    from gp_dla_detection_b200 import synthetic as syn
-    si = synthetic_inputs
-    sp = syn.make_spectra(si["model"], 4, seed=77, dla_fraction=0.5)
-    sp["all_pixel_mask"][1][:] = True
-    sub = {k: v[:3001] for k, v in si["samples"].items()}          # not a multiple of the tile size
-    for digits in (6, -1):
-        sorted_res = api.process_qsos(si["model"], sub, sp, si["prior"], gram_digits=digits)
-        os.environ["GPDLA_SORT_SAMPLES"] = "0"
-        try:
-            plain = api.process_qsos(si["model"], sub, sp, si["prior"], gram_digits=digits)
-        finally:
-            del os.environ["GPDLA_SORT_SAMPLES"]
-        for k in sorted_res:
-            assert np.array_equal(np.asarray(sorted_res[k]), np.asarray(plain[k]), equal_nan=True), (digits, k)
