@@ -71,7 +71,7 @@ struct Shape {
   static constexpr int CSTR = TS + 4;
   static constexpr int NENT = (K + 1) * (K + 2) / 2;
   static_assert(L * NW <= TMEM_COLS, "diagonal accumulators must fit in TMEM");
-  static_assert(L >= 4 && L <= 7, "digit count");
+  static_assert(L >= 2 && L <= 7, "digit count");
   __host__ __device__ static constexpr int b_offset(int rank) { return rank * L * BW_PLANE; }
   __host__ __device__ static constexpr int b_bytes(int rank) { return L * (rank < WCTAS ? BW_PLANE : BU_PLANE); }
   __host__ __device__ static constexpr uint64_t digit_bias() {
@@ -831,16 +831,9 @@ dla_loglik_i8p_kernel(LoglikArgs args, I8Args xa, int num_quasars, int tiles_per
         for (int jj = 0; jj < 8; ++jj) {
           const int idx = c_i8_stage[rank * 128 + c0 + jj];
           if (idx >= 0) {
-            // sum_t v_t 256^t with the three low and the remaining high diagonals gathered in 64-bit integers
-            // (|v_t| < 2^27: exact), then one rounding -- two conversions and one FMA on the FP64 pipe instead
-            // of L conversions and L - 1 FMAs, next to producers that are waiting for that pipe
-            long long lo = (long long)(int32_t)v[2][jj];
-            lo = (lo << 8) + (long long)(int32_t)v[1][jj];
-            lo = (lo << 8) + (long long)(int32_t)v[0][jj];
-            long long hi = (long long)(int32_t)v[L - 1][jj];
+            double acc = (double)(int32_t)v[L - 1][jj];
 #pragma unroll
-            for (int tt = L - 2; tt >= 3; --tt) hi = (hi << 8) + (long long)(int32_t)v[tt][jj];
-            const double acc = fma((double)hi, 16777216.0, (double)lo);
+            for (int tt = L - 2; tt >= 0; --tt) acc = fma(acc, 256.0, (double)(int32_t)v[tt][jj]);
             st_cluster_f64(cs_remote + (uint32_t)(idx * CSTR * 8), acc * cs[c0 + jj]);
           }
         }
