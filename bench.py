@@ -163,6 +163,9 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if distributed:
+        # NCCL's own log lines (the version banner it prints under NCCL_DEBUG) belong on stderr: stdout carries the
+        # one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     # ---- synthetic catalogue shard (weak scaling: args.quasars per GPU), model, samples, prior
