@@ -162,10 +162,12 @@ def main():
     distributed = world > 1
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # stdout carries the one JSON line and nothing else: native libraries (NCCL prints its version banner there) get
+    # stderr as their file descriptor 1 for the whole run; the JSON line goes to the saved descriptor at the end
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if distributed:
-        # NCCL's own log lines (the version banner it prints under NCCL_DEBUG) belong on stderr: stdout carries the
-        # one JSON line
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     # ---- synthetic catalogue shard (weak scaling: args.quasars per GPU), model, samples, prior
@@ -306,7 +308,8 @@ def main():
             v, dt = cpu_baseline(model, samples, prior, spectra, nq, threads)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": "%d quasars x %d samples of the same workload (%.1f s)" % (nq, NUM_SAMPLES, dt)}
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if distributed:
         dist.destroy_process_group()
 
