@@ -696,6 +696,13 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(THREADS, 1) dl
 // (remote arrivals on the owner's bar_csfull) and free again (remote arrivals on every writer's bar_csfree[owner]),
 // per-sample scalars (bar_sq, double-buffered).  All main-loop barriers run on a chunk counter that spans tiles.
 constexpr int P_THREADS = 32 * (NCTRL + NPROD + 4);
+// Timing probes of the persistent kernel (compile-time, -DGPDLA_I8P_PROBE=bits; results are then wrong): 1 no
+// tcgen05.mma issue (commits only), 2 no row-block copies, 4 producers skip digit stores and proxy fence, 8 epilogue
+// skips the TMEM drain and the Cholesky.  Measurements: DESIGN.md 4.3.
+#ifndef GPDLA_I8P_PROBE
+#define GPDLA_I8P_PROBE 0
+#endif
+constexpr int PROBE = GPDLA_I8P_PROBE;
 constexpr int REG_CTRL = 48, REG_PROD = 168, REG_EPI = 128;
 static_assert(REG_CTRL * 128 + REG_PROD * 256 + REG_EPI * 128 <= 65536, "register budgets exceed the register file");
 
@@ -817,7 +824,7 @@ dla_loglik_i8p_kernel(LoglikArgs args, I8Args xa, int num_quasars, int tiles_per
       __syncwarp();
       asm volatile("tcgen05.fence::after_thread_sync;");
       const double* cs = xa.colscale + (int64_t)q * Sh::NCOLTAB + rank * Sh::NMAX;
-      for (int c0 = 0; c0 < N; c0 += 8) {
+      for (int c0 = 0; c0 < ((PROBE & 8) ? 0 : N); c0 += 8) {
         uint32_t v[L][8];
 #pragma unroll
         for (int tt = 0; tt < L; ++tt) {
@@ -848,7 +855,7 @@ dla_loglik_i8p_kernel(LoglikArgs args, I8Args xa, int num_quasars, int tiles_per
         mbar_wait_d(&bar_sq[it & 1], (it >> 1) & 1, xa.status, 12, xa.phase, 200);            // my producers' scalars
       }
       __syncwarp();
-      factor_staged<K, CSTR>(Cs, s_q + (it & 1) * TS, s_ld + (it & 1) * TS, e * 8, lane, meta, args, q, s0);
+      if (!(PROBE & 8)) factor_staged<K, CSTR>(Cs, s_q + (it & 1) * TS, s_ld + (it & 1) * TS, e * 8, lane, meta, args, q, s0);
       __syncwarp();
       if (lane == 0) {
         const uint32_t freebar = smem_u32(&bar_csfree[rank]);
@@ -1013,15 +1020,22 @@ dla_loglik_i8p_kernel(LoglikArgs args, I8Args xa, int num_quasars, int tiles_per
         mbar_wait_d(&bar_empty[stage], ((gc / STAGES) & 1) ^ 1, xa.status, 1, xa.phase);
         uint8_t* dW = wdst0 + stage * wstride + rowoff;
         uint8_t* dU = udst0 + stage * ustride + rowoff;
+        if (PROBE & 4) {   // keep the digits alive without storing them
+          uint64_t sink = 0;
 #pragma unroll
-        for (int ss = 0; ss < SPB; ++ss) {
+          for (int ss = 0; ss < SPB; ++ss) sink ^= xw[ss] ^ (xu[ss] << 1);
+          if (sink == 0x123456789abcdefull) dW[0] = 1;
+        } else {
 #pragma unroll
-          for (int j = 0; j < L; ++j) {
-            dW[ss * 16 + j * Sh::PLANE_A] = (uint8_t)(xw[ss] >> (8 * j));
-            dU[ss * 16 + j * Sh::PLANE_A] = (uint8_t)(xu[ss] >> (8 * j));
+          for (int ss = 0; ss < SPB; ++ss) {
+#pragma unroll
+            for (int j = 0; j < L; ++j) {
+              dW[ss * 16 + j * Sh::PLANE_A] = (uint8_t)(xw[ss] >> (8 * j));
+              dU[ss * 16 + j * Sh::PLANE_A] = (uint8_t)(xu[ss] >> (8 * j));
+            }
           }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar_rows[stage]);
         if ((c & 7) == 7) {
@@ -1068,7 +1082,8 @@ dla_loglik_i8p_kernel(LoglikArgs args, I8Args xa, int num_quasars, int tiles_per
           asm volatile("tcgen05.fence::after_thread_sync;");
           const uint64_t da0 = da_stage0 + (uint64_t)(uint32_t)(stage * (Sh::A_TILE >> 4));
           const uint64_t db0 = db_buf0 + (uint64_t)(uint32_t)(buf * (Sh::B_BUF >> 4));
-          if (rank < WCTAS) issue_chunk_mmas_fixed<Sh, L, Sh::NW>(tmem_base, da0, db0, c > 0);
+          if (PROBE & 1) { (void)da0; (void)db0; }
+          else if (rank < WCTAS) issue_chunk_mmas_fixed<Sh, L, Sh::NW>(tmem_base, da0, db0, c > 0);
           else issue_chunk_mmas_fixed<Sh, L, Sh::NU>(tmem_base, da0, db0, c > 0);
           mma_commit_multicast(&bar_empty[stage], (uint16_t)((1u << CLUSTER) - 1));
           mma_commit(&bar_pempty[buf]);
@@ -1104,6 +1119,7 @@ dla_loglik_i8p_kernel(LoglikArgs args, I8Args xa, int num_quasars, int tiles_per
           const uint32_t dst_off = smem_u32(At + stage * Sh::A_TILE) + rank * Sh::ROWBLOCK;
           const uint32_t other_rows = smem_u32(Sx + stage * Sh::ROWBLOCK);
           const uint32_t fullbar = smem_u32(&bar_full[stage]);
+          if (PROBE & 2) { mbar_arrive(&bar_full[stage]); continue; }
           for (uint32_t peer = 0; peer < (uint32_t)CLUSTER; ++peer) {
             if (peer == rank) continue;
             const uint32_t src = (rank < WCTAS && peer < WCTAS) ? dst_off : other_rows;
