@@ -42,6 +42,14 @@ constexpr int THREADS = 32 * (NCTRL + NPROD);
 constexpr int STAGES = 3;           // A-operand stages
 constexpr double CAP = 0.996;       // |x| <= CAP keeps the top signed digit within [-128, 127]
 constexpr int TMEM_COLS = 512;
+// Timing probes of the persistent kernel (compile-time, -DGPDLA_I8P_PROBE=bits; results are then wrong): 1 no
+// tcgen05.mma issue (commits only), 2 no row-block copies, 4 producers skip digit stores and proxy fence, 8 epilogue
+// skips the TMEM drain and the Cholesky, 16 MMAs with M = 64 instead of 128, 32 every MMA covers one digit plane only
+// (same instruction count, N = 80 / 32).  Measurements: DESIGN.md 4.3.
+#ifndef GPDLA_I8P_PROBE
+#define GPDLA_I8P_PROBE 0
+#endif
+constexpr int PROBE = GPDLA_I8P_PROBE;
 
 template <int K, int L>
 struct Shape {
@@ -219,9 +227,10 @@ __device__ __forceinline__ void issue_chunk_mmas_fixed(uint32_t tmem_base, uint6
     const uint64_t da = da0 + (uint64_t)((i * Sh::PLANE_A) >> 4);
 #pragma unroll
     for (int t0 = 0; t0 <= i; t0 += group) {
-      const int nt = (group < i + 1 - t0) ? group : i + 1 - t0;
+      const int nt = (PROBE & 32) ? 1 : ((group < i + 1 - t0) ? group : i + 1 - t0);
       const uint64_t db = db0 + (uint64_t)(((L - 1 - i + t0) * N * KC) >> 4);
-      mma_i8(tmem_base + (uint32_t)(t0 * N), da, db, make_idesc(nt * N), (accumulate || i < L - 1) ? 1u : 0u);
+      const uint32_t idesc = (PROBE & 16) ? (make_idesc(nt * N) & ~(0x1fu << 24)) | (4u << 24) : make_idesc(nt * N);
+      mma_i8(tmem_base + (uint32_t)(t0 * N), da, db, idesc, (accumulate || i < L - 1) ? 1u : 0u);
     }
   }
 }
@@ -696,13 +705,6 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(THREADS, 1) dl
 // (remote arrivals on the owner's bar_csfull) and free again (remote arrivals on every writer's bar_csfree[owner]),
 // per-sample scalars (bar_sq, double-buffered).  All main-loop barriers run on a chunk counter that spans tiles.
 constexpr int P_THREADS = 32 * (NCTRL + NPROD + 4);
-// Timing probes of the persistent kernel (compile-time, -DGPDLA_I8P_PROBE=bits; results are then wrong): 1 no
-// tcgen05.mma issue (commits only), 2 no row-block copies, 4 producers skip digit stores and proxy fence, 8 epilogue
-// skips the TMEM drain and the Cholesky.  Measurements: DESIGN.md 4.3.
-#ifndef GPDLA_I8P_PROBE
-#define GPDLA_I8P_PROBE 0
-#endif
-constexpr int PROBE = GPDLA_I8P_PROBE;
 constexpr int REG_CTRL = 48, REG_PROD = 168, REG_EPI = 128;
 static_assert(REG_CTRL * 128 + REG_PROD * 256 + REG_EPI * 128 <= 65536, "register budgets exceed the register file");
 
