@@ -45,7 +45,8 @@ constexpr int TMEM_COLS = 512;
 // Timing probes of the persistent kernel (compile-time, -DGPDLA_I8P_PROBE=bits; results are then wrong): 1 no
 // tcgen05.mma issue (commits only), 2 no row-block copies, 4 producers skip digit stores and proxy fence, 8 epilogue
 // skips the TMEM drain and the Cholesky, 16 MMAs with M = 64 instead of 128, 32 every MMA covers one digit plane only
-// (same instruction count, N = 80 / 32).  Measurements: DESIGN.md 4.3.
+// (same instruction count, N = 80 / 32), 64 producers skip the instrument convolution (no raw-row traffic through
+// shared memory).  Measurements: DESIGN.md 4.3.
 #ifndef GPDLA_I8P_PROBE
 #define GPDLA_I8P_PROBE 0
 #endif
@@ -965,6 +966,10 @@ dla_loglik_i8p_kernel(LoglikArgs args, I8Args xa, int num_quasars, int tiles_per
         if (MODE != 2) {
           double e[SPB];
           eval_raw(lambda, e);
+          if (PROBE & 64) {   // no instrument convolution: no raw-row traffic through shared memory
+#pragma unroll
+            for (int ss = 0; ss < SPB; ++ss) a[ss] = (__double2hiint(s_nhi[row0 + ss]) < 0) ? 1.0 : e[ss];
+          } else {
 #pragma unroll
           for (int ss = 0; ss < SPB; ++ss) myraw[ss * RAWS + 6 + lane] = e[ss];
           __syncwarp();
@@ -982,6 +987,7 @@ dla_loglik_i8p_kernel(LoglikArgs args, I8Args xa, int num_quasars, int tiles_per
           if (lane < 6) {
 #pragma unroll
             for (int ss = 0; ss < SPB; ++ss) myraw[ss * RAWS + lane] = carry[ss];
+          }
           }
           if (MODE == 1) {
 #pragma unroll
