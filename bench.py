@@ -274,10 +274,12 @@ def main():
                           "epilogue warpgroup, merged slice-pair MMAs)" % digits,
                 "note": "achieved/peak = FP64-equivalent Gram rate (S n k(k+3) per quasar, SURVEY 8(d)) over the measured "
                         "FP64 DMMA peak; the contraction itself runs as exact INT8 slice products on the tcgen05 tensor "
-                        "pipe, which leaves the FP64 pipe to the Voigt/weight arithmetic -- the stage that bounds the "
-                        "kernel (ncu: IMMA sub-pipe 67 % of SM-active cycles, FP64 pipe 36 %, issue slots 47 %; the "
-                        "producers alone need 2 460 of the 3 830 cycles per 32-pixel chunk; DESIGN.md 4.3). 132 of the "
-                        "148 SMs host clusters (4-CTA cluster placement)",
+                        "pipe. On B200 FP64 arithmetic makes no progress while a tcgen05.mma executes on the same SM "
+                        "(profiles/r01_mma_vs_alu.json), so a 32-pixel chunk costs the Voigt/weight arithmetic of the "
+                        "producers (2 775 cycles) plus the tensor time of the 21 exact slice products (964 cycles) plus "
+                        "the digit stores -- the 4 400 cycles measured; the FP64 DMMA Gram would need 3 840 cycles on "
+                        "that pipe instead of 964 (DESIGN.md 4.3). 132 of the 148 SMs host clusters (4-CTA cluster "
+                        "placement)",
                 "int8_tensor": {"achieved_tops": int8_ops * args.steps / (k_ms * 1e-3) * 1e-12 if k_ms > 0 else None,
                                 "peak_tops": 4283.0, "peak_source": "profiles/r01_tcgen05_i8.txt (this pool's B200, N = 240)"},
             })
