@@ -23,7 +23,7 @@ class GpdlaParams(ctypes.Structure):
                 ("prior_z_qso_increase", ctypes.c_double), ("min_z_cut", ctypes.c_double),
                 ("max_z_cut", ctypes.c_double), ("pixel_spacing", ctypes.c_double),
                 ("num_lines", ctypes.c_int32), ("batch_quasars", ctypes.c_int32),
-                ("gram_digits", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+                ("gram_digits", ctypes.c_int32), ("rest_table", ctypes.c_int32)]
 
 
 RESULT_F64 = ["min_z_dlas", "max_z_dlas", "log_priors_no_dla", "log_priors_dla", "log_likelihoods_no_dla",
@@ -88,6 +88,10 @@ SYMBOLS = {
     "gpdla_voigt_batch_device": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p,
                                                 ctypes.c_int64, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p]),
     "gpdla_line_constants": (None, [c_double_p, c_double_p, c_double_p, c_double_p]),
+    "gpdla_rest_table": (ctypes.c_int, [ctypes.c_int32, ctypes.c_double, c_double_p, c_i32_p, c_i32_p, c_double_p,
+                                        c_double_p]),
+    "gpdla_host_alloc": (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_uint64]),
+    "gpdla_host_free": (None, [ctypes.c_void_p]),
     "gpdla_objective": (ctypes.c_int, [ctypes.c_int64, ctypes.c_int32, ctypes.c_int32] + [ctypes.c_void_p] * 6),
     "gpdla_objective_device": (ctypes.c_int, [ctypes.c_int64, ctypes.c_int32, ctypes.c_int32] + [ctypes.c_void_p] * 7),
     "gpdla_default_preload_parameters": (None, [ctypes.POINTER(GpdlaPreloadParams)]),

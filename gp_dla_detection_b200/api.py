@@ -53,15 +53,28 @@ def pad_spectra(spectra: Dict) -> Dict[str, np.ndarray]:
     return out
 
 
+def _check_planes(W, F, V, Mk, lengths, z):
+    """The padded planes must share one [Q x L_max] shape and every length must fit its row."""
+    if W.ndim != 2 or F.shape != W.shape or V.shape != W.shape or Mk.shape != W.shape:
+        raise ValueError("wavelengths, flux, noise_variance and pixel_mask must share one (Q, L_max) shape")
+    if lengths.shape != (W.shape[0],) or z.shape != (W.shape[0],):
+        raise ValueError("lengths and z_qsos must have one entry per quasar")
+    if lengths.size and (lengths.min() < 0 or lengths.max() > W.shape[1]):
+        raise ValueError("lengths must lie in [0, L_max]")
+
+
 class DLAProcessor:
     """A libgpdla context holding the learned null model, the DLA samples and the prior
     catalogue on one GPU (what process_qsos.m:4-40 loads once before its quasar loop)."""
 
     def __init__(self, model: Dict, samples: Dict, prior: Dict, params: Parameters = DEFAULT, device: int = 0,
-                 batch_quasars: int = 0, gram_digits: int = 0):
+                 batch_quasars: int = 0, gram_digits: int = 0, rest_table: int = 0):
         """``gram_digits``: arithmetic of the Gram contraction -- 0 default (exact-product INT8 tensor-core path
-        with 6 digits for k = 20, FP64 DMMA otherwise), -1 FP64 DMMA, 5 / 6 INT8 path with that many digits."""
+        with 6 digits for k = 20, FP64 DMMA otherwise), -1 FP64 DMMA, 5 / 6 INT8 path with that many digits.
+        ``rest_table``: 0 default (optical depth from the rest-frame table away from the line centres), -1 direct
+        evaluation of the line sum everywhere (``gpdla_params.rest_table``)."""
         self._lib = _lib.load()
+        self._pinned = {}
         self._ctx = ctypes.c_void_p()
         _lib.check(self._lib.gpdla_create(ctypes.byref(self._ctx), int(device)))
         self.device = int(device)
@@ -73,6 +86,7 @@ class DLAProcessor:
         p.min_z_cut, p.max_z_cut = params.min_z_cut, params.max_z_cut
         p.pixel_spacing, p.num_lines, p.batch_quasars = params.pixel_spacing, params.num_lines, int(batch_quasars)
         p.gram_digits = int(gram_digits)
+        p.rest_table = int(rest_table)
         _lib.check(self._lib.gpdla_set_parameters(self._ctx, ctypes.byref(p)), self._ctx)
         rest, mu, M, lw = (_f64(model[k]) for k in ("rest_wavelengths", "mu", "M", "log_omega"))
         if M.shape != (rest.size, M.shape[1]) or mu.size != rest.size or lw.size != rest.size:
@@ -97,6 +111,23 @@ class DLAProcessor:
         if getattr(self, "_ctx", None) is not None and self._ctx:
             self._lib.gpdla_destroy(self._ctx)
             self._ctx = ctypes.c_void_p()
+        for ptr, _ in getattr(self, "_pinned", {}).values():
+            self._lib.gpdla_host_free(ptr)
+        self._pinned = {}
+
+    def _pinned_array(self, name: str, shape, dtype=np.float64) -> np.ndarray:
+        """A page-locked host array owned by this processor (``gpdla_host_alloc``), reused while the shape
+        holds: result copies into it overlap the next batch's kernels.  Valid until the next call / ``close``."""
+        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        have = self._pinned.get(name)
+        if have is None or have[1] < nbytes:
+            if have is not None:
+                self._lib.gpdla_host_free(have[0])
+            ptr = ctypes.c_void_p()
+            _lib.check(self._lib.gpdla_host_alloc(ctypes.byref(ptr), max(nbytes, 1)))
+            self._pinned[name] = have = (ptr, nbytes)
+        buf = (ctypes.c_char * max(nbytes, 1)).from_address(have[0].value)
+        return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
 
     def __del__(self):
         try:
@@ -118,18 +149,27 @@ class DLAProcessor:
         return ms.value, n.value
 
     # ---------------------------------------------------------------- host buffers (the drop-in call)
-    def process(self, spectra: Dict, return_sample_log_likelihoods: bool = True) -> Dict[str, np.ndarray]:
+    def process(self, spectra: Dict, return_sample_log_likelihoods: bool = True,
+                pinned_results: bool = False) -> Dict[str, np.ndarray]:
+        """The body of process_qsos.m for the given spectra (host arrays in, host arrays out).
+        ``pinned_results``: ``sample_log_likelihoods_dla`` (80 KB per quasar) is returned in a page-locked buffer
+        owned by this processor -- valid until the next ``process`` call -- so that its copy overlaps compute."""
         sp = pad_spectra(spectra)
         W, F, V = _f64(sp["wavelengths"]), _f64(sp["flux"]), _f64(sp["noise_variance"])
         Mk = np.ascontiguousarray(sp["pixel_mask"], dtype=np.uint8)
-        lengths = np.ascontiguousarray(sp["lengths"], dtype=np.int32)
-        z = _f64(sp["z_qsos"])
+        lengths = np.ascontiguousarray(sp["lengths"], dtype=np.int32).ravel()
+        z = _f64(sp["z_qsos"]).ravel()
+        _check_planes(W, F, V, Mk, lengths, z)
         Q, L_max = W.shape
         S = self.num_dla_samples
         out = {n: np.full((Q, 2) if n == "model_posteriors" else (Q,), np.nan) for n in RESULT_NAMES}
         out["map_inds"] = np.full(Q, -1, dtype=np.int64)
         if return_sample_log_likelihoods:
-            out["sample_log_likelihoods_dla"] = np.full((Q, S), np.nan)
+            if pinned_results:
+                out["sample_log_likelihoods_dla"] = self._pinned_array("sll", (Q, S))
+                out["sample_log_likelihoods_dla"].fill(np.nan)
+            else:
+                out["sample_log_likelihoods_dla"] = np.full((Q, S), np.nan)
         res = _lib.GpdlaResults()
         for n in _lib.RESULT_F64:
             setattr(res, n, out[n].ctypes.data if n in out else None)
@@ -152,8 +192,9 @@ class DLAProcessor:
         sp = pad_spectra(spectra)
         W, F, V = _f64(sp["wavelengths"]), _f64(sp["flux"]), _f64(sp["noise_variance"])
         Mk = np.ascontiguousarray(sp["pixel_mask"], dtype=np.uint8)
-        lengths = np.ascontiguousarray(sp["lengths"], dtype=np.int32)
-        z = _f64(sp["z_qsos"])
+        lengths = np.ascontiguousarray(sp["lengths"], dtype=np.int32).ravel()
+        z = _f64(sp["z_qsos"]).ravel()
+        _check_planes(W, F, V, Mk, lengths, z)
         Q, L_max = W.shape
         S, MD = self.num_dla_samples, int(max_dlas)
         shapes = dict(log_priors_dla=(Q, MD), log_likelihoods_dla=(Q, MD), log_posteriors_dla=(Q, MD),
@@ -214,9 +255,10 @@ class DLAProcessor:
 
 
 def process_qsos(model: Dict, samples: Dict, spectra: Dict, prior: Dict, params: Parameters = DEFAULT,
-                 device: int = 0, return_sample_log_likelihoods: bool = True, gram_digits: int = 0) -> Dict[str, np.ndarray]:
+                 device: int = 0, return_sample_log_likelihoods: bool = True, gram_digits: int = 0,
+                 rest_table: int = 0) -> Dict[str, np.ndarray]:
     """Run the DLA detection algorithm on the given objects (process_qsos.m)."""
-    proc = DLAProcessor(model, samples, prior, params, device, gram_digits=gram_digits)
+    proc = DLAProcessor(model, samples, prior, params, device, gram_digits=gram_digits, rest_table=rest_table)
     try:
         return proc.process(spectra, return_sample_log_likelihoods)
     finally:
@@ -227,10 +269,11 @@ def process_qsos_multiple_dlas_meanflux(model: Dict, samples: Dict, spectra: Dic
                                         params: Parameters = DEFAULT, device: int = 0,
                                         base_sample_inds: Optional[np.ndarray] = None,
                                         return_samples: bool = True, batch_quasars: int = 0,
-                                        gram_digits: int = 0) -> Dict[str, np.ndarray]:
+                                        gram_digits: int = 0, rest_table: int = 0) -> Dict[str, np.ndarray]:
     """Multi-DLA / sub-DLA / mean-flux processing (multi_dlas/process_qsos_multiple_dlas_meanflux.m).
     ``samples`` additionally holds ``lls_nhi_samples``, ``Z_lls``, ``Z_dla`` (set_lls_parameters.m)."""
-    proc = DLAProcessor(model, samples, prior, params, device, batch_quasars=batch_quasars, gram_digits=gram_digits)
+    proc = DLAProcessor(model, samples, prior, params, device, batch_quasars=batch_quasars, gram_digits=gram_digits,
+                        rest_table=rest_table)
     try:
         return proc.process_multi(spectra, max_dlas, base_sample_inds, return_samples)
     finally:

@@ -7,6 +7,9 @@
 #include <string.h>
 
 #include <algorithm>
+#include <map>
+#include <mutex>
+#include <numeric>
 #include <random>
 #include <string>
 #include <vector>
@@ -16,8 +19,10 @@
 #include "gpdla_i8_kernels.cuh"
 #include "gpdla_preload.cuh"
 #include "gpdla_objective.cuh"
+#include "gpdla_rest_table.h"
 
 using namespace gpdla;
+static_assert(RT_DEG == RT_DEG_DEV, "host builder and device lookup must agree on the table's polynomial degree");
 
 // ---------------------------------------------------------------------------- Lyman series data
 // Physical data of the hydrogen Lyman series, members 1..31 (the same atomic data the reference
@@ -80,12 +85,67 @@ thread_local std::string g_err;   // errors of the context-free entry points
     }                                                                                       \
   } while (0)
 
-int upload_line_constants(std::string& err) {
+// Every entry point runs on its context's device and leaves the caller's current device as it found it.
+struct DeviceGuard {
+  int prev = -1;
+  cudaError_t status = cudaSuccess;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) status = cudaSetDevice(dev);
+  }
+  ~DeviceGuard() {
+    int cur = -1;
+    if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+  }
+};
+
+// Per-device library state (constant memory, function attributes, occupancy), shared by all contexts of the process
+// and guarded by one mutex per device: contexts on several GPUs may be driven from several host threads.
+constexpr int MAX_DEVICES = 64;
+struct DeviceState {
+  std::mutex mu;
+  bool constants = false;                    // c_lines, c_forest, c_wing3, stage-index tables uploaded
+  std::map<const void*, size_t> smem;        // kernel -> configured dynamic shared memory
+  std::map<const void*, int> clusters;       // persistent kernel -> resident clusters
+};
+DeviceState g_dev[MAX_DEVICES];
+
+// accumulator column -> augmented-triangle index of the epilogue staging area, for rank K
+template <int K>
+static void fill_stage_index(short* tab) {
+  using G = GramShape<K>;
+  for (int c = 0; c < G::NCOL; ++c) tab[c] = -1;
+  for (int p = 0; p < K; ++p) {
+    for (int q = p; q < K; ++q) tab[G::pair_index(p, q)] = (short)aug_index<K>(p, q);
+    tab[G::WT * 8 + p] = (short)aug_index<K>(p, K);
+  }
+}
+// INT8 path: accumulator column (CTA rank, n) -> augmented-triangle index (the same for every digit count)
+template <int K>
+static void fill_i8_stage_index(short* tab) {
+  using Sh = i8::Shape<K, 6>;
+  using G = GramShape<K>;
+  for (int i = 0; i < i8::CLUSTER * 128; ++i) tab[i] = -1;
+  for (int p = 0; p < K; ++p) {
+    for (int q = p; q < K; ++q) {
+      const int c = G::pair_index(p, q);
+      tab[(c / Sh::WCOLS) * 128 + c % Sh::WCOLS] = (short)aug_index<K>(p, q);
+    }
+    tab[i8::WCTAS * 128 + p] = (short)aug_index<K>(p, K);
+  }
+}
+
+constexpr int I8_K = 20;   // rank of the INT8 tensor-core Gram path
+constexpr int ORDER_GROUP = 0;   // 0: samples fully sorted by redshift (measured best: 63.5 ms per 296 quasars against 69.9 with
+                                 // scattered groups of 4 and 64.7 with scattered groups of 32)
+
+// Constant memory of the current device, once per device.
+int upload_device_constants(std::string& err) {
   int dev = -1;
   CUDA_TRY(cudaGetDevice(&dev), err);
-  static std::vector<char> done;   // per device
-  if ((int)done.size() <= dev) done.resize(dev + 1, 0);
-  if (done[dev]) return GPDLA_OK;
+  if (dev < 0 || dev >= MAX_DEVICES) { err = "device index out of range"; return GPDLA_ERR_CUDA; }
+  std::lock_guard<std::mutex> lock(g_dev[dev].mu);
+  if (g_dev[dev].constants) return GPDLA_OK;
   cudaDeviceProp prop;
   CUDA_TRY(cudaGetDeviceProperties(&prop, dev), err);
   if (prop.major != 10) {
@@ -125,41 +185,27 @@ int upload_line_constants(std::string& err) {
     w3.v2min = GPDLA_VOIGT_X0 * GPDLA_VOIGT_X0 * two_s2;
     CUDA_TRY(cudaMemcpyToSymbol(c_wing3, &w3, sizeof w3), err);
   }
-  done[dev] = 1;
+  {  // stage-index tables of every compiled rank (one table per rank: contexts of different k share a device)
+    static short t10[GramShape<10>::NCOL], t20[GramShape<20>::NCOL], t40[GramShape<40>::NCOL], ti8[i8::CLUSTER * 128];
+    fill_stage_index<10>(t10); fill_stage_index<20>(t20); fill_stage_index<40>(t40); fill_i8_stage_index<I8_K>(ti8);
+    CUDA_TRY(cudaMemcpyToSymbol(c_stage_index_10, t10, sizeof t10), err);
+    CUDA_TRY(cudaMemcpyToSymbol(c_stage_index_20, t20, sizeof t20), err);
+    CUDA_TRY(cudaMemcpyToSymbol(c_stage_index_40, t40, sizeof t40), err);
+    CUDA_TRY(cudaMemcpyToSymbol(i8::c_i8_stage, ti8, sizeof ti8), err);
+  }
+  g_dev[dev].constants = true;
   return GPDLA_OK;
 }
 
-
-// accumulator column -> augmented-triangle index of the epilogue staging area, for rank K
-template <int K>
-static int upload_stage_index(std::string& err) {
-  using G = GramShape<K>;
-  static_assert(G::NCOL <= MAX_NCOL, "stage index table too small");
-  static short tab[MAX_NCOL];
-  for (int c = 0; c < MAX_NCOL; ++c) tab[c] = -1;
-  for (int p = 0; p < K; ++p) {
-    for (int q = p; q < K; ++q) tab[G::pair_index(p, q)] = (short)aug_index<K>(p, q);
-    tab[G::WT * 8 + p] = (short)aug_index<K>(p, K);
+// dynamic shared memory opt-in of a kernel on the current context's device, once per (device, kernel, size)
+template <class Kern>
+static int configure_smem(int dev, Kern kern, size_t smem, std::string& err) {
+  std::lock_guard<std::mutex> lock(g_dev[dev].mu);
+  size_t& have = g_dev[dev].smem[(const void*)kern];
+  if (have < smem) {
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), err);
+    have = smem;
   }
-  CUDA_TRY(cudaMemcpyToSymbol(c_stage_index, tab, sizeof tab), err);
-  return GPDLA_OK;
-}
-
-// INT8 path: accumulator column (CTA rank, n) -> augmented-triangle index
-template <int K, int L>
-static int upload_i8_stage_index(std::string& err) {
-  using Sh = i8::Shape<K, L>;
-  using G = GramShape<K>;
-  static short tab[i8::CLUSTER * 128];
-  for (auto& t : tab) t = -1;
-  for (int p = 0; p < K; ++p) {
-    for (int q = p; q < K; ++q) {
-      const int c = G::pair_index(p, q);
-      tab[(c / Sh::WCOLS) * 128 + c % Sh::WCOLS] = (short)aug_index<K>(p, q);
-    }
-    tab[i8::WCTAS * 128 + p] = (short)aug_index<K>(p, K);
-  }
-  CUDA_TRY(cudaMemcpyToSymbol(i8::c_i8_stage, tab, sizeof tab), err);
   return GPDLA_OK;
 }
 
@@ -198,9 +244,14 @@ struct gpdla_ctx {
   double *d_rest = nullptr, *d_mu = nullptr, *d_M = nullptr, *d_log_omega = nullptr;
   int n_rest = 0, k = 0;
   double c_0 = 0, tau_0 = 0, beta = 0;
-  // DLA samples
+  // DLA samples; d_order = sample indices in ascending redshift offset (the order the kernels walk them in)
   double *d_offset = nullptr, *d_log_nhi = nullptr, *d_nhi = nullptr;
+  int32_t* d_order = nullptr;
   int64_t S = 0;
+  // rest-frame table of tau / N (gpdla_rest_table.h), rebuilt when num_lines / pixel_spacing change
+  double* d_rt = nullptr;
+  int rt_ncell = 0, rt_num_lines = 0;
+  double rt_pixel_spacing = 0, rt_h = 0;
   // prior catalogue
   double* d_prior_z = nullptr;
   uint8_t* d_prior_dla = nullptr;
@@ -210,18 +261,24 @@ struct gpdla_ctx {
   int64_t ws_S = 0;
   double *d_gram = nullptr, *d_qld = nullptr;   // column-split ranks: global accumulator staging
   QuasarMeta* d_meta = nullptr;
-  double *d_lam = nullptr, *d_pix = nullptr, *d_Mq = nullptr, *d_P = nullptr, *d_sll = nullptr, *d_scratch = nullptr;
+  double *d_lam = nullptr, *d_lamh = nullptr, *d_pix = nullptr, *d_Mq = nullptr, *d_P = nullptr, *d_sll = nullptr,
+         *d_scratch = nullptr;
   int64_t* d_scratch_i = nullptr;
   // INT8 tensor-core Gram path (k = 20): digit operands and scales
   int i8_batch = 0, i8_npix = 0;
   double *d_pix2 = nullptr, *d_colscale = nullptr, *d_colinv = nullptr;
   uint8_t* d_bop = nullptr;
   int* d_status = nullptr;
+  int32_t* d_f64flag = nullptr;       // [batch] flags + {count, list}: quasars the INT8 path leaves to the FP64 kernels
+  unsigned long long* d_phase = nullptr;   // GPDLA_I8_PHASES diagnostics
   // staging for the host entry point
   size_t st_bytes = 0;
   void* d_stage = nullptr;
+  cudaStream_t stream = nullptr, copy_stream = nullptr;   // the host entries' own (non-default) streams
+  cudaEvent_t ev_batch[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
   // multi-DLA path
   double* d_lls_nhi = nullptr;
+  int64_t lls_S = 0;
   double Z_lls = 0, Z_dla = 0;
   double* d_uniforms = nullptr;       // [3 x S] rand stream of rng('default')
   int mws_batch = 0, mws_npix = 0;
@@ -233,11 +290,19 @@ struct gpdla_ctx {
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
 };
 
+// Gram arithmetic of this context: digits of the INT8 path (k = 20), 0 = FP64 DMMA kernels
+static int i8_digits(const gpdla_ctx* c) {
+  int d = c->params.gram_digits;
+  if (d == 0) d = 6;
+  return (c->k == I8_K && (d == 5 || d == 6)) ? d : 0;
+}
+static bool use_i8(const gpdla_ctx* c) { return i8_digits(c) > 0; }
+
 static void free_workspace(gpdla_ctx* c) {
-  cudaFree(c->d_meta); cudaFree(c->d_lam); cudaFree(c->d_pix); cudaFree(c->d_Mq); cudaFree(c->d_P);
+  cudaFree(c->d_meta); cudaFree(c->d_lam); cudaFree(c->d_lamh); cudaFree(c->d_pix); cudaFree(c->d_Mq); cudaFree(c->d_P);
   cudaFree(c->d_sll); cudaFree(c->d_scratch); cudaFree(c->d_scratch_i); cudaFree(c->d_gram); cudaFree(c->d_qld);
   c->d_gram = c->d_qld = nullptr;
-  c->d_meta = nullptr; c->d_lam = c->d_pix = c->d_Mq = c->d_P = c->d_sll = c->d_scratch = nullptr;
+  c->d_meta = nullptr; c->d_lam = c->d_lamh = c->d_pix = c->d_Mq = c->d_P = c->d_sll = c->d_scratch = nullptr;
   c->d_scratch_i = nullptr;
   c->ws_batch = c->ws_npix = c->ws_k = 0; c->ws_S = 0;
 }
@@ -248,8 +313,10 @@ static int ensure_workspace(gpdla_ctx* c, int batch, int npix) {
   const size_t B = batch;
   CUDA_TRY(cudaMalloc(&c->d_meta, B * sizeof(QuasarMeta)), c->err);
   CUDA_TRY(cudaMalloc(&c->d_lam, B * (npix + 8) * sizeof(double)), c->err);
+  CUDA_TRY(cudaMalloc(&c->d_lamh, B * (npix + 8) * sizeof(double)), c->err);
   CUDA_TRY(cudaMalloc(&c->d_pix, B * npix * 4 * sizeof(double)), c->err);
   CUDA_TRY(cudaMalloc(&c->d_Mq, B * npix * c->k * sizeof(double)), c->err);
+  // FP64 Gram operand: the FP64 path's, and the INT8 path's fallback for quasars with zero-noise-variance pixels
   CUDA_TRY(cudaMalloc(&c->d_P, B * (npix / KC) * gram_doubles_per_chunk_all_splits(c->k) * sizeof(double)), c->err);
   CUDA_TRY(cudaMalloc(&c->d_sll, B * c->S * sizeof(double)), c->err);
   CUDA_TRY(cudaMalloc(&c->d_scratch, B * 16 * sizeof(double)), c->err);
@@ -263,96 +330,86 @@ static int ensure_workspace(gpdla_ctx* c, int batch, int npix) {
   return GPDLA_OK;
 }
 
-// schedule of the fused kernel: 1 = warp-specialised (one DMMA warp per SM sub-partition), 0 = warp-autonomous
-static int fused_schedule() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("GPDLA_SCHEDULE"); v = (e && e[0] == 'a') ? 0 : 1; }
-  return v;
+// The rest-frame table of tau / N for the context's line count and pixel spacing (built on the host in long double,
+// ~10 ms for three lines; gpdla_params.rest_table = -1 disables it: direct evaluation everywhere).
+static int ensure_rest_table(gpdla_ctx* c) {
+  if (c->params.rest_table < 0) return GPDLA_OK;
+  if (c->d_rt && c->rt_num_lines == c->params.num_lines && c->rt_pixel_spacing == c->params.pixel_spacing) return GPDLA_OK;
+  LineConstants lc;
+  fill_line_constants(&lc);
+  const RestTableHost t = build_rest_table(c->params.num_lines, c->params.pixel_spacing, RT_NEAR_PIXELS, lc.tw, lc.lc,
+                                           lc.gam, kSigma, kC);
+  int rc = dev_upload(&c->d_rt, t.coef.data(), t.coef.size(), c->err);
+  if (rc) return rc;
+  c->rt_ncell = t.ncell; c->rt_h = t.h; c->rt_num_lines = c->params.num_lines; c->rt_pixel_spacing = c->params.pixel_spacing;
+  return GPDLA_OK;
+}
+static RestTable rest_table_args(const gpdla_ctx* c) {
+  RestTable rt;
+  const bool on = c->params.rest_table >= 0 && c->d_rt != nullptr;
+  rt.coef = on ? c->d_rt : nullptr;
+  rt.ncell = c->rt_ncell;
+  rt.inv_h = 1.0 / (c->params.pixel_spacing * log(10.0));
+  rt.lam_lo = RT_LAMBDA_LO;
+  return rt;
 }
 
+// The FP64 DMMA kernels.  With la.only_list (the INT8 path's fallback) a few grid.y slots stride over the listed quasars.
+constexpr int FALLBACK_SLOTS = 8;
 template <int K, int NL, int MODE, int NSPLIT>
-static int launch_loglik(gpdla_ctx* c, LoglikArgs la, int nq, cudaStream_t st) {
-  const bool ws = fused_schedule() == 1;
-  using Cfg = LoglikConfig<K, NSPLIT>;
+static int launch_loglik(gpdla_ctx* c, LoglikArgs la, int nq, cudaStream_t st, bool timed = true) {
   using WCfg = WsConfig<K, NSPLIT>;
-  auto kern_wa = dla_loglik_kernel<K, NL, MODE, NSPLIT>;
-  auto kern_ws = dla_loglik_ws_kernel<K, NL, MODE, NSPLIT>;
-  const size_t smem = ws ? WCfg::smem_bytes(la.num_lines) : Cfg::smem_bytes(la.num_lines);
-  const int TS = ws ? WCfg::TS : Cfg::TS;
-  static size_t configured[2][64] = {};   // per schedule and device: function attributes are per device
-  const int dev = c->device & 63;
-  if (configured[ws][dev] < smem) {
-    if (ws) CUDA_TRY(cudaFuncSetAttribute(kern_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), c->err);
-    else CUDA_TRY(cudaFuncSetAttribute(kern_wa, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), c->err);
-    configured[ws][dev] = smem;
+  auto kern = dla_loglik_ws_kernel<K, NL, MODE, NSPLIT>;
+  if (la.only_list) {
+    if constexpr (K == I8_K) kern = dla_loglik_ws_list_kernel<K, NL, MODE, NSPLIT>;
+    else { c->err = "FP64 fallback list: rank without an INT8 path"; return GPDLA_ERR_UNSUPPORTED; }
   }
+  const size_t smem = WCfg::smem_bytes(la.num_lines);
+  const int TS = WCfg::TS;
+  int rc = configure_smem(c->device, kern, smem, c->err);
+  if (rc) return rc;
   const unsigned tiles = (unsigned)((la.S + (la.log_likelihoods_no_dla ? 1 : 0) + TS - 1) / TS);
-  dim3 grid(tiles, (unsigned)nq, NSPLIT);
+  dim3 grid(tiles, la.only_list ? (unsigned)std::min(nq, FALLBACK_SLOTS) : (unsigned)nq, NSPLIT);
   la.gram = c->d_gram; la.qld = c->d_qld; la.gram_rows = ((int64_t)c->S + 1 + 63) / 64 * 64;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
-  if (c->profiling) {
+  if (c->profiling && timed) {
     CUDA_TRY(cudaEventCreate(&e0), c->err);
     CUDA_TRY(cudaEventCreate(&e1), c->err);
     CUDA_TRY(cudaEventRecord(e0, st), c->err);
   }
-  if (ws) kern_ws<<<grid, WS_THREADS, smem, st>>>(la);
-  else kern_wa<<<grid, NTHREADS, smem, st>>>(la);
+  kern<<<grid, WS_THREADS, smem, st>>>(la);
   c->launches++;
   CUDA_TRY(cudaGetLastError(), c->err);
   if (NSPLIT > 1) {
     CholArgs ca;
     ca.meta = la.meta; ca.gram = c->d_gram; ca.qld = c->d_qld; ca.gram_rows = la.gram_rows; ca.S = la.S;
     ca.sample_log_likelihoods = la.sample_log_likelihoods; ca.sll_stride = la.sll_stride;
-    ca.log_likelihoods_no_dla = la.log_likelihoods_no_dla; ca.active = la.active;
-    static bool chol_configured[64] = {};
-    if (!chol_configured[dev]) {
-      CUDA_TRY(cudaFuncSetAttribute(cholesky_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)cholesky_smem_bytes<K>()), c->err);
-      chol_configured[dev] = true;
-    }
+    ca.log_likelihoods_no_dla = la.log_likelihoods_no_dla; ca.active = la.active; ca.order = la.order;
+    rc = configure_smem(c->device, cholesky_kernel<K>, cholesky_smem_bytes<K>(), c->err);
+    if (rc) return rc;
     cholesky_kernel<K><<<dim3(tiles * TS / CHOL_SAMPLES, (unsigned)nq), CHOL_SAMPLES * 4,
                          cholesky_smem_bytes<K>(), st>>>(ca);
     c->launches++;
     CUDA_TRY(cudaGetLastError(), c->err);
   }
-  if (c->profiling) {
+  if (c->profiling && timed) {
     CUDA_TRY(cudaEventRecord(e1, st), c->err);
     c->prof_events.emplace_back(e0, e1);
   }
   return GPDLA_OK;
 }
 
-// Gram path: 8 = INT8 tcgen05 (k = 20 only; digits from GPDLA_I8_DIGITS, default 6), 0 = FP64 DMMA.
-// GPDLA_GRAM=f64 forces the FP64 kernels.
-constexpr int I8_K = 20;
-static int i8_default_digits() {
-  static int v = -2;
-  if (v == -2) {
-    const char* g = getenv("GPDLA_GRAM");
-    const char* d = getenv("GPDLA_I8_DIGITS");
-    if (g && g[0] == 'f') v = -1;
-    else v = (d && d[0] == '5') ? 5 : 6;
-  }
-  return v;
-}
-// digits of the INT8 path for this context, 0 = FP64 DMMA kernels
-static int i8_digits(const gpdla_ctx* c) {
-  int d = c->params.gram_digits;
-  if (d == 0) d = i8_default_digits();
-  return (c->k == I8_K && (d == 5 || d == 6)) ? d : 0;
-}
-static bool use_i8(const gpdla_ctx* c) { return i8_digits(c) > 0; }
-
 static int ensure_i8_workspace(gpdla_ctx* c, int batch, int npix) {
   if (c->i8_batch >= batch && c->i8_npix == npix) return GPDLA_OK;
-  cudaFree(c->d_pix2); cudaFree(c->d_colscale); cudaFree(c->d_colinv); cudaFree(c->d_bop);
-  c->d_pix2 = c->d_colscale = c->d_colinv = nullptr; c->d_bop = nullptr; c->i8_batch = 0;
+  cudaFree(c->d_pix2); cudaFree(c->d_colscale); cudaFree(c->d_colinv); cudaFree(c->d_bop); cudaFree(c->d_f64flag);
+  c->d_pix2 = c->d_colscale = c->d_colinv = nullptr; c->d_bop = nullptr; c->d_f64flag = nullptr; c->i8_batch = 0;
   const size_t B = batch;
   using Sh = i8::Shape<I8_K, 6>;    // the 6-digit layout is the larger one
   CUDA_TRY(cudaMalloc(&c->d_pix2, B * npix * 2 * sizeof(double)), c->err);
   CUDA_TRY(cudaMalloc(&c->d_colscale, B * Sh::NCOLTAB * sizeof(double)), c->err);
   CUDA_TRY(cudaMalloc(&c->d_colinv, B * Sh::NCOLTAB * sizeof(double)), c->err);
   CUDA_TRY(cudaMalloc(&c->d_bop, B * (npix / KC) * Sh::CHUNK_BYTES), c->err);
+  CUDA_TRY(cudaMalloc(&c->d_f64flag, (2 * B + 2) * sizeof(int32_t)), c->err);
   if (!c->d_status) {
     CUDA_TRY(cudaMalloc(&c->d_status, sizeof(int)), c->err);
     CUDA_TRY(cudaMemset(c->d_status, 0, sizeof(int)), c->err);
@@ -364,21 +421,16 @@ static int ensure_i8_workspace(gpdla_ctx* c, int batch, int npix) {
 static i8::I8Args i8_args(gpdla_ctx* c) {
   i8::I8Args xa;
   xa.pix2 = c->d_pix2; xa.bop = c->d_bop; xa.colscale = c->d_colscale; xa.colinv = c->d_colinv; xa.status = c->d_status;
+  xa.f64flag = c->d_f64flag; xa.f64list = c->d_f64flag + c->i8_batch;
   xa.phase = nullptr;
-  { static int dbg = -1; if (dbg < 0) { const char* e = getenv("GPDLA_I8_DEBUG"); dbg = e ? atoi(e) : 0; } xa.debug = dbg; }
-  if (getenv("GPDLA_I8_PHASES")) {
-    static unsigned long long* d_phase = nullptr;
-    if (!d_phase) { cudaMalloc(&d_phase, 24 * sizeof(unsigned long long)); cudaMemset(d_phase, 0, 24 * sizeof(unsigned long long)); }
+  if (getenv("GPDLA_I8_PHASES")) {   // diagnostics only: mean barrier waits per tile, printed before the next launch
+    if (!c->d_phase) { cudaMalloc(&c->d_phase, 24 * sizeof(unsigned long long)); cudaMemset(c->d_phase, 0, 24 * sizeof(unsigned long long)); }
     unsigned long long h[24];
-    cudaMemcpy(h, d_phase, sizeof h, cudaMemcpyDeviceToHost);
-    if (h[7]) fprintf(stderr, "[i8 phases, mean cycles since CTA start over %llu CTAs] - %llu | setup %llu | producer loop end %llu | acc final %llu | recombined %llu | cluster barrier %llu | factor end %llu\n",
-                      h[7], h[0] / h[7], h[1] / h[7], h[2] / h[7], h[3] / h[7], h[4] / h[7], h[5] / h[7], h[6] / h[7]);
-    if (h[7]) fprintf(stderr, "[i8 waits, mean cycles per CTA] producers: A-stage empty (per thread) %llu | mma: A full %llu | mma: B full %llu | loader: B empty %llu | sender: rows %llu | epilogue: accumulators %llu\n",
-                      h[9] / h[7] / 256, h[10] / h[7], h[11] / h[7], h[12] / h[7], h[13] / h[7], h[14] / h[7] / 4);
+    cudaMemcpy(h, c->d_phase, sizeof h, cudaMemcpyDeviceToHost);
     if (h[7]) fprintf(stderr, "[i8 persistent waits, mean cycles per tile] producer: stage empty (per thread) %llu | mma: A full %llu, B full %llu, TMEM drained %llu | loader %llu | sender %llu | epilogue (per warp): acc final %llu, triangle free %llu, triangle full %llu, scalars %llu\n",
                       h[9] / h[7] / 256, h[10] / h[7], h[11] / h[7], h[21] / h[7], h[12] / h[7], h[13] / h[7], h[14] / h[7] / 4, h[18] / h[7] / 4, h[19] / h[7] / 4, h[20] / h[7] / 4);
-    cudaMemset(d_phase, 0, sizeof h);
-    xa.phase = d_phase;
+    cudaMemset(c->d_phase, 0, sizeof h);
+    xa.phase = c->d_phase;
   }
   return xa;
 }
@@ -386,13 +438,6 @@ static i8::I8Args i8_args(gpdla_ctx* c) {
 // K0c + K0d: scales and digit planes of the B operand for a prepared batch
 template <int L>
 static int build_i8_operands_L(gpdla_ctx* c, int nq, int npix, cudaStream_t st) {
-  static bool uploaded[64] = {};
-  const int dev = c->device & 63;
-  if (!uploaded[dev]) {
-    int rc = upload_i8_stage_index<I8_K, L>(c->err);
-    if (rc) return rc;
-    uploaded[dev] = true;
-  }
   i8::I8Args xa = i8_args(c);
   i8::i8_scales_kernel<I8_K, L><<<nq, NTHREADS, 0, st>>>(c->d_meta, c->d_pix, c->d_Mq, xa, npix);
   c->launches++;
@@ -402,10 +447,24 @@ static int build_i8_operands_L(gpdla_ctx* c, int nq, int npix, cudaStream_t st) 
   CUDA_TRY(cudaGetLastError(), c->err);
   return GPDLA_OK;
 }
+// Gram operand P of the FP64 kernels for a prepared batch (`only_list`: restricted to the listed quasars)
+static int build_f64_operand(gpdla_ctx* c, int nq, int npix, const int32_t* only_list, cudaStream_t st) {
+  const unsigned ny = only_list ? (unsigned)std::min(nq, FALLBACK_SLOTS) : (unsigned)nq;
+  GPDLA_FOR_RANK(c->k, (build_gram_operand_kernel<K, NSPLIT><<<dim3(npix / KC, ny, NSPLIT), NTHREADS, 0, st>>>(
+                            c->d_Mq, c->d_meta, c->d_P, npix, only_list)));
+  c->launches++;
+  CUDA_TRY(cudaGetLastError(), c->err);
+  return GPDLA_OK;
+}
+
 static int build_i8_operands(gpdla_ctx* c, int nq, int npix, cudaStream_t st) {
   int rc = ensure_i8_workspace(c, c->ws_batch, npix);
   if (rc) return rc;
-  return i8_digits(c) == 5 ? build_i8_operands_L<5>(c, nq, npix, st) : build_i8_operands_L<6>(c, nq, npix, st);
+  CUDA_TRY(cudaMemsetAsync(c->d_f64flag, 0, (2 * (size_t)c->i8_batch + 2) * sizeof(int32_t), st), c->err);
+  rc = i8_digits(c) == 5 ? build_i8_operands_L<5>(c, nq, npix, st) : build_i8_operands_L<6>(c, nq, npix, st);
+  if (rc) return rc;
+  // FP64 operand of the quasars the scales kernel has just flagged (normally none: a handful of idle CTAs)
+  return build_f64_operand(c, nq, npix, c->d_f64flag + c->i8_batch, st);
 }
 
 // resident 4-CTA clusters of the persistent kernel on this device (0 = query failed)
@@ -422,17 +481,9 @@ static int max_resident_clusters(Kern kern, size_t smem, int threads) {
   return n;
 }
 
-// GPDLA_I8_PERSISTENT=0 selects the one-tile-per-cluster kernel (development comparison)
-static bool i8_persistent() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("GPDLA_I8_PERSISTENT"); v = (e && e[0] == '0') ? 0 : 1; }
-  return v == 1;
-}
-
 template <int L, int NL, int MODE>
 static int launch_loglik_i8(gpdla_ctx* c, const LoglikArgs& la, int nq, cudaStream_t st) {
-  using Sh = i8::Shape<I8_K, L>;
-  const int dev = c->device & 63;
+  const int dev = c->device;
   const unsigned clusters = (unsigned)((la.S + (la.log_likelihoods_no_dla ? 1 : 0) + i8::TM - 1) / i8::TM);
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (c->profiling) {
@@ -440,33 +491,25 @@ static int launch_loglik_i8(gpdla_ctx* c, const LoglikArgs& la, int nq, cudaStre
     CUDA_TRY(cudaEventCreate(&e1), c->err);
     CUDA_TRY(cudaEventRecord(e0, st), c->err);
   }
-  if (i8_persistent()) {
-    auto kern = i8::dla_loglik_i8p_kernel<I8_K, L, NL, MODE>;
-    const size_t smem = i8::PShape<I8_K, L>::smem_bytes(la.num_lines);
-    static size_t configured[64] = {};
-    static int resident[64] = {};
-    if (configured[dev] < smem) {
-      CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), c->err);
-      configured[dev] = smem;
-      int n = max_resident_clusters(kern, smem, i8::P_THREADS);
-      const char* e = getenv("GPDLA_I8_CLUSTERS");
+  auto kern = i8::dla_loglik_i8p_kernel<I8_K, L, NL, MODE>;
+  const size_t smem = i8::PShape<I8_K, L>::smem_bytes(la.num_lines);
+  int rc = configure_smem(dev, kern, smem, c->err);
+  if (rc) return rc;
+  int resident;
+  {
+    std::lock_guard<std::mutex> lock(g_dev[dev].mu);
+    int& n = g_dev[dev].clusters[(const void*)kern];
+    if (n == 0) {
+      n = max_resident_clusters(kern, smem, i8::P_THREADS);
+      const char* e = getenv("GPDLA_I8_CLUSTERS");   // tuning aid: grid size only, same arithmetic
       if (e) n = atoi(e);
-      if (getenv("GPDLA_I8_VERBOSE")) fprintf(stderr, "[i8] resident clusters: query %d, using %d\n", max_resident_clusters(kern, smem, i8::P_THREADS), n > 0 ? n : 32);
-      resident[dev] = n > 0 ? n : 32;
+      if (n <= 0) n = 32;
     }
-    const long long tiles = (long long)nq * clusters;
-    const unsigned ncl = (unsigned)std::min<long long>(resident[dev], tiles);
-    kern<<<dim3(ncl * i8::CLUSTER, 1, 1), i8::P_THREADS, smem, st>>>(la, i8_args(c), nq, (int)clusters);
-  } else {
-    auto kern = i8::dla_loglik_i8_kernel<I8_K, L, NL, MODE>;
-    const size_t smem = Sh::smem_bytes(la.num_lines);
-    static size_t configured[64] = {};
-    if (configured[dev] < smem) {
-      CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), c->err);
-      configured[dev] = smem;
-    }
-    kern<<<dim3(clusters * i8::CLUSTER, (unsigned)nq, 1), i8::THREADS, smem, st>>>(la, i8_args(c));
+    resident = n;
   }
+  const long long tiles = (long long)nq * clusters;
+  const unsigned ncl = (unsigned)std::min<long long>(resident, tiles);
+  kern<<<dim3(ncl * i8::CLUSTER, 1, 1), i8::P_THREADS, smem, st>>>(la, i8_args(c), nq, (int)clusters);
   c->launches++;
   CUDA_TRY(cudaGetLastError(), c->err);
   if (c->profiling) {
@@ -474,13 +517,6 @@ static int launch_loglik_i8(gpdla_ctx* c, const LoglikArgs& la, int nq, cudaStre
     c->prof_events.emplace_back(e0, e1);
   }
   return GPDLA_OK;
-}
-
-template <int MODE>
-static int launch_mode_i8(gpdla_ctx* c, const LoglikArgs& la, int nq, cudaStream_t st) {
-  const bool l5 = i8_digits(c) == 5;
-  if (c->params.num_lines == 3) return l5 ? launch_loglik_i8<5, 3, MODE>(c, la, nq, st) : launch_loglik_i8<6, 3, MODE>(c, la, nq, st);
-  return l5 ? launch_loglik_i8<5, 0, MODE>(c, la, nq, st) : launch_loglik_i8<6, 0, MODE>(c, la, nq, st);
 }
 
 static int ensure_multi_workspace(gpdla_ctx* c, int batch, int npix) {
@@ -501,12 +537,28 @@ static int ensure_multi_workspace(gpdla_ctx* c, int batch, int npix) {
   return GPDLA_OK;
 }
 
+// FP64 DMMA kernels for the context's rank and line count
 template <int MODE>
-static int launch_mode(gpdla_ctx* c, const LoglikArgs& la, int nq, cudaStream_t st) {
+static int launch_mode(gpdla_ctx* c, const LoglikArgs& la, int nq, cudaStream_t st, bool timed = true) {
   int rc = GPDLA_ERR_UNSUPPORTED;
-  if (c->params.num_lines == 3) { GPDLA_FOR_RANK(c->k, (rc = launch_loglik<K, 3, MODE, NSPLIT>(c, la, nq, st))); }
-  else { GPDLA_FOR_RANK(c->k, (rc = launch_loglik<K, 0, MODE, NSPLIT>(c, la, nq, st))); }
+  if (c->params.num_lines == 3) { GPDLA_FOR_RANK(c->k, (rc = launch_loglik<K, 3, MODE, NSPLIT>(c, la, nq, st, timed))); }
+  else { GPDLA_FOR_RANK(c->k, (rc = launch_loglik<K, 0, MODE, NSPLIT>(c, la, nq, st, timed))); }
   return rc;
+}
+
+// INT8 path with its FP64 fallback: the persistent kernel skips the quasars whose scales flagged a used pixel with
+// zero noise variance (the fixed-point bound of U'' does not exist there, i8_scales_kernel); the FP64 kernels then
+// process exactly those -- FALLBACK_SLOTS idle CTA columns when there are none, no host round trip.
+template <int MODE>
+static int launch_mode_i8(gpdla_ctx* c, const LoglikArgs& la, int nq, cudaStream_t st) {
+  const bool l5 = i8_digits(c) == 5;
+  int rc;
+  if (c->params.num_lines == 3) rc = l5 ? launch_loglik_i8<5, 3, MODE>(c, la, nq, st) : launch_loglik_i8<6, 3, MODE>(c, la, nq, st);
+  else rc = l5 ? launch_loglik_i8<5, 0, MODE>(c, la, nq, st) : launch_loglik_i8<6, 0, MODE>(c, la, nq, st);
+  if (rc) return rc;
+  LoglikArgs lf = la;
+  lf.only_list = c->d_f64flag + c->i8_batch;
+  return launch_mode<MODE>(c, lf, nq, st, false);
 }
 
 template <int K>
@@ -520,6 +572,46 @@ static int launch_objective(const ObjectiveArgs& a, cudaStream_t st) {
 template <int MODE>
 static int launch_mode_any(gpdla_ctx* c, const LoglikArgs& la, int nq, cudaStream_t st) {
   return use_i8(c) ? launch_mode_i8<MODE>(c, la, nq, st) : launch_mode<MODE>(c, la, nq, st);
+}
+
+// K0 arguments for quasars [q0, q0 + nq) of a padded catalogue
+static PrepArgs prep_args(const gpdla_ctx* c, int64_t q0, int64_t L_max, const double* wavelengths, const double* flux,
+                          const double* noise_variance, const uint8_t* pixel_mask, const int32_t* lengths,
+                          const double* z_qsos, int npix, int meanflux) {
+  PrepArgs pa;
+  pa.wavelengths = wavelengths + q0 * L_max; pa.flux = flux + q0 * L_max;
+  pa.noise_variance = noise_variance + q0 * L_max; pa.pixel_mask = pixel_mask + q0 * L_max;
+  pa.lengths = lengths + q0; pa.z_qsos = z_qsos + q0; pa.L_max = L_max;
+  pa.rest_wavelengths = c->d_rest; pa.mu = c->d_mu; pa.M = c->d_M; pa.log_omega = c->d_log_omega;
+  pa.n_rest = c->n_rest; pa.k = c->k; pa.c_0 = c->c_0; pa.tau_0 = c->tau_0; pa.beta = c->beta;
+  pa.prior_z_qsos = c->d_prior_z; pa.prior_dla_ind = c->d_prior_dla; pa.n_prior = c->n_prior;
+  pa.min_lambda = c->params.min_lambda; pa.max_lambda = c->params.max_lambda;
+  pa.lya_wavelength = c->params.lya_wavelength; pa.lyman_limit = c->params.lyman_limit;
+  pa.prior_z_qso_increase = c->params.prior_z_qso_increase; pa.min_z_cut = c->params.min_z_cut;
+  pa.max_z_cut = c->params.max_z_cut; pa.pixel_spacing = c->params.pixel_spacing;
+  pa.meta = c->d_meta; pa.lam_pad = c->d_lam; pa.lamh = c->d_lamh; pa.pix = c->d_pix; pa.Mq = c->d_Mq; pa.NPIX = npix;
+  pa.inv_h = 1.0 / (c->params.pixel_spacing * log(10.0));
+  pa.meanflux = meanflux;
+  return pa;
+}
+
+// the batch-invariant part of the fused kernels' arguments
+static LoglikArgs loglik_args(const gpdla_ctx* c, int npix) {
+  LoglikArgs la;
+  memset(&la, 0, sizeof la);
+  la.meta = c->d_meta; la.lam_pad = c->d_lam; la.lamh = c->d_lamh; la.rt = rest_table_args(c); la.order = c->d_order;
+  la.pix = c->d_pix; la.P = c->d_P;
+  la.offset_samples = c->d_offset; la.nhi_samples = c->d_nhi; la.S = c->S;
+  la.num_lines = c->params.num_lines; la.NPIX = npix;
+  return la;
+}
+
+// K0 + operand builders for one batch
+static int prepare_batch(gpdla_ctx* c, const PrepArgs& pa, int nq, int npix, cudaStream_t st) {
+  prepare_quasars_kernel<<<nq, NTHREADS, 0, st>>>(pa);
+  c->launches++;
+  CUDA_TRY(cudaGetLastError(), c->err);
+  return use_i8(c) ? build_i8_operands(c, nq, npix, st) : build_f64_operand(c, nq, npix, nullptr, st);
 }
 
 __global__ void fill_i32_kernel(int32_t* p, int32_t v, int64_t n) {
@@ -538,8 +630,36 @@ void gpdla_default_parameters(gpdla_params* p) {
   p->pixel_spacing = 1e-4;
   p->num_lines = 3;
   p->batch_quasars = 0;
-  p->gram_digits = 0; p->reserved = 0;
+  p->gram_digits = 0; p->rest_table = 0;
 }
+
+int gpdla_rest_table(int32_t num_lines, double pixel_spacing, double* coef, int32_t* ncell, int32_t* degree, double* h,
+                     double* lambda_lo) {
+  if (num_lines < 1 || num_lines > GPDLA_MAX_LINES || !(pixel_spacing > 0)) return GPDLA_ERR_INVALID;
+  LineConstants lc;
+  fill_line_constants(&lc);
+  if (degree) *degree = RT_DEG;
+  if (lambda_lo) *lambda_lo = RT_LAMBDA_LO;
+  if (!coef) {
+    const double hh = pixel_spacing * log(10.0);
+    if (h) *h = hh;
+    if (ncell) *ncell = (int32_t)ceil((log(RT_LAMBDA_HI) - log(RT_LAMBDA_LO)) / hh) + 1;
+    return GPDLA_OK;
+  }
+  const RestTableHost t = build_rest_table(num_lines, pixel_spacing, RT_NEAR_PIXELS, lc.tw, lc.lc, lc.gam, kSigma, kC);
+  memcpy(coef, t.coef.data(), t.coef.size() * sizeof(double));
+  if (ncell) *ncell = t.ncell;
+  if (h) *h = t.h;
+  return GPDLA_OK;
+}
+
+int gpdla_host_alloc(void** ptr, uint64_t bytes) {
+  if (!ptr) return GPDLA_ERR_INVALID;
+  *ptr = nullptr;
+  CUDA_TRY(cudaHostAlloc(ptr, bytes > 0 ? bytes : 1, cudaHostAllocDefault), g_err);
+  return GPDLA_OK;
+}
+void gpdla_host_free(void* ptr) { if (ptr) cudaFreeHost(ptr); }
 
 void gpdla_line_constants(double* tw, double* lcs, double* gam, double* ip) {
   LineConstants lc;
@@ -554,31 +674,48 @@ int gpdla_create(gpdla_ctx** out, int device) {
   if (!out) return GPDLA_ERR_INVALID;
   *out = nullptr;
   int ndev = 0;
-  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev || device >= MAX_DEVICES) {
     g_err = "no CUDA device " + std::to_string(device) + " (libgpdla.so has no CPU fallback)";
     return GPDLA_ERR_CUDA;
   }
+  DeviceGuard guard(device);
+  if (guard.status != cudaSuccess) { g_err = cudaGetErrorString(guard.status); return GPDLA_ERR_CUDA; }
+  int rc = upload_device_constants(g_err);
+  if (rc != GPDLA_OK) return rc;
   gpdla_ctx* ctx = new gpdla_ctx;
   ctx->device = device;
   gpdla_default_parameters(&ctx->params);
-  cudaError_t e = cudaSetDevice(device);
-  if (e != cudaSuccess) { g_err = cudaGetErrorString(e); delete ctx; return GPDLA_ERR_CUDA; }
-  int rc = upload_line_constants(g_err);
-  if (rc != GPDLA_OK) { delete ctx; return rc; }
+  cudaError_t e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+  for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+    e = cudaEventCreateWithFlags(&ctx->ev_batch[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming);
+  }
+  if (e != cudaSuccess) { g_err = cudaGetErrorString(e); gpdla_destroy(ctx); return GPDLA_ERR_CUDA; }
   *out = ctx;
   return GPDLA_OK;
 }
 
 void gpdla_destroy(gpdla_ctx* c) {
   if (!c) return;
-  cudaSetDevice(c->device);
+  DeviceGuard guard(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
   free_workspace(c);
   cudaFree(c->d_rest); cudaFree(c->d_mu); cudaFree(c->d_M); cudaFree(c->d_log_omega);
-  cudaFree(c->d_offset); cudaFree(c->d_log_nhi); cudaFree(c->d_nhi);
+  cudaFree(c->d_offset); cudaFree(c->d_log_nhi); cudaFree(c->d_nhi); cudaFree(c->d_order); cudaFree(c->d_rt);
   cudaFree(c->d_prior_z); cudaFree(c->d_prior_dla); cudaFree(c->d_stage);
   cudaFree(c->d_pix2); cudaFree(c->d_colscale); cudaFree(c->d_colinv); cudaFree(c->d_bop); cudaFree(c->d_status);
+  cudaFree(c->d_f64flag); cudaFree(c->d_phase);
   cudaFree(c->d_lls_nhi); cudaFree(c->d_uniforms); cudaFree(c->d_acache); cudaFree(c->d_msll); cudaFree(c->d_mlls);
   cudaFree(c->d_cum); cudaFree(c->d_mscal); cudaFree(c->d_partners); cudaFree(c->d_active);
+  for (auto& ev : c->prof_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+  for (int i = 0; i < 2; ++i) {
+    if (c->ev_batch[i]) cudaEventDestroy(c->ev_batch[i]);
+    if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]);
+  }
+  if (c->stream) cudaStreamDestroy(c->stream);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   delete c;
 }
 
@@ -611,7 +748,8 @@ int gpdla_profile_read(gpdla_ctx* c, double* loglik_ms, int64_t* loglik_launches
 int gpdla_set_parameters(gpdla_ctx* c, const gpdla_params* p) {
   if (!c || !p) return GPDLA_ERR_INVALID;
   if (p->num_lines < 1 || p->num_lines > GPDLA_MAX_LINES || !(p->max_lambda > p->min_lambda) ||
-      p->batch_quasars < 0 || !(p->gram_digits == 0 || p->gram_digits == -1 || p->gram_digits == 5 || p->gram_digits == 6)) {
+      !(p->pixel_spacing > 0) || p->batch_quasars < 0 || !(p->rest_table == 0 || p->rest_table == -1) ||
+      !(p->gram_digits == 0 || p->gram_digits == -1 || p->gram_digits == 5 || p->gram_digits == 6)) {
     c->err = "gpdla_set_parameters: invalid parameters";
     return GPDLA_ERR_INVALID;
   }
@@ -626,12 +764,7 @@ int gpdla_set_model(gpdla_ctx* c, const double* rest, int32_t n_rest, const doub
     c->err = "gpdla_set_model: rank k=" + std::to_string(k) + " not compiled in (available: 10, 20, 40)";
     return GPDLA_ERR_UNSUPPORTED;
   }
-  CUDA_TRY(cudaSetDevice(c->device), c->err);
-  {
-    int rcs = GPDLA_OK;
-    GPDLA_FOR_RANK(k, rcs = upload_stage_index<K>(c->err));
-    if (rcs) return rcs;
-  }
+  DeviceGuard guard(c->device);
   int rc;
   if ((rc = dev_upload(&c->d_rest, rest, n_rest, c->err))) return rc;
   if ((rc = dev_upload(&c->d_mu, mu, n_rest, c->err))) return rc;
@@ -643,24 +776,95 @@ int gpdla_set_model(gpdla_ctx* c, const double* rest, int32_t n_rest, const doub
 }
 
 int gpdla_set_samples(gpdla_ctx* c, const double* offset, const double* log_nhi, const double* nhi, int64_t S) {
-  if (!c || !offset || !log_nhi || !nhi || S < 1) return GPDLA_ERR_INVALID;
-  CUDA_TRY(cudaSetDevice(c->device), c->err);
+  if (!c || !offset || !log_nhi || !nhi || S < 1 || S > 2147483647LL) return GPDLA_ERR_INVALID;
+  DeviceGuard guard(c->device);
   int rc;
   if ((rc = dev_upload(&c->d_offset, offset, S, c->err))) return rc;
   if ((rc = dev_upload(&c->d_log_nhi, log_nhi, S, c->err))) return rc;
   if ((rc = dev_upload(&c->d_nhi, nhi, S, c->err))) return rc;
+  // Order in which the kernels walk the samples (results are stored under the caller's sample index): ascending
+  // redshift offset, so that the four samples a producer warp interleaves are neighbours in redshift and share one
+  // cell of the rest-frame table per pixel, and the warps of a CTA find each other's table lines in L1.  (Groups of
+  // neighbours dealt out in a scattered order -- GPDLA_ORDER_GROUP=n, a tuning aid -- measured slower: the warps of a
+  // cluster then reach the line cores, i.e. the direct evaluation, in different chunks and wait for each other.)
+  std::vector<int32_t> sorted((size_t)S), order((size_t)S);
+  std::iota(sorted.begin(), sorted.end(), 0);
+  std::stable_sort(sorted.begin(), sorted.end(), [&](int32_t a, int32_t b) { return offset[a] < offset[b]; });
+  {
+    int64_t group = ORDER_GROUP;
+    if (const char* e = getenv("GPDLA_ORDER_GROUP")) group = atoll(e);   // tuning aid (0 = fully sorted)
+    const int64_t G = group > 0 ? S / group : 0;                         // full groups; a partial last group stays last
+    int64_t A = (int64_t)(0.6180339887 * (double)G);
+    auto gcd = [](int64_t a, int64_t b) { while (b) { const int64_t t = a % b; a = b; b = t; } return a; };
+    while (G > 1 && gcd(A, G) != 1) ++A;
+    if (group < 0) std::iota(sorted.begin(), sorted.end(), 0);           // diagnosis: the caller's order
+    for (int64_t pos = 0; pos < S; ++pos) {
+      const int64_t pg = group > 0 ? pos / group : 0;
+      order[(size_t)pos] = (G > 1 && pg < G) ? sorted[(size_t)(((pg * A) % G) * group + pos % group)] : sorted[(size_t)pos];
+    }
+  }
+  if ((rc = dev_upload(&c->d_order, order.data(), (size_t)S, c->err))) return rc;
+  if (c->S != S) {   // sub-DLA samples and the resampling stream are per sample count: they must be set again
+    cudaFree(c->d_lls_nhi); cudaFree(c->d_uniforms);
+    c->d_lls_nhi = c->d_uniforms = nullptr; c->lls_S = 0;
+  }
   c->S = S;
   return GPDLA_OK;
 }
 
 int gpdla_set_prior(gpdla_ctx* c, const double* z_qsos, const uint8_t* dla_ind, int64_t n) {
   if (!c || n < 0 || (n > 0 && (!z_qsos || !dla_ind))) return GPDLA_ERR_INVALID;
-  CUDA_TRY(cudaSetDevice(c->device), c->err);
+  DeviceGuard guard(c->device);
   int rc;
   if ((rc = dev_upload(&c->d_prior_z, z_qsos, n, c->err))) return rc;
   if ((rc = dev_upload(&c->d_prior_dla, dla_ind, n, c->err))) return rc;
   c->n_prior = n;
   return GPDLA_OK;
+}
+
+// One batch (<= workspace batch) of quasars [q0, q0 + nq) of the device-resident catalogue through K0 .. K4.
+// `sll` / `llno`: where this batch's [nq x S] sample log-likelihoods and [nq] null-model log-likelihoods go.
+static int process_batch(gpdla_ctx* c, int64_t q0, int nq, int64_t L_max, const double* wavelengths, const double* flux,
+                         const double* noise_variance, const uint8_t* pixel_mask, const int32_t* lengths,
+                         const double* z_qsos, const gpdla_results* out, double* sll, double* llno, int npix,
+                         cudaStream_t st) {
+  const int batch = c->ws_batch;
+  int rc = prepare_batch(c, prep_args(c, q0, L_max, wavelengths, flux, noise_variance, pixel_mask, lengths, z_qsos, npix, 0),
+                         nq, npix, st);
+  if (rc) return rc;
+  LoglikArgs la = loglik_args(c, npix);
+  la.sample_log_likelihoods = sll; la.log_likelihoods_no_dla = llno; la.sll_stride = c->S;
+  if ((rc = launch_mode_any<0>(c, la, nq, st))) return rc;
+
+  EvidenceArgs ea;
+  ea.meta = c->d_meta; ea.sample_log_likelihoods = sll; ea.log_likelihoods_no_dla = llno;
+  ea.offset_samples = c->d_offset; ea.log_nhi_samples = c->d_log_nhi; ea.S = c->S;
+  double* scr = c->d_scratch + batch;   // 15 more scratch columns of `batch` doubles
+  auto pick = [&](double* p, int col) { return p ? p + q0 : scr + (size_t)col * batch; };
+  ea.min_z_dlas = pick(out->min_z_dlas, 0); ea.max_z_dlas = pick(out->max_z_dlas, 1);
+  ea.log_priors_no_dla = pick(out->log_priors_no_dla, 2); ea.log_priors_dla = pick(out->log_priors_dla, 3);
+  ea.log_likelihoods_dla = pick(out->log_likelihoods_dla, 4);
+  ea.log_posteriors_no_dla = pick(out->log_posteriors_no_dla, 5);
+  ea.log_posteriors_dla = pick(out->log_posteriors_dla, 6);
+  ea.model_posteriors = out->model_posteriors ? out->model_posteriors + 2 * q0 : scr + (size_t)7 * batch;   // 2 cols
+  ea.p_no_dlas = pick(out->p_no_dlas, 9); ea.p_dlas = pick(out->p_dlas, 10);
+  ea.map_z_dlas = pick(out->map_z_dlas, 11); ea.map_log_nhis = pick(out->map_log_nhis, 12);
+  ea.map_inds = out->map_inds ? out->map_inds + q0 : c->d_scratch_i;
+  evidence_kernel<<<nq, NTHREADS, 0, st>>>(ea);
+  c->launches++;
+  CUDA_TRY(cudaGetLastError(), c->err);
+  return GPDLA_OK;
+}
+
+static int check_ready(gpdla_ctx* c, const char* who) {
+  if (!c->d_M || !c->d_offset || c->n_prior < 0) {
+    c->err = std::string(who) + ": set_model, set_samples and set_prior must be called first";
+    return GPDLA_ERR_STATE;
+  }
+  return GPDLA_OK;
+}
+static int default_batch(const gpdla_ctx* c) {
+  return c->params.batch_quasars > 0 ? c->params.batch_quasars : (rank_splits(c->k) > 1 ? 37 : 296);
 }
 
 int gpdla_process_qsos_device(gpdla_ctx* c, int64_t Q, int64_t L_max, const double* wavelengths, const double* flux,
@@ -671,108 +875,51 @@ int gpdla_process_qsos_device(gpdla_ctx* c, int64_t Q, int64_t L_max, const doub
     c->err = "gpdla_process_qsos_device: invalid arguments";
     return GPDLA_ERR_INVALID;
   }
-  if (!c->d_M || !c->d_offset || c->n_prior < 0) {
-    c->err = "gpdla_process_qsos: set_model, set_samples and set_prior must be called first";
-    return GPDLA_ERR_STATE;
-  }
+  int rc = check_ready(c, "gpdla_process_qsos_device");
+  if (rc) return rc;
   if (Q == 0) return GPDLA_OK;
-  CUDA_TRY(cudaSetDevice(c->device), c->err);
+  DeviceGuard guard(c->device);
+  if ((rc = ensure_rest_table(c))) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const int npix = (int)((L_max + KC - 1) / KC) * KC;
-  int batch = c->params.batch_quasars > 0 ? c->params.batch_quasars : (rank_splits(c->k) > 1 ? 37 : 296);
-  batch = (int)std::min<int64_t>(batch, Q);
-  int rc = ensure_workspace(c, batch, npix);
-  if (rc) return rc;
-  batch = c->ws_batch;
-
+  if ((rc = ensure_workspace(c, (int)std::min<int64_t>(default_batch(c), Q), npix))) return rc;
+  const int batch = c->ws_batch;
   for (int64_t q0 = 0; q0 < Q; q0 += batch) {
     const int nq = (int)std::min<int64_t>(batch, Q - q0);
-    PrepArgs pa;
-    pa.wavelengths = wavelengths + q0 * L_max; pa.flux = flux + q0 * L_max;
-    pa.noise_variance = noise_variance + q0 * L_max; pa.pixel_mask = pixel_mask + q0 * L_max;
-    pa.lengths = lengths + q0; pa.z_qsos = z_qsos + q0; pa.L_max = L_max;
-    pa.rest_wavelengths = c->d_rest; pa.mu = c->d_mu; pa.M = c->d_M; pa.log_omega = c->d_log_omega;
-    pa.n_rest = c->n_rest; pa.k = c->k; pa.c_0 = c->c_0; pa.tau_0 = c->tau_0; pa.beta = c->beta;
-    pa.prior_z_qsos = c->d_prior_z; pa.prior_dla_ind = c->d_prior_dla; pa.n_prior = c->n_prior;
-    pa.min_lambda = c->params.min_lambda; pa.max_lambda = c->params.max_lambda;
-    pa.lya_wavelength = c->params.lya_wavelength; pa.lyman_limit = c->params.lyman_limit;
-    pa.prior_z_qso_increase = c->params.prior_z_qso_increase; pa.min_z_cut = c->params.min_z_cut;
-    pa.max_z_cut = c->params.max_z_cut; pa.pixel_spacing = c->params.pixel_spacing;
-    pa.meta = c->d_meta; pa.lam_pad = c->d_lam; pa.pix = c->d_pix; pa.Mq = c->d_Mq; pa.NPIX = npix;
-    pa.meanflux = 0;
-    prepare_quasars_kernel<<<nq, NTHREADS, 0, st>>>(pa);
-    c->launches++;
-    CUDA_TRY(cudaGetLastError(), c->err);
-    if (use_i8(c)) {
-      if ((rc = build_i8_operands(c, nq, npix, st))) return rc;
-    } else {
-      GPDLA_FOR_RANK(c->k, (build_gram_operand_kernel<K, NSPLIT><<<dim3(npix / KC, nq, NSPLIT), NTHREADS, 0, st>>>(c->d_Mq, c->d_meta, c->d_P, npix)));
-      c->launches++;
-      CUDA_TRY(cudaGetLastError(), c->err);
-    }
-
     double* sll = out->sample_log_likelihoods_dla ? out->sample_log_likelihoods_dla + q0 * c->S : c->d_sll;
     double* llno = out->log_likelihoods_no_dla ? out->log_likelihoods_no_dla + q0 : c->d_scratch;
-    LoglikArgs la;
-    la.meta = c->d_meta; la.lam_pad = c->d_lam; la.pix = c->d_pix; la.P = c->d_P;
-    la.offset_samples = c->d_offset; la.nhi_samples = c->d_nhi; la.S = c->S;
-    la.num_lines = c->params.num_lines; la.NPIX = npix;
-    la.sample_log_likelihoods = sll; la.log_likelihoods_no_dla = llno;
-    la.sll_stride = c->S; la.acache = nullptr; la.partners = nullptr; la.num_partners = 0; la.active = nullptr;
-    la.phase_cycles = nullptr;
-#ifdef GPDLA_PHASE_TIMING
-    {
-      static long long* d_phase = nullptr;
-      if (!d_phase) { cudaMalloc(&d_phase, 16 * sizeof(long long)); cudaMemset(d_phase, 0, 16 * sizeof(long long)); }
-      la.phase_cycles = d_phase;
-      long long h[16];
-      cudaMemcpy(h, d_phase, sizeof h, cudaMemcpyDeviceToHost);
-      fprintf(stderr, "[phase cycles so far] P:raw+conv %lld | P:wait_empty %lld | P:weights %lld | C:wait_full %lld | C:wait_tma %lld | C:dmma %lld | - %lld | C:epilogue %lld\n",
-              h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7]);
-      fprintf(stderr, "[core path] cycles %lld, warp-evals with core %lld of %lld\n", h[8], h[9], h[10]);
-    }
-#endif
-    if ((rc = launch_mode_any<0>(c, la, nq, st))) return rc;
-
-    EvidenceArgs ea;
-    ea.meta = c->d_meta; ea.sample_log_likelihoods = sll; ea.log_likelihoods_no_dla = llno;
-    ea.offset_samples = c->d_offset; ea.log_nhi_samples = c->d_log_nhi; ea.S = c->S;
-    double* scr = c->d_scratch + batch;   // 15 more scratch columns of `batch` doubles
-    auto pick = [&](double* p, int col) { return p ? p + q0 : scr + (size_t)col * batch; };
-    ea.min_z_dlas = pick(out->min_z_dlas, 0); ea.max_z_dlas = pick(out->max_z_dlas, 1);
-    ea.log_priors_no_dla = pick(out->log_priors_no_dla, 2); ea.log_priors_dla = pick(out->log_priors_dla, 3);
-    ea.log_likelihoods_dla = pick(out->log_likelihoods_dla, 4);
-    ea.log_posteriors_no_dla = pick(out->log_posteriors_no_dla, 5);
-    ea.log_posteriors_dla = pick(out->log_posteriors_dla, 6);
-    ea.model_posteriors = out->model_posteriors ? out->model_posteriors + 2 * q0 : scr + (size_t)7 * batch;   // 2 cols
-    ea.p_no_dlas = pick(out->p_no_dlas, 9); ea.p_dlas = pick(out->p_dlas, 10);
-    ea.map_z_dlas = pick(out->map_z_dlas, 11); ea.map_log_nhis = pick(out->map_log_nhis, 12);
-    ea.map_inds = out->map_inds ? out->map_inds + q0 : c->d_scratch_i;
-    evidence_kernel<<<nq, NTHREADS, 0, st>>>(ea);
-    c->launches++;
-    CUDA_TRY(cudaGetLastError(), c->err);
+    if ((rc = process_batch(c, q0, nq, L_max, wavelengths, flux, noise_variance, pixel_mask, lengths, z_qsos, out, sll, llno,
+                            npix, st)))
+      return rc;
   }
   return GPDLA_OK;
 }
 
+// Host buffers in, host buffers out (the drop-in call).  Everything runs on the context's own non-blocking streams:
+// inputs go up once, then batch t + 1 is computed while the [nq x S] sample log-likelihoods of batch t -- the one
+// large output, 80 KB per quasar -- travel back on the copy stream from a double-buffered device block.
 int gpdla_process_qsos(gpdla_ctx* c, int64_t Q, int64_t L_max, const double* wavelengths, const double* flux,
                        const double* noise_variance, const uint8_t* pixel_mask, const int32_t* lengths,
                        const double* z_qsos, const gpdla_results* out) {
   if (!c) return GPDLA_ERR_INVALID;
-  if (Q < 0 || L_max < 1 || !out) { c->err = "gpdla_process_qsos: invalid arguments"; return GPDLA_ERR_INVALID; }
-  if (!c->d_M || !c->d_offset || c->n_prior < 0) {
-    c->err = "gpdla_process_qsos: set_model, set_samples and set_prior must be called first";
-    return GPDLA_ERR_STATE;
+  if (Q < 0 || L_max < 1 || !out || (Q > 0 && (!wavelengths || !flux || !noise_variance || !pixel_mask || !lengths || !z_qsos))) {
+    c->err = "gpdla_process_qsos: invalid arguments";
+    return GPDLA_ERR_INVALID;
   }
+  int rc = check_ready(c, "gpdla_process_qsos");
+  if (rc) return rc;
   if (Q == 0) return GPDLA_OK;
-  CUDA_TRY(cudaSetDevice(c->device), c->err);
-  const size_t QL = (size_t)Q * L_max;
+  DeviceGuard guard(c->device);
+  if ((rc = ensure_rest_table(c))) return rc;
+  const int npix = (int)((L_max + KC - 1) / KC) * KC;
+  if ((rc = ensure_workspace(c, (int)std::min<int64_t>(default_batch(c), Q), npix))) return rc;
+  const int batch = c->ws_batch;
+  const size_t QL = (size_t)Q * L_max, S = (size_t)c->S;
   const bool want_sll = out->sample_log_likelihoods_dla != nullptr;
-  // one device staging block: 3 double planes + lengths/z + mask + 14 result columns (+ Q x S)
+  // one device staging block: 3 double planes + z + 14 result columns + map_inds + lengths + mask (+ 2 x [batch x S])
   const size_t n_res = 14;
-  // (+ 16 bytes of rounding slack for each of the 9 sub-blocks carved out below)
-  size_t bytes = 3 * QL * 8 + (size_t)Q * 8 + (n_res + 1) * Q * 8 + (size_t)Q * 8 + (size_t)Q * 4 + QL + 9 * 16 +
-                 (want_sll ? (size_t)Q * c->S * 8 : 0);
+  size_t bytes = 3 * QL * 8 + (size_t)Q * 8 + (n_res + 1) * Q * 8 + (size_t)Q * 8 + (size_t)Q * 4 + QL + 10 * 16 +
+                 (want_sll ? 2 * (size_t)batch * S * 8 : 0);
   if (c->st_bytes < bytes) {
     cudaFree(c->d_stage); c->d_stage = nullptr; c->st_bytes = 0;
     CUDA_TRY(cudaMalloc(&c->d_stage, bytes), c->err);
@@ -784,10 +931,11 @@ int gpdla_process_qsos(gpdla_ctx* c, int64_t Q, int64_t L_max, const double* wav
   double* d_z = (double*)take(Q * 8);
   double* d_res = (double*)take((n_res + 1) * Q * 8);
   int64_t* d_map = (int64_t*)take(Q * 8);
-  double* d_sll = want_sll ? (double*)take((size_t)Q * c->S * 8) : nullptr;
+  double* d_sllbuf[2] = {nullptr, nullptr};
+  if (want_sll) { d_sllbuf[0] = (double*)take((size_t)batch * S * 8); d_sllbuf[1] = (double*)take((size_t)batch * S * 8); }
   int32_t* d_len = (int32_t*)take(Q * 4);
   uint8_t* d_m = (uint8_t*)take(QL);
-  cudaStream_t st = 0;
+  cudaStream_t st = c->stream, cs = c->copy_stream;
   CUDA_TRY(cudaMemcpyAsync(d_w, wavelengths, QL * 8, cudaMemcpyHostToDevice, st), c->err);
   CUDA_TRY(cudaMemcpyAsync(d_f, flux, QL * 8, cudaMemcpyHostToDevice, st), c->err);
   CUDA_TRY(cudaMemcpyAsync(d_v, noise_variance, QL * 8, cudaMemcpyHostToDevice, st), c->err);
@@ -803,9 +951,34 @@ int gpdla_process_qsos(gpdla_ctx* c, int64_t Q, int64_t L_max, const double* wav
   dr.map_z_dlas = d_res + 10 * Q; dr.map_log_nhis = d_res + 11 * Q;
   dr.model_posteriors = d_res + 12 * Q;   // 2 columns
   dr.map_inds = d_map;
-  dr.sample_log_likelihoods_dla = d_sll;
-  int rc = gpdla_process_qsos_device(c, Q, L_max, d_w, d_f, d_v, d_m, d_len, d_z, &dr, st);
-  if (rc) return rc;
+  dr.sample_log_likelihoods_dla = nullptr;
+  // batch t is enqueued BEFORE the copy of batch t - 1 is issued: with a pageable destination cudaMemcpyAsync holds
+  // the host thread until the copy is done, and the GPU must already have its next batch by then
+  auto copy_back = [&](int tt) -> int {
+    const int64_t q0 = (int64_t)tt * batch;
+    const int nq = (int)std::min<int64_t>(batch, Q - q0);
+    const int b = tt & 1;
+    CUDA_TRY(cudaStreamWaitEvent(cs, c->ev_batch[b], 0), c->err);
+    CUDA_TRY(cudaMemcpyAsync(out->sample_log_likelihoods_dla + (size_t)q0 * S, d_sllbuf[b], (size_t)nq * S * 8,
+                             cudaMemcpyDeviceToHost, cs), c->err);
+    CUDA_TRY(cudaEventRecord(c->ev_copied[b], cs), c->err);
+    return GPDLA_OK;
+  };
+  int t = 0;
+  for (int64_t q0 = 0; q0 < Q; q0 += batch, ++t) {
+    const int nq = (int)std::min<int64_t>(batch, Q - q0);
+    const int b = t & 1;
+    double* sll = want_sll ? d_sllbuf[b] : c->d_sll;
+    if (want_sll && t >= 2) CUDA_TRY(cudaStreamWaitEvent(st, c->ev_copied[b], 0), c->err);   // buffer b is on the host
+    if ((rc = process_batch(c, q0, nq, L_max, d_w, d_f, d_v, d_m, d_len, d_z, &dr, sll, dr.log_likelihoods_no_dla + q0, npix,
+                            st)))
+      return rc;
+    if (want_sll) {
+      CUDA_TRY(cudaEventRecord(c->ev_batch[b], st), c->err);
+      if (t >= 1 && (rc = copy_back(t - 1))) return rc;
+    }
+  }
+  if (want_sll && (rc = copy_back(t - 1))) return rc;
   double* hptr[12] = {out->min_z_dlas, out->max_z_dlas, out->log_priors_no_dla, out->log_priors_dla,
                       out->log_likelihoods_no_dla, out->log_likelihoods_dla, out->log_posteriors_no_dla,
                       out->log_posteriors_dla, out->p_no_dlas, out->p_dlas, out->map_z_dlas, out->map_log_nhis};
@@ -814,10 +987,8 @@ int gpdla_process_qsos(gpdla_ctx* c, int64_t Q, int64_t L_max, const double* wav
   if (out->model_posteriors)
     CUDA_TRY(cudaMemcpyAsync(out->model_posteriors, d_res + 12 * Q, 2 * Q * 8, cudaMemcpyDeviceToHost, st), c->err);
   if (out->map_inds) CUDA_TRY(cudaMemcpyAsync(out->map_inds, d_map, Q * 8, cudaMemcpyDeviceToHost, st), c->err);
-  if (want_sll)
-    CUDA_TRY(cudaMemcpyAsync(out->sample_log_likelihoods_dla, d_sll, (size_t)Q * c->S * 8, cudaMemcpyDeviceToHost, st),
-             c->err);
   CUDA_TRY(cudaStreamSynchronize(st), c->err);
+  CUDA_TRY(cudaStreamSynchronize(cs), c->err);
   return GPDLA_OK;
 }
 
@@ -834,13 +1005,13 @@ void gpdla_matlab_default_rand(double* out, int64_t n) {
 int gpdla_set_lls_samples(gpdla_ctx* c, const double* lls_nhi, int64_t S, double Z_lls, double Z_dla) {
   if (!c || !lls_nhi || S < 1 || !(Z_lls > 0) || !(Z_dla > 0)) return GPDLA_ERR_INVALID;
   if (c->S != S) { c->err = "gpdla_set_lls_samples: call gpdla_set_samples first (same sample count)"; return GPDLA_ERR_STATE; }
-  CUDA_TRY(cudaSetDevice(c->device), c->err);
+  DeviceGuard guard(c->device);
   int rc;
   if ((rc = dev_upload(&c->d_lls_nhi, lls_nhi, S, c->err))) return rc;
   std::vector<double> u(3 * (size_t)S);
   gpdla_matlab_default_rand(u.data(), (int64_t)u.size());
   if ((rc = dev_upload(&c->d_uniforms, u.data(), u.size(), c->err))) return rc;
-  c->Z_lls = Z_lls; c->Z_dla = Z_dla;
+  c->Z_lls = Z_lls; c->Z_dla = Z_dla; c->lls_S = S;
   return GPDLA_OK;
 }
 
@@ -861,17 +1032,19 @@ int gpdla_process_qsos_multi_device(gpdla_ctx* c, int64_t Q, int64_t L_max, cons
                             out->MAP_z_dlas, out->MAP_log_nhis, out->MAP_inds};
   for (const void* r : required)
     if (Q > 0 && !r) { c->err = "gpdla_process_qsos_multi_device: only the three large outputs may be NULL"; return GPDLA_ERR_INVALID; }
-  if (!c->d_M || !c->d_offset || c->n_prior < 0 || !c->d_lls_nhi) {
+  if (!c->d_M || !c->d_offset || c->n_prior < 0 || !c->d_lls_nhi || c->lls_S != c->S) {
     c->err = "gpdla_process_qsos_multi: set_model, set_samples, set_prior and set_lls_samples must be called first";
     return GPDLA_ERR_STATE;
   }
   if (Q == 0) return GPDLA_OK;
-  CUDA_TRY(cudaSetDevice(c->device), c->err);
+  DeviceGuard guard(c->device);
+  int rc = ensure_rest_table(c);
+  if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const int npix = (int)((L_max + KC - 1) / KC) * KC;
   int batch = c->params.batch_quasars > 0 ? c->params.batch_quasars : (rank_splits(c->k) > 1 ? 37 : 148);
   batch = (int)std::min<int64_t>(batch, Q);
-  int rc = ensure_workspace(c, batch, npix);
+  rc = ensure_workspace(c, batch, npix);
   if (rc) return rc;
   rc = ensure_multi_workspace(c, batch, npix);
   if (rc) return rc;
@@ -882,28 +1055,9 @@ int gpdla_process_qsos_multi_device(gpdla_ctx* c, int64_t Q, int64_t L_max, cons
 
   for (int64_t q0 = 0; q0 < Q; q0 += batch) {
     const int nq = (int)std::min<int64_t>(batch, Q - q0);
-    PrepArgs pa;
-    pa.wavelengths = wavelengths + q0 * L_max; pa.flux = flux + q0 * L_max;
-    pa.noise_variance = noise_variance + q0 * L_max; pa.pixel_mask = pixel_mask + q0 * L_max;
-    pa.lengths = lengths + q0; pa.z_qsos = z_qsos + q0; pa.L_max = L_max;
-    pa.rest_wavelengths = c->d_rest; pa.mu = c->d_mu; pa.M = c->d_M; pa.log_omega = c->d_log_omega;
-    pa.n_rest = c->n_rest; pa.k = c->k; pa.c_0 = c->c_0; pa.tau_0 = c->tau_0; pa.beta = c->beta;
-    pa.prior_z_qsos = c->d_prior_z; pa.prior_dla_ind = c->d_prior_dla; pa.n_prior = c->n_prior;
-    pa.min_lambda = c->params.min_lambda; pa.max_lambda = c->params.max_lambda;
-    pa.lya_wavelength = c->params.lya_wavelength; pa.lyman_limit = c->params.lyman_limit;
-    pa.prior_z_qso_increase = c->params.prior_z_qso_increase; pa.min_z_cut = c->params.min_z_cut;
-    pa.max_z_cut = c->params.max_z_cut; pa.pixel_spacing = c->params.pixel_spacing;
-    pa.meta = c->d_meta; pa.lam_pad = c->d_lam; pa.pix = c->d_pix; pa.Mq = c->d_Mq; pa.NPIX = npix;
-    pa.meanflux = 1;
-    prepare_quasars_kernel<<<nq, NTHREADS, 0, st>>>(pa);
-    c->launches++;
-    CUDA_TRY(cudaGetLastError(), c->err);
-    if (use_i8(c)) {
-      if ((rc = build_i8_operands(c, nq, npix, st))) return rc;
-    } else {
-      GPDLA_FOR_RANK(c->k, (build_gram_operand_kernel<K, NSPLIT><<<dim3(npix / KC, nq, NSPLIT), NTHREADS, 0, st>>>(c->d_Mq, c->d_meta, c->d_P, npix)));
-      c->launches++;
-    }
+    if ((rc = prepare_batch(c, prep_args(c, q0, L_max, wavelengths, flux, noise_variance, pixel_mask, lengths, z_qsos, npix, 1),
+                            nq, npix, st)))
+      return rc;
     fill_i32_kernel<<<(nq + 255) / 256, 256, 0, st>>>(c->d_active, 1, nq);
     c->launches++;
     CUDA_TRY(cudaMemsetAsync(c->d_partners, 0, (size_t)nq * 3 * c->S * sizeof(int32_t), st), c->err);   // :313 zeros
@@ -915,10 +1069,8 @@ int gpdla_process_qsos_multi_device(gpdla_ctx* c, int64_t Q, int64_t L_max, cons
     double* slls = out->sample_log_likelihoods_lls ? out->sample_log_likelihoods_lls + q0 * S : c->d_mlls;
     int32_t* partners = c->d_partners;
 
-    LoglikArgs la;
-    la.meta = c->d_meta; la.lam_pad = c->d_lam; la.pix = c->d_pix; la.P = c->d_P;
-    la.offset_samples = c->d_offset; la.S = S; la.num_lines = c->params.num_lines; la.NPIX = npix;
-    la.acache = c->d_acache; la.partners = partners; la.active = c->d_active; la.phase_cycles = nullptr;
+    LoglikArgs la = loglik_args(c, npix);
+    la.acache = c->d_acache; la.partners = partners; la.active = c->d_active;
 
     MultiLevelArgs ma;
     ma.meta = c->d_meta; ma.S = S; ma.max_dlas = MD; ma.partners = partners;
@@ -984,7 +1136,11 @@ int gpdla_process_qsos_multi(gpdla_ctx* c, int64_t Q, int64_t L_max, const doubl
     return GPDLA_ERR_INVALID;
   }
   if (Q == 0) return GPDLA_OK;
-  CUDA_TRY(cudaSetDevice(c->device), c->err);
+  if (!wavelengths || !flux || !noise_variance || !pixel_mask || !lengths || !z_qsos) {
+    c->err = "gpdla_process_qsos_multi: NULL input array";
+    return GPDLA_ERR_INVALID;
+  }
+  DeviceGuard guard(c->device);
   const size_t QL = (size_t)Q * L_max, S = (size_t)c->S, MD = max_dlas;
   // device staging: inputs, then every output (small ones always, large ones when requested)
   struct Item { void** dev; const void* host_in; void* host_out; size_t bytes; };
@@ -1034,7 +1190,7 @@ int gpdla_process_qsos_multi(gpdla_ctx* c, int64_t Q, int64_t L_max, const doubl
     c->st_bytes = bytes;
   }
   char* p = (char*)c->d_stage;
-  cudaStream_t st = 0;
+  cudaStream_t st = c->stream;
   for (auto& it : items) {
     *it.dev = p; p += (it.bytes + 255) / 256 * 256;
     if (it.host_in) CUDA_TRY(cudaMemcpyAsync(*it.dev, it.host_in, it.bytes, cudaMemcpyHostToDevice, st), c->err);
@@ -1054,7 +1210,7 @@ int gpdla_voigt_batch_device(const double* lambdas, int64_t num_points, const do
     g_err = "gpdla_voigt: invalid arguments (need 7 <= num_points <= 16.7M, 1 <= num_lines <= 31, S >= 1)";
     return GPDLA_ERR_INVALID;
   }
-  int rc = upload_line_constants(g_err);
+  int rc = upload_device_constants(g_err);
   if (rc) return rc;
   const int64_t n_out = num_points - 6;
   dim3 grid((unsigned)S, (unsigned)((n_out + NTHREADS - 1) / NTHREADS));

@@ -17,14 +17,13 @@
 // shared-memory-to-shared-memory copy each (DSMEM, completion on the receiver's mbarrier).  CTAs 0..2
 // contract W'' with a third of the Gram columns each (N = 80), CTA 3 contracts U'' with M'' (N = 32): TMEM
 // holds L diagonals x N columns per CTA.  The P''/M'' digit chunk arrives by 1-D TMA.  One tcgen05.mma spans up
-// to three consecutive digit planes / diagonals (issue_chunk_mmas: 9 instructions for the 21 slice pairs).  After
+// to three consecutive digit planes / diagonals (issue_chunk_mmas_fixed: 9 instructions for the 21 slice pairs).  After
 // the last chunk the accumulators are recombined, sent to the CTA that produced the sample (DSMEM stores) and
 // factorised there (factor_staged, the same Cholesky as the FP64 kernels).
 //
-// Two kernels share this scheme: dla_loglik_i8p_kernel (shipped) keeps the clusters resident and overlaps the
-// epilogue of a tile with the main loop of the next one (own warpgroup, setmaxnreg); dla_loglik_i8_kernel runs one
-// tile per cluster and carries the development instrumentation (GPDLA_I8_PERSISTENT=0, GPDLA_I8_PHASES,
-// GPDLA_I8_DEBUG).  Measurements, failed variants and the interference probes: DESIGN.md 4.3.
+// dla_loglik_i8p_kernel keeps the clusters resident and overlaps the epilogue of a tile with the main loop of the
+// next one (own warpgroup, setmaxnreg).  Measurements, failed variants and the interference probes: DESIGN.md 4.3;
+// the one-tile-per-cluster development kernel of round 1 is kept as a record in profiles/experiments/.
 #pragma once
 #include "gpdla_kernels.cuh"
 
@@ -99,9 +98,6 @@ struct Shape {
   static constexpr size_t OFF_CS = OFF_B + 2ull * B_BUF;
   static constexpr size_t OFF_RAW = OFF_CS + (size_t)NENT * CSTR * 8;
   static constexpr size_t OFF_MISC = OFF_RAW + (size_t)TS * RAWS * 8;
-  __host__ __device__ static constexpr size_t smem_bytes(int num_lines) {
-    return OFF_MISC + (size_t)TS * (num_lines + 4) * 8 + 32 * 8 + 3 * TS * 4 + 64;
-  }
 };
 
 // accumulator column (rank, n) -> augmented-triangle index of the staging area (-1: padding column)
@@ -113,8 +109,10 @@ struct I8Args {
   double* colscale;        // [Q x 4 x NMAX]  2^(e_c - 2F + 8(L-1)): accumulator -> Gram entry
   double* colinv;          // [Q x 4 x NMAX]  2^-e_c
   int* status;             // != 0: a barrier wait timed out (kernel traps)
-  int debug;               // timing experiments (GPDLA_I8_DEBUG, one-tile-per-cluster kernel only): 2 skip MMA issue, 4 skip row-block copies
-  unsigned long long* phase;   // nullable: [16] summed cycles per phase (GPDLA_I8_PHASES)
+  int32_t* f64flag;        // [Q] set by i8_scales_kernel: 1 = a used pixel has zero noise variance, the fixed-point bound
+                           // of U'' does not exist -> this quasar is left to the FP64 kernels (skipped here)
+  int32_t* f64list;        // {count, q_0, q_1, ...}: the same quasars as a list (LoglikArgs::only_list of the fallback)
+  unsigned long long* phase;   // nullable: [24] summed wait cycles per barrier (GPDLA_I8_PHASES diagnostics)
 };
 
 // ------------------------------------------------------------------------------------------ PTX helpers
@@ -173,20 +171,6 @@ __device__ __forceinline__ void mma_i8(uint32_t tmem_d, uint64_t da, uint64_t db
       "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(0u)
       : "memory");
 }
-// A operand from TMEM (128 lanes x 8 columns per digit plane, staged by tcgen05.cp.128x256b with the same matrix
-// descriptor as the shared-memory A operand).  Validated (exact results) but measured slower than reading A from
-// shared memory; kept for reference, not used by the shipped kernels.
-__device__ __forceinline__ void mma_i8_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n}\n" ::"r"(tmem_d),
-      "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate), "r"(0u)
-      : "memory");
-}
-// shared memory (matrix descriptor, 128 rows x 256 bits) -> TMEM, ordered with the MMAs of the issuing thread
-__device__ __forceinline__ void tmem_cp_128x256b(uint32_t tmem_dst, uint64_t sdesc) {
-  asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(tmem_dst), "l"(sdesc) : "memory");
-}
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -200,26 +184,10 @@ __device__ __forceinline__ void mma_commit_multicast(uint64_t* bar, uint16_t mas
 // The L (L + 1) / 2 slice-pair products of one chunk.  Digit plane i of A pairs with the B planes j = L-1-i .. L-1,
 // which are consecutive in shared memory, into the diagonals t = i + j - (L-1) = 0 .. i, which are consecutive in
 // TMEM: up to 256 / n accumulator blocks are therefore covered by ONE tcgen05.mma whose N spans several planes.
-// 6 digits: 9 instructions instead of 21 (5 digits: 7 instead of 15).  What the instruction count buys is measured
-// in DESIGN.md 4.3: every tcgen05.mma slows the producers by the same amount regardless of its size.
-template <class Sh, int L>
-__device__ __forceinline__ void issue_chunk_mmas(uint32_t tmem_base, uint32_t a0, uint32_t b0, int n, bool accumulate) {
-  const int group = 256 / n;                       // diagonals per instruction (3 for N = 80, 8 for N = 32)
-#pragma unroll
-  for (int i = L - 1; i >= 0; --i) {               // plane L-1 first: it reaches every diagonal, so it may overwrite
-    const uint64_t da = make_desc(a0 + i * Sh::PLANE_A, Sh::LBO_A, Sh::SBO_A);
-    for (int t0 = 0; t0 <= i; t0 += group) {
-      const int nt = min(group, i + 1 - t0);
-      const uint64_t db = make_desc(b0 + (L - 1 - i + t0) * n * KC, 128, 256);
-      mma_i8(tmem_base + (uint32_t)(t0 * n), da, db, make_idesc(nt * n), (accumulate || i < L - 1) ? 1u : 0u);
-    }
-  }
-}
-
-// The same instruction list with every descriptor offset an immediate (N is a template parameter): the issuing
-// thread shares an SM sub-partition with two producer warps, and each instruction it spends on descriptor
-// arithmetic is an issue slot taken from them (the cost of an MMA does not depend on its size).
-// da0 / db0 are the descriptors of digit plane 0 of the A stage / B buffer.
+// 6 digits: 9 instructions instead of 21 (5 digits: 7 instead of 15).  Every descriptor offset is an immediate (N is
+// a template parameter): the issuing thread shares an SM sub-partition with two producer warps, and each instruction
+// it spends on descriptor arithmetic is an issue slot taken from them (the cost of an MMA does not
+// depend on its size).  da0 / db0 are the descriptors of digit plane 0 of the A stage / B buffer.
 template <class Sh, int L, int N>
 __device__ __forceinline__ void issue_chunk_mmas_fixed(uint32_t tmem_base, uint64_t da0, uint64_t db0, bool accumulate) {
   constexpr int group = 256 / N;
@@ -246,16 +214,23 @@ __global__ void __launch_bounds__(NTHREADS) i8_scales_kernel(const QuasarMeta* _
   const int q = blockIdx.x, tid = threadIdx.x;
   const double* pq = pix + (int64_t)q * NPIX * 4;
   double* p2 = xa.pix2 + (int64_t)q * NPIX * 2;
+  bool unbounded = false;
   for (int i = tid; i < NPIX; i += NTHREADS) {
     const double y = pq[i * 4 + 0], v = pq[i * 4 + 1], mu = pq[i * 4 + 2], om2 = pq[i * 4 + 3];
     const double cw = CAP * (om2 + v);
     // b = max over 0 <= a <= 1 of a / (a^2 om2 + v): at a = sqrt(v / om2) if that is < 1, else at a = 1
     const double b = (v >= om2) ? 1.0 / (om2 + v) : 0.5 / sqrt(om2 * v);
     const double yy = fabs(y) + fabs(mu);
+    // v = 0 (masked and padding pixels carry v = 1): u = a (y - a mu) / (a^2 om2) has no bound as a -> 0, and the
+    // reference divides by zero once the profile saturates (process_qsos.m:194-198, log_mvnpdf_low_rank.m:13)
+    unbounded |= !(v > 0.0) || !isfinite(b) || !isfinite(cw);
     const double cu = (yy > 0.0 && isfinite(b)) ? CAP / (b * yy) : 0.0;
     p2[i * 2 + 0] = cw; p2[i * 2 + 1] = cu;
   }
-  __syncthreads();
+  if (__syncthreads_or(unbounded) && tid == 0 && meta[q].nchunks > 0) {
+    xa.f64flag[q] = 1;
+    xa.f64list[1 + atomicAdd(&xa.f64list[0], 1)] = q;
+  }
   // column maxima of |P''| and |M''| over the pixels, tiled through shared memory (M rows and 1/cw, 1/cu of 32 pixels)
   const int n_u = meta[q].n_u;
   const double* mq = Mq + (int64_t)q * NPIX * K;
@@ -362,341 +337,6 @@ __global__ void __launch_bounds__(NTHREADS) i8_build_operand_kernel(const Quasar
 }
 
 // ------------------------------------------------------------------------------------------
-// K1+K2+K3 fused, INT8 tensor-core Gram.  grid = (4 * ceil((S + 1) / 128), quasars), cluster (4, 1, 1).
-template <int K, int L, int NL, int MODE>
-__global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(THREADS, 1) dla_loglik_i8_kernel(LoglikArgs args, I8Args xa) {
-  using Sh = Shape<K, L>;
-  constexpr int CSTR = Sh::CSTR;
-  const int q = blockIdx.y;
-  const QuasarMeta meta = args.meta[q];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t rank = cluster_ctarank();
-  const long long T0 = clock64();
-  auto phase_add = [&](int idx, long long t) { if (xa.phase && lane == 0) atomicAdd(&xa.phase[idx], (unsigned long long)(t - T0)); };
-  const int64_t s0 = (int64_t)(blockIdx.x / CLUSTER) * TM + (int64_t)rank * TS;   // first sample produced here
-  const int64_t S = args.S;
-
-  if (meta.nchunks == 0 || (args.active != nullptr && args.active[q] == 0)) {     // whole cluster takes this exit
-    for (int i = tid; i < TS; i += THREADS) {
-      const int64_t s = s0 + i;
-      if (s < S) args.sample_log_likelihoods[(int64_t)q * args.sll_stride + s] = NAN;
-      else if (s == S && args.log_likelihoods_no_dla) args.log_likelihoods_no_dla[q] = NAN;
-    }
-    return;
-  }
-
-  extern __shared__ __align__(1024) unsigned char smem_raw[];
-  uint8_t* At = smem_raw + Sh::OFF_A;                                      // [STAGES][A_TILE]   MMA A operand
-  uint8_t* Sx = smem_raw + Sh::OFF_SX;                                     // [STAGES][ROWBLOCK] rows of the other kind
-  uint8_t* Bt = smem_raw + Sh::OFF_B;                                      // [2][B_BUF]
-  double* Cs = reinterpret_cast<double*>(smem_raw + Sh::OFF_CS);           // [NENT][CSTR] epilogue staging
-  double* rawbuf = reinterpret_cast<double*>(smem_raw + Sh::OFF_RAW);      // [TS][RAWS]
-  double* s_nhi = reinterpret_cast<double*>(smem_raw + Sh::OFF_MISC);      // [TS]
-  double* s_q = s_nhi + TS;                                                // [TS]  sum r^2/d
-  double* s_ld = s_q + TS;                                                 // [TS]  sum log d
-  double* s_mult = s_ld + TS;                                              // [num_lines][TS]
-  const int num_lines = (NL > 0) ? NL : args.num_lines;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_mult + (size_t)TS * num_lines + TS);
-  uint64_t* bar_full = bars;                    // [STAGES] A tile complete (own rows + 3 remote row blocks)
-  uint64_t* bar_empty = bar_full + STAGES;      // [STAGES] all four CTAs' MMAs have consumed the stage
-  uint64_t* bar_rows = bar_empty + STAGES;      // [STAGES] local producers have written their rows
-  uint64_t* bar_pfull = bar_rows + STAGES;      // [2] B chunk landed
-  uint64_t* bar_pempty = bar_pfull + 2;         // [2] B chunk consumed
-  uint64_t* bar_acc = bar_pempty + 2;           // accumulators final
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 24);
-  int* s_part = reinterpret_cast<int*>(bars + 32);                          // [3][TS] partner samples (MODE 2)
-
-  for (int i = tid; i < TS; i += THREADS) {                                 // per-sample parameters
-    const int64_t s = s0 + i;
-    const bool is_null = s >= S;
-    const double z = is_null ? 0.0
-                             : __dadd_rn(meta.min_z_dla, __dmul_rn(meta.max_z_dla - meta.min_z_dla, args.offset_samples[s]));
-    s_nhi[i] = is_null ? -1.0 : args.nhi_samples[s];     // negative marks the null-model slot
-    s_ld[i] = 0.0;
-    for (int j = 0; j < num_lines; ++j) s_mult[j * TS + i] = line_multiplier(j, z);
-    if (MODE == 2) {
-      for (int j = 0; j < args.num_partners; ++j)
-        s_part[j * TS + i] = is_null ? 0 : args.partners[((int64_t)q * 3 + j) * S + s];
-    }
-  }
-  if (tid == 0) {
-    for (int i = 0; i < STAGES; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], CLUSTER); mbar_init(&bar_rows[i], NPROD); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&bar_pfull[i], 1); mbar_init(&bar_pempty[i], 1); }
-    mbar_init(bar_acc, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "n"(TMEM_COLS));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;");
-  __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;");
-  const uint32_t tmem_base = *s_tmem;
-  cluster_sync_all();                  // every CTA's barriers are initialised before any remote traffic
-  if (warp == 0) phase_add(1, clock64());   // setup done
-
-  const int N = rank < WCTAS ? Sh::NW : Sh::NU;
-  const uint32_t b_bytes = (uint32_t)Sh::b_bytes(rank);
-  const uint8_t* bsrc = xa.bop + (int64_t)q * (args.NPIX / KC) * Sh::CHUNK_BYTES + Sh::b_offset(rank);
-  const int nchunks = meta.nchunks;
-
-  if (warp >= NCTRL) {
-    // =========================================================================== PRODUCER
-    // lane = pixel; the warp's 4 samples are interleaved in one instruction stream (12 dependency chains)
-    const int pr = warp - NCTRL;
-    const int row0 = pr * SPB;
-    const double* lam = args.lam_pad + (int64_t)q * (args.NPIX + 8);
-    const double* pix = args.pix + (int64_t)q * args.NPIX * 4;
-    const double* pix2 = xa.pix2 + (int64_t)q * args.NPIX * 2;
-    double* const cache_q = (MODE != 0) ? args.acache + (int64_t)q * S * args.NPIX : nullptr;
-    // digit destinations: the kind this CTA contracts goes straight into its A tile, the other into Sx
-    const uint32_t own_block = rank * Sh::ROWBLOCK;
-    uint8_t* const wdst0 = (rank < WCTAS) ? At + own_block : Sx;
-    uint8_t* const udst0 = (rank < WCTAS) ? Sx : At + own_block;
-    const uint32_t wstride = (rank < WCTAS) ? Sh::A_TILE : Sh::ROWBLOCK;   // bytes between stages
-    const uint32_t ustride = (rank < WCTAS) ? Sh::ROWBLOCK : Sh::A_TILE;
-    const uint32_t rowoff = (row0 / 8) * Sh::SBO_A + (row0 % 8) * 16 + (lane / 16) * Sh::LBO_A + (lane % 16);
-
-    auto eval_raw = [&](double lambda, double (&e)[SPB]) {        // voigt.c:282-292, 4 samples at one wavelength
-      const double* mymult = s_mult + row0;
-      const double* mynhi = s_nhi + row0;
-      double tau[SPB];
-      if (NL == 3) {
-        unsigned coremask = 0;
-#pragma unroll
-        for (int ss = 0; ss < SPB; ++ss) {
-          bool core;
-          tau[ss] = tau_sum_3_wing(lambda, mymult[ss], mymult[TS + ss], mymult[2 * TS + ss], core);
-          coremask |= core ? (1u << ss) : 0u;
-        }
-        if (coremask) {
-#pragma unroll
-          for (int ss = 0; ss < SPB; ++ss)
-            if (coremask & (1u << ss)) tau[ss] = tau_sum_3_exact(lambda, mymult[ss], mymult[TS + ss], mymult[2 * TS + ss]);
-        }
-      } else {
-#pragma unroll
-        for (int ss = 0; ss < SPB; ++ss) tau[ss] = tau_sum_generic(lambda, mymult + ss, TS, num_lines);
-      }
-#pragma unroll
-      for (int ss = 0; ss < SPB; ++ss) e[ss] = -mynhi[ss] * tau[ss];
-#pragma unroll
-      for (int ss = 0; ss < SPB; ++ss) e[ss] = exp_nonpos(e[ss]);                  // voigt.c:291
-    };
-    double* myraw = rawbuf + row0 * RAWS;
-    if (MODE != 2) {   // leading pad pixels p = 0..5
-      double e[SPB];
-      eval_raw(lam[lane < 6 ? lane : 5], e);
-      if (lane < 6) {
-#pragma unroll
-        for (int ss = 0; ss < SPB; ++ss) myraw[ss * RAWS + lane] = e[ss];
-      }
-    }
-    double qacc[SPB], ldm[SPB];
-    int lde[SPB];
-#pragma unroll
-    for (int ss = 0; ss < SPB; ++ss) { qacc[ss] = 0.0; ldm[ss] = 1.0; lde[ss] = 0; }
-
-    constexpr uint64_t BIAS = Sh::digit_bias();
-    const double MAGIC = Sh::magic();
-    const uint64_t KADD = BIAS - (uint64_t)__double_as_longlong(MAGIC);
-
-    // pixel data of the next chunk is fetched one chunk ahead (global/L2 latency off the critical path)
-    double lambda_n = lam[6 + lane];
-    double2 p01n = *reinterpret_cast<const double2*>(pix + (int64_t)lane * 4);
-    double2 p23n = *reinterpret_cast<const double2*>(pix + (int64_t)lane * 4 + 2);
-    double2 p45n = *reinterpret_cast<const double2*>(pix2 + (int64_t)lane * 2);
-    for (int c = 0; c < nchunks; ++c) {
-      const int stage = c % STAGES;
-      const int i = c * KC + lane;
-      const double lambda = lambda_n;
-      const double y = p01n.x, v = p01n.y, mu = p23n.x, om2 = p23n.y, cw = p45n.x, cu = p45n.y;
-      if (c + 1 < nchunks) {
-        lambda_n = lam[i + KC + 6];
-        p01n = *reinterpret_cast<const double2*>(pix + (int64_t)(i + KC) * 4);
-        p23n = *reinterpret_cast<const double2*>(pix + (int64_t)(i + KC) * 4 + 2);
-        p45n = *reinterpret_cast<const double2*>(pix2 + (int64_t)(i + KC) * 2);
-      }
-      double a[SPB];
-      if (MODE != 2) {
-        // ---- raw profile for the KC new padded pixels, then the instrument convolution (voigt.c:297-299)
-        double e[SPB];
-        eval_raw(lambda, e);
-#pragma unroll
-        for (int ss = 0; ss < SPB; ++ss) myraw[ss * RAWS + 6 + lane] = e[ss];
-        __syncwarp();
-        double carry[SPB];
-#pragma unroll
-        for (int ss = 0; ss < SPB; ++ss) {
-          const double* rb = myraw + ss * RAWS;
-          double acc_a = 0.0;
-#pragma unroll
-          for (int t = 0; t < 7; ++t) acc_a = fma(rb[lane + t], c_lines.ip[t], acc_a);
-          carry[ss] = rb[KC + (lane < 6 ? lane : 0)];
-          a[ss] = (__double2hiint(s_nhi[row0 + ss]) < 0) ? 1.0 : acc_a;   // null model (N marked negative)
-        }
-        __syncwarp();
-        if (lane < 6) {
-#pragma unroll
-          for (int ss = 0; ss < SPB; ++ss) myraw[ss * RAWS + lane] = carry[ss];   // last 6 pixels -> front of the row
-        }
-        if (MODE == 1) {   // keep the level-1 absorption rows for the higher multi-DLA levels
-#pragma unroll
-          for (int ss = 0; ss < SPB; ++ss) {
-            const int64_t smp = s0 + row0 + ss;
-            if (smp < S) cache_q[smp * args.NPIX + i] = a[ss];
-          }
-        }
-      } else {
-        // absorption = voigt(sample) .* voigt(partner 1) .* ...   (...meanflux.m:342-351), from the cache
-#pragma unroll
-        for (int ss = 0; ss < SPB; ++ss) {
-          const int64_t smp = min(s0 + row0 + ss, S - 1);
-          a[ss] = cache_q[smp * args.NPIX + i];
-        }
-        for (int j = 0; j < args.num_partners; ++j) {
-          double bb[SPB];
-#pragma unroll
-          for (int ss = 0; ss < SPB; ++ss) bb[ss] = cache_q[(int64_t)s_part[j * TS + row0 + ss] * args.NPIX + i];
-#pragma unroll
-          for (int ss = 0; ss < SPB; ++ss) a[ss] = a[ss] * bb[ss];
-        }
-      }
-      // ---- weights -> fixed point -> signed 8-bit digits
-      uint64_t xw[SPB], xu[SPB];
-#pragma unroll
-      for (int ss = 0; ss < SPB; ++ss) {
-        const double a2 = a[ss] * a[ss];
-        const double d = fma(a2, om2, v);                // dla_omega2 + noise variance  (process_qsos.m:194,198)
-        const double rd = fast_rcp(d);
-        const double r = fma(-a[ss], mu, y);             // y - dla_mu
-        const double t1 = r * rd;
-        const double wn = (a2 * rd) * cw;                // W'' in [0, CAP]
-        const double un = (a[ss] * t1) * cu;             // U'' in [-CAP, CAP]
-        xw[ss] = ((uint64_t)__double_as_longlong(__dadd_rn(wn, MAGIC)) + KADD) ^ BIAS;
-        xu[ss] = ((uint64_t)__double_as_longlong(__dadd_rn(un, MAGIC)) + KADD) ^ BIAS;
-        qacc[ss] = fma(r, t1, qacc[ss]);
-        ldm[ss] *= d;
-      }
-      // the stage is free once all four CTAs' MMAs have consumed its previous contents
-      mbar_wait_d(&bar_empty[stage], ((c / STAGES) & 1) ^ 1, xa.status, 1, xa.phase);
-      uint8_t* dW = wdst0 + stage * wstride + rowoff;
-      uint8_t* dU = udst0 + stage * ustride + rowoff;
-#pragma unroll
-      for (int ss = 0; ss < SPB; ++ss) {
-#pragma unroll
-        for (int j = 0; j < L; ++j) {
-          dW[ss * 16 + j * Sh::PLANE_A] = (uint8_t)(xw[ss] >> (8 * j));
-          dU[ss * 16 + j * Sh::PLANE_A] = (uint8_t)(xu[ss] >> (8 * j));
-        }
-      }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic stores -> visible to the async proxy
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_rows[stage]);
-      if ((c & 7) == 7) {   // keep the running products of d in range: move their exponents to integers
-#pragma unroll
-        for (int ss = 0; ss < SPB; ++ss) {
-          const int hi = __double2hiint(ldm[ss]);
-          const int e2 = ((hi >> 20) & 0x7ff) - 1023;
-          lde[ss] += e2;
-          ldm[ss] = __hiloint2double(hi - (e2 << 20), __double2loint(ldm[ss]));
-        }
-      }
-    }
-    if (pr == 0) phase_add(2, clock64());   // producer main loop done
-#pragma unroll
-    for (int ss = 0; ss < SPB; ++ss) {   // per-sample scalars: sum r^2/d and sum log d
-      const double qs = warp_sum(qacc[ss]);
-      const double ld = warp_sum(log(ldm[ss]) + (double)lde[ss] * 0.693147180559945309417);
-      if (lane == 0) { s_q[row0 + ss] = qs; s_ld[row0 + ss] = ld; }
-    }
-  } else {
-    // =========================================================================== CONTROL WARPS
-    if (warp == 0 && lane == 0) {
-      // ---- MMA issuer: for every chunk, the L (L + 1) / 2 slice-pair products, one accumulator per diagonal
-      for (int c = 0; c < nchunks; ++c) {
-        const int stage = c % STAGES, buf = c & 1;
-        mbar_wait_d(&bar_full[stage], (c / STAGES) & 1, xa.status, 2, xa.phase, 100);
-        mbar_wait_d(&bar_pfull[buf], (c >> 1) & 1, xa.status, 3, xa.phase);
-        asm volatile("tcgen05.fence::after_thread_sync;");
-        const uint32_t a0 = smem_u32(At + stage * Sh::A_TILE);
-        const uint32_t b0 = smem_u32(Bt + buf * Sh::B_BUF);
-        if (!(xa.debug & 2)) issue_chunk_mmas<Sh, L>(tmem_base, a0, b0, N, c > 0);
-        mma_commit_multicast(&bar_empty[stage], (uint16_t)((1u << CLUSTER) - 1));   // frees the stage in all CTAs
-        mma_commit(&bar_pempty[buf]);
-      }
-      mma_commit(bar_acc);
-    } else if (warp == 1 && lane == 0) {
-      // ---- B-operand loader (1-D TMA bulk copies, double buffer)
-      for (int c = 0; c < nchunks; ++c) {
-        const int buf = c & 1;
-        if (c >= 2) mbar_wait_d(&bar_pempty[buf], ((c >> 1) - 1) & 1, xa.status, 4, xa.phase, 100);
-        mbar_expect_tx(&bar_pfull[buf], b_bytes);
-        tma_load_1d(Bt + buf * Sh::B_BUF, bsrc + (int64_t)c * Sh::CHUNK_BYTES, b_bytes, &bar_pfull[buf]);
-      }
-    } else if (warp == 2 && lane == 0) {
-      // ---- row-block sender: this CTA's 32 rows of W'' / U'' digits to the CTAs that contract them
-      for (int c = 0; c < nchunks; ++c) {
-        const int stage = c % STAGES;
-        mbar_wait_d(&bar_rows[stage], (c / STAGES) & 1, xa.status, 5, xa.phase, 100);
-        const uint32_t dst_off = smem_u32(At + stage * Sh::A_TILE) + rank * Sh::ROWBLOCK;   // same offset in every CTA
-        const uint32_t own_rows = dst_off;
-        const uint32_t other_rows = smem_u32(Sx + stage * Sh::ROWBLOCK);
-        const uint32_t fullbar = smem_u32(&bar_full[stage]);
-        for (uint32_t peer = 0; peer < (uint32_t)CLUSTER; ++peer) {
-          if (peer == rank || (xa.debug & 4)) continue;
-          // W CTA -> W CTA: own rows; W CTA -> U CTA and U CTA -> W CTA: the rows kept in Sx
-          const uint32_t src = (rank < WCTAS && peer < WCTAS) ? own_rows : other_rows;
-          dsmem_bulk_copy(mapa(dst_off, peer), src, Sh::ROWBLOCK, mapa(fullbar, peer));
-        }
-        mbar_arrive_expect_tx(&bar_full[stage], (xa.debug & 4) ? 0u : (uint32_t)((CLUSTER - 1) * Sh::ROWBLOCK));   // own rows are in place; 3 blocks inbound
-      }
-    }
-    __syncwarp();
-    // ---- epilogue part 1: recombine the diagonals, send every sample's entries to the CTA that produced it
-    if (lane == 0) mbar_wait_d(bar_acc, 0, xa.status, 6, xa.phase);
-    __syncwarp();
-    if (warp == 0) phase_add(3, clock64());   // accumulators final
-    asm volatile("tcgen05.fence::after_thread_sync;");
-    const double* cs = xa.colscale + (int64_t)q * Sh::NCOLTAB + rank * Sh::NMAX;
-    const uint32_t cs_remote = mapa(smem_u32(Cs), (uint32_t)warp) + (uint32_t)lane * 8;   // rows 32 warp.. belong to CTA `warp`
-    const uint32_t taddr0 = tmem_base + ((uint32_t)(warp * 32) << 16);
-    for (int c0 = 0; c0 < N; c0 += 8) {
-      uint32_t v[L][8];
-#pragma unroll
-      for (int t = 0; t < L; ++t) {
-        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                     : "=r"(v[t][0]), "=r"(v[t][1]), "=r"(v[t][2]), "=r"(v[t][3]), "=r"(v[t][4]), "=r"(v[t][5]), "=r"(v[t][6]),
-                       "=r"(v[t][7])
-                     : "r"(taddr0 + (uint32_t)(t * N + c0)));
-      }
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-      for (int jj = 0; jj < 8; ++jj) {
-        const int idx = c_i8_stage[rank * 128 + c0 + jj];
-        if (idx >= 0) {
-          double acc = (double)(int32_t)v[L - 1][jj];
-#pragma unroll
-          for (int t = L - 2; t >= 0; --t) acc = fma(acc, 256.0, (double)(int32_t)v[t][jj]);
-          st_cluster_f64(cs_remote + (uint32_t)(idx * CSTR * 8), acc * cs[c0 + jj]);
-        }
-      }
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;");
-    if (warp == 0) phase_add(4, clock64());   // recombination done
-  }
-  cluster_sync_all();     // all Gram entries delivered; s_q, s_ld final; no remote access to this CTA after this
-  if (warp == 0) phase_add(5, clock64());     // cluster barrier passed
-  if (warp >= NCTRL) return;
-  asm volatile("tcgen05.fence::after_thread_sync;");
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
-  // ---- epilogue part 2 (K3): warp w factorises samples 8w .. 8w+7 of this CTA
-  factor_staged<K, CSTR>(Cs, s_q, s_ld, warp * 8, lane, meta, args, q, s0);
-  if (warp == 0) { phase_add(6, clock64()); if (xa.phase && lane == 0) atomicAdd(&xa.phase[7], 1ull); }
-}
-
-// ------------------------------------------------------------------------------------------
 // Persistent variant (shipped).  The grid holds as many 4-CTA clusters as the GPU can keep resident; each cluster
 // walks the (quasar, 128-sample tile) list with stride = number of clusters.  A CTA has 16 warps in four
 // warpgroups with their own register budgets (setmaxnreg): control (MMA issuer, B loader, row-block sender; 48
@@ -737,7 +377,7 @@ struct PShape {
   static constexpr size_t OFF_MISC = Sh::OFF_MISC;
   __host__ __device__ static constexpr size_t smem_bytes(int num_lines) {
     // per-sample arrays: nhi, q[2], ld[2], mult[num_lines + 1]; 64 barriers; partner indices
-    return OFF_MISC + (size_t)TS * (num_lines + 6) * 8 + 64 * 8 + 3 * TS * 4 + 64;
+    return OFF_MISC + (size_t)TS * (num_lines + 6) * 8 + 64 * 8 + 4 * TS * 4 + 64;
   }
 };
 
@@ -763,7 +403,8 @@ dla_loglik_i8p_kernel(LoglikArgs args, I8Args xa, int num_quasars, int tiles_per
   double* s_ld = s_q + 2 * TS;                                             // [2][TS]  sum log d
   double* s_mult = s_ld + 2 * TS;                                          // [num_lines][TS]
   const int num_lines = (NL > 0) ? NL : args.num_lines;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_mult + (size_t)TS * num_lines + TS);
+  double* s_K = s_mult + (size_t)TS * num_lines;                           // [TS]  rest-frame table offsets
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_K + TS);
   uint64_t* bar_full = bars;                    // [STAGES]
   uint64_t* bar_empty = bar_full + STAGES;      // [STAGES]
   uint64_t* bar_rows = bar_empty + STAGES;      // [STAGES]
@@ -776,6 +417,7 @@ dla_loglik_i8p_kernel(LoglikArgs args, I8Args xa, int num_quasars, int tiles_per
   uint64_t* bar_csfree = bar_csfull + 1;        // [CLUSTER] CTA w has finished factorising: its triangle may be rewritten
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 32);
   int* s_part = reinterpret_cast<int*>(bars + 64);                         // [3][TS]
+  int* s_so = s_part + 3 * TS;                                             // [TS]  sample index of every tile row
 
   if (tid == 0) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], CLUSTER); mbar_init(&bar_rows[i], NPROD); }
@@ -798,7 +440,9 @@ dla_loglik_i8p_kernel(LoglikArgs args, I8Args xa, int num_quasars, int tiles_per
   const uint32_t b_bytes = (uint32_t)Sh::b_bytes(rank);
   // a tile is skipped by every role alike when its quasar has no usable pixel or is inactive
   auto tile_quasar = [&](int t) { return t / tiles_per_quasar; };
-  auto tile_live = [&](int q, const QuasarMeta& m) { return m.nchunks > 0 && !(args.active != nullptr && args.active[q] == 0); };
+  auto tile_live = [&](int q, const QuasarMeta& m) {
+    return m.nchunks > 0 && !(args.active != nullptr && args.active[q] == 0) && xa.f64flag[q] == 0;
+  };
 
   if (warp >= NCTRL + NPROD) {
     // =========================================================================== EPILOGUE WARPGROUP
@@ -813,7 +457,7 @@ dla_loglik_i8p_kernel(LoglikArgs args, I8Args xa, int num_quasars, int tiles_per
       const QuasarMeta meta = args.meta[q];
       const int64_t s0 = (int64_t)(t % tiles_per_quasar) * TM + (int64_t)rank * TS;
       if (!tile_live(q, meta)) {
-        if (lane < 8) {
+        if (lane < 8 && xa.f64flag[q] == 0) {   // dead quasar: NaN results; a flagged one belongs to the FP64 kernels
           const int64_t s = s0 + e * 8 + lane;
           if (s < S) args.sample_log_likelihoods[(int64_t)q * args.sll_stride + s] = NAN;
           else if (s == S && args.log_likelihoods_no_dla) args.log_likelihoods_no_dla[q] = NAN;
@@ -894,13 +538,15 @@ dla_loglik_i8p_kernel(LoglikArgs args, I8Args xa, int num_quasars, int tiles_per
         const int i = row0 + lane;
         const int64_t s = s0 + i;
         const bool is_null = s >= S;
-        const double z = is_null ? 0.0
-                                 : __dadd_rn(meta.min_z_dla, __dmul_rn(meta.max_z_dla - meta.min_z_dla, args.offset_samples[s]));
-        s_nhi[i] = is_null ? -1.0 : args.nhi_samples[s];
+        const int64_t so = sample_at(args, is_null ? S - 1 : s);   // the null-model slot borrows a redshift (a == 1 anyway)
+        const double z = __dadd_rn(meta.min_z_dla, __dmul_rn(meta.max_z_dla - meta.min_z_dla, args.offset_samples[so]));
+        s_nhi[i] = is_null ? -1.0 : args.nhi_samples[so];
+        s_K[i] = rest_table_offset(args.rt, z, meta.lam_ref);
+        s_so[i] = (int)so;
         for (int j = 0; j < num_lines; ++j) s_mult[j * TS + i] = line_multiplier(j, z);
         if (MODE == 2) {
           for (int j = 0; j < args.num_partners; ++j)
-            s_part[j * TS + i] = is_null ? 0 : args.partners[((int64_t)q * 3 + j) * S + s];
+            s_part[j * TS + i] = is_null ? 0 : args.partners[((int64_t)q * 3 + j) * S + so];
         }
       }
       __syncwarp();
@@ -909,35 +555,19 @@ dla_loglik_i8p_kernel(LoglikArgs args, I8Args xa, int num_quasars, int tiles_per
       const double* pix2 = xa.pix2 + (int64_t)q * args.NPIX * 2;
       double* const cache_q = (MODE != 0) ? args.acache + (int64_t)q * S * args.NPIX : nullptr;
 
-      auto eval_raw = [&](double lambda, double (&e)[SPB]) {        // voigt.c:282-292, 4 samples at one wavelength
-        const double* mymult = s_mult + row0;
-        const double* mynhi = s_nhi + row0;
+      // tau / N: from the rest-frame table (one cell per lane serves the warp's four samples), directly where the
+      // cell is near a line centre or the four samples are too far apart in redshift
+      const double* lamh = args.lamh + (int64_t)q * (args.NPIX + 8);
+      double K_mid;
+      const int tab_mode = (MODE != 2) ? group_cell<SPB>(args.rt, s_K + row0, K_mid) : 0;
+      auto eval_raw = [&](double lambda, double lh, double (&e)[SPB]) {   // voigt.c:282-292, 4 samples at one wavelength
         double tau[SPB];
-        if (NL == 3) {
-          unsigned coremask = 0;
-#pragma unroll
-          for (int ss = 0; ss < SPB; ++ss) {
-            bool core;
-            tau[ss] = tau_sum_3_wing(lambda, mymult[ss], mymult[TS + ss], mymult[2 * TS + ss], core);
-            coremask |= core ? (1u << ss) : 0u;
-          }
-          if (coremask) {
-#pragma unroll
-            for (int ss = 0; ss < SPB; ++ss)
-              if (coremask & (1u << ss)) tau[ss] = tau_sum_3_exact(lambda, mymult[ss], mymult[TS + ss], mymult[2 * TS + ss]);
-          }
-        } else {
-#pragma unroll
-          for (int ss = 0; ss < SPB; ++ss) tau[ss] = tau_sum_generic(lambda, mymult + ss, TS, num_lines);
-        }
-#pragma unroll
-        for (int ss = 0; ss < SPB; ++ss) e[ss] = -mynhi[ss] * tau[ss];
-#pragma unroll
-        for (int ss = 0; ss < SPB; ++ss) e[ss] = exp_nonpos(e[ss]);                  // voigt.c:291
+        tau_samples<NL, SPB>(args.rt, tab_mode, K_mid, lambda, lh, s_mult + row0, TS, s_K + row0, num_lines, tau);
+        raw_from_tau<SPB>(tau, s_nhi + row0, e);
       };
       if (MODE != 2) {   // leading pad pixels p = 0..5
         double e[SPB];
-        eval_raw(lam[lane < 6 ? lane : 5], e);
+        eval_raw(lam[lane < 6 ? lane : 5], lamh[lane < 6 ? lane : 5], e);
         if (lane < 6) {
 #pragma unroll
           for (int ss = 0; ss < SPB; ++ss) myraw[ss * RAWS + lane] = e[ss];
@@ -947,17 +577,19 @@ dla_loglik_i8p_kernel(LoglikArgs args, I8Args xa, int num_quasars, int tiles_per
       int lde[SPB];
 #pragma unroll
       for (int ss = 0; ss < SPB; ++ss) { qacc[ss] = 0.0; ldm[ss] = 1.0; lde[ss] = 0; }
-      double lambda_n = lam[6 + lane];
+      // pixel data of the next chunk is fetched one chunk ahead (global/L2 latency off the critical path)
+      double lambda_n = lam[6 + lane], lh_n = lamh[6 + lane];
       double2 p01n = *reinterpret_cast<const double2*>(pix + (int64_t)lane * 4);
       double2 p23n = *reinterpret_cast<const double2*>(pix + (int64_t)lane * 4 + 2);
       double2 p45n = *reinterpret_cast<const double2*>(pix2 + (int64_t)lane * 2);
       for (int c = 0; c < nchunks; ++c, ++gc) {
         const int stage = gc % STAGES;
         const int i = c * KC + lane;
-        const double lambda = lambda_n;
+        const double lambda = lambda_n, lh = lh_n;
         const double y = p01n.x, v = p01n.y, mu = p23n.x, om2 = p23n.y, cw = p45n.x, cu = p45n.y;
         if (c + 1 < nchunks) {
           lambda_n = lam[i + KC + 6];
+          lh_n = lamh[i + KC + 6];
           p01n = *reinterpret_cast<const double2*>(pix + (int64_t)(i + KC) * 4);
           p23n = *reinterpret_cast<const double2*>(pix + (int64_t)(i + KC) * 4 + 2);
           p45n = *reinterpret_cast<const double2*>(pix2 + (int64_t)(i + KC) * 2);
@@ -965,7 +597,7 @@ dla_loglik_i8p_kernel(LoglikArgs args, I8Args xa, int num_quasars, int tiles_per
         double a[SPB];
         if (MODE != 2) {
           double e[SPB];
-          eval_raw(lambda, e);
+          eval_raw(lambda, lh, e);
           if (PROBE & 64) {   // no instrument convolution: no raw-row traffic through shared memory
 #pragma unroll
             for (int ss = 0; ss < SPB; ++ss) a[ss] = (__double2hiint(s_nhi[row0 + ss]) < 0) ? 1.0 : e[ss];
@@ -991,17 +623,12 @@ dla_loglik_i8p_kernel(LoglikArgs args, I8Args xa, int num_quasars, int tiles_per
           }
           if (MODE == 1) {
 #pragma unroll
-            for (int ss = 0; ss < SPB; ++ss) {
-              const int64_t smp = s0 + row0 + ss;
-              if (smp < S) cache_q[smp * args.NPIX + i] = a[ss];
-            }
+            for (int ss = 0; ss < SPB; ++ss)
+              if (s0 + row0 + ss < S) cache_q[(int64_t)s_so[row0 + ss] * args.NPIX + i] = a[ss];
           }
         } else {
 #pragma unroll
-          for (int ss = 0; ss < SPB; ++ss) {
-            const int64_t smp = min(s0 + row0 + ss, S - 1);
-            a[ss] = cache_q[smp * args.NPIX + i];
-          }
+          for (int ss = 0; ss < SPB; ++ss) a[ss] = cache_q[(int64_t)s_so[row0 + ss] * args.NPIX + i];
           for (int j = 0; j < args.num_partners; ++j) {
             double bb[SPB];
 #pragma unroll

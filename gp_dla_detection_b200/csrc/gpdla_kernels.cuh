@@ -3,7 +3,7 @@
 //   K0  prepare_quasars_kernel   process_qsos.m:96-181   window/mask, priors, model interpolation,
 //                                                        z range, padded grid, Gram operand P
 //   K1  voigt_batch_kernel       voigt.c:253-304         stand-alone absorption profiles (API `voigt`)
-//   K1+K2+K3 dla_loglik_kernel   process_qsos.m:185-199 + log_mvnpdf_low_rank.m:5-34, fused:
+//   K1+K2+K3 dla_loglik_ws_kernel process_qsos.m:185-199 + log_mvnpdf_low_rank.m:5-34, fused:
 //        Voigt profile -> weights -> FP64 DMMA Gram/projection -> Cholesky, log-det, quadratic form
 //   K4  evidence_kernel          process_qsos.m:203-233 + generate_ascii_catalog.m:73-80
 //
@@ -30,6 +30,7 @@ struct QuasarMeta {               // one per quasar, written by K0
   double min_z_dla, max_z_dla;    // process_qsos.m:159-160
   double log_prior_no_dla, log_prior_dla;   // process_qsos.m:128-131
   int prior_num_quasars, prior_num_dlas;    // the counts behind them (multi-DLA priors, ...meanflux.m:190-216)
+  double lam_ref;                 // first wavelength of the padded grid: lamh[p] = ln(lam_pad[p] / lam_ref) / h
 };
 
 // Lyman-series forest data for the mean-flux suppression of the multi-DLA path
@@ -72,12 +73,18 @@ struct SplitShape {
 constexpr int ASTR = KC + 4;      // row stride of the W/U operand tiles (== 4 mod 16)
 
 // Epilogue staging layout: the symmetric Gram (p <= q < K) and the projected vector (q = K) as one
-// augmented upper triangle, entry (p, q) at aug_index(p, q).  c_stage_index maps an accumulator column
-// to that index (-1 for padding columns); filled by the host for the compiled rank.
+// augmented upper triangle, entry (p, q) at aug_index(p, q).  stage_index_table<K>() maps an accumulator column
+// to that index (-1 for padding columns); filled by the host for every compiled rank.
 template <int K>
 __host__ __device__ constexpr int aug_index(int p, int q) { return p * (K + 1) - p * (p - 1) / 2 + (q - p); }
-constexpr int MAX_NCOL = 1024;
-__constant__ short c_stage_index[MAX_NCOL];
+// One table per compiled rank (contexts of different rank may share a device).
+__constant__ short c_stage_index_10[GramShape<10>::NCOL];
+__constant__ short c_stage_index_20[GramShape<20>::NCOL];
+__constant__ short c_stage_index_40[GramShape<40>::NCOL];
+template <int K> __device__ __forceinline__ const short* stage_index_table();
+template <> __device__ __forceinline__ const short* stage_index_table<10>() { return c_stage_index_10; }
+template <> __device__ __forceinline__ const short* stage_index_table<20>() { return c_stage_index_20; }
+template <> __device__ __forceinline__ const short* stage_index_table<40>() { return c_stage_index_40; }
 
 // ------------------------------------------------------------------------------------------
 // small helpers
@@ -147,6 +154,8 @@ struct PrepArgs {
   // outputs
   QuasarMeta* meta;
   double* lam_pad;          // [Q x (NPIX + 8)]
+  double* lamh;             // [Q x (NPIX + 8)]  ln(lam_pad / lam_pad[0]) / h: position on the rest-frame table's grid
+  double inv_h;             // 1 / (pixel_spacing ln 10)
   double* pix;              // [Q x NPIX x 4]  (y, v, mu, omega2)
   double* Mq;               // [Q x NPIX x k]  interpolated M rows (zero for masked / padding pixels)
   int NPIX;
@@ -161,7 +170,7 @@ __device__ __forceinline__ double interp_linear(const double* xp, const double* 
 
 __global__ void __launch_bounds__(NTHREADS) prepare_quasars_kernel(PrepArgs a) {
   const int q = blockIdx.x, tid = threadIdx.x;
-  const int64_t L = a.lengths[q];
+  const int64_t L = min(max((int64_t)a.lengths[q], (int64_t)0), a.L_max);   // a length beyond the padded row is clamped
   const double z_qso = a.z_qsos[q];
   const double* wl = a.wavelengths + q * a.L_max;
   const double* fl = a.flux + q * a.L_max;
@@ -218,11 +227,15 @@ __global__ void __launch_bounds__(NTHREADS) prepare_quasars_kernel(PrepArgs a) {
   const int n_used = s_n;
   const int NPIX = a.NPIX;
   double* lam = a.lam_pad + (int64_t)q * (NPIX + 8);
+  double* lamh = a.lamh + (int64_t)q * (NPIX + 8);
   double* pix = a.pix + (int64_t)q * NPIX * 4;
   double* Mq = a.Mq + (int64_t)q * NPIX * a.k;
+  // first padded wavelength (same expression as p = 0 below)
+  const double lam_ref = n_used > 0 ? exp10(log10(s_minu) - 3 * a.pixel_spacing) : 1.0;
 
   if (tid == 0) {
     QuasarMeta m;
+    m.lam_ref = lam_ref;
     m.n_u = n_u; m.n = n_used; m.nchunks = (n_u + KC - 1) / KC; m.first = s_first;
     // set_parameters.m:65-73
     m.max_z_dla = (s_maxw / a.lya_wavelength - 1.0) - a.max_z_cut;
@@ -256,6 +269,7 @@ __global__ void __launch_bounds__(NTHREADS) prepare_quasars_kernel(PrepArgs a) {
       v = exp10(ex);
     }
     lam[p] = v;
+    lamh[p] = log1p((v - lam_ref) / lam_ref) * a.inv_h;
   }
 
   // per-pixel model interpolation (process_qsos.m:138-146)
@@ -314,14 +328,19 @@ __global__ void __launch_bounds__(NTHREADS) prepare_quasars_kernel(PrepArgs a) {
 template <int K, int NSPLIT>
 __global__ void __launch_bounds__(NTHREADS) build_gram_operand_kernel(const double* __restrict__ Mq,
                                                                       const QuasarMeta* __restrict__ meta,
-                                                                      double* __restrict__ P, int NPIX) {
+                                                                      double* __restrict__ P, int NPIX,
+                                                                      const int32_t* __restrict__ only_list) {
   using G = GramShape<K>;
   using SS = SplitShape<K, NSPLIT>;
-  const int q = blockIdx.y;
   const int chunk = blockIdx.x;
   const int split = blockIdx.z;
-  if (chunk >= meta[q].nchunks) return;
   __shared__ double sM[KC][K + 1];
+  // all quasars of the batch (grid.y = quasars), or the listed ones (grid.y slots stride over the list)
+  const int nlist = only_list ? only_list[0] : (int)gridDim.y;
+  for (int qi = blockIdx.y; qi < nlist; qi += gridDim.y) {
+  const int q = only_list ? only_list[1 + qi] : qi;
+  if (chunk >= meta[q].nchunks) continue;
+  __syncthreads();
   const double* src = Mq + ((int64_t)q * NPIX + (int64_t)chunk * KC) * K;
   for (int t = threadIdx.x; t < KC * K; t += NTHREADS) sM[t / K][t % K] = src[t];
   __syncthreads();
@@ -351,6 +370,7 @@ __global__ void __launch_bounds__(NTHREADS) build_gram_operand_kernel(const doub
       }
     }
     dst[t] = v;
+  }
   }
 }
 
@@ -391,6 +411,9 @@ __global__ void __launch_bounds__(NTHREADS) voigt_batch_kernel(const double* __r
 struct LoglikArgs {
   const QuasarMeta* meta;
   const double* lam_pad;      // [Q x (NPIX + 8)]
+  const double* lamh;         // [Q x (NPIX + 8)]  grid positions for the rest-frame table
+  RestTable rt;               // rest-frame table of tau / N (coef == nullptr: direct evaluation everywhere)
+  const int32_t* order;       // [S] samples in ascending redshift offset (tile position -> sample); nullptr = identity
   const double* pix;          // [Q x NPIX x 4]
   const double* P;            // [Q x NPIX/KC x KC x BSTR]
   const double* offset_samples;
@@ -407,50 +430,20 @@ struct LoglikArgs {
   const int32_t* partners;          // [Q x 3 x S] 0-based base_sample_inds; level l uses rows 0..l-2
   int num_partners;
   const int32_t* active;            // [Q] or nullptr; 0 = quasar finished early (:460-464) -> NaN
+  const int32_t* only_list;         // dla_loglik_ws_list_kernel: {count, q_0, q_1, ...}, the quasars to process -- the INT8
+                                    // path's FP64 fallback for zero-noise-variance pixels
   // column-split ranks (NSPLIT > 1): accumulators and per-sample scalars leave through global memory
   double* gram;                     // [Q x rows x NCOL], rows = sample tiles * 64
   double* qld;                      // [Q x rows x 2]  (sum r^2/d, sum log d)
   int64_t gram_rows;
-  long long* phase_cycles;          // debug builds (-DGPDLA_PHASE_TIMING): [16] summed cycles per phase
 };
 
-#ifdef GPDLA_PHASE_TIMING
-#define PHASE_T(var) long long var = clock64()
-#define PHASE_ADD(idx, t0, t1) do { if (tid == 0) atomicAdd((unsigned long long*)&args.phase_cycles[idx], (unsigned long long)((t1) - (t0))); } while (0)
-#define WS_PHASE_ADD(w, idx, t0, t1) do { if (lane == 0 && warp == (w)) atomicAdd((unsigned long long*)&args.phase_cycles[idx], (unsigned long long)((t1) - (t0))); } while (0)
-#else
-#define PHASE_T(var)
-#define PHASE_ADD(idx, t0, t1)
-#define WS_PHASE_ADD(w, idx, t0, t1)
-#endif
 
-// Warp-autonomous schedule.  A CTA of 8 warps handles 64 samples of one quasar; warp w owns samples
-// [8w, 8w+8) end to end: it evaluates their Voigt profiles and weights for a chunk of KC pixels into its
-// private rows of the operand tiles, then runs the FP64 DMMA contraction of those 8 rows against the
-// shared P chunk (one m8 tile x all n8 tiles, accumulators in registers).  No CTA-wide barrier sits in
-// the main loop: the only shared resource is the double-buffered P chunk, brought in by 1-D TMA bulk
-// copies; the warp that finishes a chunk last re-arms that buffer.  Warps drift apart, so DMMA phases of
-// some warps overlap the latency-bound profile phases of others.
-template <int K, int NSPLIT>
-struct LoglikConfig {
-  using G = GramShape<K>;
-  using SS = SplitShape<K, NSPLIT>;
-  static constexpr int NWARPS = NTHREADS / 32;
-  static constexpr int SPW = 8;                        // samples per warp = one m8 tile
-  static constexpr int TS = NWARPS * SPW;              // samples per CTA
-  static constexpr size_t B_BYTES = 2ull * SS::CHUNK_DOUBLES * 8;
-  static constexpr size_t A_BYTES = 2ull * TS * ASTR * 8;
-  static constexpr size_t RAW_BYTES = (size_t)TS * RAWW * 8;
-  // epilogue staging [(K+1)(K+2)/2 - 1 entries][CSTR], aliases the P buffers and the operand tiles;
-  // CSTR == 4 (mod 16): the four lanes of a quad read consecutive entries without bank conflicts
-  static constexpr int CSTR = TS + 4;
-  static constexpr size_t C_BYTES = (size_t)((K + 1) * (K + 2) / 2) * CSTR * 8;
-  static_assert(NSPLIT > 1 || C_BYTES <= B_BYTES + A_BYTES, "epilogue staging must fit in the P buffers + operand tiles");
-  static_assert(SS::NTL * 4 <= 200, "accumulators must fit in registers (use more column splits)");
-  __host__ __device__ static constexpr size_t smem_bytes(int num_lines) {
-    return B_BYTES + A_BYTES + RAW_BYTES + (size_t)TS * (num_lines + 4) * 8 + 64 + 3 * TS * 4;
-  }
-};
+// Tile position -> sample index (samples are processed in ascending redshift so that the warps of a CTA look up
+// neighbouring cells of the rest-frame table; results go back to the caller's order).
+__device__ __forceinline__ int64_t sample_at(const LoglikArgs& args, int64_t pos) {
+  return args.order ? (int64_t)args.order[pos] : pos;
+}
 
 // One k4-step of the contraction for one warp: NT n8 tiles, B fragments fetched pairwise with 16-byte loads
 // from the pair-interleaved P chunk row `brow2` (= chunk + k * BSTR + 2 * gid).
@@ -484,7 +477,7 @@ __device__ __forceinline__ void stage_and_factor(double (&acc)[NT][2], double* C
   // C fragment: lane holds row gid, columns 2 tig, 2 tig + 1 of each n8 tile
 #pragma unroll
   for (int ni = 0; ni < NT; ++ni) {
-    const int i0 = c_stage_index[ni * 8 + tig * 2], i1 = c_stage_index[ni * 8 + tig * 2 + 1];
+    const int i0 = stage_index_table<K>()[ni * 8 + tig * 2], i1 = stage_index_table<K>()[ni * 8 + tig * 2 + 1];
     if (i0 >= 0) Cs[i0 * CSTR + row0 + gid] = acc[ni][0];
     if (i1 >= 0) Cs[i1 * CSTR + row0 + gid] = acc[ni][1];
   }
@@ -536,7 +529,7 @@ __device__ __forceinline__ void factor_staged(double* Cs, const double* s_q, con
       const double logdet = s_ld[sl] + log(prod0) + log(prod1);             //                           :30
       const double lp = -0.5 * (quad + logdet + (double)meta.n * LOG_2PI);  //                           :32
       const int64_t s = s0 + sl;
-      if (s < S) args.sample_log_likelihoods[(int64_t)q * args.sll_stride + s] = lp;
+      if (s < S) args.sample_log_likelihoods[(int64_t)q * args.sll_stride + sample_at(args, s)] = lp;
       else if (s == S && args.log_likelihoods_no_dla) args.log_likelihoods_no_dla[q] = lp;
     }
   }
@@ -544,260 +537,6 @@ __device__ __forceinline__ void factor_staged(double* Cs, const double* s_q, con
 
 // MODE 0: single-DLA / sub-DLA pass;  MODE 1: same, and the convolved absorption rows are stored in
 // args.acache;  MODE 2: multi-DLA level >= 2, absorption = product of cached rows (sample and partners).
-template <int K, int NL, int MODE, int NSPLIT>
-__global__ void __launch_bounds__(NTHREADS, 1) dla_loglik_kernel(LoglikArgs args) {
-  using Cfg = LoglikConfig<K, NSPLIT>;
-  using G = GramShape<K>;
-  using SS = SplitShape<K, NSPLIT>;
-  constexpr int TS = Cfg::TS, SPW = Cfg::SPW, NT = SS::NTL, CSTR = Cfg::CSTR;
-  const int split = (NSPLIT > 1) ? blockIdx.z : 0;
-  const int tile0 = split * SS::NTL;            // first global n8 tile of this CTA
-  const int q = blockIdx.y;
-  const QuasarMeta meta = args.meta[q];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int64_t s0 = (int64_t)blockIdx.x * TS;
-  const int64_t S = args.S;
-
-  // nothing usable in this spectrum (process_qsos.m:74-82), or the level loop already ended for this
-  // quasar (...meanflux.m:460-464): NaN results
-  if (meta.nchunks == 0 || (args.active != nullptr && args.active[q] == 0)) {
-    for (int i = tid; i < TS && split == 0; i += NTHREADS) {
-      int64_t s = s0 + i;
-      if (s < S) args.sample_log_likelihoods[(int64_t)q * args.sll_stride + s] = NAN;
-      else if (s == S && args.log_likelihoods_no_dla) args.log_likelihoods_no_dla[q] = NAN;
-    }
-    return;
-  }
-
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  double* Bt = reinterpret_cast<double*>(smem_raw);                       // [2][KC][BSTR]
-  double* Wt = reinterpret_cast<double*>(smem_raw + Cfg::B_BYTES);        // [TS][ASTR]
-  double* Ut = Wt + TS * ASTR;                                            // [TS][ASTR]
-  double* rawbuf = Ut + TS * ASTR;                                        // [TS][RAWW]
-  double* s_nhi = rawbuf + TS * RAWW;                                     // [TS]
-  double* s_q = s_nhi + TS;                                               // [TS]   sum r^2/d
-  double* s_ld = s_q + TS;                                                // [TS]   sum log d
-  double* s_mult = s_ld + TS;                                             // [num_lines][TS]
-  const int num_lines = (NL > 0) ? NL : args.num_lines;
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(s_mult + (size_t)TS * num_lines + TS);   // full[2]
-  int* s_done = reinterpret_cast<int*>(mbar + 2);                                        // [2] warps done with buffer
-  int* s_part = s_done + 2;                                                               // [3][TS] partner samples (MODE 2)
-  double* Cs = reinterpret_cast<double*>(smem_raw);                       // epilogue: [entries][CSTR]
-
-  // per-sample parameters: z_s (process_qsos.m:162-164), N_s, line multipliers (voigt.c:279)
-  for (int i = tid; i < TS; i += NTHREADS) {
-    int64_t s = s0 + i;
-    bool is_null = s >= S;
-    double z = is_null ? 0.0
-                       : __dadd_rn(meta.min_z_dla, __dmul_rn(meta.max_z_dla - meta.min_z_dla, args.offset_samples[s]));
-    s_nhi[i] = is_null ? -1.0 : args.nhi_samples[s];     // negative marks the null-model slot
-    for (int j = 0; j < num_lines; ++j) s_mult[j * TS + i] = line_multiplier(j, z);
-    if (MODE == 2) {
-      for (int j = 0; j < args.num_partners; ++j)
-        s_part[j * TS + i] = is_null ? 0 : args.partners[((int64_t)q * 3 + j) * S + s];
-    }
-  }
-  const double* lam = args.lam_pad + (int64_t)q * (args.NPIX + 8);
-  const double* pix = args.pix + (int64_t)q * args.NPIX * 4;
-  const double* Pq = args.P + ((int64_t)q * NSPLIT + split) * (args.NPIX / KC) * SS::CHUNK_DOUBLES;
-  constexpr uint32_t CHUNK_BYTES = SS::CHUNK_DOUBLES * 8;
-  if (tid == 0) {
-    mbar_init(&mbar[0], 1);
-    mbar_init(&mbar[1], 1);
-    s_done[0] = 0; s_done[1] = 0;
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    mbar_expect_tx(&mbar[0], CHUNK_BYTES);
-    tma_load_1d(Bt, Pq, CHUNK_BYTES, &mbar[0]);
-    if (meta.nchunks > 1) {
-      mbar_expect_tx(&mbar[1], CHUNK_BYTES);
-      tma_load_1d(Bt + SS::CHUNK_DOUBLES, Pq + SS::CHUNK_DOUBLES, CHUNK_BYTES, &mbar[1]);
-    }
-  }
-  __syncthreads();
-
-  // this warp's private rows
-  double* myW = Wt + warp * SPW * ASTR;
-  double* myU = Ut + warp * SPW * ASTR;
-  double* myraw = rawbuf + warp * SPW * RAWW;
-  const double* mynhi = s_nhi + warp * SPW;
-  const double* mymult = s_mult + warp * SPW;
-
-  // raw-profile evaluation for this warp's samples at padded pixel p.  The common (wing) path is one
-  // basic block over all SPW samples so their dependency chains interleave; pixels within X0 Doppler
-  // widths of a line centre (<= 7 per line per sample) are redone by the exact routine.
-  auto eval_raw = [&](int p) {
-    const double lambda = lam[p];
-    double tau[SPW];
-    if (NL == 3) {
-      unsigned coremask = 0;
-#pragma unroll
-      for (int ss = 0; ss < SPW; ++ss) {
-        bool core;
-        tau[ss] = tau_sum_3_wing(lambda, mymult[ss], mymult[TS + ss], mymult[2 * TS + ss], core);
-        coremask |= core ? (1u << ss) : 0u;
-      }
-      if (coremask) {
-#pragma unroll
-        for (int ss = 0; ss < SPW; ++ss)
-          if (coremask & (1u << ss)) tau[ss] = tau_sum_3_exact(lambda, mymult[ss], mymult[TS + ss], mymult[2 * TS + ss]);
-      }
-    } else {
-#pragma unroll
-      for (int ss = 0; ss < SPW; ++ss) tau[ss] = tau_sum_generic(lambda, mymult + ss, TS, num_lines);
-    }
-    // all shared-memory loads before the first store: the compiler cannot prove s_nhi and rawbuf do
-    // not alias, and a load stuck behind a store would serialise the SPW exponentials
-    double e[SPW];
-#pragma unroll
-    for (int ss = 0; ss < SPW; ++ss) e[ss] = -mynhi[ss] * tau[ss];
-#pragma unroll
-    for (int ss = 0; ss < SPW; ++ss) e[ss] = exp_nonpos(e[ss]);                    // voigt.c:291
-#pragma unroll
-    for (int ss = 0; ss < SPW; ++ss) myraw[ss * RAWW + (p & (RAWW - 1))] = e[ss];
-  };
-  if (MODE != 2) eval_raw(lane < 6 ? lane : 5);   // leading pad pixels p = 0..5 (extra lanes repeat p = 5)
-  double* const cache_q = (MODE != 0) ? args.acache + (int64_t)q * S * args.NPIX : nullptr;
-
-  // accumulators: 8 samples x NCOL columns per warp
-  double acc[NT][2];
-#pragma unroll
-  for (int ni = 0; ni < NT; ++ni) acc[ni][0] = acc[ni][1] = 0.0;
-  double qacc[SPW], ldm[SPW];
-  int lde[SPW];
-#pragma unroll
-  for (int ss = 0; ss < SPW; ++ss) { qacc[ss] = 0.0; ldm[ss] = 1.0; lde[ss] = 0; }
-  const int gid = lane >> 2, tig = lane & 3;
-
-  PHASE_T(t_start);
-  for (int c = 0; c < meta.nchunks; ++c) {
-    // ---- A1: raw profile for the KC new padded pixels
-    PHASE_T(t_a1);
-    if (MODE != 2) eval_raw(c * KC + 6 + lane);
-    __syncwarp();
-    PHASE_T(t_a1e);
-    // ---- A2: instrument convolution + weights
-    {
-      const int i = c * KC + lane;
-      const double2 p01 = *reinterpret_cast<const double2*>(pix + (int64_t)i * 4);
-      const double2 p23 = *reinterpret_cast<const double2*>(pix + (int64_t)i * 4 + 2);
-      const double y = p01.x, v = p01.y, mu = p23.x, om2 = p23.y;
-      // loads first (convolution), stores last: see the aliasing note in eval_raw
-      double a[SPW];
-      if (MODE != 2) {
-#pragma unroll
-        for (int ss = 0; ss < SPW; ++ss) {
-          const double* rb = myraw + ss * RAWW;
-          double acc_a = 0.0;
-#pragma unroll
-          for (int t = 0; t < 7; ++t) acc_a = fma(rb[(i + t) & (RAWW - 1)], c_lines.ip[t], acc_a);   // voigt.c:297-299
-          a[ss] = (__double2hiint(mynhi[ss]) < 0) ? 1.0 : acc_a;   // null model (N marked negative): no absorption
-        }
-        if (MODE == 1 && split == 0) {   // keep the level-1 absorption rows for the higher multi-DLA levels
-#pragma unroll
-          for (int ss = 0; ss < SPW; ++ss) {
-            const int64_t smp = s0 + warp * SPW + ss;
-            if (smp < S) cache_q[smp * args.NPIX + i] = a[ss];
-          }
-        }
-      } else {
-        // absorption = voigt(sample) .* voigt(partner 1) .* ...   (...meanflux.m:342-351), from the cache
-#pragma unroll
-        for (int ss = 0; ss < SPW; ++ss) {
-          const int64_t smp = min(s0 + warp * SPW + ss, S - 1);
-          a[ss] = cache_q[smp * args.NPIX + i];
-        }
-        for (int j = 0; j < args.num_partners; ++j) {
-          double b[SPW];
-#pragma unroll
-          for (int ss = 0; ss < SPW; ++ss) b[ss] = cache_q[(int64_t)s_part[j * TS + warp * SPW + ss] * args.NPIX + i];
-#pragma unroll
-          for (int ss = 0; ss < SPW; ++ss) a[ss] = a[ss] * b[ss];
-        }
-      }
-#pragma unroll
-      for (int ss = 0; ss < SPW; ++ss) {
-        const double a2 = a[ss] * a[ss];
-        const double d = fma(a2, om2, v);                // dla_omega2 + noise variance  (process_qsos.m:194,198)
-        const double rd = fast_rcp(d);
-        const double r = fma(-a[ss], mu, y);             // y - dla_mu
-        const double t1 = r * rd;
-        myW[ss * ASTR + lane] = a2 * rd;
-        myU[ss * ASTR + lane] = a[ss] * t1;
-        qacc[ss] = fma(r, t1, qacc[ss]);
-        ldm[ss] *= d;
-      }
-      if ((c & 7) == 7) {   // keep the running product of d in range: move its exponent to an integer
-#pragma unroll
-        for (int ss = 0; ss < SPW; ++ss) {
-          int hi = __double2hiint(ldm[ss]);
-          int e = ((hi >> 20) & 0x7ff) - 1023;
-          lde[ss] += e;
-          ldm[ss] = __hiloint2double(hi - (e << 20), __double2loint(ldm[ss]));
-        }
-      }
-    }
-    __syncwarp();
-    PHASE_T(t_a2e);
-    mbar_wait(&mbar[c & 1], (c >> 1) & 1);
-    PHASE_T(t_mb);
-    // ---- B: FP64 tensor-core contraction  acc += [W|U] (8 x KC) . P_chunk (KC x NCOL)
-    {
-      const double* Bc = Bt + (c & 1) * SS::CHUNK_DOUBLES;
-#pragma unroll
-      for (int ks = 0; ks < KC / 4; ++ks) {
-        const double aw = myW[gid * ASTR + ks * 4 + tig];
-        const double au = myU[gid * ASTR + ks * 4 + tig];
-        dmma_k4_step<NT, G::WT>(acc, aw, au, Bc + (ks * 4 + tig) * SS::BSTR + 2 * gid, tile0, gid);
-      }
-    }
-    __syncwarp();
-    PHASE_T(t_be);
-    // ---- release the P buffer; the last warp to finish this chunk re-arms it with chunk c + 2
-    if (lane == 0 && c + 2 < meta.nchunks) {
-      const int done = atomicAdd(&s_done[c & 1], 1);
-      if (done == Cfg::NWARPS - 1) {
-        s_done[c & 1] = 0;
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_expect_tx(&mbar[c & 1], CHUNK_BYTES);
-        tma_load_1d(Bt + (c & 1) * SS::CHUNK_DOUBLES, Pq + (int64_t)(c + 2) * SS::CHUNK_DOUBLES, CHUNK_BYTES,
-                    &mbar[c & 1]);
-      }
-    }
-    PHASE_ADD(0, t_a1, t_a1e); PHASE_ADD(2, t_a1e, t_a2e); PHASE_ADD(4, t_a2e, t_mb); PHASE_ADD(5, t_mb, t_be);
-  }
-  PHASE_T(t_loop_end);
-  PHASE_ADD(6, t_start, t_loop_end);
-
-  // ---- per-sample scalars: sum r^2/d and sum log d
-#pragma unroll
-  for (int ss = 0; ss < SPW; ++ss) {
-    double qs = warp_sum(qacc[ss]);
-    double ld = warp_sum(log(ldm[ss]) + (double)lde[ss] * 0.693147180559945309417);
-    if (lane == 0) { s_q[warp * SPW + ss] = qs; s_ld[warp * SPW + ss] = ld; }
-  }
-  __syncwarp();
-  if (NSPLIT > 1) {
-    // column-split ranks: accumulators (and, from split 0, the per-sample scalars) go to global memory;
-    // cholesky_kernel finishes the job
-    const int64_t row = s0 + warp * SPW + gid;
-    double* grow = args.gram + ((int64_t)q * args.gram_rows + row) * G::NCOL + tile0 * 8 + tig * 2;
-#pragma unroll
-    for (int ni = 0; ni < NT; ++ni) *reinterpret_cast<double2*>(grow + ni * 8) = make_double2(acc[ni][0], acc[ni][1]);
-    if (split == 0 && lane < SPW) {
-      double* qd = args.qld + ((int64_t)q * args.gram_rows + s0 + warp * SPW + lane) * 2;
-      qd[0] = s_q[warp * SPW + lane]; qd[1] = s_ld[warp * SPW + lane];
-    }
-    return;
-  }
-  __syncthreads();   // every warp is done with the P buffers -> the staging area may alias them
-  stage_and_factor<K, NT, CSTR>(acc, Cs, s_q, s_ld, warp * SPW, lane, meta, args, q, s0);
-#ifdef GPDLA_PHASE_TIMING
-  __syncthreads();
-  PHASE_T(t_end);
-  PHASE_ADD(7, t_loop_end, t_end);
-#endif
-}
-
 // ------------------------------------------------------------------------------------------
 // Warp-specialised schedule.
 //
@@ -832,6 +571,147 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// tau / N of SPB samples at one wavelength by direct evaluation of the line sum (lane = pixel)   voigt.c:282-290:
+// branch-free wing formula for all samples, then the exact routine for the lanes within X0 Doppler widths of a core.
+//   mymult[j * mstride + ss]: line multipliers (voigt.c:279)
+template <int SPB>
+struct TauRow { double t[SPB]; };
+
+// Kept out of line on purpose: the direct evaluation runs in < 10 % of the chunks but needs far more registers than
+// the rest of the producer loop; inlined, it costs the common path its instruction-level parallelism (measured: the
+// whole kernel 20 % slower).
+template <int NL, int SPB>
+__device__ __noinline__ TauRow<SPB> tau_direct(double lambda, const double* mymult, int mstride, int num_lines) {
+  TauRow<SPB> out;
+  double (&tau)[SPB] = out.t;
+  if (NL == 3) {
+    const int lane = threadIdx.x & 31;
+    unsigned cm[SPB], any = 0;
+#pragma unroll
+    for (int ss = 0; ss < SPB; ++ss) {
+      bool core;
+      tau[ss] = tau_sum_3_wing(lambda, mymult[ss], mymult[mstride + ss], mymult[2 * mstride + ss], core);
+      cm[ss] = __ballot_sync(0xffffffffu, core);
+      any |= cm[ss];
+    }
+    if (any) {   // warp-uniform
+      // The (sample, pixel) pairs within X0 Doppler widths of a line core -- at most 7 pixels per sample, and the SPB
+      // samples of a warp are neighbours in redshift, so they all arrive in this chunk -- are dealt out one per lane
+      // and evaluated by ONE pass of the exact routine instead of SPB divergent passes with 7 active lanes each.
+      int off[SPB + 1];
+      off[0] = 0;
+#pragma unroll
+      for (int ss = 0; ss < SPB; ++ss) off[ss + 1] = off[ss] + __popc(cm[ss]);
+      if (off[SPB] <= 32) {
+        int ss_i = 0;
+#pragma unroll
+        for (int ss = 1; ss < SPB; ++ss) ss_i = (lane >= off[ss]) ? ss : ss_i;
+        unsigned mask_i = cm[0];
+        int off_i = 0;
+#pragma unroll
+        for (int ss = 1; ss < SPB; ++ss) { mask_i = (ss_i == ss) ? cm[ss] : mask_i; off_i = (ss_i == ss) ? off[ss] : off_i; }
+        const bool have = lane < off[SPB];
+        const int src = have ? (int)__fns(mask_i, 0, lane - off_i + 1) : 0;       // pixel lane of this lane's pair
+        const double lam_i = __shfl_sync(0xffffffffu, lambda, src);
+        const double t = tau_sum_3_exact(lam_i, mymult[ss_i], mymult[mstride + ss_i], mymult[2 * mstride + ss_i]);
+        const unsigned below = (1u << lane) - 1u;
+#pragma unroll
+        for (int ss = 0; ss < SPB; ++ss) {
+          const double v = __shfl_sync(0xffffffffu, t, (off[ss] + __popc(cm[ss] & below)) & 31);
+          if ((cm[ss] >> lane) & 1u) tau[ss] = v;
+        }
+      } else {
+#pragma unroll
+        for (int ss = 0; ss < SPB; ++ss)
+          if ((cm[ss] >> lane) & 1u)
+            tau[ss] = tau_sum_3_exact(lambda, mymult[ss], mymult[mstride + ss], mymult[2 * mstride + ss]);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int ss = 0; ss < SPB; ++ss) tau[ss] = tau_sum_generic(lambda, mymult + ss, mstride, num_lines);
+  }
+  return out;
+}
+
+// tau / N of SPB samples from the cell fetched for this lane; returns true (warp-uniform) when some lane's cell is
+// one of those left to direct evaluation.  All 32 lanes must call this together.
+template <int SPB>
+__device__ __forceinline__ bool tau_from_cell(const RestCell& rc, const double* myK, double (&tau)[SPB]) {
+  unsigned worst = 0;
+#pragma unroll
+  for (int ss = 0; ss < SPB; ++ss) {
+    tau[ss] = rest_table_eval(rc, myK[ss]);
+    worst = max(worst, (unsigned)__double2hiint(tau[ss]));
+  }
+  return __any_sync(0xffffffffu, worst >= 0x7ff00000u);
+}
+
+// tau / N of SPB samples, each from its own cell (samples too far apart in redshift to share one).  Out of line like the
+// direct evaluation: a mode for sparse sample sets that must not cost the common path registers.
+template <int SPB>
+__device__ __noinline__ TauRow<SPB> tau_own_cells(const RestTable& rt, double lh, const double* myK) {
+  TauRow<SPB> out;
+#pragma unroll
+  for (int ss = 0; ss < SPB; ++ss) {
+    RestCell rc;
+    const double K = myK[ss];
+    rest_table_fetch(rt, lh, K, rc);
+    out.t[ss] = rest_table_eval(rc, K);
+  }
+  return out;
+}
+
+// tau / N of the SPB samples of a group at one wavelength.  `tab_mode` (see group_cell): 1 = the group's common cell of
+// the rest-frame table, 2 = the samples are too far apart in redshift to share a cell (few samples per quasar): one cell
+// per sample, 0 = no table.  Where a cell is near a line centre the whole warp evaluates directly.  The coefficient
+// loads hit L1 when the warps of a CTA work on neighbouring redshifts (a line holds 16 cells and is used by every warp
+// for one or two chunks); all 32 lanes must call this together.
+template <int NL, int SPB>
+__device__ __forceinline__ void tau_samples(const RestTable& rt, int tab_mode, double K_mid, double lambda, double lh,
+                                            const double* mymult, int mstride, const double* myK, int num_lines,
+                                            double (&tau)[SPB]) {
+  bool direct = tab_mode == 0;
+  if (tab_mode == 1) {
+    RestCell rc;
+    rest_table_fetch(rt, lh, K_mid, rc);
+    direct = tau_from_cell<SPB>(rc, myK, tau);
+  } else if (tab_mode == 2) {
+    const TauRow<SPB> r = tau_own_cells<SPB>(rt, lh, myK);
+    unsigned worst = 0;
+#pragma unroll
+    for (int ss = 0; ss < SPB; ++ss) { tau[ss] = r.t[ss]; worst = max(worst, (unsigned)__double2hiint(tau[ss])); }
+    direct = __any_sync(0xffffffffu, worst >= 0x7ff00000u);
+  }
+  if (direct) {
+    const TauRow<SPB> r = tau_direct<NL, SPB>(lambda, mymult, mstride, num_lines);
+#pragma unroll
+    for (int ss = 0; ss < SPB; ++ss) tau[ss] = r.t[ss];
+  }
+}
+
+// raw absorption exp(-N tau)   voigt.c:291.  All shared-memory loads come before the caller's first store: the
+// compiler cannot prove that the per-sample arrays and the raw rows do not alias, and a load stuck behind a store
+// would serialise the SPB exponentials.
+template <int SPB>
+__device__ __forceinline__ void raw_from_tau(const double (&tau)[SPB], const double* mynhi, double (&e)[SPB]) {
+#pragma unroll
+  for (int ss = 0; ss < SPB; ++ss) e[ss] = -mynhi[ss] * tau[ss];
+#pragma unroll
+  for (int ss = 0; ss < SPB; ++ss) e[ss] = exp_nonpos(e[ss]);
+}
+
+// K_mid of a group of SPB consecutive tile rows (their table offsets in myK) and how the table serves them: 1 = one
+// cell for the group, 2 = one cell per sample, 0 = table disabled
+template <int SPB>
+__device__ __forceinline__ int group_cell(const RestTable& rt, const double* myK, double& K_mid) {
+  double lo = myK[0], hi = myK[0];
+#pragma unroll
+  for (int ss = 1; ss < SPB; ++ss) { lo = fmin(lo, myK[ss]); hi = fmax(hi, myK[ss]); }
+  K_mid = 0.5 * (lo + hi);
+  return rt.coef == nullptr ? 0 : ((hi - lo) <= RT_MAX_SPREAD ? 1 : 2);
+}
+
 template <int K, int NSPLIT>
 struct WsConfig {
   using G = GramShape<K>;
@@ -849,25 +729,31 @@ struct WsConfig {
   static_assert(SS::NTL * 4 + 40 <= 168, "accumulators must fit in the consumer's registers");
   static constexpr int NBAR = 2 + 2 * WS_STAGES * WS_CONSUMERS;
   __host__ __device__ static constexpr size_t smem_bytes(int num_lines) {
-    return B_BYTES + A_BYTES + RAW_BYTES + (size_t)TS * (num_lines + 4) * 8 + NBAR * 8 + 64 + 3 * TS * 4;
+    return B_BYTES + A_BYTES + RAW_BYTES + (size_t)TS * (num_lines + 4) * 8 + NBAR * 8 + 64 + 4 * TS * 4;
   }
 };
 
+__device__ __forceinline__ void mbar_inval(uint64_t* bar) {
+  asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// One (quasar, sample tile, column split) of the warp-specialised FP64 kernel.
 template <int K, int NL, int MODE, int NSPLIT>
-__global__ void __launch_bounds__(WS_THREADS, 1) dla_loglik_ws_kernel(LoglikArgs args) {
+__device__ __forceinline__ void ws_tile(const LoglikArgs& args, const int q) {
   using Cfg = WsConfig<K, NSPLIT>;
   using G = GramShape<K>;
   using SS = SplitShape<K, NSPLIT>;
   constexpr int TS = Cfg::TS, SPW = Cfg::SPW, SPB = Cfg::SPB, SPP = Cfg::SPP, NT = SS::NTL, CSTR = Cfg::CSTR;
   const int split = (NSPLIT > 1) ? blockIdx.z : 0;
   const int tile0 = split * SS::NTL;
-  const int q = blockIdx.y;
   const QuasarMeta meta = args.meta[q];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t s0 = (int64_t)blockIdx.x * TS;
   const int64_t S = args.S;
 
-  if (meta.nchunks == 0 || (args.active != nullptr && args.active[q] == 0)) {   // see dla_loglik_kernel
+  // nothing usable in this spectrum (process_qsos.m:74-82), or the level loop already ended for this quasar
+  // (...meanflux.m:460-464): NaN results
+  if (meta.nchunks == 0 || (args.active != nullptr && args.active[q] == 0)) {
     for (int i = tid; i < TS && split == 0; i += WS_THREADS) {
       int64_t s = s0 + i;
       if (s < S) args.sample_log_likelihoods[(int64_t)q * args.sll_stride + s] = NAN;
@@ -886,24 +772,28 @@ __global__ void __launch_bounds__(WS_THREADS, 1) dla_loglik_ws_kernel(LoglikArgs
   double* s_ld = s_q + TS;                                                // [TS]   sum log d
   double* s_mult = s_ld + TS;                                             // [num_lines][TS]
   const int num_lines = (NL > 0) ? NL : args.num_lines;
-  uint64_t* bar_p = reinterpret_cast<uint64_t*>(s_mult + (size_t)TS * num_lines + TS);   // P chunk full[2]
+  double* s_K = s_mult + (size_t)TS * num_lines;                           // [TS]   rest-frame table offsets
+  uint64_t* bar_p = reinterpret_cast<uint64_t*>(s_K + TS);                 // P chunk full[2]
   uint64_t* bar_full = bar_p + 2;                                          // [consumer][stage] rows ready
   uint64_t* bar_empty = bar_full + WS_STAGES * WS_CONSUMERS;               // [consumer][stage] rows consumed
   int* s_done = reinterpret_cast<int*>(bar_empty + WS_STAGES * WS_CONSUMERS);   // [2] consumers done with P buffer
   int* s_part = s_done + 2;                                                // [3][TS] partner samples (MODE 2)
+  int* s_so = s_part + 3 * TS;                                             // [TS]   sample index of every tile row
   double* Cs = reinterpret_cast<double*>(smem_raw);                       // epilogue: [entries][CSTR]
 
   for (int i = tid; i < TS; i += WS_THREADS) {                             // per-sample parameters
-    int64_t s = s0 + i;
-    bool is_null = s >= S;
-    double z = is_null ? 0.0
-                       : __dadd_rn(meta.min_z_dla, __dmul_rn(meta.max_z_dla - meta.min_z_dla, args.offset_samples[s]));
-    s_nhi[i] = is_null ? -1.0 : args.nhi_samples[s];     // negative marks the null-model slot
+    const int64_t s = s0 + i;
+    const bool is_null = s >= S;
+    const int64_t so = sample_at(args, is_null ? S - 1 : s);   // the null-model slot borrows a redshift (a == 1 anyway)
+    const double z = __dadd_rn(meta.min_z_dla, __dmul_rn(meta.max_z_dla - meta.min_z_dla, args.offset_samples[so]));
+    s_nhi[i] = is_null ? -1.0 : args.nhi_samples[so];    // negative marks the null-model slot
     s_ld[i] = 0.0;
+    s_K[i] = rest_table_offset(args.rt, z, meta.lam_ref);
+    s_so[i] = (int)so;
     for (int j = 0; j < num_lines; ++j) s_mult[j * TS + i] = line_multiplier(j, z);
     if (MODE == 2) {
       for (int j = 0; j < args.num_partners; ++j)
-        s_part[j * TS + i] = is_null ? 0 : args.partners[((int64_t)q * 3 + j) * S + s];
+        s_part[j * TS + i] = is_null ? 0 : args.partners[((int64_t)q * 3 + j) * S + so];
     }
   }
   const double* Pq = args.P + ((int64_t)q * NSPLIT + split) * (args.NPIX / KC) * SS::CHUNK_DOUBLES;
@@ -937,38 +827,19 @@ __global__ void __launch_bounds__(WS_THREADS, 1) dla_loglik_ws_kernel(LoglikArgs
     auto batch_row0 = [&](int b) { return batch_consumer(b) * SPW + ((pr + b * WS_PRODUCERS) / WS_CONSUMERS) * SPB; };
 
     // raw (unconvolved) absorption of 4 samples (rows row0..row0+3) at one wavelength    voigt.c:282-292
-    auto eval_raw = [&](int row0, double lambda, double (&e)[SPB]) {
-      const double* mymult = s_mult + row0;
-      const double* mynhi = s_nhi + row0;
-      double tau[SPB];
-      if (NL == 3) {
-        unsigned coremask = 0;
-#pragma unroll
-        for (int ss = 0; ss < SPB; ++ss) {
-          bool core;
-          tau[ss] = tau_sum_3_wing(lambda, mymult[ss], mymult[TS + ss], mymult[2 * TS + ss], core);
-          coremask |= core ? (1u << ss) : 0u;
-        }
-        if (coremask) {
-#pragma unroll
-          for (int ss = 0; ss < SPB; ++ss)
-            if (coremask & (1u << ss)) tau[ss] = tau_sum_3_exact(lambda, mymult[ss], mymult[TS + ss], mymult[2 * TS + ss]);
-        }
-      } else {
-#pragma unroll
-        for (int ss = 0; ss < SPB; ++ss) tau[ss] = tau_sum_generic(lambda, mymult + ss, TS, num_lines);
-      }
-#pragma unroll
-      for (int ss = 0; ss < SPB; ++ss) e[ss] = -mynhi[ss] * tau[ss];
-#pragma unroll
-      for (int ss = 0; ss < SPB; ++ss) e[ss] = exp_nonpos(e[ss]);                  // voigt.c:291
+    const double* lamh = args.lamh + (int64_t)q * (args.NPIX + 8);
+    auto eval_raw = [&](int row0, double lambda, double lh, double (&e)[SPB]) {
+      double tau[SPB], K_mid;
+      const int tab_mode = group_cell<SPB>(args.rt, s_K + row0, K_mid);
+      tau_samples<NL, SPB>(args.rt, tab_mode, K_mid, lambda, lh, s_mult + row0, TS, s_K + row0, num_lines, tau);
+      raw_from_tau<SPB>(tau, s_nhi + row0, e);
     };
     if (MODE != 2) {   // leading pad pixels p = 0..5
-      const double lambda0 = lam[lane < 6 ? lane : 5];
+      const double lambda0 = lam[lane < 6 ? lane : 5], lh0 = lamh[lane < 6 ? lane : 5];
 #pragma unroll
       for (int b = 0; b < SPP / SPB; ++b) {
         double e[SPB];
-        eval_raw(batch_row0(b), lambda0, e);
+        eval_raw(batch_row0(b), lambda0, lh0, e);
         if (lane < 6) {
 #pragma unroll
           for (int ss = 0; ss < SPB; ++ss) rawbuf[(batch_row0(b) + ss) * RAWS + lane] = e[ss];
@@ -981,16 +852,17 @@ __global__ void __launch_bounds__(WS_THREADS, 1) dla_loglik_ws_kernel(LoglikArgs
     for (int ss = 0; ss < SPP; ++ss) { qacc[ss] = 0.0; ldm[ss] = 1.0; lde[ss] = 0; }
 
     // pixel data of the next chunk is fetched one chunk ahead (global/L2 latency off the critical path)
-    double lambda_n = lam[6 + lane];
+    double lambda_n = lam[6 + lane], lh_n = lamh[6 + lane];
     double2 p01n = *reinterpret_cast<const double2*>(pix + (int64_t)lane * 4);
     double2 p23n = *reinterpret_cast<const double2*>(pix + (int64_t)lane * 4 + 2);
     for (int c = 0; c < meta.nchunks; ++c) {
       const int stage = c % WS_STAGES;
       const int i = c * KC + lane;
-      const double lambda = lambda_n;
+      const double lambda = lambda_n, lh = lh_n;
       const double y = p01n.x, v = p01n.y, mu = p23n.x, om2 = p23n.y;
       if (c + 1 < meta.nchunks) {
         lambda_n = lam[i + KC + 6];
+        lh_n = lamh[i + KC + 6];
         p01n = *reinterpret_cast<const double2*>(pix + (int64_t)(i + KC) * 4);
         p23n = *reinterpret_cast<const double2*>(pix + (int64_t)(i + KC) * 4 + 2);
       }
@@ -1002,7 +874,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) dla_loglik_ws_kernel(LoglikArgs
         if (MODE != 2) {
           // ---- raw profile for the KC new padded pixels, then the instrument convolution (voigt.c:297-299)
           double e[SPB];
-          eval_raw(row0, lambda, e);
+          eval_raw(row0, lambda, lh, e);
 #pragma unroll
           for (int ss = 0; ss < SPB; ++ss) myraw[ss * RAWS + 6 + lane] = e[ss];
           __syncwarp();
@@ -1023,18 +895,13 @@ __global__ void __launch_bounds__(WS_THREADS, 1) dla_loglik_ws_kernel(LoglikArgs
           }
           if (MODE == 1 && split == 0) {   // keep the level-1 absorption rows for the higher multi-DLA levels
 #pragma unroll
-            for (int ss = 0; ss < SPB; ++ss) {
-              const int64_t smp = s0 + row0 + ss;
-              if (smp < S) cache_q[smp * args.NPIX + i] = a[ss];
-            }
+            for (int ss = 0; ss < SPB; ++ss)
+              if (s0 + row0 + ss < S) cache_q[(int64_t)s_so[row0 + ss] * args.NPIX + i] = a[ss];
           }
         } else {
           // absorption = voigt(sample) .* voigt(partner 1) .* ...   (...meanflux.m:342-351), from the cache
 #pragma unroll
-          for (int ss = 0; ss < SPB; ++ss) {
-            const int64_t smp = min(s0 + row0 + ss, S - 1);
-            a[ss] = cache_q[smp * args.NPIX + i];
-          }
+          for (int ss = 0; ss < SPB; ++ss) a[ss] = cache_q[(int64_t)s_so[row0 + ss] * args.NPIX + i];
           for (int j = 0; j < args.num_partners; ++j) {
             double bb[SPB];
 #pragma unroll
@@ -1117,8 +984,14 @@ __global__ void __launch_bounds__(WS_THREADS, 1) dla_loglik_ws_kernel(LoglikArgs
     }
   }
   __syncthreads();   // all operand/P buffers are dead -> the staging area may alias them; s_q, s_ld are final
+  if (tid == 0) {    // the barriers are re-initialised if this CTA goes on to another quasar (only_list)
+    mbar_inval(&bar_p[0]); mbar_inval(&bar_p[1]);
+    for (int i = 0; i < WS_STAGES * WS_CONSUMERS; ++i) { mbar_inval(&bar_full[i]); mbar_inval(&bar_empty[i]); }
+  }
   if (warp >= WS_CONSUMERS) return;
-  if (NSPLIT > 1) {   // column-split ranks: see dla_loglik_kernel
+  if (NSPLIT > 1) {
+    // column-split ranks: accumulators (and, from split 0, the per-sample scalars) go to global memory;
+    // cholesky_kernel finishes the job
     const int gid = lane >> 2, tig = lane & 3;
     const int64_t row = s0 + warp * SPW + gid;
     double* grow = args.gram + ((int64_t)q * args.gram_rows + row) * G::NCOL + tile0 * 8 + tig * 2;
@@ -1131,6 +1004,22 @@ __global__ void __launch_bounds__(WS_THREADS, 1) dla_loglik_ws_kernel(LoglikArgs
     return;
   }
   stage_and_factor<K, NT, CSTR>(acc, Cs, s_q, s_ld, warp * SPW, lane, meta, args, q, s0);
+}
+
+// grid = (sample tiles, quasars, column splits)
+template <int K, int NL, int MODE, int NSPLIT>
+__global__ void __launch_bounds__(WS_THREADS, 1) dla_loglik_ws_kernel(LoglikArgs args) {
+  ws_tile<K, NL, MODE, NSPLIT>(args, blockIdx.y);
+}
+// The same for the quasars listed in args.only_list = {count, q_0, q_1, ...}: grid.y slots stride over the list (a
+// separate kernel: the loop around the tile costs the compiler 500 bytes of spills, which the main kernel must not pay)
+template <int K, int NL, int MODE, int NSPLIT>
+__global__ void __launch_bounds__(WS_THREADS, 1) dla_loglik_ws_list_kernel(LoglikArgs args) {
+  const int nlist = args.only_list[0];
+  for (int qi = blockIdx.y; qi < nlist; qi += gridDim.y) {
+    ws_tile<K, NL, MODE, NSPLIT>(args, args.only_list[1 + qi]);
+    __syncthreads();
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1147,6 +1036,7 @@ struct CholArgs {
   int64_t sll_stride;
   double* log_likelihoods_no_dla;   // nullable
   const int32_t* active;
+  const int32_t* order;             // tile position -> sample index (see LoglikArgs)
 };
 
 constexpr int CHOL_SAMPLES = 16;              // samples per CTA of cholesky_kernel
@@ -1167,7 +1057,7 @@ __global__ void __launch_bounds__(CHOL_SAMPLES * 4) cholesky_kernel(CholArgs a) 
   // stage the accumulator rows: coalesced along columns, scattered into the augmented triangle
   const double* g0 = a.gram + ((int64_t)q * a.gram_rows + row0) * G::NCOL;
   for (int c = tid; c < G::NCOL; c += CHOL_SAMPLES * 4) {   // one (divergent) table lookup per column
-    const int idx = c_stage_index[c];
+    const int idx = stage_index_table<K>()[c];
     if (idx >= 0) {
 #pragma unroll 8
       for (int r = 0; r < CHOL_SAMPLES; ++r) Cs[idx * CHOL_STRIDE + r] = g0[(int64_t)r * G::NCOL + c];
@@ -1213,7 +1103,7 @@ __global__ void __launch_bounds__(CHOL_SAMPLES * 4) cholesky_kernel(CholArgs a) 
     const double quad = qd[0] - zsum;                                            // :28
     const double logdet = qd[1] + (log(prod[0]) + log(prod[1])) + (log(prod[2]) + log(prod[3]));   // :30
     const double lp = -0.5 * (quad + logdet + (double)meta.n * LOG_2PI);         // :32
-    if (row < a.S) a.sample_log_likelihoods[(int64_t)q * a.sll_stride + row] = lp;
+    if (row < a.S) a.sample_log_likelihoods[(int64_t)q * a.sll_stride + (a.order ? (int64_t)a.order[row] : row)] = lp;
     else if (row == a.S && a.log_likelihoods_no_dla) a.log_likelihoods_no_dla[q] = lp;
   }
 }

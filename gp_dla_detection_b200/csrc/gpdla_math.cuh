@@ -191,4 +191,53 @@ __device__ __noinline__ double tau_sum_3_exact(double lambda, double m0, double 
   return (t0 + t1) + t2;
 }
 
+// ------------------------------------------------------------------------------------------
+// Rest-frame table of tau / N (gpdla_rest_table.h): the raw absorption of voigt.c:282-291 depends on the pixel and
+// the sample only through the absorber rest-frame wavelength, so away from the line cores the three (or num_lines)
+// Voigt evaluations per (sample, pixel) collapse into one polynomial per 1e-4-dex cell.
+//   u = ln(lambda_obs / lambda_ref) / h - ln((1 + z) lambda_lo / lambda_ref) / h = lh_pixel - K_sample
+//   tau / N = sum_p coef[p][cell] (u - cell)^p        for any cell with |u - cell| <= 1
+// The samples a producer warp interleaves are neighbours in redshift (K within RT_MAX_SPREAD of each other), so one
+// cell per (warp, pixel) -- the one nearest to lh - K_mid -- serves them all: its coefficients are fetched once,
+// a chunk ahead, and each sample evaluates the polynomial at its own s.  NaN coefficients mark the cells near a line
+// centre (and the two end cells, which catch clamped indices): the warp then evaluates directly.
+constexpr int RT_DEG_DEV = 8;
+constexpr double RT_MAX_SPREAD = 1.0;   // = 2 (RT_HALF_WIDTH - 1/2): largest K_max - K_min one cell can serve
+struct RestTable {
+  const double* coef;   // [RT_DEG_DEV + 1][ncell]; nullptr = table disabled
+  int ncell;
+  double inv_h;         // 1 / (pixel spacing in ln units)
+  double lam_lo;        // rest wavelength of cell 0 (Angstrom)
+};
+struct RestCell {       // one lane's cell for the current chunk
+  double cf[RT_DEG_DEV + 1];
+  double base;          // lh - cell: s = base - K
+};
+
+// K of the formula above for a sample at redshift z in a quasar whose padded grid starts at lam_ref
+__device__ __forceinline__ double rest_table_offset(const RestTable& rt, double z, double lam_ref) {
+  return log((1.0 + z) * (rt.lam_lo / lam_ref)) * rt.inv_h;
+}
+
+// issue the loads of the cell nearest to lh - K_mid (no use of the loaded values here: the caller consumes them a
+// chunk later, so the L2 / L1 latency stays off the critical path)
+__device__ __forceinline__ void rest_table_fetch(const RestTable& rt, double lh, double K_mid, RestCell& rc) {
+  const double RT_MAGIC = 6755399441055744.0;   // 1.5 * 2^52: x + MAGIC has ulp 1
+  const double um = (lh - K_mid) + RT_MAGIC;
+  int ci = __double2loint(um);                  // round-to-nearest-even integer of lh - K_mid
+  rc.base = lh - (um - RT_MAGIC);               // exact
+  ci = min(max(ci, 0), rt.ncell - 1);
+  const double* cp = rt.coef + ci;
+#pragma unroll
+  for (int p = 0; p <= RT_DEG_DEV; ++p) rc.cf[p] = __ldg(cp + (size_t)p * rt.ncell);
+}
+// tau / N of one sample in the fetched cell; NaN (hi word >= 0x7ff00000) where the caller must evaluate directly
+__device__ __forceinline__ double rest_table_eval(const RestCell& rc, double K) {
+  const double s = rc.base - K;
+  double t = rc.cf[RT_DEG_DEV];
+#pragma unroll
+  for (int p = RT_DEG_DEV - 1; p >= 0; --p) t = fma(t, s, rc.cf[p]);
+  return t;
+}
+
 }  // namespace gpdla

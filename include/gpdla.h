@@ -20,7 +20,8 @@
  *
  * Plain pointers and sizes only; no CPU fallback -- every function needs a CUDA device of
  * compute capability 10.0 and returns GPDLA_ERR_CUDA otherwise.  All functions are
- * re-entrant per context; a context must not be used from two threads at once.
+ * re-entrant per context (contexts, also on different devices, may be driven from different host threads); a context
+ * must not be used from two threads at once.  Every entry point leaves the caller's current CUDA device unchanged.
  */
 #ifndef GPDLA_H
 #define GPDLA_H
@@ -55,11 +56,14 @@ typedef struct {
   int32_t batch_quasars;        /* quasars processed per launch group (workspace size); 0 = default */
   int32_t gram_digits;          /* arithmetic of the Gram/projection contraction (log_mvnpdf_low_rank.m:22-28):
                                  *  0 = default: exact-product INT8 tensor-core path with 6 signed 8-bit digits per
-                                 *      factor (47 fractional bits; k = 20 only -- other ranks use FP64 DMMA);
-                                 *      the environment variables GPDLA_GRAM=f64 / GPDLA_I8_DIGITS=5 change the default
+                                 *      factor (47 fractional bits; k = 20 only -- other ranks use FP64 DMMA; a quasar
+                                 *      with a used pixel of zero noise variance falls back to FP64 DMMA by itself)
                                  * -1 = FP64 DMMA tensor cores
                                  *  5, 6 = INT8 path with that many digits (5: 39 fractional bits, ~1e-11 relative) */
-  int32_t reserved;
+  int32_t rest_table;           /* evaluation of the optical depth tau(lambda_obs / (1 + z_dla)) of voigt.c:282-290 inside
+                                 * the fused kernels:  0 = default: per-cell polynomials of a rest-frame table wherever the
+                                 *      pixel is >= 13 pixels from every line centre (5e-13 relative), direct evaluation
+                                 *      of the line sum elsewhere;  -1 = direct evaluation everywhere */
 } gpdla_params;
 
 /* process_qsos.m:74-82,236-244 result variables; each array has Q entries unless noted.
@@ -214,6 +218,19 @@ int gpdla_voigt(const double* lambdas, int64_t num_points, double z, double N, i
 /* Batched, device buffers: profile[s, :] = voigt(lambdas, z[s], N[s], num_lines), [S x (num_points-6)] */
 int gpdla_voigt_batch_device(const double* lambdas, int64_t num_points, const double* z, const double* N,
                              int64_t S, int32_t num_lines, double* profile, void* stream);
+
+/* The rest-frame table of tau / N the fused kernels use (see gpdla_params.rest_table), as the library builds it for
+ * `num_lines` lines and cells of `pixel_spacing` dex, for verification: cell c is centred at rest wavelength
+ * lambda_lo * exp(c * h) and holds the coefficients coef[p * ncell + c], p = 0..degree, of a polynomial in
+ * s = ln(lambda / centre) / h, |s| <= 1/2; NaN marks the cells left to direct evaluation.  `coef` may be NULL
+ * (sizes only); otherwise it must hold (degree + 1) * ncell doubles (call once with NULL to size it).  Pure host. */
+int gpdla_rest_table(int32_t num_lines, double pixel_spacing, double* coef, int32_t* ncell, int32_t* degree,
+                     double* h, double* lambda_lo);
+
+/* Page-locked host memory for the buffers of gpdla_process_qsos (optional: pageable buffers work, pinned ones let
+ * the result copies overlap the next batch).  cudaHostAlloc / cudaFreeHost behind a C signature. */
+int gpdla_host_alloc(void** ptr, uint64_t bytes);
+void gpdla_host_free(void* ptr);
 
 /* Lyman-series constants as the library computes them (voigt.c:31-220,242-251), for verification:
  * each output has GPDLA_MAX_LINES entries (instrument_profile: 7).  Pure host function. */

@@ -193,8 +193,9 @@ def test_batching_and_device_entry_agree_with_host_entry(api, synthetic_inputs):
     dev = proc.process_device(t["wavelengths"], t["flux"], t["noise_variance"], t["pixel_mask"], t["lengths"],
                               t["z_qsos"], return_sample_log_likelihoods=True)
     torch.cuda.synchronize()
-    # kernels per batch: prepare, [scales + digit operands | FP64 Gram operand], fused log-likelihood, evidence
-    assert proc.launch_count - n0 in (5 * 3, 4 * 3)   # 3 batches; 5 on the INT8 Gram path, 4 on the FP64 one
+    # kernels per batch: prepare, [scales + digit operands + (idle) FP64 fallback operand | FP64 Gram operand], fused
+    # log-likelihood [+ (idle) FP64 fallback], evidence
+    assert proc.launch_count - n0 in (7 * 3, 4 * 3)   # 3 batches; 7 on the INT8 Gram path, 4 on the FP64 one
     for k in one:
         assert np.array_equal(one[k], dev[k].cpu().numpy(), equal_nan=True), k
 
@@ -349,39 +350,114 @@ def test_state_errors(api, synthetic_inputs):
     assert res["p_dlas"].shape == (0,)
 
 
-def test_persistent_and_one_tile_kernels_agree(api, synthetic_inputs, tmp_path):
-    """The shipped persistent INT8 kernel and the one-tile-per-cluster development kernel (GPDLA_I8_PERSISTENT=0,
-    read once per process, hence the subprocess) agree to rounding: the integer slice products are exact and the
-    recombination / Cholesky code is shared; only the compiler's FMA contraction of the FP64 producer arithmetic
-    differs between the two kernels (measured on a B200: not bit-identical), so the comparison is at 1e-12."""
-    import os, subprocess, sys
+def test_rest_table_agrees_with_direct_evaluation(api, synthetic_inputs):
+    """The optical depth from the rest-frame table (default) against the direct evaluation of the line sum
+    (rest_table = -1, the arithmetic of voigt.c:282-290 term by term), on both Gram paths and at full sample count:
+    the table's polynomials are within 5e-13 of tau / N, which moves the log-likelihoods by < 1e-11 relative."""
+    from gp_dla_detection_b200 import synthetic as syn
+    from oracle import process_qsos_oracle as O
+    si = synthetic_inputs
+    sp = syn.make_spectra(si["model"], 4, seed=41, dla_fraction=0.75)
+    sp["all_pixel_mask"][2][::3] = True
+    ref = O.process_qsos(si["model"], si["samples"], sp, si["prior"], engine="c")
+    b = ref["sample_log_likelihoods_dla"]
+    for digits in (6, -1):
+        tab = api.process_qsos(si["model"], si["samples"], sp, si["prior"], gram_digits=digits, rest_table=0)
+        direct = api.process_qsos(si["model"], si["samples"], sp, si["prior"], gram_digits=digits, rest_table=-1)
+        a, d = tab["sample_log_likelihoods_dla"], direct["sample_log_likelihoods_dla"]
+        assert np.max(np.abs(a - d) / np.abs(d)) < 1e-11, (digits, np.max(np.abs(a - d) / np.abs(d)))
+        for r in (tab, direct):
+            assert np.max(np.abs(r["sample_log_likelihoods_dla"] - b) / np.abs(b)) < 1e-11
+            assert np.array_equal(r["map_inds"], ref["map_inds"])
+        assert np.array_equal(tab["log_likelihoods_no_dla"], direct["log_likelihoods_no_dla"])   # a == 1: no table involved
+    # a wavelength grid that is NOT the 1e-4-dex BOSS grid (2.5x coarser, irregular): cells are skipped, the table still holds
+    rng = np.random.default_rng(8)
+    sp2 = syn.make_spectra(si["model"], 2, seed=43, dla_fraction=1.0)
+    for q in range(2):
+        keep = np.sort(rng.choice(len(sp2["all_flux"][q]), size=len(sp2["all_flux"][q]) * 2 // 5, replace=False))
+        for k in ("all_wavelengths", "all_flux", "all_noise_variance", "all_pixel_mask"):
+            sp2[k][q] = sp2[k][q][keep]
+        sp2["all_wavelengths"][q] = sp2["all_wavelengths"][q] * (1 + 3e-5 * rng.standard_normal(keep.size))
+        sp2["all_wavelengths"][q].sort()
+    sub = {k: v[::10] for k, v in si["samples"].items()}
+    tab = api.process_qsos(si["model"], sub, sp2, si["prior"])
+    ref2 = O.process_qsos(si["model"], sub, sp2, si["prior"], engine="c")
+    assert_parity(tab, ref2)
+
+
+def test_zero_noise_variance_pixels(api, synthetic_inputs):
+    """A used pixel with noise_variance == 0 (process_qsos.m:194-198 then has d = a^2 omega^2 only): the INT8 path
+    has no fixed-point bound for its projection weights there, flags the quasar and leaves it to the FP64 kernels;
+    the other quasars of the batch stay on the INT8 path.  Results against the oracle either way."""
+    from gp_dla_detection_b200 import synthetic as syn
+    from oracle import process_qsos_oracle as O
+    si = synthetic_inputs
+    sp = syn.make_spectra(si["model"], 4, seed=51, dla_fraction=0.5)
+    for q in (1, 3):
+        # pixels redward of every sampled DLA (max_z_dla stops 3000 km/s = 43 pixels short of the quasar's Lyman alpha),
+        # where the absorption never reaches zero: d = a^2 omega^2 stays positive, as it does for the reference
+        nv = sp["all_noise_variance"][q]
+        w = np.asarray(sp["all_wavelengths"][q]) / (1 + sp["z_qsos"][q])
+        used = np.flatnonzero(~np.asarray(sp["all_pixel_mask"][q]) & (w >= 911.75) & (w <= 1215.75))
+        nv[used[[-3, -11, -12, -24]]] = 0.0
+    sub = {k: v[::8] for k, v in si["samples"].items()}
+    res = api.process_qsos(si["model"], sub, sp, si["prior"])
+    ref = O.process_qsos(si["model"], sub, sp, si["prior"], engine="c")
+    assert np.all(np.isfinite(res["sample_log_likelihoods_dla"]))
+    assert_parity(res, ref)
+    # the quasars without such pixels did not change path: bit-identical to a run without the flagged ones
+    clean = {k: ([v[0], v[2]] if isinstance(v, list) else np.asarray(v)[[0, 2]]) for k, v in sp.items()}
+    res2 = api.process_qsos(si["model"], sub, clean, si["prior"])
+    assert np.array_equal(res["sample_log_likelihoods_dla"][[0, 2]], res2["sample_log_likelihoods_dla"])
+    # more flagged quasars than the fallback launch has slots
+    sp3 = syn.make_spectra(si["model"], 11, seed=52, dla_fraction=0.5)
+    for q in range(11):
+        w = np.asarray(sp3["all_wavelengths"][q]) / (1 + sp3["z_qsos"][q])
+        used = np.flatnonzero(~np.asarray(sp3["all_pixel_mask"][q]) & (w >= 911.75) & (w <= 1215.75))
+        sp3["all_noise_variance"][q][used[-2 - q]] = 0.0
+    sub3 = {k: v[::50] for k, v in si["samples"].items()}
+    assert_parity(api.process_qsos(si["model"], sub3, sp3, si["prior"]), O.process_qsos(si["model"], sub3, sp3, si["prior"], engine="c"))
+
+
+def test_contexts_of_different_rank_share_a_device(api, synthetic_inputs):
+    """Two live contexts with different k (and a third on the other Gram path) interleaved on one GPU give what each
+    gives alone: the per-rank tables in constant memory belong to the rank, not to the last context created."""
     from gp_dla_detection_b200 import synthetic as syn
     si = synthetic_inputs
-    sp = syn.make_spectra(si["model"], 5, seed=31, dla_fraction=0.6)
-    sp["all_pixel_mask"][3][:] = True          # an empty quasar among live ones
-    sub = {k: v[::7] for k, v in si["samples"].items()}
-    here = api.process_qsos(si["model"], sub, sp, si["prior"], gram_digits=6)
-    script = tmp_path / "one_tile.py"
-    out = tmp_path / "one_tile.npz"
-    script.write_text(
-        "import sys, numpy as np\n"
-        "sys.path.insert(0, %r)\n"
-        "from gp_dla_detection_b200 import api, synthetic as syn\n"
-        "model, samples, prior = syn.make_model(), syn.make_samples(10000), syn.make_prior()\n"
-        "sp = syn.make_spectra(model, 5, seed=31, dla_fraction=0.6)\n"
-        "sp['all_pixel_mask'][3][:] = True\n"
-        "sub = {k: v[::7] for k, v in samples.items()}\n"
-        "r = api.process_qsos(model, sub, sp, prior, gram_digits=6)\n"
-        "np.savez(%r, **r)\n" % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), str(out)))
-    env = dict(os.environ, GPDLA_I8_PERSISTENT="0")
-    subprocess.run([sys.executable, str(script)], check=True, env=env, timeout=600)
-    other = np.load(out)
-    for k in here:
-        a, b = np.asarray(here[k], dtype=np.float64), np.asarray(other[k], dtype=np.float64)
-        assert np.array_equal(np.isnan(a), np.isnan(b)), k
-        if k in ("map_inds", "map_z_dlas", "map_log_nhis", "min_z_dlas", "max_z_dlas", "log_priors_dla", "log_priors_no_dla"):
-            assert np.array_equal(a, b, equal_nan=True), k
-        else:
-            ok = ~np.isnan(a)
-            assert np.all(np.abs(a[ok] - b[ok]) <= 1e-12 * np.maximum(1.0, np.abs(b[ok]))), k
+    sub = {k: v[::25] for k, v in si["samples"].items()}
+    models = {k: syn.make_model(k) for k in (10, 40, 20)}
+    spectra = {k: syn.make_spectra(models[k], 2, seed=60 + k, dla_fraction=0.5) for k in models}
+    alone = {k: api.process_qsos(models[k], sub, spectra[k], si["prior"]) for k in models}
+    procs = {k: api.DLAProcessor(models[k], sub, si["prior"]) for k in (10, 40, 20)}
+    procs["20f"] = api.DLAProcessor(models[20], sub, si["prior"], gram_digits=-1)
+    try:
+        for _ in range(2):
+            for k in (10, 40, 20, 10, 20, 40):
+                r = procs[k].process(spectra[k])
+                for name in alone[k]:
+                    assert np.array_equal(r[name], alone[k][name], equal_nan=True), (k, name)
+        rf = procs["20f"].process(spectra[20])
+        assert np.allclose(rf["sample_log_likelihoods_dla"], alone[20]["sample_log_likelihoods_dla"], rtol=1e-11, atol=0)
+    finally:
+        for p in procs.values():
+            p.close()
 
+
+def test_pinned_results_and_full_output_pipeline(api, synthetic_inputs):
+    """The host entry returns sample_log_likelihoods_dla batch by batch on its copy stream while the next batch
+    computes; with three batches (double-buffered device block reused) and a page-locked destination the rows are
+    those of the one-batch run."""
+    from gp_dla_detection_b200 import synthetic as syn
+    si = synthetic_inputs
+    sp = syn.make_spectra(si["model"], 7, seed=71, dla_fraction=0.5)
+    sub = {k: v[::20] for k, v in si["samples"].items()}
+    one = api.process_qsos(si["model"], sub, sp, si["prior"])
+    proc = api.DLAProcessor(si["model"], sub, si["prior"], batch_quasars=3)
+    try:
+        r = proc.process(sp, pinned_results=True)
+        for name in one:
+            assert np.array_equal(np.asarray(r[name]), one[name], equal_nan=True), name
+        r2 = proc.process(sp, return_sample_log_likelihoods=False)
+        assert "sample_log_likelihoods_dla" not in r2 and np.array_equal(r2["p_dlas"], one["p_dlas"], equal_nan=True)
+    finally:
+        proc.close()
