@@ -136,6 +136,33 @@ def run_reference(args):
     }))
 
 
+def spot_check(proc, model, samples, prior, spectra, timed_out, nq, threads):
+    """The CPU restatement on the first `nq` quasars of the timed workload against (a) the outputs of the timed device
+    run itself and (b) a fresh call that also returns the sample log-likelihoods.  north_star: same MAP sample,
+    log-likelihoods within 1e-8 relative, p_dla within 1e-6 absolute.  Returns (cpu quasars/s, seconds, block)."""
+    from oracle import process_qsos_oracle as O
+    sp = {k: v[:nq] for k, v in spectra.items()}
+    t0 = time.perf_counter()
+    ref = O.process_qsos(model, samples, sp, prior, num_lines=NUM_LINES, engine="c", nthreads=threads)
+    dt = time.perf_counter() - t0
+    got = proc.process(sp, return_sample_log_likelihoods=True)
+    rel = lambda a, b: float(np.nanmax(np.abs(np.asarray(a) - np.asarray(b)) / np.abs(np.asarray(b))))
+    timed = {k: v[:nq].cpu().numpy() for k, v in timed_out.items()}
+    block = {
+        "quasars": nq,
+        "max_rel_sample_ll": rel(got["sample_log_likelihoods_dla"], ref["sample_log_likelihoods_dla"]),
+        "max_rel_ll": max(rel(timed[k], ref[k]) for k in ("log_likelihoods_dla", "log_likelihoods_no_dla",
+                                                          "log_posteriors_dla", "log_posteriors_no_dla")),
+        "same_map": bool(np.array_equal(timed["map_inds"], ref["map_inds"])),
+        "max_abs_p_dla": float(np.nanmax(np.abs(timed["p_dlas"] - ref["p_dlas"]))),
+        "timed_run_equals_fresh_call": bool(all(np.array_equal(timed[k], got[k], equal_nan=True) for k in timed)),
+        "against": "oracle/c (C restatement of process_qsos.m + voigt.c + log_mvnpdf_low_rank.m), same inputs",
+    }
+    block["ok"] = bool(block["max_rel_sample_ll"] < 1e-8 and block["max_rel_ll"] < 1e-8 and block["same_map"]
+                       and block["max_abs_p_dla"] < 1e-6)
+    return nq / dt, dt, block
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -148,6 +175,11 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gram-digits", type=int, default=0, choices=[-1, 0, 5, 6],
                     help="Gram arithmetic: 0 default (INT8 tensor-core path, 6 digits), -1 FP64 DMMA, 5/6 INT8 digits")
+    ap.add_argument("--alt-steps", type=int, default=1,
+                    help="timed steps of the secondary leg on the FP64 DMMA Gram (gram_digits = -1); 0 = skip")
+    ap.add_argument("--strong-steps", type=int, default=1,
+                    help="timed passes of the strong-scaling leg (configs[2]: 162 861 quasars split over the ranks); 0 = skip")
+    ap.add_argument("--catalog-quasars", type=int, default=162861, help="size of the full catalogue (configs[2])")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -182,61 +214,107 @@ def main():
     masked_in = np.array([np.count_nonzero(np.asarray(m)[(w / (1 + z) >= 911.75) & (w / (1 + z) <= 1215.75)])
                           for w, m, z in zip(spectra["all_wavelengths"], spectra["all_pixel_mask"], spectra["z_qsos"])])
     n_pix = n_used - masked_in               # used pixels n_q
-    flops_per_step = float(np.sum(n_pix) * NUM_SAMPLES * K_RANK * (K_RANK + 3))   # n k (k+3) per sample
+    flops_q = n_pix * float(NUM_SAMPLES * K_RANK * (K_RANK + 3))   # n k (k+3) per sample
+    flops_per_step = float(np.sum(flops_q))
 
     proc = api.DLAProcessor(model, samples, prior, device=local_rank, gram_digits=args.gram_digits)
     host = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in pad.items()}
     dtens = {k: v.to(dev) for k, v in host.items()}
     order = ("wavelengths", "flux", "noise_variance", "pixel_mask", "lengths", "z_qsos")
 
-    def step_device():
-        return proc.process_device(*[dtens[k] for k in order])
-
     def barrier():
         if distributed:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def timed_device(p, tensors, steps):
+        """`steps` passes of the device-resident path, CUDA events on the launching stream, max over ranks."""
+        barrier()
+        p.set_profiling(True)
+        p.profile_read()
+        n0 = p.launch_count
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            o = p.process_device(*[tensors[k] for k in order])
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if distributed:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        k_ms, k_n = p.profile_read()
+        p.set_profiling(False)
+        return float(t.item()), o, p.launch_count - n0, k_ms, k_n
+
     # ---- device-resident timing (inputs already in HBM)
     for _ in range(args.warmup):
-        out = step_device()
-    barrier()
-    proc.set_profiling(True)
-    proc.profile_read()
-    launches0 = proc.launch_count
+        proc.process_device(*[dtens[k] for k in order])
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        out = step_device()
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
+    ms, out, launches, k_ms, k_n = timed_device(proc, dtens, args.steps)
     clocks = sampler.stop() if sampler else None
-    launches = proc.launch_count - launches0
-    k_ms, k_n = proc.profile_read()
-    proc.set_profiling(False)
-    tms = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if distributed:
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-    ms = float(tms.item())
     value = world * Q * args.steps / (ms * 1e-3)
 
     # ---- end to end through the public API: pinned host buffers in, host results out, every step
     hnp = {k: v.numpy() for k, v in host.items()}
-    for _ in range(2):
-        proc.process(hnp, return_sample_log_likelihoods=False)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        res = proc.process(hnp, return_sample_log_likelihoods=False)
-    torch.cuda.synchronize()
-    te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-    if distributed:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * Q * args.steps / float(te.item())
+
+    def timed_e2e(want_sll):
+        for _ in range(2):
+            proc.process(hnp, return_sample_log_likelihoods=want_sll, pinned_results=True)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            r = proc.process(hnp, return_sample_log_likelihoods=want_sll, pinned_results=True)
+        torch.cuda.synchronize()
+        te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if distributed:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        return world * Q * args.steps / float(te.item()), r
+
+    e2e_value, res = timed_e2e(False)
+    e2e_full_value, res_full = timed_e2e(True)
     h2d = int(sum(hnp[k].nbytes for k in order))
     d2h = int(Q * (14 * 8 + 8))
+    d2h_full = d2h + int(Q * NUM_SAMPLES * 8)
+    full_equal = bool(all(np.array_equal(res[k], res_full[k], equal_nan=True) for k in res))
+    del res_full
+
+    # ---- secondary leg: the FP64 DMMA Gram (the arithmetic north_star names literally), same workload
+    alt = None
+    if args.alt_steps > 0 and args.gram_digits != -1:
+        proc64 = api.DLAProcessor(model, samples, prior, device=local_rank, gram_digits=-1)
+        proc64.process_device(*[dtens[k] for k in order])
+        ms64, out64, _, k64_ms, k64_n = timed_device(proc64, dtens, args.alt_steps)
+        peak, _ = fp64_peak()
+        ach = flops_per_step * args.alt_steps / (k64_ms * 1e-3) * 1e-12
+        a, b = out64["log_likelihoods_dla"].cpu().numpy(), out["log_likelihoods_dla"].cpu().numpy()
+        alt = {"gram_arithmetic": "FP64 DMMA (mma.sync m8n8k4 f64), dla_loglik_ws_kernel", "steps": args.alt_steps,
+               "value": world * Q * args.alt_steps / (ms64 * 1e-3), "unit": UNIT, "ms_per_step": ms64 / args.alt_steps,
+               "roofline": {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                            "kernel_ms_per_step": k64_ms / args.alt_steps, "kernel_launches": int(k64_n)},
+               "max_rel_log_likelihoods_dla_vs_primary": float(np.nanmax(np.abs(a - b) / np.abs(b)))}
+        proc64.close()
+        del proc64, out64
+
+    # ---- strong-scaling leg: configs[2], the full catalogue split across the ranks (no data-path collective)
+    strong = None
+    if args.strong_steps > 0:
+        Qcat = args.catalog_quasars
+        # the catalogue is the 10 000-quasar synthetic shard of rank 0's seed repeated; contiguous blocks balanced by
+        # cost (pixels in the modelled window), as sharding.partition_by_cost does for a real catalogue
+        base = api.pad_spectra(syn.make_spectra(model, Q, shard=0)) if rank != 0 else pad
+        idx = np.arange(Qcat) % Q
+        blocks = sharding.partition_by_cost(sharding.quasar_costs(base)[idx], world)
+        b0, b1 = blocks[rank]
+        sel = torch.from_numpy(idx[b0:b1]).to(dev)
+        bt = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in base.items()} if rank != 0 else dtens
+        cat = {k: bt[k].index_select(0, sel).contiguous() for k in order}
+        ms_s, out_s, _, _, _ = timed_device(proc, cat, args.strong_steps)
+        strong = {"workload": "configs[2]: %d-quasar synthetic catalogue (the %d-quasar shard repeated), quasars split "
+                              "across %d rank(s) by cost" % (Qcat, Q, world),
+                  "value": Qcat * args.strong_steps / (ms_s * 1e-3), "unit": UNIT, "scaling": "strong",
+                  "seconds_per_catalogue": ms_s * 1e-3 / args.strong_steps, "steps": args.strong_steps,
+                  "quasars_this_rank": int(b1 - b0)}
+        del cat, out_s
 
     # ---- multi-GPU: the one collective of the path, a gather of per-quasar records (outside the hot loop)
     if distributed:
@@ -245,12 +323,11 @@ def main():
         full = sharding.gather_records(rec, blocks, device=dev)
         assert full.shape == (world * Q, sharding.RECORD_WIDTH)
 
+    ok = True
     if rank == 0:
         peak, peak_src = fp64_peak()
         achieved = flops_per_step * args.steps / (k_ms * 1e-3) * 1e-12 if k_ms > 0 else None
-        digits = args.gram_digits
-        if digits == 0:
-            digits = -1 if os.environ.get("GPDLA_GRAM", "").startswith("f") else (5 if os.environ.get("GPDLA_I8_DIGITS") == "5" else 6)
+        digits = args.gram_digits if args.gram_digits != 0 else 6
         i8 = digits in (5, 6)
         traffic, traffic_grid = ncu_traffic(i8)
         roof = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
@@ -260,7 +337,8 @@ def main():
                 "algorithmic_flops_per_launch": flops_per_step * args.steps / max(int(k_n), 1),
                 "kernel_ms_per_step": k_ms / args.steps, "kernel_launches": int(k_n),
                 "kernel_share_of_step": k_ms / ms,
-                "algorithmic_flops_per_step": flops_per_step, "peak_source": peak_src}
+                "algorithmic_flops_per_step": flops_per_step, "peak_source": peak_src,
+                "peak_nominal": 40.0, "peak_nominal_source": "NVIDIA HGX B200 datasheet, FP64 tensor, per GPU"}
         if i8:
             # int8 operations the tcgen05 MMAs execute: per cluster (128 samples) and 32-pixel chunk, L(L+1)/2 slice
             # pairs x (3 CTAs x N=80 + 1 CTA x N=32) columns x 128 rows x 32 pixels x 2
@@ -269,17 +347,17 @@ def main():
             clusters = (NUM_SAMPLES + 1 + 127) // 128
             int8_ops = float(chunks) * clusters * pairs * 2.0 * 128 * 32 * (3 * 80 + 32)
             roof.update({
-                "kernel": "dla_loglik_i8p_kernel (fused Voigt + exact-product INT8 tcgen05 Gram, %d signed 8-bit digits per "
-                          "factor, s32 TMEM accumulators + Cholesky; persistent 4-CTA clusters, DSMEM row-block exchange, "
-                          "epilogue warpgroup, merged slice-pair MMAs)" % digits,
-                "note": "achieved/peak = FP64-equivalent Gram rate (S n k(k+3) per quasar, SURVEY 8(d)) over the measured "
-                        "FP64 DMMA peak; the contraction itself runs as exact INT8 slice products on the tcgen05 tensor "
-                        "pipe. On B200 FP64 arithmetic makes no progress while a tcgen05.mma executes on the same SM "
-                        "(profiles/r01_mma_vs_alu.json), so a 32-pixel chunk costs the Voigt/weight arithmetic of the "
-                        "producers (2 775 cycles) plus the tensor time of the 21 exact slice products (964 cycles) plus "
-                        "the digit stores -- the 4 400 cycles measured; the FP64 DMMA Gram would need 3 840 cycles on "
-                        "that pipe instead of 964 (DESIGN.md 4.3). 132 of the 148 SMs host clusters (4-CTA cluster "
-                        "placement)",
+                "kernel": "dla_loglik_i8p_kernel (fused optical depth from a rest-frame table + instrument convolution + "
+                          "exact-product INT8 tcgen05 Gram, %d signed 8-bit digits per factor, s32 TMEM accumulators + "
+                          "Cholesky; persistent 4-CTA clusters, DSMEM row-block exchange, epilogue warpgroup, merged "
+                          "slice-pair MMAs, MN-major digit tiles)" % digits,
+                "note": "achieved/peak = FP64-equivalent Gram rate (S n k(k+3) per quasar, SURVEY 8(d)) over the "
+                        "builder-measured FP64 DMMA peak (MEASURED_PEAKS.json has no FP64 entry; nominal 40 beside it); "
+                        "the contraction itself runs as exact INT8 slice products on the tcgen05 tensor pipe, see "
+                        "int8_tensor. On B200 FP64 arithmetic makes no progress while a tcgen05.mma executes on the "
+                        "same SM (profiles/r01_mma_vs_alu.json; ncu: sm__pipe_shared = fp64 + tensor), so a 32-pixel "
+                        "chunk costs the producers' FP64 work plus the tensor time of the 21 exact slice products "
+                        "(DESIGN.md 4.3-4.4). 132 of the 148 SMs host clusters (4-CTA cluster placement)",
                 "int8_tensor": {"achieved_tops": int8_ops * args.steps / (k_ms * 1e-3) * 1e-12 if k_ms > 0 else None,
                                 "peak_tops": 4283.0, "peak_source": "profiles/r01_tcgen05_i8.txt (this pool's B200, N = 240)"},
             })
@@ -300,20 +378,34 @@ def main():
                                            "fractional bits)" % (digits, 8 * digits - 1)) if i8 else "FP64 DMMA",
                        "sharding": "quasars split across ranks, no data-path collective; one all_gather of records"},
             "gpu_launches": int(launches),
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "note": "DLAProcessor.process: pinned host planes in, the 15 per-quasar result columns out"},
+            "e2e_full": {"value": e2e_full_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_full,
+                         "note": "the same call returning sample_log_likelihoods_dla as well (process_qsos.m:236-244 saves "
+                                 "it): 80 KB per quasar into a page-locked buffer, batch t copied while batch t + 1 computes",
+                         "other_outputs_equal_e2e": full_equal},
             "roofline": roof,
             "clocks": clocks,
         }
+        if alt is not None:
+            line["alt"] = alt
+        if strong is not None:
+            line["strong"] = strong
         if not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             nq = args.cpu_baseline_quasars
-            v, dt = cpu_baseline(model, samples, prior, spectra, nq, threads)
+            v, dt, block = spot_check(proc, model, samples, prior, spectra, out, nq, threads)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": "%d quasars x %d samples of the same workload (%.1f s)" % (nq, NUM_SAMPLES, dt)}
+            line["parity_spot"] = block
+            ok = block["ok"]
         sys.stdout.flush()
         os.write(json_fd, (json.dumps(line) + "\n").encode())
     if distributed:
         dist.destroy_process_group()
+    if not ok:
+        sys.stderr.write("bench.py: the timed outputs disagree with the CPU restatement beyond north_star's tolerance\n")
+        sys.exit(1)
 
 
 if __name__ == "__main__":

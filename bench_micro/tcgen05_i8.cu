@@ -24,7 +24,14 @@ constexpr uint32_t LBO = 128, SBO = 256;
 #define A_SBO 256
 #endif
 // A operand layout as in the fused kernel: K halves A_LBO apart, 8-row groups A_SBO apart (digit planes interleaved)
+// -DA_MN: A is MN-major (no swizzle): 16 consecutive rows (M) are the 16 bytes of a granule, 8 consecutive k are 8
+// granules (one 128-byte core matrix), k blocks of 8 are A_LBO apart, row blocks of 16 are A_SBO apart
+// (canonical layout ((1,n),(8,k)):((X,SBO),(1,LBO)) in 16-byte units); instruction descriptor bit 15 = A MN-major.
+#ifdef A_MN
+constexpr int A_SLAB_BYTES = (M / 16) * A_SBO;
+#else
 constexpr int A_SLAB_BYTES = (M / 8) * A_SBO;
+#endif
 constexpr int TMEM_COLS = N <= 32 ? 32 : N <= 64 ? 64 : N <= 128 ? 128 : 256;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -34,7 +41,11 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo = LBO
 }
 // kind::i8 instruction descriptor: D = s32, A = B = signed 8-bit, both K-major, N >> 3, M >> 4
 __host__ __device__ constexpr uint32_t make_idesc() {
-  return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+  return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24)
+#ifdef A_MN
+         | (1u << 15)
+#endif
+      ;
 }
 __device__ __forceinline__ bool mbar_wait_bounded(uint64_t* bar, uint32_t parity, int max_iter) {
   for (int it = 0; it < max_iter; ++it) {
@@ -57,11 +68,18 @@ __global__ void __launch_bounds__(128, 1) k_i8(const int8_t* __restrict__ A, con
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // stage operands in the canonical layout (16-byte granules)
+#ifdef A_MN
+  for (int e = tid; e < ksteps * M * KMMA; e += 128) {       // A: byte by byte into the MN-major layout
+    int s = e / (M * KMMA), r = (e / KMMA) % M, k = e % KMMA;
+    sA[(size_t)s * A_SLAB_BYTES + (r / 16) * A_SBO + (k / 8) * A_LBO + (k % 8) * 16 + (r % 16)] = (uint8_t)A[(size_t)r * K + s * KMMA + k];
+  }
+#else
   for (int g = tid; g < ksteps * M * 2; g += 128) {          // A: granule = (kstep, row, half)
     int s = g / (M * 2), r = (g / 2) % M, h = g % 2;
     *reinterpret_cast<int4*>(sA + (size_t)s * A_SLAB_BYTES + (r / 8) * A_SBO + h * A_LBO + (r % 8) * 16) =
         *reinterpret_cast<const int4*>(A + (size_t)r * K + s * KMMA + h * 16);
   }
+#endif
   for (int g = tid; g < ksteps * N * 2; g += 128) {
     int s = g / (N * 2), r = (g / 2) % N, h = g % 2;
     *reinterpret_cast<int4*>(sB + (size_t)s * B_SLAB + (r / 8) * SBO + h * LBO + (r % 8) * 16) =
@@ -88,7 +106,11 @@ __global__ void __launch_bounds__(128, 1) k_i8(const int8_t* __restrict__ A, con
       const uint32_t idesc = make_idesc();
       for (int rep = 0; rep < reps; ++rep) {
         for (int s = 0; s < ksteps; ++s) {
+#ifdef A_DESC_SWAP
+          const uint64_t da = make_desc(smem_u32(sA + (size_t)s * A_SLAB_BYTES), A_SBO, A_LBO);
+#else
           const uint64_t da = make_desc(smem_u32(sA + (size_t)s * A_SLAB_BYTES), A_LBO, A_SBO);
+#endif
           const uint64_t db = make_desc(smem_u32(sB + (size_t)s * B_SLAB));
           const uint32_t accumulate = (s > 0) ? 1u : 0u;
           asm volatile(

@@ -59,18 +59,16 @@ struct Shape {
   static constexpr int NU = (K + 15) / 16 * 16;                   // MMA N of the U CTA (32)
   static constexpr int NMAX = NW > NU ? NW : NU;
   static constexpr int F = 8 * L - 1;                             // fractional bits
-  // A tile (128 samples x 32 pixels x L digits), K-major, no swizzle: 8-row x 16-byte core matrices, the two K
-  // halves LBO_A apart, the L digit planes of an 8-row group side by side (PLANE_A apart), groups SBO_A apart.
-  // LBO_A = 144 instead of the dense 128 shifts the second K half by 4 banks, so that a producer warp's byte
-  // stores (lanes 0-15 / 16-31 = the two halves of one row) do not collide.
-#ifndef GPDLA_I8_LBO_A
-#define GPDLA_I8_LBO_A 144
-#endif
-  static constexpr int LBO_A = GPDLA_I8_LBO_A;
-  static constexpr int PLANE_A = (LBO_A == 128) ? 256 : 288;
+  // A tile (128 samples x 32 pixels x L digits), MN-major (samples contiguous), no swizzle: a 16-byte granule holds one
+  // pixel of 16 consecutive samples, 8 consecutive pixels make a 128-byte core matrix, pixel blocks of 8 are LBO_A apart,
+  // the L digit planes of a 16-sample group lie side by side (PLANE_A apart), groups are SBO_A apart (canonical layout
+  // ((1,n),(8,k)):((X,SBO),(1,LBO)) in 16-byte units, validated by bench_micro/tcgen05_i8.cu -DA_MN).  A producer lane
+  // (= pixel) holds the digits of its warp's 4 consecutive samples: one 32-bit store per digit plane.
+  static constexpr int LBO_A = 128;
+  static constexpr int PLANE_A = (KC / 8) * LBO_A;
   static constexpr int SBO_A = PLANE_A * L;
-  static constexpr int ROWBLOCK = (TS / 8) * SBO_A;               // one CTA's 32 rows, all digit planes: contiguous
-  static constexpr int A_TILE = (TM / 8) * SBO_A;
+  static constexpr int ROWBLOCK = (TS / 16) * SBO_A;              // one CTA's 32 rows, all digit planes: contiguous
+  static constexpr int A_TILE = (TM / 16) * SBO_A;
   static constexpr int BW_PLANE = NW * KC, BU_PLANE = NU * KC;    // bytes of one digit plane of the B operand
   static constexpr int B_MAX = L * (BW_PLANE > BU_PLANE ? BW_PLANE : BU_PLANE);
   static constexpr int CHUNK_BYTES = L * (WCTAS * BW_PLANE + BU_PLANE);   // all four CTAs' B operand, one chunk
@@ -155,14 +153,14 @@ __device__ __forceinline__ void dsmem_bulk_copy(uint32_t dst_cluster, uint32_t s
 __device__ __forceinline__ void st_cluster_f64(uint32_t addr, double v) {
   asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
 }
-// K-major, no-swizzle shared-memory matrix descriptor (validated by bench_micro/tcgen05_i8.cu)
+// no-swizzle shared-memory matrix descriptor (K-major B operand and MN-major A operand validated by bench_micro/tcgen05_i8.cu)
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
   return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) |
          (1ull << 46);
 }
-// kind::i8 instruction descriptor: D = s32, A = B = signed 8-bit, both K-major, N >> 3, M >> 4
+// kind::i8 instruction descriptor: D = s32, A = B = signed 8-bit, A MN-major (bit 15), B K-major, N >> 3, M >> 4
 __host__ __device__ constexpr uint32_t make_idesc(int n) {
-  return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+  return (2u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
 }
 __device__ __forceinline__ void mma_i8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -371,6 +369,32 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
   if (phase) atomicAdd(&phase[8 + code], (unsigned long long)(clock64() - t0));
 }
 
+// The digits of a producer lane's 4 consecutive samples (x[ss] holds the L signed digits of sample ss in its low
+// bytes) as one 32-bit word per digit plane -- byte b = sample b, the MN-major A layout -- by 4 x 4 byte transposes
+// (8 PRMT for planes 0..3, 4 for planes 4..5).
+template <int L, int PLANE>
+__device__ __forceinline__ void store_digit_planes(uint8_t* dst, const uint64_t (&x)[SPB]) {
+  static_assert(SPB == 4, "one 32-bit word = 4 samples");
+  const uint32_t a0 = (uint32_t)x[0], a1 = (uint32_t)x[1], a2 = (uint32_t)x[2], a3 = (uint32_t)x[3];
+  const uint32_t t0 = __byte_perm(a0, a1, 0x5140), t1 = __byte_perm(a2, a3, 0x5140);
+  const uint32_t t2 = __byte_perm(a0, a1, 0x7362), t3 = __byte_perm(a2, a3, 0x7362);
+  uint32_t* d = reinterpret_cast<uint32_t*>(dst);
+  d[0] = __byte_perm(t0, t1, 0x5410);
+  d[PLANE / 4] = __byte_perm(t0, t1, 0x7632);
+  if (L > 2) d[2 * (PLANE / 4)] = __byte_perm(t2, t3, 0x5410);
+  if (L > 3) d[3 * (PLANE / 4)] = __byte_perm(t2, t3, 0x7632);
+  if (L > 4) {
+    const uint32_t h0 = (uint32_t)(x[0] >> 32), h1 = (uint32_t)(x[1] >> 32), h2 = (uint32_t)(x[2] >> 32), h3 = (uint32_t)(x[3] >> 32);
+    const uint32_t u0 = __byte_perm(h0, h1, 0x5140), u1 = __byte_perm(h2, h3, 0x5140);
+    d[4 * (PLANE / 4)] = __byte_perm(u0, u1, 0x5410);
+    if (L > 5) d[5 * (PLANE / 4)] = __byte_perm(u0, u1, 0x7632);
+    if (L > 6) {
+      const uint32_t u2 = __byte_perm(h0, h1, 0x7362), u3 = __byte_perm(h2, h3, 0x7362);
+      d[6 * (PLANE / 4)] = __byte_perm(u2, u3, 0x5410);
+    }
+  }
+}
+
 template <int K, int L>
 struct PShape {
   using Sh = Shape<K, L>;
@@ -520,7 +544,7 @@ dla_loglik_i8p_kernel(LoglikArgs args, I8Args xa, int num_quasars, int tiles_per
     uint8_t* const udst0 = (rank < WCTAS) ? Sx : At + own_block;
     const uint32_t wstride = (rank < WCTAS) ? Sh::A_TILE : Sh::ROWBLOCK;
     const uint32_t ustride = (rank < WCTAS) ? Sh::ROWBLOCK : Sh::A_TILE;
-    const uint32_t rowoff = (row0 / 8) * Sh::SBO_A + (row0 % 8) * 16 + (lane / 16) * Sh::LBO_A + (lane % 16);
+    const uint32_t rowoff = (row0 / 16) * Sh::SBO_A + (row0 % 16) + (lane / 8) * Sh::LBO_A + (lane % 8) * 16;
     constexpr uint64_t BIAS = Sh::digit_bias();
     const double MAGIC = Sh::magic();
     const uint64_t KADD = BIAS - (uint64_t)__double_as_longlong(MAGIC);
@@ -645,10 +669,10 @@ dla_loglik_i8p_kernel(LoglikArgs args, I8Args xa, int num_quasars, int tiles_per
           const double rd = fast_rcp(d);
           const double r = fma(-a[ss], mu, y);
           const double t1 = r * rd;
-          const double wn = (a2 * rd) * cw;
-          const double un = (a[ss] * t1) * cu;
-          xw[ss] = ((uint64_t)__double_as_longlong(__dadd_rn(wn, MAGIC)) + KADD) ^ BIAS;
-          xu[ss] = ((uint64_t)__double_as_longlong(__dadd_rn(un, MAGIC)) + KADD) ^ BIAS;
+          // W'' = w cw in [0, CAP], U'' = u cu in [-CAP, CAP], rounded once to F fractional bits by the fused add of
+          // the magic constant; + KADD, ^ BIAS turn the two's-complement fixed-point value into L signed digits
+          xw[ss] = ((uint64_t)__double_as_longlong(fma(a2 * rd, cw, MAGIC)) + KADD) ^ BIAS;
+          xu[ss] = ((uint64_t)__double_as_longlong(fma(a[ss] * t1, cu, MAGIC)) + KADD) ^ BIAS;
           qacc[ss] = fma(r, t1, qacc[ss]);
           ldm[ss] *= d;
         }
@@ -661,14 +685,8 @@ dla_loglik_i8p_kernel(LoglikArgs args, I8Args xa, int num_quasars, int tiles_per
           for (int ss = 0; ss < SPB; ++ss) sink ^= xw[ss] ^ (xu[ss] << 1);
           if (sink == 0x123456789abcdefull) dW[0] = 1;
         } else {
-#pragma unroll
-          for (int ss = 0; ss < SPB; ++ss) {
-#pragma unroll
-            for (int j = 0; j < L; ++j) {
-              dW[ss * 16 + j * Sh::PLANE_A] = (uint8_t)(xw[ss] >> (8 * j));
-              dU[ss * 16 + j * Sh::PLANE_A] = (uint8_t)(xu[ss] >> (8 * j));
-            }
-          }
+          store_digit_planes<L, Sh::PLANE_A>(dW, xw);
+          store_digit_planes<L, Sh::PLANE_A>(dU, xu);
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         }
         __syncwarp();
