@@ -275,6 +275,8 @@ struct gpdla_ctx {
   size_t st_bytes = 0;
   void* d_stage = nullptr;
   cudaStream_t stream = nullptr, copy_stream = nullptr;   // the host entries' own (non-default) streams
+  cudaStream_t side_stream = nullptr;                     // FP64 kernels running beside the INT8 kernel (f64_share)
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaEvent_t ev_batch[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
   // multi-DLA path
   double* d_lls_nhi = nullptr;
@@ -385,6 +387,7 @@ static int launch_loglik(gpdla_ctx* c, LoglikArgs la, int nq, cudaStream_t st, b
     ca.meta = la.meta; ca.gram = c->d_gram; ca.qld = c->d_qld; ca.gram_rows = la.gram_rows; ca.S = la.S;
     ca.sample_log_likelihoods = la.sample_log_likelihoods; ca.sll_stride = la.sll_stride;
     ca.log_likelihoods_no_dla = la.log_likelihoods_no_dla; ca.active = la.active; ca.order = la.order;
+    ca.q_offset = la.q_offset;
     rc = configure_smem(c->device, cholesky_kernel<K>, cholesky_smem_bytes<K>(), c->err);
     if (rc) return rc;
     cholesky_kernel<K><<<dim3(tiles * TS / CHOL_SAMPLES, (unsigned)nq), CHOL_SAMPLES * 4,
@@ -448,10 +451,10 @@ static int build_i8_operands_L(gpdla_ctx* c, int nq, int npix, cudaStream_t st) 
   return GPDLA_OK;
 }
 // Gram operand P of the FP64 kernels for a prepared batch (`only_list`: restricted to the listed quasars)
-static int build_f64_operand(gpdla_ctx* c, int nq, int npix, const int32_t* only_list, cudaStream_t st) {
+static int build_f64_operand(gpdla_ctx* c, int q0, int nq, int npix, const int32_t* only_list, cudaStream_t st) {
   const unsigned ny = only_list ? (unsigned)std::min(nq, FALLBACK_SLOTS) : (unsigned)nq;
   GPDLA_FOR_RANK(c->k, (build_gram_operand_kernel<K, NSPLIT><<<dim3(npix / KC, ny, NSPLIT), NTHREADS, 0, st>>>(
-                            c->d_Mq, c->d_meta, c->d_P, npix, only_list)));
+                            c->d_Mq, c->d_meta, c->d_P, npix, only_list, q0)));
   c->launches++;
   CUDA_TRY(cudaGetLastError(), c->err);
   return GPDLA_OK;
@@ -464,7 +467,7 @@ static int build_i8_operands(gpdla_ctx* c, int nq, int npix, cudaStream_t st) {
   rc = i8_digits(c) == 5 ? build_i8_operands_L<5>(c, nq, npix, st) : build_i8_operands_L<6>(c, nq, npix, st);
   if (rc) return rc;
   // FP64 operand of the quasars the scales kernel has just flagged (normally none: a handful of idle CTAs)
-  return build_f64_operand(c, nq, npix, c->d_f64flag + c->i8_batch, st);
+  return build_f64_operand(c, 0, nq, npix, c->d_f64flag + c->i8_batch, st);
 }
 
 // resident 4-CTA clusters of the persistent kernel on this device (0 = query failed)
@@ -606,12 +609,59 @@ static LoglikArgs loglik_args(const gpdla_ctx* c, int npix) {
   return la;
 }
 
-// K0 + operand builders for one batch
-static int prepare_batch(gpdla_ctx* c, const PrepArgs& pa, int nq, int npix, cudaStream_t st) {
+// How many of a batch's nq quasars go to the FP64 DMMA kernels while the INT8 kernel works on the others: the 4-CTA
+// clusters of the persistent INT8 kernel occupy 132 of the 148 SMs (cluster placement within the GPCs), and the FP64
+// kernel -- no clusters, one CTA per SM -- runs on the 16 that are left, on a second stream.  The share balances the two
+// (measured per-SM rates 23.7 against 36.8 quasars/s); small batches stay whole, so that their results do not depend on
+// which path a quasar happened to land on.
+constexpr int SPLIT_MIN_QUASARS = 148;
+static int f64_share(const gpdla_ctx* c, int nq) {
+  if (!use_i8(c) || nq < SPLIT_MIN_QUASARS) return 0;
+  double share = 0.072;
+  if (const char* e = getenv("GPDLA_F64_SHARE")) share = atof(e);   // tuning aid
+  return std::max(0, std::min(nq / 2, (int)lround(share * nq)));
+}
+
+// K0 + operand builders for one batch; the last `nq_f64` quasars get the FP64 operand (see f64_share)
+static int prepare_batch(gpdla_ctx* c, const PrepArgs& pa, int nq, int nq_f64, int npix, cudaStream_t st) {
   prepare_quasars_kernel<<<nq, NTHREADS, 0, st>>>(pa);
   c->launches++;
   CUDA_TRY(cudaGetLastError(), c->err);
-  return use_i8(c) ? build_i8_operands(c, nq, npix, st) : build_f64_operand(c, nq, npix, nullptr, st);
+  if (!use_i8(c)) return build_f64_operand(c, 0, nq, npix, nullptr, st);
+  int rc = build_i8_operands(c, nq - nq_f64, npix, st);
+  if (rc == GPDLA_OK && nq_f64 > 0) rc = build_f64_operand(c, nq - nq_f64, nq_f64, npix, nullptr, st);
+  return rc;
+}
+
+// The fused kernels of one batch in MODE: the INT8 kernel on quasars [0, nq - nq_f64) on `st` and, concurrently on
+// the context's side stream, the FP64 kernels on the last nq_f64 quasars; `st` continues when both are done.
+template <int MODE>
+static int launch_split(gpdla_ctx* c, const LoglikArgs& la, int nq, int nq_f64, cudaStream_t st) {
+  if (nq_f64 <= 0) return launch_mode_any<MODE>(c, la, nq, st);
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  const bool timed = c->profiling;
+  if (timed) {   // one interval around the concurrent pair
+    CUDA_TRY(cudaEventCreate(&e0), c->err);
+    CUDA_TRY(cudaEventCreate(&e1), c->err);
+    CUDA_TRY(cudaEventRecord(e0, st), c->err);
+    c->profiling = false;
+  }
+  CUDA_TRY(cudaEventRecord(c->ev_fork, st), c->err);
+  int rc = launch_mode_i8<MODE>(c, la, nq - nq_f64, st);      // enqueued first: its clusters get their SMs first
+  if (rc == GPDLA_OK) {
+    CUDA_TRY(cudaStreamWaitEvent(c->side_stream, c->ev_fork, 0), c->err);
+    LoglikArgs lf = la;
+    lf.q_offset = nq - nq_f64;
+    rc = launch_mode<MODE>(c, lf, nq_f64, c->side_stream, false);
+    CUDA_TRY(cudaEventRecord(c->ev_join, c->side_stream), c->err);
+    CUDA_TRY(cudaStreamWaitEvent(st, c->ev_join, 0), c->err);
+  }
+  if (timed) {
+    c->profiling = true;
+    CUDA_TRY(cudaEventRecord(e1, st), c->err);
+    c->prof_events.emplace_back(e0, e1);
+  }
+  return rc;
 }
 
 __global__ void fill_i32_kernel(int32_t* p, int32_t v, int64_t n) {
@@ -687,6 +737,9 @@ int gpdla_create(gpdla_ctx** out, int device) {
   gpdla_default_parameters(&ctx->params);
   cudaError_t e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
   for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
     e = cudaEventCreateWithFlags(&ctx->ev_batch[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming);
@@ -701,6 +754,7 @@ void gpdla_destroy(gpdla_ctx* c) {
   DeviceGuard guard(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+  if (c->side_stream) cudaStreamSynchronize(c->side_stream);
   free_workspace(c);
   cudaFree(c->d_rest); cudaFree(c->d_mu); cudaFree(c->d_M); cudaFree(c->d_log_omega);
   cudaFree(c->d_offset); cudaFree(c->d_log_nhi); cudaFree(c->d_nhi); cudaFree(c->d_order); cudaFree(c->d_rt);
@@ -716,6 +770,9 @@ void gpdla_destroy(gpdla_ctx* c) {
   }
   if (c->stream) cudaStreamDestroy(c->stream);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  if (c->side_stream) cudaStreamDestroy(c->side_stream);
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  if (c->ev_join) cudaEventDestroy(c->ev_join);
   delete c;
 }
 
@@ -829,12 +886,13 @@ static int process_batch(gpdla_ctx* c, int64_t q0, int nq, int64_t L_max, const 
                          const double* z_qsos, const gpdla_results* out, double* sll, double* llno, int npix,
                          cudaStream_t st) {
   const int batch = c->ws_batch;
+  const int nq_f64 = f64_share(c, nq);
   int rc = prepare_batch(c, prep_args(c, q0, L_max, wavelengths, flux, noise_variance, pixel_mask, lengths, z_qsos, npix, 0),
-                         nq, npix, st);
+                         nq, nq_f64, npix, st);
   if (rc) return rc;
   LoglikArgs la = loglik_args(c, npix);
   la.sample_log_likelihoods = sll; la.log_likelihoods_no_dla = llno; la.sll_stride = c->S;
-  if ((rc = launch_mode_any<0>(c, la, nq, st))) return rc;
+  if ((rc = launch_split<0>(c, la, nq, nq_f64, st))) return rc;
 
   EvidenceArgs ea;
   ea.meta = c->d_meta; ea.sample_log_likelihoods = sll; ea.log_likelihoods_no_dla = llno;
@@ -1055,8 +1113,9 @@ int gpdla_process_qsos_multi_device(gpdla_ctx* c, int64_t Q, int64_t L_max, cons
 
   for (int64_t q0 = 0; q0 < Q; q0 += batch) {
     const int nq = (int)std::min<int64_t>(batch, Q - q0);
+    const int nq_f64 = f64_share(c, nq);
     if ((rc = prepare_batch(c, prep_args(c, q0, L_max, wavelengths, flux, noise_variance, pixel_mask, lengths, z_qsos, npix, 1),
-                            nq, npix, st)))
+                            nq, nq_f64, npix, st)))
       return rc;
     fill_i32_kernel<<<(nq + 255) / 256, 256, 0, st>>>(c->d_active, 1, nq);
     c->launches++;
@@ -1083,11 +1142,11 @@ int gpdla_process_qsos_multi_device(gpdla_ctx* c, int64_t Q, int64_t L_max, cons
     // level 1 (+ null model), absorption rows cached                         ...meanflux.m:342-361
     la.nhi_samples = c->d_nhi; la.sample_log_likelihoods = sll; la.sll_stride = sll_stride;
     la.log_likelihoods_no_dla = out->log_likelihoods_no_dla + q0; la.num_partners = 0;
-    if ((rc = launch_mode_any<1>(c, la, nq, st))) return rc;
+    if ((rc = launch_split<1>(c, la, nq, nq_f64, st))) return rc;
     // sub-DLA model                                                           ...meanflux.m:365-380
     la.nhi_samples = c->d_lls_nhi; la.sample_log_likelihoods = slls; la.sll_stride = S;
     la.log_likelihoods_no_dla = nullptr;
-    if ((rc = launch_mode_any<0>(c, la, nq, st))) return rc;
+    if ((rc = launch_split<0>(c, la, nq, nq_f64, st))) return rc;
     ma.level = 0; ma.sll = slls; ma.sll_stride = S; ma.log_likelihoods = out->log_likelihoods_lls + q0;
     multi_level_kernel<<<nq, NTHREADS, 0, st>>>(ma);
     c->launches++;
@@ -1095,7 +1154,7 @@ int gpdla_process_qsos_multi_device(gpdla_ctx* c, int64_t Q, int64_t L_max, cons
       if (level >= 2) {
         la.nhi_samples = c->d_nhi; la.sample_log_likelihoods = sll + (int64_t)(level - 1) * S;
         la.sll_stride = sll_stride; la.log_likelihoods_no_dla = nullptr; la.num_partners = level - 1;
-        if ((rc = launch_mode_any<2>(c, la, nq, st))) return rc;
+        if ((rc = launch_split<2>(c, la, nq, nq_f64, st))) return rc;
       }
       ma.level = level; ma.sll = sll + (int64_t)(level - 1) * S; ma.sll_stride = sll_stride;
       ma.log_likelihoods = out->log_likelihoods_dla + q0 * MD;

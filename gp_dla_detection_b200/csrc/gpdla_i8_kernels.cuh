@@ -601,6 +601,18 @@ dla_loglik_i8p_kernel(LoglikArgs args, I8Args xa, int num_quasars, int tiles_per
       int lde[SPB];
 #pragma unroll
       for (int ss = 0; ss < SPB; ++ss) { qacc[ss] = 0.0; ldm[ss] = 1.0; lde[ss] = 0; }
+      double rows_n[4][SPB];   // MODE 2: cached absorption rows (sample, partners) of the next chunk
+      auto load_rows = [&](int ipix) {
+#pragma unroll
+        for (int ss = 0; ss < SPB; ++ss) rows_n[0][ss] = cache_q[(int64_t)s_so[row0 + ss] * args.NPIX + ipix];
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+          if (j < args.num_partners) {
+#pragma unroll
+            for (int ss = 0; ss < SPB; ++ss) rows_n[1 + j][ss] = cache_q[(int64_t)s_part[j * TS + row0 + ss] * args.NPIX + ipix];
+          }
+      };
+      if (MODE == 2) load_rows(lane);
       // pixel data of the next chunk is fetched one chunk ahead (global/L2 latency off the critical path)
       double lambda_n = lam[6 + lane], lh_n = lamh[6 + lane];
       double2 p01n = *reinterpret_cast<const double2*>(pix + (int64_t)lane * 4);
@@ -651,15 +663,17 @@ dla_loglik_i8p_kernel(LoglikArgs args, I8Args xa, int num_quasars, int tiles_per
               if (s0 + row0 + ss < S) cache_q[(int64_t)s_so[row0 + ss] * args.NPIX + i] = a[ss];
           }
         } else {
+          // absorption = voigt(sample) .* voigt(partner 1) .* ...   (...meanflux.m:342-351): cached rows, fetched one
+          // chunk ahead (HBM latency: the cache is 100 MB per quasar, and a producer has nothing else to overlap it with)
 #pragma unroll
-          for (int ss = 0; ss < SPB; ++ss) a[ss] = cache_q[(int64_t)s_so[row0 + ss] * args.NPIX + i];
-          for (int j = 0; j < args.num_partners; ++j) {
-            double bb[SPB];
+          for (int ss = 0; ss < SPB; ++ss) a[ss] = rows_n[0][ss];
 #pragma unroll
-            for (int ss = 0; ss < SPB; ++ss) bb[ss] = cache_q[(int64_t)s_part[j * TS + row0 + ss] * args.NPIX + i];
+          for (int j = 0; j < 3; ++j)
+            if (j < args.num_partners) {
 #pragma unroll
-            for (int ss = 0; ss < SPB; ++ss) a[ss] = a[ss] * bb[ss];
-          }
+              for (int ss = 0; ss < SPB; ++ss) a[ss] = a[ss] * rows_n[1 + j][ss];
+            }
+          if (c + 1 < nchunks) load_rows(i + KC);
         }
         uint64_t xw[SPB], xu[SPB];
 #pragma unroll

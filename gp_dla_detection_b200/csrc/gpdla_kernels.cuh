@@ -329,16 +329,16 @@ template <int K, int NSPLIT>
 __global__ void __launch_bounds__(NTHREADS) build_gram_operand_kernel(const double* __restrict__ Mq,
                                                                       const QuasarMeta* __restrict__ meta,
                                                                       double* __restrict__ P, int NPIX,
-                                                                      const int32_t* __restrict__ only_list) {
+                                                                      const int32_t* __restrict__ only_list, int q_offset) {
   using G = GramShape<K>;
   using SS = SplitShape<K, NSPLIT>;
   const int chunk = blockIdx.x;
   const int split = blockIdx.z;
   __shared__ double sM[KC][K + 1];
-  // all quasars of the batch (grid.y = quasars), or the listed ones (grid.y slots stride over the list)
+  // grid.y quasars of the batch from q_offset on, or the listed ones (grid.y slots stride over the list)
   const int nlist = only_list ? only_list[0] : (int)gridDim.y;
   for (int qi = blockIdx.y; qi < nlist; qi += gridDim.y) {
-  const int q = only_list ? only_list[1 + qi] : qi;
+  const int q = only_list ? only_list[1 + qi] : qi + q_offset;
   if (chunk >= meta[q].nchunks) continue;
   __syncthreads();
   const double* src = Mq + ((int64_t)q * NPIX + (int64_t)chunk * KC) * K;
@@ -430,6 +430,7 @@ struct LoglikArgs {
   const int32_t* partners;          // [Q x 3 x S] 0-based base_sample_inds; level l uses rows 0..l-2
   int num_partners;
   const int32_t* active;            // [Q] or nullptr; 0 = quasar finished early (:460-464) -> NaN
+  int q_offset;                     // dla_loglik_ws_kernel: first quasar of the batch this launch covers (grid.y counts from it)
   const int32_t* only_list;         // dla_loglik_ws_list_kernel: {count, q_0, q_1, ...}, the quasars to process -- the INT8
                                     // path's FP64 fallback for zero-noise-variance pixels
   // column-split ranks (NSPLIT > 1): accumulators and per-sample scalars leave through global memory
@@ -1009,7 +1010,7 @@ __device__ __forceinline__ void ws_tile(const LoglikArgs& args, const int q) {
 // grid = (sample tiles, quasars, column splits)
 template <int K, int NL, int MODE, int NSPLIT>
 __global__ void __launch_bounds__(WS_THREADS, 1) dla_loglik_ws_kernel(LoglikArgs args) {
-  ws_tile<K, NL, MODE, NSPLIT>(args, blockIdx.y);
+  ws_tile<K, NL, MODE, NSPLIT>(args, (int)blockIdx.y + args.q_offset);
 }
 // The same for the quasars listed in args.only_list = {count, q_0, q_1, ...}: grid.y slots stride over the list (a
 // separate kernel: the loop around the tile costs the compiler 500 bytes of spills, which the main kernel must not pay)
@@ -1037,6 +1038,7 @@ struct CholArgs {
   double* log_likelihoods_no_dla;   // nullable
   const int32_t* active;
   const int32_t* order;             // tile position -> sample index (see LoglikArgs)
+  int q_offset;
 };
 
 constexpr int CHOL_SAMPLES = 16;              // samples per CTA of cholesky_kernel
@@ -1048,7 +1050,7 @@ template <int K>
 __global__ void __launch_bounds__(CHOL_SAMPLES * 4) cholesky_kernel(CholArgs a) {
   using G = GramShape<K>;
   constexpr int NQ = (K + 3) / 4 + 1;            // columns per quad lane, upper bound
-  const int q = blockIdx.y;
+  const int q = (int)blockIdx.y + a.q_offset;
   const QuasarMeta meta = a.meta[q];
   if (meta.nchunks == 0 || (a.active != nullptr && a.active[q] == 0)) return;   // NaNs already written
   extern __shared__ __align__(16) double Cs[];   // [aug entries][CHOL_STRIDE]

@@ -461,3 +461,28 @@ def test_pinned_results_and_full_output_pipeline(api, synthetic_inputs):
         assert "sample_log_likelihoods_dla" not in r2 and np.array_equal(r2["p_dlas"], one["p_dlas"], equal_nan=True)
     finally:
         proc.close()
+
+
+def test_large_batches_use_both_gram_paths(api, synthetic_inputs, monkeypatch):
+    """A batch of >= 148 quasars is split: the persistent INT8 kernel's 4-CTA clusters occupy 132 of the 148 SMs, and
+    the last ~7 % of the batch run through the FP64 DMMA kernels on the other 16 at the same time (second stream).
+    Every quasar must come out exactly as the path that processed it computes it alone, and both within tolerance of
+    each other."""
+    from gp_dla_detection_b200 import synthetic as syn
+    si = synthetic_inputs
+    Q = 160
+    sp = syn.make_spectra(si["model"], Q, seed=81, dla_fraction=0.3)
+    sub = {k: v[::125] for k, v in si["samples"].items()}          # 80 samples: one tile
+    split = api.process_qsos(si["model"], sub, sp, si["prior"])
+    monkeypatch.setenv("GPDLA_F64_SHARE", "0")
+    whole = api.process_qsos(si["model"], sub, sp, si["prior"])
+    monkeypatch.delenv("GPDLA_F64_SHARE")
+    f64 = api.process_qsos(si["model"], sub, sp, si["prior"], gram_digits=-1)
+    n2 = int(round(0.072 * Q))
+    for k in split:
+        a, w, f = np.asarray(split[k]), np.asarray(whole[k]), np.asarray(f64[k])
+        assert np.array_equal(a[:Q - n2], w[:Q - n2], equal_nan=True), k
+        assert np.array_equal(a[Q - n2:], f[Q - n2:], equal_nan=True), k
+    assert not np.array_equal(split["sample_log_likelihoods_dla"][Q - n2:], whole["sample_log_likelihoods_dla"][Q - n2:])
+    assert np.allclose(split["sample_log_likelihoods_dla"], whole["sample_log_likelihoods_dla"], rtol=1e-11, atol=0, equal_nan=True)
+    assert np.array_equal(split["map_inds"], whole["map_inds"])
