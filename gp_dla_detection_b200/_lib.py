@@ -94,6 +94,10 @@ SYMBOLS = {
     "gpdla_host_free": (None, [ctypes.c_void_p]),
     "gpdla_objective": (ctypes.c_int, [ctypes.c_int64, ctypes.c_int32, ctypes.c_int32] + [ctypes.c_void_p] * 6),
     "gpdla_objective_device": (ctypes.c_int, [ctypes.c_int64, ctypes.c_int32, ctypes.c_int32] + [ctypes.c_void_p] * 7),
+    "gpdla_objective_lyseries": (ctypes.c_int, [ctypes.c_int64, ctypes.c_int32, ctypes.c_int32] + [ctypes.c_void_p] * 3
+                                 + [ctypes.c_int32, c_double_p, c_double_p] + [ctypes.c_void_p] * 3),
+    "gpdla_objective_lyseries_device": (ctypes.c_int, [ctypes.c_int64, ctypes.c_int32, ctypes.c_int32] + [ctypes.c_void_p] * 3
+                                        + [ctypes.c_int32, c_double_p, c_double_p] + [ctypes.c_void_p] * 4),
     "gpdla_default_preload_parameters": (None, [ctypes.POINTER(GpdlaPreloadParams)]),
     "gpdla_preload_qsos": (ctypes.c_int, [ctypes.c_int64, ctypes.c_int64] + [ctypes.c_void_p] * 7
                            + [ctypes.POINTER(GpdlaPreloadParams), ctypes.c_int64] + [ctypes.c_void_p] * 7),

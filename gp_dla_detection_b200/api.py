@@ -367,10 +367,22 @@ def preload_qsos_device(flux, loglam, ivar, and_mask, lengths, z_qsos, filter_fl
     return out
 
 
-def objective(x, centered_rest_fluxes, lya_1pzs, rest_noise_variances, device: int = 0):
-    """``[f, g] = objective(x, centered_rest_fluxes, lya_1pzs, rest_noise_variances)`` of objective.m:12-73 on the
-    GPU: negative log-likelihood of the training set and its gradient, ``x = [M(:); log_omega; log c_0; log tau_0;
-    log beta]`` (M column-major as in MATLAB).  Host arrays in, ``(float, ndarray)`` out."""
+def _forest_arrays(num_forest_lines, all_transition_wavelengths, all_oscillator_strengths):
+    nl = int(num_forest_lines)
+    if nl == 0:
+        return 0, None, None
+    tw, osc = _f64(all_transition_wavelengths).ravel(), _f64(all_oscillator_strengths).ravel()
+    if not (1 <= nl <= _lib.MAX_LINES) or tw.size < nl or osc.size < nl:
+        raise ValueError("num_forest_lines must be 1..31 with that many transition wavelengths and oscillator strengths")
+    return nl, tw, osc
+
+
+def objective_lyseries(x, centered_rest_fluxes, lya_1pzs, rest_noise_variances, num_forest_lines,
+                       all_transition_wavelengths, all_oscillator_strengths, device: int = 0):
+    """``[f, g] = objective_lyseries(x, centered_rest_fluxes, lya_1pzs, rest_noise_variances, num_forest_lines,
+    all_transition_wavelengths, all_oscillator_strengths)`` of multi_dlas/objective_lyseries.m:13-87 on the GPU: the
+    training objective with the Lyman-series effective optical depth (multi_dlas/spectrum_loss_lyseries.m:20-47).
+    ``num_forest_lines = 0`` is ``objective``."""
     import torch
     lib = _lib.load()
     y, z1, nv, xx = _f64(centered_rest_fluxes), _f64(lya_1pzs), _f64(rest_noise_variances), _f64(x)
@@ -378,19 +390,31 @@ def objective(x, centered_rest_fluxes, lya_1pzs, rest_noise_variances, device: i
     k = (xx.size - 3) // P - 1                                            # objective.m:17
     if xx.size != P * (k + 1) + 3 or z1.shape != y.shape or nv.shape != y.shape:
         raise ValueError("x must have num_pixels * (k + 1) + 3 entries and the three data matrices one shape")
+    nl, tw, osc = _forest_arrays(num_forest_lines, all_transition_wavelengths, all_oscillator_strengths)
     f = np.zeros(1); g = np.zeros(xx.size)
     vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
     with torch.cuda.device(device):
-        _lib.check(lib.gpdla_objective(N, P, k, vp(y), vp(z1), vp(nv), vp(xx), vp(f), vp(g)))
+        _lib.check(lib.gpdla_objective_lyseries(N, P, k, vp(y), vp(z1), vp(nv), nl, _dp(tw) if nl else None,
+                                                _dp(osc) if nl else None, vp(xx), vp(f), vp(g)))
     return float(f[0]), g
+
+
+def objective(x, centered_rest_fluxes, lya_1pzs, rest_noise_variances, device: int = 0):
+    """``[f, g] = objective(x, centered_rest_fluxes, lya_1pzs, rest_noise_variances)`` of objective.m:12-73 on the
+    GPU: negative log-likelihood of the training set and its gradient, ``x = [M(:); log_omega; log c_0; log tau_0;
+    log beta]`` (M column-major as in MATLAB).  Host arrays in, ``(float, ndarray)`` out."""
+    return objective_lyseries(x, centered_rest_fluxes, lya_1pzs, rest_noise_variances, 0, None, None, device)
 
 
 class TrainingObjective:
     """The training matrices of learn_qso_model.m:36-75 resident on one GPU; ``ev(x) -> (f, g)`` evaluates
     objective.m for a parameter vector (what minFunc calls at learn_qso_model.m:97-99), uploading only ``x``."""
 
-    def __init__(self, centered_rest_fluxes, lya_1pzs, rest_noise_variances, k: int, device: int = 0):
+    def __init__(self, centered_rest_fluxes, lya_1pzs, rest_noise_variances, k: int, device: int = 0,
+                 num_forest_lines: int = 0, all_transition_wavelengths=None, all_oscillator_strengths=None):
+        """``num_forest_lines > 0`` selects objective_lyseries.m (learn_qso_model_meanflux.m:140-142)."""
         import torch
+        self.nl, self.tw, self.osc = _forest_arrays(num_forest_lines, all_transition_wavelengths, all_oscillator_strengths)
         self._lib = _lib.load()
         self._torch = torch
         self.dev = torch.device("cuda", device)
@@ -407,8 +431,9 @@ class TrainingObjective:
         """x on the device -> (f, g) device tensors (asynchronous)."""
         ptr = lambda t: ctypes.c_void_p(t.data_ptr())
         with self._torch.cuda.device(self.dev):
-            _lib.check(self._lib.gpdla_objective_device(self.N, self.P, self.k, ptr(self.y), ptr(self.z1), ptr(self.nv),
-                                                        ptr(x_dev), ptr(self.f), ptr(self.g), ctypes.c_void_p(stream)))
+            _lib.check(self._lib.gpdla_objective_lyseries_device(
+                self.N, self.P, self.k, ptr(self.y), ptr(self.z1), ptr(self.nv), self.nl, _dp(self.tw) if self.nl else None,
+                _dp(self.osc) if self.nl else None, ptr(x_dev), ptr(self.f), ptr(self.g), ctypes.c_void_p(stream)))
         return self.f, self.g
 
     def __call__(self, x):

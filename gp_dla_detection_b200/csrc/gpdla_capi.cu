@@ -564,11 +564,23 @@ static int launch_mode_i8(gpdla_ctx* c, const LoglikArgs& la, int nq, cudaStream
   return launch_mode<MODE>(c, lf, nq, st, false);
 }
 
+// both stages of the training objective: persistent CTAs with private partial gradients, then their sum
 template <int K>
-static int launch_objective(const ObjectiveArgs& a, cudaStream_t st) {
+static int launch_objective(ObjectiveArgs a, cudaStream_t st) {
   const size_t smem = objective_smem_bytes<K>(a.P);
+  int dev = 0, sms = 0, per_sm = 0;
+  CUDA_TRY(cudaGetDevice(&dev), g_err);
   CUDA_TRY(cudaFuncSetAttribute(objective_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), g_err);
-  objective_kernel<K><<<(unsigned)a.N, OBJ_THREADS, smem, st>>>(a);
+  CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev), g_err);
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, objective_kernel<K>, OBJ_THREADS, smem), g_err);
+  const int64_t nx = (int64_t)a.P * (K + 1) + 3;
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(a.N, (int64_t)sms * std::max(per_sm, 1)));
+  CUDA_TRY(cudaMallocAsync(&a.partial, (size_t)grid * (nx + 1) * sizeof(double), st), g_err);
+  objective_kernel<K><<<grid, OBJ_THREADS, smem, st>>>(a);
+  CUDA_TRY(cudaGetLastError(), g_err);
+  objective_reduce_kernel<<<(unsigned)((nx + 1 + 255) / 256), 256, 0, st>>>(a.partial, grid, nx, a.g, a.f);
+  CUDA_TRY(cudaGetLastError(), g_err);
+  CUDA_TRY(cudaFreeAsync(a.partial, st), g_err);
   return GPDLA_OK;
 }
 
@@ -1381,10 +1393,12 @@ int gpdla_preload_qsos(int64_t Q, int64_t L_in, const double* flux, const double
   return rc;
 }
 
-int gpdla_objective_device(int64_t num_quasars, int32_t num_pixels, int32_t k, const double* centered_rest_fluxes,
-                           const double* lya_1pzs, const double* rest_noise_variances, const double* x, double* f,
-                           double* g, void* stream) {
-  if (num_quasars < 0 || num_pixels < 1 || !x || !f || !g ||
+int gpdla_objective_lyseries_device(int64_t num_quasars, int32_t num_pixels, int32_t k, const double* centered_rest_fluxes,
+                                    const double* lya_1pzs, const double* rest_noise_variances, int32_t num_forest_lines,
+                                    const double* all_transition_wavelengths, const double* all_oscillator_strengths,
+                                    const double* x, double* f, double* g, void* stream) {
+  if (num_quasars < 0 || num_pixels < 1 || !x || !f || !g || num_forest_lines < 0 || num_forest_lines > GPDLA_MAX_LINES ||
+      (num_forest_lines > 0 && (!all_transition_wavelengths || !all_oscillator_strengths)) ||
       (num_quasars > 0 && (!centered_rest_fluxes || !lya_1pzs || !rest_noise_variances))) {
     g_err = "gpdla_objective_device: invalid arguments";
     return GPDLA_ERR_INVALID;
@@ -1394,25 +1408,30 @@ int gpdla_objective_device(int64_t num_quasars, int32_t num_pixels, int32_t k, c
     return GPDLA_ERR_UNSUPPORTED;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  const int64_t nx = (int64_t)num_pixels * (k + 1) + 3;
-  CUDA_TRY(cudaMemsetAsync(f, 0, sizeof(double), st), g_err);
-  CUDA_TRY(cudaMemsetAsync(g, 0, nx * sizeof(double), st), g_err);
   ObjectiveArgs a;
+  memset(&a, 0, sizeof a);
   a.y = centered_rest_fluxes; a.lya_1pz = lya_1pzs; a.nv = rest_noise_variances; a.x = x; a.f = f; a.g = g;
-  a.N = num_quasars; a.P = num_pixels;
-  if (num_quasars > 0) {
-    int rc = GPDLA_OK;
-    GPDLA_FOR_RANK(k, (rc = launch_objective<K>(a, st)));
-    if (rc) return rc;
-    CUDA_TRY(cudaGetLastError(), g_err);
-  }
+  a.N = num_quasars; a.P = num_pixels; a.num_forest_lines = num_forest_lines;
+  for (int l = 0; l < num_forest_lines; ++l) { a.tw[l] = all_transition_wavelengths[l]; a.osc[l] = all_oscillator_strengths[l]; }
+  int rc = GPDLA_OK;
+  GPDLA_FOR_RANK(k, (rc = launch_objective<K>(a, st)));
+  if (rc) return rc;
   objective_prior_kernel<<<1, 1, 0, st>>>(x, g, (int64_t)num_pixels * (k + 1));
   CUDA_TRY(cudaGetLastError(), g_err);
   return GPDLA_OK;
 }
 
-int gpdla_objective(int64_t num_quasars, int32_t num_pixels, int32_t k, const double* centered_rest_fluxes,
-                    const double* lya_1pzs, const double* rest_noise_variances, const double* x, double* f, double* g) {
+int gpdla_objective_device(int64_t num_quasars, int32_t num_pixels, int32_t k, const double* centered_rest_fluxes,
+                           const double* lya_1pzs, const double* rest_noise_variances, const double* x, double* f,
+                           double* g, void* stream) {
+  return gpdla_objective_lyseries_device(num_quasars, num_pixels, k, centered_rest_fluxes, lya_1pzs, rest_noise_variances, 0,
+                                         nullptr, nullptr, x, f, g, stream);
+}
+
+int gpdla_objective_lyseries(int64_t num_quasars, int32_t num_pixels, int32_t k, const double* centered_rest_fluxes,
+                             const double* lya_1pzs, const double* rest_noise_variances, int32_t num_forest_lines,
+                             const double* all_transition_wavelengths, const double* all_oscillator_strengths, const double* x,
+                             double* f, double* g) {
   if (num_quasars < 0 || num_pixels < 1 || k < 1 || !x || !f || !g) { g_err = "gpdla_objective: invalid arguments"; return GPDLA_ERR_INVALID; }
   const size_t NP = (size_t)num_quasars * num_pixels, nx = (size_t)num_pixels * (k + 1) + 3;
   double* base = nullptr;
@@ -1423,7 +1442,8 @@ int gpdla_objective(int64_t num_quasars, int32_t num_pixels, int32_t k, const do
   up(d_y, centered_rest_fluxes, NP * 8); up(d_z, lya_1pzs, NP * 8); up(d_v, rest_noise_variances, NP * 8); up(d_x, x, nx * 8);
   int rc = GPDLA_ERR_CUDA;
   if (e == cudaSuccess) {
-    rc = gpdla_objective_device(num_quasars, num_pixels, k, d_y, d_z, d_v, d_x, d_f, d_g, 0);
+    rc = gpdla_objective_lyseries_device(num_quasars, num_pixels, k, d_y, d_z, d_v, num_forest_lines, all_transition_wavelengths,
+                                         all_oscillator_strengths, d_x, d_f, d_g, 0);
     if (rc == GPDLA_OK) {
       e = cudaMemcpy(f, d_f, 8, cudaMemcpyDeviceToHost);
       if (e == cudaSuccess) e = cudaMemcpy(g, d_g, nx * 8, cudaMemcpyDeviceToHost);
@@ -1432,6 +1452,12 @@ int gpdla_objective(int64_t num_quasars, int32_t num_pixels, int32_t k, const do
   if (e != cudaSuccess) { g_err = cudaGetErrorString(e); rc = GPDLA_ERR_CUDA; }
   cudaFree(base);
   return rc;
+}
+
+int gpdla_objective(int64_t num_quasars, int32_t num_pixels, int32_t k, const double* centered_rest_fluxes,
+                    const double* lya_1pzs, const double* rest_noise_variances, const double* x, double* f, double* g) {
+  return gpdla_objective_lyseries(num_quasars, num_pixels, k, centered_rest_fluxes, lya_1pzs, rest_noise_variances, 0, nullptr,
+                                  nullptr, x, f, g);
 }
 
 }  // extern "C"

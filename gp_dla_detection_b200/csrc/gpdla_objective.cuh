@@ -1,9 +1,15 @@
 // GP training objective on the device: objective.m:12-73 + spectrum_loss.m:14-74.
 //   f(x) = -sum_i log N(y_i; 0, M M' + diag(sigma_i^2 + omega^2 (c_0 + 1 - exp(-tau_0 (1+z)^beta))^2)),  g = df/dx,
 //   x = [vec M (column-major P x k); log omega (P); log c_0; log tau_0; log beta].
-// One CTA per training spectrum, the same Woodbury algebra as the hot path (B = I + M' D^-1 M, Cholesky):
+// With num_forest_lines > 0 the noise model is the Lyman-series one of multi_dlas/spectrum_loss_lyseries.m:20-47 and
+// multi_dlas/objective_lyseries.m:13-87: the effective optical depth sums the series members that lie below the quasar,
+//   tau(z) = tau_0 (1+z)^beta + sum_{l >= 2} tau_0 lambda_l f_l / (lambda_1 f_1) [(1+z_l)^beta if 1+z_l <= 1+z_qso],
+// with 1 + z_qso taken from the last column of the quasar's lya_1pzs row (objective_lyseries.m:46).
+// A CTA works through training spectra with the same Woodbury algebra as the hot path (B = I + M' D^-1 M, Cholesky):
 //   C M = I - B^-1  =>  K^-1 M = D^-1 M B^-1,  diag K^-1 = d^-1 - rowdot(D^-1 M B^-1, D^-1 M)
-// so no n x n or k x n intermediate is formed; gradients are accumulated with FP64 atomics (RED.F64).
+// so no n x n or k x n intermediate is formed.  Two-stage reduction: every CTA of the (resident-sized) grid adds the
+// gradients of its spectra into its own partial vector with plain loads and stores, objective_reduce_kernel sums the
+// partial vectors -- no floating-point atomics, and a result that does not depend on the order of arrival.
 #pragma once
 #include <stdint.h>
 #include <math.h>
@@ -17,8 +23,12 @@ struct ObjectiveArgs {
   const double* x;        // parameters
   double* f;              // scalar
   double* g;              // gradient, layout of x
+  double* partial;        // [grid][nx + 1] per-CTA partial gradients, then the partial objective value
   int64_t N;
   int P;
+  int num_forest_lines;   // 0: objective.m / spectrum_loss.m; > 0: the Lyman-series variant
+  double tw[MAX_LINES];   // all_transition_wavelengths (any unit: only ratios enter)   set_parameters_multi.m:77-109
+  double osc[MAX_LINES];  // all_oscillator_strengths                                   set_parameters_multi.m:110-142
 };
 
 constexpr int OBJ_THREADS = 256;
@@ -32,11 +42,12 @@ __host__ __device__ constexpr size_t objective_smem_bytes(int P) {
 
 template <int K>
 __global__ void __launch_bounds__(OBJ_THREADS, (K <= 20) ? 2 : 1) objective_kernel(ObjectiveArgs a) {
-  const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int P = a.P;
-  const double* y = a.y + (int64_t)s * P;
-  const double* z1 = a.lya_1pz + (int64_t)s * P;
-  const double* nv = a.nv + (int64_t)s * P;
+  const int64_t nx = (int64_t)P * (K + 1) + 3;
+  double* part = a.partial + (int64_t)blockIdx.x * (nx + 1);
+  for (int64_t e = tid; e <= nx; e += OBJ_THREADS) part[e] = 0.0;
+  double f_cta = 0.0, c0_cta = 0.0, tau_cta = 0.0, beta_cta = 0.0;   // thread 0's running sums over this CTA's spectra
   const double* M = a.x;                          // M(i, j) = x[j P + i]
   const double* log_omega = a.x + (int64_t)P * K;
   const double c_0 = exp(a.x[(int64_t)P * (K + 1)]), tau_0 = exp(a.x[(int64_t)P * (K + 1) + 1]),
@@ -53,8 +64,14 @@ __global__ void __launch_bounds__(OBJ_THREADS, (K <= 20) ? 2 : 1) objective_kern
   double* wv = v1 + K;                                             // [K] (K^-1 y)' M
   double* red = wv + 2 * K;                                        // [64] reductions
   int* idx = reinterpret_cast<int*>(red + 64);                     // [P] valid pixels
-  __shared__ int s_n, s_cnt[OBJ_THREADS / 32];
+  __shared__ int s_cnt[OBJ_THREADS / 32];
 
+  for (int64_t s = blockIdx.x; s < a.N; s += gridDim.x) {
+  const double* y = a.y + s * P;
+  const double* z1 = a.lya_1pz + s * P;
+  const double* nv = a.nv + s * P;
+  const double zq1 = z1[P - 1];                   // 1 + z_qso   (objective_lyseries.m:46)
+  __syncthreads();                                // the previous spectrum's shared arrays are dead
   // ---- valid pixels (objective.m:42), compacted in order
   int base = 0;
   for (int i0 = 0; i0 < P; i0 += OBJ_THREADS) {
@@ -70,11 +87,17 @@ __global__ void __launch_bounds__(OBJ_THREADS, (K <= 20) ? 2 : 1) objective_kern
     __syncthreads();
   }
   const int n = base;
-  if (n == 0) return;
+  if (n == 0) continue;
 
   // per-pixel noise model (spectrum_loss.m:21-31)
   auto noise_terms = [&](int i, double& od, double& ab, double& sf, double& an) {
     od = tau_0 * pow(z1[i], beta);                 // lya_optical_depth
+    for (int l = 1; l < a.num_forest_lines; ++l) { // spectrum_loss_lyseries.m:29-40
+      double lyman_1pz = a.tw[0] * z1[i] / a.tw[l];
+      lyman_1pz = (lyman_1pz <= zq1) ? lyman_1pz : 0.0;
+      const double tau = tau_0 * a.tw[l] * a.osc[l] / (a.tw[0] * a.osc[0]);
+      od = od + tau * pow(lyman_1pz, beta);
+    }
     ab = exp(-od);                                 // lya_absorption
     sf = 1.0 - ab + c_0;                           // scaling_factor
     an = exp(2.0 * log_omega[i]) * (sf * sf);      // absorption_noise
@@ -201,8 +224,8 @@ __global__ void __launch_bounds__(OBJ_THREADS, (K <= 20) ? 2 : 1) objective_kern
   // ---- pass 2: K^-1 M = D^-1 M B^-1, diag K^-1, every gradient; one atomic per entry of dM:
   //      dM(i, :) = K^-1 M (i, :) - K^-1 y (i) w   (:54-55)
   double g_c0 = 0.0, g_tau = 0.0, g_beta = 0.0;
-  double* gM = a.g;
-  double* gom = a.g + (int64_t)P * K;
+  double* gM = part;
+  double* gom = part + (int64_t)P * K;
   for (int t = tid; t < n; t += OBJ_THREADS) {
     const int i = idx[t];
     const double di = dinv[t], ky = kiy[t];
@@ -216,13 +239,13 @@ __global__ void __launch_bounds__(OBJ_THREADS, (K <= 20) ? 2 : 1) objective_kern
 #pragma unroll
       for (int c = 0; c < K; ++c) tj = fma(r[c], Binv[c * (K + 1) + j], tj);
       diagk = fma(-tj, r[j], diagk);                                                       // diag K^-1 (:58)
-      atomicAdd(&gM[(int64_t)j * P + i], fma(-ky, wv[j], tj));
+      gM[(int64_t)j * P + i] += fma(-ky, wv[j], tj);   // this CTA's own partial vector: no other writer
     }
     double od, ab, sf, an;
     noise_terms(i, od, ab, sf, an);
     const double om2 = exp(2.0 * log_omega[i]);
     const double kk = ky * ky - diagk;
-    atomicAdd(&gom[i], -(an * kk));                                                        // dlog_omega (:61)
+    gom[i] -= an * kk;                                                                     // dlog_omega (:61)
     double da = c_0 * om2 * sf;                                                            // (:64-65)
     g_c0 -= da * kk;
     da = om2 * sf * od * ab;                                                               // (:68-69)
@@ -244,11 +267,24 @@ __global__ void __launch_bounds__(OBJ_THREADS, (K <= 20) ? 2 : 1) objective_kern
   g_c0 = block_reduce(g_c0); g_tau = block_reduce(g_tau); g_beta = block_reduce(g_beta);
   if (tid == 0) {
     const double log_2pi = 1.83787706640934534;                                            // (:17)
-    atomicAdd(a.f, 0.5 * (quad + (ld + 2.0 * logdetB) + n * log_2pi));                     // (:48-52)
-    atomicAdd(&a.g[(int64_t)P * (K + 1)], g_c0);
-    atomicAdd(&a.g[(int64_t)P * (K + 1) + 1], g_tau);
-    atomicAdd(&a.g[(int64_t)P * (K + 1) + 2], g_beta);
+    f_cta += 0.5 * (quad + (ld + 2.0 * logdetB) + n * log_2pi);                            // (:48-52)
+    c0_cta += g_c0; tau_cta += g_tau; beta_cta += g_beta;
   }
+  }   // spectra of this CTA
+  if (tid == 0) {
+    part[(int64_t)P * (K + 1)] = c0_cta; part[(int64_t)P * (K + 1) + 1] = tau_cta; part[(int64_t)P * (K + 1) + 2] = beta_cta;
+    part[nx] = f_cta;
+  }
+}
+
+// second stage: g[e] = sum over the CTAs' partial vectors (fixed order), f likewise
+__global__ void objective_reduce_kernel(const double* __restrict__ partial, int nparts, int64_t nx, double* __restrict__ g,
+                                        double* __restrict__ f) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e > nx) return;
+  double v = 0.0;
+  for (int b = 0; b < nparts; ++b) v += partial[(int64_t)b * (nx + 1) + e];
+  if (e < nx) g[e] = v; else *f = v;
 }
 
 // priors on tau_0 and beta (Kim et al. 2007), objective.m:59-71

@@ -207,6 +207,19 @@ int gpdla_preload_qsos_device(int64_t Q, int64_t L_in, const double* flux, const
  * centered_rest_fluxes, lya_1pzs, rest_noise_variances of learn_qso_model.m:36-75, [num_quasars x num_pixels]
  * row-major, NaN in centered_rest_fluxes = pixel not observed (objective.m:42).  g has the layout of x.
  * Context-free; the _device entry (device pointers for data, x, f, g) is asynchronous on `stream`. */
+/* The Lyman-series variant the multi-DLA model is trained with: multi_dlas/objective_lyseries.m:13-87 +
+ * multi_dlas/spectrum_loss_lyseries.m:14-91.  Same x, data matrices and outputs; the effective optical depth sums the
+ * first num_forest_lines series members (all_transition_wavelengths, all_oscillator_strengths of
+ * set_parameters_multi.m:76-142, host arrays) that lie below the quasar, whose 1 + z is the LAST column of its lya_1pzs
+ * row (objective_lyseries.m:46).  num_forest_lines = 0 is gpdla_objective. */
+int gpdla_objective_lyseries(int64_t num_quasars, int32_t num_pixels, int32_t k, const double* centered_rest_fluxes,
+                             const double* lya_1pzs, const double* rest_noise_variances, int32_t num_forest_lines,
+                             const double* all_transition_wavelengths, const double* all_oscillator_strengths,
+                             const double* x, double* f, double* g);
+int gpdla_objective_lyseries_device(int64_t num_quasars, int32_t num_pixels, int32_t k, const double* centered_rest_fluxes,
+                                    const double* lya_1pzs, const double* rest_noise_variances, int32_t num_forest_lines,
+                                    const double* all_transition_wavelengths, const double* all_oscillator_strengths,
+                                    const double* x, double* f, double* g, void* stream);
 int gpdla_objective(int64_t num_quasars, int32_t num_pixels, int32_t k, const double* centered_rest_fluxes,
                     const double* lya_1pzs, const double* rest_noise_variances, const double* x, double* f, double* g);
 int gpdla_objective_device(int64_t num_quasars, int32_t num_pixels, int32_t k, const double* centered_rest_fluxes,

@@ -1,5 +1,6 @@
 r"""TEST INFRASTRUCTURE (oracle): literal NumPy restatement of the reference's GP training objective,
-spectrum_loss.m:14-74 and objective.m:12-73, in the reference's operation order (chol upper, L \ (L' \ ...)).
+spectrum_loss.m:14-74 and objective.m:12-73 and of their Lyman-series variants multi_dlas/spectrum_loss_lyseries.m:14-91,
+multi_dlas/objective_lyseries.m:13-87, in the reference's operation order (chol upper, L \ (L' \ ...)).
 Parity unpinned against MATLAB outputs; pinned by tests/test_objective.py: dense multivariate-normal log-density
 and central finite differences of every gradient block."""
 import numpy as np
@@ -8,10 +9,21 @@ from scipy.linalg import solve_triangular
 log_2pi = 1.83787706640934534
 
 
-def spectrum_loss(y, lya_1pz, noise_variance, M, omega2, c_0, tau_0, beta):
+def spectrum_loss(y, lya_1pz, noise_variance, M, omega2, c_0, tau_0, beta, lyseries=None):
+    """spectrum_loss.m:14-74; with ``lyseries = (num_forest_lines, all_transition_wavelengths, all_oscillator_strengths,
+    zqso_1pz)`` multi_dlas/spectrum_loss_lyseries.m:14-91 (the two differ in the optical depth only, :20-41)."""
     n, k = M.shape
-    lya_optical_depth = tau_0 * lya_1pz ** beta                       # :21
-    lya_absorption = np.exp(-lya_optical_depth)                       # :22
+    lya_optical_depth = tau_0 * lya_1pz ** beta                       # :21 / lyseries :23
+    if lyseries is not None:
+        num_forest_lines, tw, osc, zqso_1pz = lyseries
+        for i in range(1, num_forest_lines):                          # lyseries :29-40 (MATLAB i = 2..num_forest_lines)
+            lyman_1pz = tw[0] * lya_1pz / tw[i]
+            with np.errstate(invalid="ignore"):
+                indicator = lyman_1pz <= zqso_1pz
+            lyman_1pz = lyman_1pz * indicator
+            tau = tau_0 * tw[i] * osc[i] / (tw[0] * osc[0])
+            lya_optical_depth = lya_optical_depth + tau * lyman_1pz ** beta
+    lya_absorption = np.exp(-lya_optical_depth)                       # :22 / lyseries :41
     scaling_factor = 1 - lya_absorption + c_0                         # :25
     absorption_noise = omega2 * scaling_factor ** 2                   # :26
     d = noise_variance + absorption_noise                             # :28
@@ -38,7 +50,9 @@ def spectrum_loss(y, lya_1pz, noise_variance, M, omega2, c_0, tau_0, beta):
     return nlog_p, dM, dlog_omega, dlog_c_0, dlog_tau_0, dlog_beta
 
 
-def objective(x, centered_rest_fluxes, lya_1pzs, rest_noise_variances, priors=True):
+def objective(x, centered_rest_fluxes, lya_1pzs, rest_noise_variances, priors=True, lyseries=None):
+    """objective.m:12-73; with ``lyseries = (num_forest_lines, all_transition_wavelengths, all_oscillator_strengths)``
+    multi_dlas/objective_lyseries.m:13-87 (zqso_1pz = lya_1pzs(i, end), :46)."""
     num_quasars, num_pixels = centered_rest_fluxes.shape
     k = (x.size - 3) // num_pixels - 1                                # :17
     M = x[:num_pixels * k].reshape(k, num_pixels).T                   # :19-20 (column-major reshape)
@@ -54,7 +68,7 @@ def objective(x, centered_rest_fluxes, lya_1pzs, rest_noise_variances, priors=Tr
         if not ind.any():
             continue
         r = spectrum_loss(centered_rest_fluxes[i, ind], lya_1pzs[i, ind], rest_noise_variances[i, ind], M[ind], omega2[ind],
-                          c_0, tau_0, beta)
+                          c_0, tau_0, beta, None if lyseries is None else tuple(lyseries) + (lya_1pzs[i, -1],))
         f += r[0]; dM[ind] += r[1]; dlog_omega[ind] += r[2]
         dlog_c_0 += r[3]; dlog_tau_0 += r[4]; dlog_beta += r[5]
     if priors:
