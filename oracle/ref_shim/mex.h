@@ -19,6 +19,8 @@ size_t   mxGetNumberOfElements(const mxArray *a);
 mxArray *mxCreateDoubleMatrix(size_t m, size_t n, mxComplexity flag); /* zero-filled */
 void    *mxMalloc(size_t n);
 void     mxFree(void *p);
+/* error exit of a MEX function: the shim records the message and longjmps back to the harness (tests/test_integration_shims.py) */
+void     mexErrMsgIdAndTxt(const char *id, const char *fmt, ...);
 
 void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]);
 #endif
