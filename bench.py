@@ -40,7 +40,7 @@ def fp64_peak():
 def ncu_traffic(i8):
     """DRAM bytes of one fused log-likelihood launch (296-quasar batch) from the committed ncu --set full capture."""
     try:
-        d = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_loglik_i8_full.json" if i8 else "r01_ncu_loglik_full.json")))
+        d = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_loglik_i8_full.json" if i8 else "r02_ncu_loglik_ws_full.json")))
         return d["dram_bytes_per_launch"], d["Grid Size"]["value"]
     except Exception:
         return None, None
@@ -333,10 +333,13 @@ def main():
         roof = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                 "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                 "traffic_note": "dram__bytes_read+write of one launch with grid %s (one 296-quasar batch; this "
-                                "run launches the same batch size), ncu --set full" % traffic_grid,
+                                "run launches the same batch size), ncu --set full, profiles/r02_ncu_loglik_*_full.json" % traffic_grid,
                 "algorithmic_flops_per_launch": flops_per_step * args.steps / max(int(k_n), 1),
                 "kernel_ms_per_step": k_ms / args.steps, "kernel_launches": int(k_n),
                 "kernel_share_of_step": k_ms / ms,
+                "timed_interval": "CUDA events on the launching stream around each batch's fused kernels: the persistent INT8 "
+                                  "kernel on 132 SMs and, concurrently on the 16 SMs its clusters cannot occupy, the FP64 DMMA "
+                                  "kernel on the last 7 % of the batch (second stream, joined before the interval ends)",
                 "algorithmic_flops_per_step": flops_per_step, "peak_source": peak_src,
                 "peak_nominal": 40.0, "peak_nominal_source": "NVIDIA HGX B200 datasheet, FP64 tensor, per GPU"}
         if i8:

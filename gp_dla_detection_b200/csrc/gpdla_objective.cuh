@@ -8,8 +8,8 @@
 // A CTA works through training spectra with the same Woodbury algebra as the hot path (B = I + M' D^-1 M, Cholesky):
 //   C M = I - B^-1  =>  K^-1 M = D^-1 M B^-1,  diag K^-1 = d^-1 - rowdot(D^-1 M B^-1, D^-1 M)
 // so no n x n or k x n intermediate is formed.  Two-stage reduction: every CTA of the (resident-sized) grid adds the
-// gradients of its spectra into its own partial vector with plain loads and stores, objective_reduce_kernel sums the
-// partial vectors -- no floating-point atomics, and a result that does not depend on the order of arrival.
+// gradients of its spectra into its own partial vector (one writer per vector, so the sums are in a fixed order and the
+// result is the same on every evaluation), objective_reduce_kernel sums the partial vectors.
 #pragma once
 #include <stdint.h>
 #include <math.h>
@@ -239,13 +239,15 @@ __global__ void __launch_bounds__(OBJ_THREADS, (K <= 20) ? 2 : 1) objective_kern
 #pragma unroll
       for (int c = 0; c < K; ++c) tj = fma(r[c], Binv[c * (K + 1) + j], tj);
       diagk = fma(-tj, r[j], diagk);                                                       // diag K^-1 (:58)
-      gM[(int64_t)j * P + i] += fma(-ky, wv[j], tj);   // this CTA's own partial vector: no other writer
+      // this CTA's own partial vector: no other writer, and one add per entry and spectrum in spectrum order -- the
+      // reduction instruction (no load-add-store round trip through L2 in the inner loop) keeps the sum deterministic
+      atomicAdd(&gM[(int64_t)j * P + i], fma(-ky, wv[j], tj));
     }
     double od, ab, sf, an;
     noise_terms(i, od, ab, sf, an);
     const double om2 = exp(2.0 * log_omega[i]);
     const double kk = ky * ky - diagk;
-    gom[i] -= an * kk;                                                                     // dlog_omega (:61)
+    atomicAdd(&gom[i], -(an * kk));                                                        // dlog_omega (:61)
     double da = c_0 * om2 * sf;                                                            // (:64-65)
     g_c0 -= da * kk;
     da = om2 * sf * od * ab;                                                               // (:68-69)
