@@ -185,6 +185,11 @@ int upload_device_constants(std::string& err) {
     w3.v2min = GPDLA_VOIGT_X0 * GPDLA_VOIGT_X0 * two_s2;
     CUDA_TRY(cudaMemcpyToSymbol(c_wing3, &w3, sizeof w3), err);
   }
+  {  // 2^(j/256) for exp_nonpos, correctly rounded from long double
+    double t[256];
+    for (int j = 0; j < 256; ++j) t[j] = (double)exp2l((long double)j / 256.0L);
+    CUDA_TRY(cudaMemcpyToSymbol(g_exp2_tab, t, sizeof t), err);
+  }
   {  // stage-index tables of every compiled rank (one table per rank: contexts of different k share a device)
     static short t10[GramShape<10>::NCOL], t20[GramShape<20>::NCOL], t40[GramShape<40>::NCOL], ti8[i8::CLUSTER * 128];
     fill_stage_index<10>(t10); fill_stage_index<20>(t20); fill_stage_index<40>(t40); fill_i8_stage_index<I8_K>(ti8);
@@ -266,7 +271,7 @@ struct gpdla_ctx {
   int64_t* d_scratch_i = nullptr;
   // INT8 tensor-core Gram path (k = 20): digit operands and scales
   int i8_batch = 0, i8_npix = 0;
-  double *d_pix2 = nullptr, *d_colscale = nullptr, *d_colinv = nullptr;
+  double *d_pix2 = nullptr, *d_pix8 = nullptr, *d_colscale = nullptr, *d_colinv = nullptr;
   uint8_t* d_bop = nullptr;
   int* d_status = nullptr;
   int32_t* d_f64flag = nullptr;       // [batch] flags + {count, list}: quasars the INT8 path leaves to the FP64 kernels
@@ -341,7 +346,11 @@ static int ensure_rest_table(gpdla_ctx* c) {
   fill_line_constants(&lc);
   const RestTableHost t = build_rest_table(c->params.num_lines, c->params.pixel_spacing, RT_NEAR_PIXELS, lc.tw, lc.lc,
                                            lc.gam, kSigma, kC);
-  int rc = dev_upload(&c->d_rt, t.coef.data(), t.coef.size(), c->err);
+  // device layout: the coefficients of a cell side by side (RestTable)
+  std::vector<double> cells((size_t)t.ncell * RT_CELL_STRIDE, 0.0);
+  for (int p = 0; p <= RT_DEG_DEV; ++p)
+    for (int ci = 0; ci < t.ncell; ++ci) cells[(size_t)ci * RT_CELL_STRIDE + p] = t.coef[(size_t)p * t.ncell + ci];
+  int rc = dev_upload(&c->d_rt, cells.data(), cells.size(), c->err);
   if (rc) return rc;
   c->rt_ncell = t.ncell; c->rt_h = t.h; c->rt_num_lines = c->params.num_lines; c->rt_pixel_spacing = c->params.pixel_spacing;
   return GPDLA_OK;
@@ -404,11 +413,12 @@ static int launch_loglik(gpdla_ctx* c, LoglikArgs la, int nq, cudaStream_t st, b
 
 static int ensure_i8_workspace(gpdla_ctx* c, int batch, int npix) {
   if (c->i8_batch >= batch && c->i8_npix == npix) return GPDLA_OK;
-  cudaFree(c->d_pix2); cudaFree(c->d_colscale); cudaFree(c->d_colinv); cudaFree(c->d_bop); cudaFree(c->d_f64flag);
-  c->d_pix2 = c->d_colscale = c->d_colinv = nullptr; c->d_bop = nullptr; c->d_f64flag = nullptr; c->i8_batch = 0;
+  cudaFree(c->d_pix2); cudaFree(c->d_pix8); cudaFree(c->d_colscale); cudaFree(c->d_colinv); cudaFree(c->d_bop); cudaFree(c->d_f64flag);
+  c->d_pix2 = c->d_pix8 = c->d_colscale = c->d_colinv = nullptr; c->d_bop = nullptr; c->d_f64flag = nullptr; c->i8_batch = 0;
   const size_t B = batch;
   using Sh = i8::Shape<I8_K, 6>;    // the 6-digit layout is the larger one
   CUDA_TRY(cudaMalloc(&c->d_pix2, B * npix * 2 * sizeof(double)), c->err);
+  CUDA_TRY(cudaMalloc(&c->d_pix8, B * npix * 8 * sizeof(double)), c->err);
   CUDA_TRY(cudaMalloc(&c->d_colscale, B * Sh::NCOLTAB * sizeof(double)), c->err);
   CUDA_TRY(cudaMalloc(&c->d_colinv, B * Sh::NCOLTAB * sizeof(double)), c->err);
   CUDA_TRY(cudaMalloc(&c->d_bop, B * (npix / KC) * Sh::CHUNK_BYTES), c->err);
@@ -423,10 +433,10 @@ static int ensure_i8_workspace(gpdla_ctx* c, int batch, int npix) {
 
 static i8::I8Args i8_args(gpdla_ctx* c) {
   i8::I8Args xa;
-  xa.pix2 = c->d_pix2; xa.bop = c->d_bop; xa.colscale = c->d_colscale; xa.colinv = c->d_colinv; xa.status = c->d_status;
+  xa.pix2 = c->d_pix2; xa.pix8 = c->d_pix8; xa.bop = c->d_bop; xa.colscale = c->d_colscale; xa.colinv = c->d_colinv; xa.status = c->d_status;
   xa.f64flag = c->d_f64flag; xa.f64list = c->d_f64flag + c->i8_batch;
   xa.phase = nullptr;
-  if (getenv("GPDLA_I8_PHASES")) {   // diagnostics only: mean barrier waits per tile, printed before the next launch
+  if (GPDLA_I8P_PHASES && getenv("GPDLA_I8_PHASES")) {   // diagnostics only: mean barrier waits per tile, printed before the next launch
     if (!c->d_phase) { cudaMalloc(&c->d_phase, 24 * sizeof(unsigned long long)); cudaMemset(c->d_phase, 0, 24 * sizeof(unsigned long long)); }
     unsigned long long h[24];
     cudaMemcpy(h, c->d_phase, sizeof h, cudaMemcpyDeviceToHost);
@@ -442,7 +452,7 @@ static i8::I8Args i8_args(gpdla_ctx* c) {
 template <int L>
 static int build_i8_operands_L(gpdla_ctx* c, int nq, int npix, cudaStream_t st) {
   i8::I8Args xa = i8_args(c);
-  i8::i8_scales_kernel<I8_K, L><<<nq, NTHREADS, 0, st>>>(c->d_meta, c->d_pix, c->d_Mq, xa, npix);
+  i8::i8_scales_kernel<I8_K, L><<<nq, NTHREADS, 0, st>>>(c->d_meta, c->d_pix, c->d_Mq, c->d_lam, c->d_lamh, xa, npix);
   c->launches++;
   CUDA_TRY(cudaGetLastError(), c->err);
   i8::i8_build_operand_kernel<I8_K, L><<<dim3(npix / KC, nq), NTHREADS, 0, st>>>(c->d_meta, c->d_Mq, xa, npix);
@@ -771,7 +781,7 @@ void gpdla_destroy(gpdla_ctx* c) {
   cudaFree(c->d_rest); cudaFree(c->d_mu); cudaFree(c->d_M); cudaFree(c->d_log_omega);
   cudaFree(c->d_offset); cudaFree(c->d_log_nhi); cudaFree(c->d_nhi); cudaFree(c->d_order); cudaFree(c->d_rt);
   cudaFree(c->d_prior_z); cudaFree(c->d_prior_dla); cudaFree(c->d_stage);
-  cudaFree(c->d_pix2); cudaFree(c->d_colscale); cudaFree(c->d_colinv); cudaFree(c->d_bop); cudaFree(c->d_status);
+  cudaFree(c->d_pix2); cudaFree(c->d_pix8); cudaFree(c->d_colscale); cudaFree(c->d_colinv); cudaFree(c->d_bop); cudaFree(c->d_status);
   cudaFree(c->d_f64flag); cudaFree(c->d_phase);
   cudaFree(c->d_lls_nhi); cudaFree(c->d_uniforms); cudaFree(c->d_acache); cudaFree(c->d_msll); cudaFree(c->d_mlls);
   cudaFree(c->d_cum); cudaFree(c->d_mscal); cudaFree(c->d_partners); cudaFree(c->d_active);

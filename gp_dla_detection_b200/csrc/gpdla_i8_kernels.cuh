@@ -50,6 +50,11 @@ constexpr int TMEM_COLS = 512;
 #define GPDLA_I8P_PROBE 0
 #endif
 constexpr int PROBE = GPDLA_I8P_PROBE;
+// Barrier-wait accounting (-DGPDLA_I8P_PHASES=1 and GPDLA_I8_PHASES=1 in the environment): compiled out of the product
+// build -- the null-pointer test and the clock reads around every wait cost the producers issue slots.
+#ifndef GPDLA_I8P_PHASES
+#define GPDLA_I8P_PHASES 0
+#endif
 
 template <int K, int L>
 struct Shape {
@@ -103,6 +108,8 @@ __constant__ short c_i8_stage[CLUSTER * 128];
 
 struct I8Args {
   double* pix2;            // [Q x NPIX x 2]  (cw, cu)
+  double* pix8;            // [Q x NPIX x 8]  the producers' per-pixel record (lambda, lh, y, v, mu, omega2, cw, cu): one
+                           // address and four 128-bit loads per lane and chunk
   uint8_t* bop;            // [Q x NPIX/KC x CHUNK_BYTES]  digit planes of P'' (ranks 0..2) and M'' (rank 3)
   double* colscale;        // [Q x 4 x NMAX]  2^(e_c - 2F + 8(L-1)): accumulator -> Gram entry
   double* colinv;          // [Q x 4 x NMAX]  2^-e_c
@@ -112,6 +119,8 @@ struct I8Args {
   int32_t* f64list;        // {count, q_0, q_1, ...}: the same quasars as a list (LoglikArgs::only_list of the fallback)
   unsigned long long* phase;   // nullable: [24] summed wait cycles per barrier (GPDLA_I8_PHASES diagnostics)
 };
+
+__device__ __forceinline__ unsigned long long* phase_ptr(const I8Args& xa) { return GPDLA_I8P_PHASES ? xa.phase : nullptr; }
 
 // ------------------------------------------------------------------------------------------ PTX helpers
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
@@ -206,12 +215,16 @@ __device__ __forceinline__ void issue_chunk_mmas_fixed(uint32_t tmem_base, uint6
 // K0c: per-pixel scales (cw, cu) and per-column exponents of the digit operands.  One CTA per quasar.
 template <int K, int L>
 __global__ void __launch_bounds__(NTHREADS) i8_scales_kernel(const QuasarMeta* __restrict__ meta, const double* __restrict__ pix,
-                                                             const double* __restrict__ Mq, I8Args xa, int NPIX) {
+                                                             const double* __restrict__ Mq, const double* __restrict__ lam_pad,
+                                                             const double* __restrict__ lamh, I8Args xa, int NPIX) {
   using Sh = Shape<K, L>;
   using G = GramShape<K>;
   const int q = blockIdx.x, tid = threadIdx.x;
   const double* pq = pix + (int64_t)q * NPIX * 4;
   double* p2 = xa.pix2 + (int64_t)q * NPIX * 2;
+  double2* p8 = reinterpret_cast<double2*>(xa.pix8 + (int64_t)q * NPIX * 8);
+  const double* lq = lam_pad + (int64_t)q * (NPIX + 8) + 6;     // pixel i sits at position i + 6 of the padded grid
+  const double* lhq = lamh + (int64_t)q * (NPIX + 8) + 6;
   bool unbounded = false;
   for (int i = tid; i < NPIX; i += NTHREADS) {
     const double y = pq[i * 4 + 0], v = pq[i * 4 + 1], mu = pq[i * 4 + 2], om2 = pq[i * 4 + 3];
@@ -224,6 +237,8 @@ __global__ void __launch_bounds__(NTHREADS) i8_scales_kernel(const QuasarMeta* _
     unbounded |= !(v > 0.0) || !isfinite(b) || !isfinite(cw);
     const double cu = (yy > 0.0 && isfinite(b)) ? CAP / (b * yy) : 0.0;
     p2[i * 2 + 0] = cw; p2[i * 2 + 1] = cu;
+    p8[i * 4 + 0] = make_double2(lq[i], lhq[i]); p8[i * 4 + 1] = make_double2(y, v);
+    p8[i * 4 + 2] = make_double2(mu, om2); p8[i * 4 + 3] = make_double2(cw, cu);
   }
   if (__syncthreads_or(unbounded) && tid == 0 && meta[q].nchunks > 0) {
     xa.f64flag[q] = 1;
@@ -489,8 +504,8 @@ dla_loglik_i8p_kernel(LoglikArgs args, I8Args xa, int num_quasars, int tiles_per
         continue;
       }
       if (lane == 0) {
-        mbar_wait_d(bar_acc, it & 1, xa.status, 6, xa.phase, 500);   // latency-insensitive: poll rarely
-        if (it > 0) mbar_wait_cluster(&bar_csfree[e], (it - 1) & 1, xa.status, 10, xa.phase);   // CTA e is done with its previous triangle
+        mbar_wait_d(bar_acc, it & 1, xa.status, 6, phase_ptr(xa), 500);   // latency-insensitive: poll rarely
+        if (it > 0) mbar_wait_cluster(&bar_csfree[e], (it - 1) & 1, xa.status, 10, phase_ptr(xa));   // CTA e is done with its previous triangle
       }
       __syncwarp();
       asm volatile("tcgen05.fence::after_thread_sync;");
@@ -522,8 +537,8 @@ dla_loglik_i8p_kernel(LoglikArgs args, I8Args xa, int num_quasars, int tiles_per
       if (lane == 0) {
         mbar_arrive(bar_tfree);                      // the MMA issuer may overwrite the accumulators
         mbar_arrive_cluster(csfull_remote);          // this CTA's share of CTA e's triangle is in place
-        mbar_wait_cluster(bar_csfull, it & 1, xa.status, 11, xa.phase);                 // all four shares of my triangle
-        mbar_wait_d(&bar_sq[it & 1], (it >> 1) & 1, xa.status, 12, xa.phase, 200);            // my producers' scalars
+        mbar_wait_cluster(bar_csfull, it & 1, xa.status, 11, phase_ptr(xa));                 // all four shares of my triangle
+        mbar_wait_d(&bar_sq[it & 1], (it >> 1) & 1, xa.status, 12, phase_ptr(xa), 200);            // my producers' scalars
       }
       __syncwarp();
       if (!(PROBE & 8)) factor_staged<K, CSTR>(Cs, s_q + (it & 1) * TS, s_ld + (it & 1) * TS, e * 8, lane, meta, args, q, s0);
@@ -550,6 +565,8 @@ dla_loglik_i8p_kernel(LoglikArgs args, I8Args xa, int num_quasars, int tiles_per
     const uint64_t KADD = BIAS - (uint64_t)__double_as_longlong(MAGIC);
     double* myraw = rawbuf + row0 * RAWS;
     int gc = 0, it = 0;                               // chunk counter across tiles, live-tile counter
+    int stage = 0;                                    // = gc % STAGES
+    uint32_t empty_parity = 1;                        // = ((gc / STAGES) & 1) ^ 1
     for (int t = cluster_id; t < num_tiles; t += num_clusters) {
       const int q = tile_quasar(t);
       const QuasarMeta meta = args.meta[q];
@@ -575,8 +592,7 @@ dla_loglik_i8p_kernel(LoglikArgs args, I8Args xa, int num_quasars, int tiles_per
       }
       __syncwarp();
       const double* lam = args.lam_pad + (int64_t)q * (args.NPIX + 8);
-      const double* pix = args.pix + (int64_t)q * args.NPIX * 4;
-      const double* pix2 = xa.pix2 + (int64_t)q * args.NPIX * 2;
+      const double2* pix8 = reinterpret_cast<const double2*>(xa.pix8 + (int64_t)q * args.NPIX * 8);
       double* const cache_q = (MODE != 0) ? args.acache + (int64_t)q * S * args.NPIX : nullptr;
 
       // tau / N: from the rest-frame table (one cell per lane serves the warp's four samples), directly where the
@@ -587,7 +603,7 @@ dla_loglik_i8p_kernel(LoglikArgs args, I8Args xa, int num_quasars, int tiles_per
       auto eval_raw = [&](double lambda, double lh, double (&e)[SPB]) {   // voigt.c:282-292, 4 samples at one wavelength
         double tau[SPB];
         tau_samples<NL, SPB>(args.rt, tab_mode, K_mid, lambda, lh, s_mult + row0, TS, s_K + row0, num_lines, tau);
-        raw_from_tau<SPB>(tau, s_nhi + row0, e);
+        raw_from_tau<SPB, false>(tau, s_nhi + row0, e);   // polynomial exponential: see exp_nonpos
       };
       if (MODE != 2) {   // leading pad pixels p = 0..5
         double e[SPB];
@@ -614,21 +630,15 @@ dla_loglik_i8p_kernel(LoglikArgs args, I8Args xa, int num_quasars, int tiles_per
       };
       if (MODE == 2) load_rows(lane);
       // pixel data of the next chunk is fetched one chunk ahead (global/L2 latency off the critical path)
-      double lambda_n = lam[6 + lane], lh_n = lamh[6 + lane];
-      double2 p01n = *reinterpret_cast<const double2*>(pix + (int64_t)lane * 4);
-      double2 p23n = *reinterpret_cast<const double2*>(pix + (int64_t)lane * 4 + 2);
-      double2 p45n = *reinterpret_cast<const double2*>(pix2 + (int64_t)lane * 2);
+      const double2* prec = pix8 + (int64_t)lane * 4;
+      double2 plln = prec[0], p01n = prec[1], p23n = prec[2], p45n = prec[3];
       for (int c = 0; c < nchunks; ++c, ++gc) {
-        const int stage = gc % STAGES;
         const int i = c * KC + lane;
-        const double lambda = lambda_n, lh = lh_n;
+        const double lambda = plln.x, lh = plln.y;
         const double y = p01n.x, v = p01n.y, mu = p23n.x, om2 = p23n.y, cw = p45n.x, cu = p45n.y;
         if (c + 1 < nchunks) {
-          lambda_n = lam[i + KC + 6];
-          lh_n = lamh[i + KC + 6];
-          p01n = *reinterpret_cast<const double2*>(pix + (int64_t)(i + KC) * 4);
-          p23n = *reinterpret_cast<const double2*>(pix + (int64_t)(i + KC) * 4 + 2);
-          p45n = *reinterpret_cast<const double2*>(pix2 + (int64_t)(i + KC) * 2);
+          prec += KC * 4;
+          plln = prec[0]; p01n = prec[1]; p23n = prec[2]; p45n = prec[3];
         }
         double a[SPB];
         if (MODE != 2) {
@@ -690,7 +700,7 @@ dla_loglik_i8p_kernel(LoglikArgs args, I8Args xa, int num_quasars, int tiles_per
           qacc[ss] = fma(r, t1, qacc[ss]);
           ldm[ss] *= d;
         }
-        mbar_wait_d(&bar_empty[stage], ((gc / STAGES) & 1) ^ 1, xa.status, 1, xa.phase);
+        mbar_wait_d(&bar_empty[stage], empty_parity, xa.status, 1, phase_ptr(xa));
         uint8_t* dW = wdst0 + stage * wstride + rowoff;
         uint8_t* dU = udst0 + stage * ustride + rowoff;
         if (PROBE & 4) {   // keep the digits alive without storing them
@@ -705,6 +715,7 @@ dla_loglik_i8p_kernel(LoglikArgs args, I8Args xa, int num_quasars, int tiles_per
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar_rows[stage]);
+        if (++stage == STAGES) { stage = 0; empty_parity ^= 1u; }
         if ((c & 7) == 7) {
 #pragma unroll
           for (int ss = 0; ss < SPB; ++ss) {
@@ -725,7 +736,7 @@ dla_loglik_i8p_kernel(LoglikArgs args, I8Args xa, int num_quasars, int tiles_per
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_sq[it & 1]);
-      if (xa.phase && pr == 0 && lane == 0) atomicAdd(&xa.phase[7], 1ull);
+      if (GPDLA_I8P_PHASES && xa.phase && pr == 0 && lane == 0) atomicAdd(&xa.phase[7], 1ull);
       ++it;
     }
   } else {
@@ -741,11 +752,11 @@ dla_loglik_i8p_kernel(LoglikArgs args, I8Args xa, int num_quasars, int tiles_per
         const int q = tile_quasar(t);
         const QuasarMeta meta = args.meta[q];
         if (!tile_live(q, meta)) continue;
-        if (it > 0) mbar_wait_d(bar_tfree, (it - 1) & 1, xa.status, 13, xa.phase, 100);   // accumulators of the previous tile read out
+        if (it > 0) mbar_wait_d(bar_tfree, (it - 1) & 1, xa.status, 13, phase_ptr(xa), 100);   // accumulators of the previous tile read out
         for (int c = 0; c < meta.nchunks; ++c, ++gc) {
           const int stage = gc % STAGES, buf = gc & 1;
-          mbar_wait_d(&bar_full[stage], (gc / STAGES) & 1, xa.status, 2, xa.phase, 100);
-          mbar_wait_d(&bar_pfull[buf], (gc >> 1) & 1, xa.status, 3, xa.phase);
+          mbar_wait_d(&bar_full[stage], (gc / STAGES) & 1, xa.status, 2, phase_ptr(xa), 100);
+          mbar_wait_d(&bar_pfull[buf], (gc >> 1) & 1, xa.status, 3, phase_ptr(xa));
           asm volatile("tcgen05.fence::after_thread_sync;");
           const uint64_t da0 = da_stage0 + (uint64_t)(uint32_t)(stage * (Sh::A_TILE >> 4));
           const uint64_t db0 = db_buf0 + (uint64_t)(uint32_t)(buf * (Sh::B_BUF >> 4));
@@ -768,7 +779,7 @@ dla_loglik_i8p_kernel(LoglikArgs args, I8Args xa, int num_quasars, int tiles_per
         const uint8_t* bsrc = xa.bop + (int64_t)q * (args.NPIX / KC) * Sh::CHUNK_BYTES + Sh::b_offset(rank);
         for (int c = 0; c < meta.nchunks; ++c, ++gc) {
           const int buf = gc & 1;
-          if (gc >= 2) mbar_wait_d(&bar_pempty[buf], ((gc >> 1) - 1) & 1, xa.status, 4, xa.phase, 100);
+          if (gc >= 2) mbar_wait_d(&bar_pempty[buf], ((gc >> 1) - 1) & 1, xa.status, 4, phase_ptr(xa), 100);
           mbar_expect_tx(&bar_pfull[buf], b_bytes);
           tma_load_1d(Bt + buf * Sh::B_BUF, bsrc + (int64_t)c * Sh::CHUNK_BYTES, b_bytes, &bar_pfull[buf]);
         }
@@ -782,7 +793,7 @@ dla_loglik_i8p_kernel(LoglikArgs args, I8Args xa, int num_quasars, int tiles_per
         if (!tile_live(q, meta)) continue;
         for (int c = 0; c < meta.nchunks; ++c, ++gc) {
           const int stage = gc % STAGES;
-          mbar_wait_d(&bar_rows[stage], (gc / STAGES) & 1, xa.status, 5, xa.phase, 100);
+          mbar_wait_d(&bar_rows[stage], (gc / STAGES) & 1, xa.status, 5, phase_ptr(xa), 100);
           const uint32_t dst_off = smem_u32(At + stage * Sh::A_TILE) + rank * Sh::ROWBLOCK;
           const uint32_t other_rows = smem_u32(Sx + stage * Sh::ROWBLOCK);
           const uint32_t fullbar = smem_u32(&bar_full[stage]);

@@ -694,12 +694,12 @@ __device__ __forceinline__ void tau_samples(const RestTable& rt, int tab_mode, d
 // raw absorption exp(-N tau)   voigt.c:291.  All shared-memory loads come before the caller's first store: the
 // compiler cannot prove that the per-sample arrays and the raw rows do not alias, and a load stuck behind a store
 // would serialise the SPB exponentials.
-template <int SPB>
+template <int SPB, bool EXP_TABLE = (GPDLA_EXP_TABLE != 0)>
 __device__ __forceinline__ void raw_from_tau(const double (&tau)[SPB], const double* mynhi, double (&e)[SPB]) {
 #pragma unroll
   for (int ss = 0; ss < SPB; ++ss) e[ss] = -mynhi[ss] * tau[ss];
 #pragma unroll
-  for (int ss = 0; ss < SPB; ++ss) e[ss] = exp_nonpos(e[ss]);
+  for (int ss = 0; ss < SPB; ++ss) e[ss] = exp_nonpos<EXP_TABLE>(e[ss]);
 }
 
 // K_mid of a group of SPB consecutive tile rows (their table offsets in myK) and how the table serves them: 1 = one

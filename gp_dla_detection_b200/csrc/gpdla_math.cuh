@@ -70,14 +70,39 @@ __device__ __forceinline__ double tau_wing(int j, double u) {
   return c_lines.kwing[j] * u * fma(-t, b, a);
 }
 
-// exp(x) for x <= 0 (and small positive x), branch-free: Cody-Waite reduction, degree-11 polynomial
-// (tools/gen_voigt_tables.py), exponent assembled in integer registers.  The argument is clamped at -708.
+// exp(x) for x <= 0 (and small positive x), branch-free.  The argument is clamped at -708.
+//   GPDLA_EXP_TABLE (default): x = (256 n + j) ln2 / 256 + r, |r| <= ln2 / 512: exp(x) = 2^n T[j] (1 + q(r)) with the
+//   256-entry table T[j] = 2^(j/256) (correctly rounded, 2 KB, L1-resident) and q = r + r^2/2 + r^3/6 + r^4/24
+//   (truncation 3.8e-17 relative): 9 FP64 instructions instead of 15 -- FP64 issue is what bounds the producers.
+//   Otherwise: Cody-Waite reduction to |r| <= ln2 / 2 and a degree-11 polynomial (tools/gen_voigt_tables.py).
+// Both assemble the exponent in integer registers and agree with libm to ~1 ulp (tests/test_gpu_parity.py, 5e-15).
 __constant__ double c_exp_poly[12] = GPDLA_EXP_POLY;
+__device__ double g_exp2_tab[256];   // 2^(j/256), filled by upload_device_constants
+#ifndef GPDLA_EXP_TABLE
+#define GPDLA_EXP_TABLE 1
+#endif
+// TABLE = false selects the polynomial: the persistent INT8 kernel is bound by issue slots and dependency chains, not by
+// FP64 throughput, and measured 0.5 % (table in shared memory) to 2.5 % (table through L1) slower with the table, while
+// the FP64 DMMA kernels gain 1.6 % from it.
+template <bool TABLE = (GPDLA_EXP_TABLE != 0)>
 __device__ __forceinline__ double exp_nonpos(double x) {
   const double SHIFT = 6755399441055744.0;   // 1.5 * 2^52
   // x <= 0 (or tiny positive): "below -708" is an unsigned compare of the high word (integer pipe)
   const bool tiny = (unsigned)__double2hiint(x) > 0xC0862000u;   // x < -708 (hi word of -708.0 is 0xC0862000)
   const double xc = tiny ? -708.0 : x;
+  if (TABLE) {
+  double kd = fma(xc, 256.0 * 1.4426950408889634074, SHIFT);
+  const int k = __double2loint(kd);
+  kd -= SHIFT;
+  double r = fma(kd, -6.93147180369123816490e-01 / 256.0, xc);
+  r = fma(kd, -1.90821492927058770002e-10 / 256.0, r);
+  const double T = __ldg(&g_exp2_tab[k & 255]);
+  double a = fma(r, 1.0 / 24.0, 1.0 / 6.0);
+  a = fma(a, r, 0.5);
+  a = fma(a, r, 1.0);
+  const double p = fma(T, a * r, T);
+  return __hiloint2double(__double2hiint(p) + ((k >> 8) << 20), __double2loint(p));
+  }
   double kd = fma(xc, 1.4426950408889634074, SHIFT);
   const int k = __double2loint(kd);
   kd -= SHIFT;
@@ -202,9 +227,11 @@ __device__ __noinline__ double tau_sum_3_exact(double lambda, double m0, double 
 // a chunk ahead, and each sample evaluates the polynomial at its own s.  NaN coefficients mark the cells near a line
 // centre (and the two end cells, which catch clamped indices): the warp then evaluates directly.
 constexpr int RT_DEG_DEV = 8;
+constexpr int RT_CELL_STRIDE = 10;      // doubles per cell on the device: the 9 coefficients of a cell side by side, 16-byte
+                                        // aligned -- one address per lane and 128-bit loads with immediate offsets
 constexpr double RT_MAX_SPREAD = 1.0;   // = 2 (RT_HALF_WIDTH - 1/2): largest K_max - K_min one cell can serve
 struct RestTable {
-  const double* coef;   // [RT_DEG_DEV + 1][ncell]; nullptr = table disabled
+  const double* coef;   // [ncell][RT_CELL_STRIDE]; nullptr = table disabled
   int ncell;
   double inv_h;         // 1 / (pixel spacing in ln units)
   double lam_lo;        // rest wavelength of cell 0 (Angstrom)
@@ -227,9 +254,14 @@ __device__ __forceinline__ void rest_table_fetch(const RestTable& rt, double lh,
   int ci = __double2loint(um);                  // round-to-nearest-even integer of lh - K_mid
   rc.base = lh - (um - RT_MAGIC);               // exact
   ci = min(max(ci, 0), rt.ncell - 1);
-  const double* cp = rt.coef + ci;
+  static_assert(RT_DEG_DEV == 8 && RT_CELL_STRIDE == 10, "four 128-bit loads and one 64-bit load per cell");
+  const double2* cp = reinterpret_cast<const double2*>(rt.coef + (size_t)ci * RT_CELL_STRIDE);
 #pragma unroll
-  for (int p = 0; p <= RT_DEG_DEV; ++p) rc.cf[p] = __ldg(cp + (size_t)p * rt.ncell);
+  for (int p = 0; p < 4; ++p) {
+    const double2 c2 = __ldg(cp + p);
+    rc.cf[2 * p] = c2.x; rc.cf[2 * p + 1] = c2.y;
+  }
+  rc.cf[8] = __ldg(reinterpret_cast<const double*>(cp + 4));
 }
 // tau / N of one sample in the fetched cell; NaN (hi word >= 0x7ff00000) where the caller must evaluate directly
 __device__ __forceinline__ double rest_table_eval(const RestCell& rc, double K) {
