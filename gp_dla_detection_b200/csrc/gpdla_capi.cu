@@ -135,7 +135,13 @@ static void fill_i8_stage_index(short* tab) {
   }
 }
 
-constexpr int I8_K = 20;   // rank of the INT8 tensor-core Gram path
+constexpr int I8_K = 20;   // rank whose INT8 tensor-core Gram fits one cluster's TMEM (shared-memory Cholesky epilogue)
+constexpr int I8_K_EXT = 40;   // rank whose Gram columns take contract-only passes as well (i8::Shape::EXT)
+// (rank, digits) combinations of the INT8 path compiled into the library
+#define GPDLA_FOR_I8(k, digits, CALL)                                                    \
+  if ((k) == I8_K && (digits) == 5) { constexpr int K = I8_K, L = 5; (void)K; (void)L; CALL; }        \
+  else if ((k) == I8_K) { constexpr int K = I8_K, L = 6; (void)K; (void)L; CALL; }                   \
+  else if ((k) == I8_K_EXT) { constexpr int K = I8_K_EXT, L = 6; (void)K; (void)L; CALL; }
 constexpr int ORDER_GROUP = 0;   // 0: samples fully sorted by redshift (measured best: 63.5 ms per 296 quasars against 69.9 with
                                  // scattered groups of 4 and 64.7 with scattered groups of 32)
 
@@ -270,7 +276,9 @@ struct gpdla_ctx {
          *d_scratch = nullptr;
   int64_t* d_scratch_i = nullptr;
   // INT8 tensor-core Gram path (k = 20): digit operands and scales
-  int i8_batch = 0, i8_npix = 0;
+  int i8_batch = 0, i8_npix = 0, i8_k = 0;
+  int64_t i8_S = 0;
+  uint8_t* d_adig = nullptr;          // k = 40: stored W'' digit tiles (i8::Shape::EXT)
   double *d_pix2 = nullptr, *d_pix8 = nullptr, *d_colscale = nullptr, *d_colinv = nullptr;
   uint8_t* d_bop = nullptr;
   int* d_status = nullptr;
@@ -301,8 +309,11 @@ struct gpdla_ctx {
 static int i8_digits(const gpdla_ctx* c) {
   int d = c->params.gram_digits;
   if (d == 0) d = 6;
+  if (c->k == I8_K_EXT && (d == 5 || d == 6)) return 6;   // k = 40: six digits only
   return (c->k == I8_K && (d == 5 || d == 6)) ? d : 0;
 }
+// rows of the global accumulator staging per quasar: the S samples + the null-model slot, in whole 128-sample tiles
+static int64_t gram_rows(const gpdla_ctx* c) { return ((int64_t)c->S + 1 + i8::TM - 1) / i8::TM * i8::TM; }
 static bool use_i8(const gpdla_ctx* c) { return i8_digits(c) > 0; }
 
 static void free_workspace(gpdla_ctx* c) {
@@ -329,7 +340,7 @@ static int ensure_workspace(gpdla_ctx* c, int batch, int npix) {
   CUDA_TRY(cudaMalloc(&c->d_scratch, B * 16 * sizeof(double)), c->err);
   CUDA_TRY(cudaMalloc(&c->d_scratch_i, B * sizeof(int64_t)), c->err);
   if (rank_splits(c->k) > 1) {
-    const size_t rows = ((size_t)c->S + 1 + 63) / 64 * 64;
+    const size_t rows = (size_t)gram_rows(c);
     CUDA_TRY(cudaMalloc(&c->d_gram, B * rows * rank_ncol(c->k) * sizeof(double)), c->err);
     CUDA_TRY(cudaMalloc(&c->d_qld, B * rows * 2 * sizeof(double)), c->err);
   }
@@ -372,7 +383,7 @@ static int launch_loglik(gpdla_ctx* c, LoglikArgs la, int nq, cudaStream_t st, b
   using WCfg = WsConfig<K, NSPLIT>;
   auto kern = dla_loglik_ws_kernel<K, NL, MODE, NSPLIT>;
   if (la.only_list) {
-    if constexpr (K == I8_K) kern = dla_loglik_ws_list_kernel<K, NL, MODE, NSPLIT>;
+    if constexpr (K == I8_K || K == I8_K_EXT) kern = dla_loglik_ws_list_kernel<K, NL, MODE, NSPLIT>;
     else { c->err = "FP64 fallback list: rank without an INT8 path"; return GPDLA_ERR_UNSUPPORTED; }
   }
   const size_t smem = WCfg::smem_bytes(la.num_lines);
@@ -381,7 +392,7 @@ static int launch_loglik(gpdla_ctx* c, LoglikArgs la, int nq, cudaStream_t st, b
   if (rc) return rc;
   const unsigned tiles = (unsigned)((la.S + (la.log_likelihoods_no_dla ? 1 : 0) + TS - 1) / TS);
   dim3 grid(tiles, la.only_list ? (unsigned)std::min(nq, FALLBACK_SLOTS) : (unsigned)nq, NSPLIT);
-  la.gram = c->d_gram; la.qld = c->d_qld; la.gram_rows = ((int64_t)c->S + 1 + 63) / 64 * 64;
+  la.gram = c->d_gram; la.qld = c->d_qld; la.gram_rows = gram_rows(c);
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (c->profiling && timed) {
     CUDA_TRY(cudaEventCreate(&e0), c->err);
@@ -391,7 +402,7 @@ static int launch_loglik(gpdla_ctx* c, LoglikArgs la, int nq, cudaStream_t st, b
   kern<<<grid, WS_THREADS, smem, st>>>(la);
   c->launches++;
   CUDA_TRY(cudaGetLastError(), c->err);
-  if (NSPLIT > 1) {
+  if (NSPLIT > 1 && !la.only_list) {   // a list is the INT8 path's fallback: its Cholesky launch covers the batch
     CholArgs ca;
     ca.meta = la.meta; ca.gram = c->d_gram; ca.qld = c->d_qld; ca.gram_rows = la.gram_rows; ca.S = la.S;
     ca.sample_log_likelihoods = la.sample_log_likelihoods; ca.sll_stride = la.sll_stride;
@@ -399,7 +410,7 @@ static int launch_loglik(gpdla_ctx* c, LoglikArgs la, int nq, cudaStream_t st, b
     ca.q_offset = la.q_offset;
     rc = configure_smem(c->device, cholesky_kernel<K>, cholesky_smem_bytes<K>(), c->err);
     if (rc) return rc;
-    cholesky_kernel<K><<<dim3(tiles * TS / CHOL_SAMPLES, (unsigned)nq), CHOL_SAMPLES * 4,
+    cholesky_kernel<K><<<dim3(tiles * TS / CHOL_SAMPLES, (unsigned)nq), CHOL_THREADS,
                          cholesky_smem_bytes<K>(), st>>>(ca);
     c->launches++;
     CUDA_TRY(cudaGetLastError(), c->err);
@@ -412,28 +423,33 @@ static int launch_loglik(gpdla_ctx* c, LoglikArgs la, int nq, cudaStream_t st, b
 }
 
 static int ensure_i8_workspace(gpdla_ctx* c, int batch, int npix) {
-  if (c->i8_batch >= batch && c->i8_npix == npix) return GPDLA_OK;
+  if (c->i8_batch >= batch && c->i8_npix == npix && c->i8_k == c->k && c->i8_S == c->S) return GPDLA_OK;
   cudaFree(c->d_pix2); cudaFree(c->d_pix8); cudaFree(c->d_colscale); cudaFree(c->d_colinv); cudaFree(c->d_bop); cudaFree(c->d_f64flag);
-  c->d_pix2 = c->d_pix8 = c->d_colscale = c->d_colinv = nullptr; c->d_bop = nullptr; c->d_f64flag = nullptr; c->i8_batch = 0;
+  cudaFree(c->d_adig);
+  c->d_pix2 = c->d_pix8 = c->d_colscale = c->d_colinv = nullptr; c->d_bop = c->d_adig = nullptr; c->d_f64flag = nullptr; c->i8_batch = 0;
   const size_t B = batch;
-  using Sh = i8::Shape<I8_K, 6>;    // the 6-digit layout is the larger one
+  size_t ncoltab = 0, chunk_bytes = 0, a_tile = 0;   // the 6-digit layout is the larger one
+  GPDLA_FOR_I8(c->k, 6, (ncoltab = i8::Shape<K, L>::NCOLTAB, chunk_bytes = i8::Shape<K, L>::CHUNK_BYTES,
+                         a_tile = i8::Shape<K, L>::EXT ? i8::Shape<K, L>::A_TILE : 0));
   CUDA_TRY(cudaMalloc(&c->d_pix2, B * npix * 2 * sizeof(double)), c->err);
   CUDA_TRY(cudaMalloc(&c->d_pix8, B * npix * 8 * sizeof(double)), c->err);
-  CUDA_TRY(cudaMalloc(&c->d_colscale, B * Sh::NCOLTAB * sizeof(double)), c->err);
-  CUDA_TRY(cudaMalloc(&c->d_colinv, B * Sh::NCOLTAB * sizeof(double)), c->err);
-  CUDA_TRY(cudaMalloc(&c->d_bop, B * (npix / KC) * Sh::CHUNK_BYTES), c->err);
+  CUDA_TRY(cudaMalloc(&c->d_colscale, B * ncoltab * sizeof(double)), c->err);
+  CUDA_TRY(cudaMalloc(&c->d_colinv, B * ncoltab * sizeof(double)), c->err);
+  CUDA_TRY(cudaMalloc(&c->d_bop, B * (npix / KC) * chunk_bytes), c->err);
+  if (a_tile)   // W'' digit tiles of the whole batch for the contract-only passes
+    CUDA_TRY(cudaMalloc(&c->d_adig, B * (size_t)(gram_rows(c) / i8::TM) * (npix / KC) * a_tile), c->err);
   CUDA_TRY(cudaMalloc(&c->d_f64flag, (2 * B + 2) * sizeof(int32_t)), c->err);
   if (!c->d_status) {
     CUDA_TRY(cudaMalloc(&c->d_status, sizeof(int)), c->err);
     CUDA_TRY(cudaMemset(c->d_status, 0, sizeof(int)), c->err);
   }
-  c->i8_batch = batch; c->i8_npix = npix;
+  c->i8_batch = batch; c->i8_npix = npix; c->i8_k = c->k; c->i8_S = c->S;
   return GPDLA_OK;
 }
 
 static i8::I8Args i8_args(gpdla_ctx* c) {
   i8::I8Args xa;
-  xa.pix2 = c->d_pix2; xa.pix8 = c->d_pix8; xa.bop = c->d_bop; xa.colscale = c->d_colscale; xa.colinv = c->d_colinv; xa.status = c->d_status;
+  xa.pix2 = c->d_pix2; xa.pix8 = c->d_pix8; xa.adig = c->d_adig; xa.bop = c->d_bop; xa.colscale = c->d_colscale; xa.colinv = c->d_colinv; xa.status = c->d_status;
   xa.f64flag = c->d_f64flag; xa.f64list = c->d_f64flag + c->i8_batch;
   xa.phase = nullptr;
   if (GPDLA_I8P_PHASES && getenv("GPDLA_I8_PHASES")) {   // diagnostics only: mean barrier waits per tile, printed before the next launch
@@ -449,13 +465,13 @@ static i8::I8Args i8_args(gpdla_ctx* c) {
 }
 
 // K0c + K0d: scales and digit planes of the B operand for a prepared batch
-template <int L>
+template <int K, int L>
 static int build_i8_operands_L(gpdla_ctx* c, int nq, int npix, cudaStream_t st) {
   i8::I8Args xa = i8_args(c);
-  i8::i8_scales_kernel<I8_K, L><<<nq, NTHREADS, 0, st>>>(c->d_meta, c->d_pix, c->d_Mq, c->d_lam, c->d_lamh, xa, npix);
+  i8::i8_scales_kernel<K, L><<<nq, NTHREADS, 0, st>>>(c->d_meta, c->d_pix, c->d_Mq, c->d_lam, c->d_lamh, xa, npix);
   c->launches++;
   CUDA_TRY(cudaGetLastError(), c->err);
-  i8::i8_build_operand_kernel<I8_K, L><<<dim3(npix / KC, nq), NTHREADS, 0, st>>>(c->d_meta, c->d_Mq, xa, npix);
+  i8::i8_build_operand_kernel<K, L><<<dim3(npix / KC, nq), NTHREADS, 0, st>>>(c->d_meta, c->d_Mq, xa, npix);
   c->launches++;
   CUDA_TRY(cudaGetLastError(), c->err);
   return GPDLA_OK;
@@ -474,7 +490,8 @@ static int build_i8_operands(gpdla_ctx* c, int nq, int npix, cudaStream_t st) {
   int rc = ensure_i8_workspace(c, c->ws_batch, npix);
   if (rc) return rc;
   CUDA_TRY(cudaMemsetAsync(c->d_f64flag, 0, (2 * (size_t)c->i8_batch + 2) * sizeof(int32_t), st), c->err);
-  rc = i8_digits(c) == 5 ? build_i8_operands_L<5>(c, nq, npix, st) : build_i8_operands_L<6>(c, nq, npix, st);
+  rc = GPDLA_ERR_UNSUPPORTED;
+  GPDLA_FOR_I8(c->k, i8_digits(c), (rc = build_i8_operands_L<K, L>(c, nq, npix, st)));
   if (rc) return rc;
   // FP64 operand of the quasars the scales kernel has just flagged (normally none: a handful of idle CTAs)
   return build_f64_operand(c, 0, nq, npix, c->d_f64flag + c->i8_batch, st);
@@ -494,8 +511,10 @@ static int max_resident_clusters(Kern kern, size_t smem, int threads) {
   return n;
 }
 
-template <int L, int NL, int MODE>
-static int launch_loglik_i8(gpdla_ctx* c, const LoglikArgs& la, int nq, cudaStream_t st) {
+template <int K, int L, int NL, int MODE>
+static int launch_loglik_i8(gpdla_ctx* c, LoglikArgs la, int nq, cudaStream_t st) {
+  using Sh = i8::Shape<K, L>;
+  la.gram = c->d_gram; la.qld = c->d_qld; la.gram_rows = gram_rows(c);
   const int dev = c->device;
   const unsigned clusters = (unsigned)((la.S + (la.log_likelihoods_no_dla ? 1 : 0) + i8::TM - 1) / i8::TM);
   cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -504,8 +523,8 @@ static int launch_loglik_i8(gpdla_ctx* c, const LoglikArgs& la, int nq, cudaStre
     CUDA_TRY(cudaEventCreate(&e1), c->err);
     CUDA_TRY(cudaEventRecord(e0, st), c->err);
   }
-  auto kern = i8::dla_loglik_i8p_kernel<I8_K, L, NL, MODE>;
-  const size_t smem = i8::PShape<I8_K, L>::smem_bytes(la.num_lines);
+  auto kern = i8::dla_loglik_i8p_kernel<K, L, NL, MODE>;
+  const size_t smem = i8::PShape<K, L>::smem_bytes(la.num_lines);
   int rc = configure_smem(dev, kern, smem, c->err);
   if (rc) return rc;
   int resident;
@@ -525,6 +544,25 @@ static int launch_loglik_i8(gpdla_ctx* c, const LoglikArgs& la, int nq, cudaStre
   kern<<<dim3(ncl * i8::CLUSTER, 1, 1), i8::P_THREADS, smem, st>>>(la, i8_args(c), nq, (int)clusters);
   c->launches++;
   CUDA_TRY(cudaGetLastError(), c->err);
+  if constexpr (Sh::EXT) {
+    // the column blocks beyond the producing cluster's three: contract-only passes over the stored W'' digit tiles
+    auto ckern = i8::gram_contract_i8_kernel<K, L>;
+    const size_t csmem = i8::CShape<K, L>::SMEM;
+    rc = configure_smem(dev, ckern, csmem, c->err);
+    if (rc) return rc;
+    int cres;
+    {
+      std::lock_guard<std::mutex> lock(g_dev[dev].mu);
+      int& n = g_dev[dev].clusters[(const void*)ckern];
+      if (n == 0) n = max_resident_clusters(ckern, csmem, i8::C_THREADS);
+      if (n <= 0) n = 32;
+      cres = n;
+    }
+    const unsigned ccl = (unsigned)std::min<long long>(cres, tiles * Sh::CPASSES);
+    ckern<<<dim3(ccl * i8::CLUSTER, 1, 1), i8::C_THREADS, csmem, st>>>(la, i8_args(c), nq, (int)clusters);
+    c->launches++;
+    CUDA_TRY(cudaGetLastError(), c->err);
+  }
   if (c->profiling) {
     CUDA_TRY(cudaEventRecord(e1, st), c->err);
     c->prof_events.emplace_back(e0, e1);
@@ -564,14 +602,28 @@ static int launch_mode(gpdla_ctx* c, const LoglikArgs& la, int nq, cudaStream_t 
 // process exactly those -- FALLBACK_SLOTS idle CTA columns when there are none, no host round trip.
 template <int MODE>
 static int launch_mode_i8(gpdla_ctx* c, const LoglikArgs& la, int nq, cudaStream_t st) {
-  const bool l5 = i8_digits(c) == 5;
-  int rc;
-  if (c->params.num_lines == 3) rc = l5 ? launch_loglik_i8<5, 3, MODE>(c, la, nq, st) : launch_loglik_i8<6, 3, MODE>(c, la, nq, st);
-  else rc = l5 ? launch_loglik_i8<5, 0, MODE>(c, la, nq, st) : launch_loglik_i8<6, 0, MODE>(c, la, nq, st);
+  int rc = GPDLA_ERR_UNSUPPORTED;
+  if (c->params.num_lines == 3) { GPDLA_FOR_I8(c->k, i8_digits(c), (rc = launch_loglik_i8<K, L, 3, MODE>(c, la, nq, st))); }
+  else { GPDLA_FOR_I8(c->k, i8_digits(c), (rc = launch_loglik_i8<K, L, 0, MODE>(c, la, nq, st))); }
   if (rc) return rc;
   LoglikArgs lf = la;
   lf.only_list = c->d_f64flag + c->i8_batch;
-  return launch_mode<MODE>(c, lf, nq, st, false);
+  rc = launch_mode<MODE>(c, lf, nq, st, false);
+  if (rc || c->k != I8_K_EXT) return rc;
+  // k = 40: every path above left its accumulators in the global staging rows; one Cholesky launch for the batch
+  CholArgs ca;
+  ca.meta = la.meta; ca.gram = c->d_gram; ca.qld = c->d_qld; ca.gram_rows = gram_rows(c); ca.S = la.S;
+  ca.sample_log_likelihoods = la.sample_log_likelihoods; ca.sll_stride = la.sll_stride;
+  ca.log_likelihoods_no_dla = la.log_likelihoods_no_dla; ca.active = la.active; ca.order = la.order;
+  ca.q_offset = la.q_offset;
+  rc = configure_smem(c->device, cholesky_kernel<I8_K_EXT>, cholesky_smem_bytes<I8_K_EXT>(), c->err);
+  if (rc) return rc;
+  const int64_t rows = la.S + (la.log_likelihoods_no_dla ? 1 : 0);
+  cholesky_kernel<I8_K_EXT><<<dim3((unsigned)((rows + CHOL_SAMPLES - 1) / CHOL_SAMPLES), (unsigned)nq), CHOL_THREADS,
+                              cholesky_smem_bytes<I8_K_EXT>(), st>>>(ca);
+  c->launches++;
+  CUDA_TRY(cudaGetLastError(), c->err);
+  return GPDLA_OK;
 }
 
 // both stages of the training objective: persistent CTAs with private partial gradients, then their sum
@@ -781,7 +833,7 @@ void gpdla_destroy(gpdla_ctx* c) {
   cudaFree(c->d_rest); cudaFree(c->d_mu); cudaFree(c->d_M); cudaFree(c->d_log_omega);
   cudaFree(c->d_offset); cudaFree(c->d_log_nhi); cudaFree(c->d_nhi); cudaFree(c->d_order); cudaFree(c->d_rt);
   cudaFree(c->d_prior_z); cudaFree(c->d_prior_dla); cudaFree(c->d_stage);
-  cudaFree(c->d_pix2); cudaFree(c->d_pix8); cudaFree(c->d_colscale); cudaFree(c->d_colinv); cudaFree(c->d_bop); cudaFree(c->d_status);
+  cudaFree(c->d_pix2); cudaFree(c->d_pix8); cudaFree(c->d_colscale); cudaFree(c->d_colinv); cudaFree(c->d_bop); cudaFree(c->d_adig); cudaFree(c->d_status);
   cudaFree(c->d_f64flag); cudaFree(c->d_phase);
   cudaFree(c->d_lls_nhi); cudaFree(c->d_uniforms); cudaFree(c->d_acache); cudaFree(c->d_msll); cudaFree(c->d_mlls);
   cudaFree(c->d_cum); cudaFree(c->d_mscal); cudaFree(c->d_partners); cudaFree(c->d_active);

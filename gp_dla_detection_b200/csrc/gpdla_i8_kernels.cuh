@@ -56,12 +56,22 @@ constexpr int PROBE = GPDLA_I8P_PROBE;
 #define GPDLA_I8P_PHASES 0
 #endif
 
+// Gram columns beyond what one cluster's TMEM holds (k = 40: 820 pair columns): the W'' columns are cut into WBLOCKS
+// blocks of WCOLS columns (MMA N = NW = 80 each).  The producing kernel contracts blocks 0..2 (CTAs 0..2) and the U''
+// columns (CTA 3) and, when there are more blocks (EXT), stores its W'' digit tiles; gram_contract_i8_kernel then
+// contracts the stored tiles with blocks 3.. -- four per cluster pass, no FP64 work -- and the accumulators of all
+// blocks leave through the global staging rows of the column-split FP64 path (LoglikArgs::gram) to cholesky_kernel.
 template <int K, int L>
 struct Shape {
   using G = GramShape<K>;
-  static constexpr int WCOLS = (G::NPAIR + WCTAS - 1) / WCTAS;    // useful Gram columns per W CTA (70)
-  static constexpr int NW = (WCOLS + 15) / 16 * 16;               // MMA N of a W CTA (80)
-  static constexpr int NU = (K + 15) / 16 * 16;                   // MMA N of the U CTA (32)
+  static constexpr int WBLOCKS = (G::NPAIR <= WCTAS * 80) ? WCTAS : WCTAS + CLUSTER * ((G::NPAIR - WCTAS * 80 + CLUSTER * 80 - 1) / (CLUSTER * 80));
+  static constexpr bool EXT = WBLOCKS > WCTAS;
+  static constexpr int CPASSES = (WBLOCKS - WCTAS) / CLUSTER;     // cluster passes of the contract-only kernel
+  static constexpr int NSLOT = WBLOCKS + 1;                       // column blocks: W'' blocks, then the U'' block
+  static constexpr int USLOT = WBLOCKS;
+  static constexpr int WCOLS = (G::NPAIR + WBLOCKS - 1) / WBLOCKS;   // useful Gram columns per W block (70; k = 40: 75)
+  static constexpr int NW = (WCOLS + 15) / 16 * 16;               // MMA N of a W block (80)
+  static constexpr int NU = (K + 15) / 16 * 16;                   // MMA N of the U block (32; k = 40: 48)
   static constexpr int NMAX = NW > NU ? NW : NU;
   static constexpr int F = 8 * L - 1;                             // fractional bits
   // A tile (128 samples x 32 pixels x L digits), MN-major (samples contiguous), no swizzle: a 16-byte granule holds one
@@ -75,16 +85,24 @@ struct Shape {
   static constexpr int ROWBLOCK = (TS / 16) * SBO_A;              // one CTA's 32 rows, all digit planes: contiguous
   static constexpr int A_TILE = (TM / 16) * SBO_A;
   static constexpr int BW_PLANE = NW * KC, BU_PLANE = NU * KC;    // bytes of one digit plane of the B operand
+  static constexpr int L_BW = L * BW_PLANE;                       // one W block's B operand of a chunk
   static constexpr int B_MAX = L * (BW_PLANE > BU_PLANE ? BW_PLANE : BU_PLANE);
-  static constexpr int CHUNK_BYTES = L * (WCTAS * BW_PLANE + BU_PLANE);   // all four CTAs' B operand, one chunk
+  static constexpr int CHUNK_BYTES = L * (WBLOCKS * BW_PLANE + BU_PLANE);   // every column block's B operand, one chunk
   static constexpr int B_BUF = B_MAX;
-  static constexpr int NCOLTAB = CLUSTER * NMAX;                  // per-quasar column table [rank][NMAX]
+  static constexpr int NCOLTAB = NSLOT * NMAX;                    // per-quasar column table [slot][NMAX]
   static constexpr int CSTR = TS + 4;
   static constexpr int NENT = (K + 1) * (K + 2) / 2;
-  static_assert(L * NW <= TMEM_COLS, "diagonal accumulators must fit in TMEM");
+  static_assert(L * NW <= TMEM_COLS && L * NU <= TMEM_COLS, "diagonal accumulators must fit in TMEM");
+  static_assert(WBLOCKS * WCOLS >= G::NPAIR && NW <= 80, "column blocks must cover the pair columns");
   static_assert(L >= 2 && L <= 7, "digit count");
-  __host__ __device__ static constexpr int b_offset(int rank) { return rank * L * BW_PLANE; }
-  __host__ __device__ static constexpr int b_bytes(int rank) { return L * (rank < WCTAS ? BW_PLANE : BU_PLANE); }
+  __host__ __device__ static constexpr int b_offset(int slot) { return slot * L * BW_PLANE; }
+  __host__ __device__ static constexpr int b_bytes(int slot) { return L * (slot < WBLOCKS ? BW_PLANE : BU_PLANE); }
+  // column block of a CTA of the producing kernel
+  __host__ __device__ static constexpr int slot_of_rank(int rank) { return rank < WCTAS ? rank : USLOT; }
+  // Gram column (GramShape order: pair columns, then the projection at WT * 8) of accumulator column n of a block; -1 = padding
+  __host__ __device__ static constexpr int gram_column(int slot, int n) {
+    return slot < WBLOCKS ? ((n < WCOLS && slot * WCOLS + n < G::NPAIR) ? slot * WCOLS + n : -1) : (n < K ? G::WT * 8 + n : -1);
+  }
   __host__ __device__ static constexpr uint64_t digit_bias() {
     uint64_t b = 0;
     for (int i = 0; i < L; ++i) b |= (uint64_t)0x80 << (8 * i);
@@ -99,7 +117,7 @@ struct Shape {
   static constexpr size_t OFF_SX = OFF_A + (size_t)STAGES * A_TILE;
   static constexpr size_t OFF_B = OFF_SX + (size_t)STAGES * ROWBLOCK;
   static constexpr size_t OFF_CS = OFF_B + 2ull * B_BUF;
-  static constexpr size_t OFF_RAW = OFF_CS + (size_t)NENT * CSTR * 8;
+  static constexpr size_t OFF_RAW = OFF_CS + (EXT ? 0 : (size_t)NENT * CSTR * 8);   // EXT: no staging triangle in shared memory
   static constexpr size_t OFF_MISC = OFF_RAW + (size_t)TS * RAWS * 8;
 };
 
@@ -117,6 +135,7 @@ struct I8Args {
   int32_t* f64flag;        // [Q] set by i8_scales_kernel: 1 = a used pixel has zero noise variance, the fixed-point bound
                            // of U'' does not exist -> this quasar is left to the FP64 kernels (skipped here)
   int32_t* f64list;        // {count, q_0, q_1, ...}: the same quasars as a list (LoglikArgs::only_list of the fallback)
+  uint8_t* adig;           // EXT ranks: [Q x tiles x NPIX/KC x A_TILE] W'' digit tiles written by the producing kernel
   unsigned long long* phase;   // nullable: [24] summed wait cycles per barrier (GPDLA_I8_PHASES diagnostics)
 };
 
@@ -188,6 +207,17 @@ __device__ __forceinline__ void mma_commit_multicast(uint64_t* bar, uint16_t mas
                : "memory");
 }
 
+// shared::cta -> global bulk copy (bulk async-group completion)
+__device__ __forceinline__ void bulk_store_global(void* dst, uint32_t src_cta, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_cta), "r"(bytes) : "memory");
+}
+// global -> the same shared-memory offset of every CTA in `mask`, completion (bytes) on each destination's mbarrier
+__device__ __forceinline__ void tma_load_1d_multicast(uint32_t dst_cta, const void* src, uint32_t bytes, uint32_t bar_cta, uint16_t mask) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(dst_cta),
+               "l"(src), "r"(bytes), "r"(bar_cta), "h"(mask)
+               : "memory");
+}
+
 // The L (L + 1) / 2 slice-pair products of one chunk.  Digit plane i of A pairs with the B planes j = L-1-i .. L-1,
 // which are consecutive in shared memory, into the diagonals t = i + j - (L-1) = 0 .. i, which are consecutive in
 // TMEM: up to 256 / n accumulator blocks are therefore covered by ONE tcgen05.mma whose N spans several planes.
@@ -249,16 +279,17 @@ __global__ void __launch_bounds__(NTHREADS) i8_scales_kernel(const QuasarMeta* _
   const double* mq = Mq + (int64_t)q * NPIX * K;
   __shared__ double sM[KC][K + 1];
   __shared__ double sr[KC][2];
-  static_assert(Sh::NCOLTAB <= 2 * NTHREADS, "column table entries per thread");
-  int cp[2] = {-1, -1}, cq[2] = {0, 0}, crank[2] = {0, 0};
-  double mx2[2] = {0.0, 0.0};
+  constexpr int EPT = (Sh::NCOLTAB + NTHREADS - 1) / NTHREADS;   // column table entries per thread
+  int cp[EPT], cq[EPT], crank[EPT];
+  double mx2[EPT];
 #pragma unroll
-  for (int m = 0; m < 2; ++m) {
+  for (int m = 0; m < EPT; ++m) {
+    cp[m] = -1; cq[m] = 0; crank[m] = 0; mx2[m] = 0.0;
     const int idx = tid + m * NTHREADS;
     if (idx >= Sh::NCOLTAB) continue;
-    const int rank = idx / Sh::NMAX, n = idx % Sh::NMAX;
+    const int rank = idx / Sh::NMAX, n = idx % Sh::NMAX;   // rank = column block: W'' blocks, then the U'' block
     crank[m] = rank;
-    if (rank < WCTAS) {
+    if (rank < Sh::WBLOCKS) {
       const int c = rank * Sh::WCOLS + n;
       if (n < Sh::WCOLS && c < G::NPAIR) {
         int p = 0;
@@ -277,10 +308,10 @@ __global__ void __launch_bounds__(NTHREADS) i8_scales_kernel(const QuasarMeta* _
     }
     __syncthreads();
 #pragma unroll
-    for (int m = 0; m < 2; ++m) {
+    for (int m = 0; m < EPT; ++m) {
       if (cp[m] < 0) continue;
       for (int r = 0; r < KC; ++r) {
-        const double x = (crank[m] < WCTAS) ? __dmul_rn(__dmul_rn(sM[r][cp[m]], sM[r][cq[m]]), sr[r][0])
+        const double x = (crank[m] < Sh::WBLOCKS) ? __dmul_rn(__dmul_rn(sM[r][cp[m]], sM[r][cq[m]]), sr[r][0])
                                             : __dmul_rn(sM[r][cp[m]], sr[r][1]);
         mx2[m] = fmax(mx2[m], fabs(x));
       }
@@ -288,7 +319,7 @@ __global__ void __launch_bounds__(NTHREADS) i8_scales_kernel(const QuasarMeta* _
     __syncthreads();
   }
 #pragma unroll
-  for (int m = 0; m < 2; ++m) {
+  for (int m = 0; m < EPT; ++m) {
     const int idx = tid + m * NTHREADS;
     if (idx >= Sh::NCOLTAB) continue;
     const double mx = mx2[m];
@@ -303,7 +334,7 @@ __global__ void __launch_bounds__(NTHREADS) i8_scales_kernel(const QuasarMeta* _
   }
 }
 
-// K0d: digit planes of P'' and M'' in the tcgen05 K-major core-matrix layout, [Q][chunk][rank][digit][N x 32 B].
+// K0d: digit planes of P'' and M'' in the tcgen05 K-major core-matrix layout, [Q][chunk][column block][digit][N x 32 B].
 template <int K, int L>
 __global__ void __launch_bounds__(NTHREADS) i8_build_operand_kernel(const QuasarMeta* __restrict__ meta,
                                                                     const double* __restrict__ Mq, I8Args xa, int NPIX) {
@@ -322,14 +353,14 @@ __global__ void __launch_bounds__(NTHREADS) i8_build_operand_kernel(const Quasar
   __syncthreads();
   uint8_t* dst = xa.bop + ((int64_t)q * (NPIX / KC) + chunk) * Sh::CHUNK_BYTES;
   const double* cinv = xa.colinv + (int64_t)q * Sh::NCOLTAB;
-  constexpr int ROWS = WCTAS * Sh::NW + Sh::NU;
+  constexpr int ROWS = Sh::WBLOCKS * Sh::NW + Sh::NU;
   for (int t = threadIdx.x; t < ROWS * KC; t += NTHREADS) {
     const int k = t % KC, row = t / KC;
-    const int rank = row < WCTAS * Sh::NW ? row / Sh::NW : WCTAS;
+    const int rank = row < Sh::WBLOCKS * Sh::NW ? row / Sh::NW : Sh::WBLOCKS;   // column block
     const int n = row - rank * Sh::NW;
-    const int N = rank < WCTAS ? Sh::NW : Sh::NU;
+    const int N = rank < Sh::WBLOCKS ? Sh::NW : Sh::NU;
     double x = 0.0;
-    if (rank < WCTAS) {
+    if (rank < Sh::WBLOCKS) {
       const int c = rank * Sh::WCOLS + n;
       if (n < Sh::WCOLS && c < G::NPAIR) {
         int p = 0;
@@ -410,6 +441,165 @@ __device__ __forceinline__ void store_digit_planes(uint8_t* dst, const uint64_t 
   }
 }
 
+// One warp's quarter of the TMEM accumulators (32 rows = lanes, the L diagonals of N columns each) recombined in FP64
+// and written to the global staging rows: `grow` = this lane's row, columns in GramShape order.
+template <class Sh, int L>
+__device__ __forceinline__ void drain_to_gram(uint32_t taddr0, int N, int slot, const double* cs, double* grow, int c_begin = 0,
+                                              int c_end = 1 << 30) {
+  for (int c0 = c_begin; c0 < min(N, c_end); c0 += 8) {
+    uint32_t v[L][8];
+#pragma unroll
+    for (int tt = 0; tt < L; ++tt) {
+      asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                   : "=r"(v[tt][0]), "=r"(v[tt][1]), "=r"(v[tt][2]), "=r"(v[tt][3]), "=r"(v[tt][4]), "=r"(v[tt][5]),
+                     "=r"(v[tt][6]), "=r"(v[tt][7])
+                   : "r"(taddr0 + (uint32_t)(tt * N + c0)));
+    }
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) {
+      const int col = Sh::gram_column(slot, c0 + jj);
+      if (col >= 0) {
+        double acc = (double)(int32_t)v[L - 1][jj];
+#pragma unroll
+        for (int tt = L - 2; tt >= 0; --tt) acc = fma(acc, 256.0, (double)(int32_t)v[tt][jj]);
+        grow[col] = acc * cs[c0 + jj];
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Contract-only passes of the EXT ranks (k = 40).  The W'' digit tiles the producing kernel stored are contracted with
+// the column blocks it did not cover: a cluster of 4 CTAs takes one (cluster pass, quasar, 128-sample tile) at a time, CTA r
+// owning block WCTAS + 4 (pass) + r.  Per 32-pixel chunk every CTA fetches a quarter of the A tile and multicasts it to
+// the four CTAs (one read of the tile from L2 / HBM per cluster) and fetches its own B block; no FP64 work, no producers:
+// the tensor pipe is the only busy unit.  Warp 0: MMA issuer, warp 1: loader, warps 4..11: epilogue (two warps per TMEM
+// lane quarter, half of the columns each: the tensor pipe idles while the single accumulator buffer is drained).
+constexpr int C_THREADS = 384;
+constexpr int C_EPI_WARPS = 8;
+constexpr int C_STAGES = 4;
+template <int K, int L>
+struct CShape {
+  using Sh = Shape<K, L>;
+  static constexpr size_t OFF_A = 0;
+  static constexpr size_t OFF_B = OFF_A + (size_t)C_STAGES * Sh::A_TILE;
+  static constexpr size_t OFF_BAR = OFF_B + (size_t)C_STAGES * Sh::L_BW;
+  static constexpr size_t SMEM = OFF_BAR + 32 * 8 + 16;
+};
+
+template <int K, int L>
+__global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(C_THREADS, 1)
+gram_contract_i8_kernel(LoglikArgs args, I8Args xa, int num_quasars, int tiles_per_quasar) {
+  using Sh = Shape<K, L>;
+  using CS = CShape<K, L>;
+  static_assert(Sh::EXT, "ranks whose pair columns fit one cluster have no contract-only passes");
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cluster_id = blockIdx.x / CLUSTER, num_clusters = gridDim.x / CLUSTER;
+  const int tiles_per_pass = num_quasars * tiles_per_quasar;
+  const int num_tiles = tiles_per_pass * Sh::CPASSES;
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  uint8_t* At = smem_raw + CS::OFF_A;
+  uint8_t* Bt = smem_raw + CS::OFF_B;
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem_raw + CS::OFF_BAR);   // [C_STAGES]
+  uint64_t* bar_empty = bar_full + C_STAGES;                                   // [C_STAGES]
+  uint64_t* bar_acc = bar_empty + C_STAGES;
+  uint64_t* bar_tfree = bar_acc + 1;
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_full + 24);
+  if (tid == 0) {
+    for (int i = 0; i < C_STAGES; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], CLUSTER); }
+    mbar_init(bar_acc, 1); mbar_init(bar_tfree, C_EPI_WARPS);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "n"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;");
+  const uint32_t tmem_base = *s_tmem;
+  cluster_sync_all();
+
+  auto tile_live = [&](int q, const QuasarMeta& m) {
+    return m.nchunks > 0 && !(args.active != nullptr && args.active[q] == 0) && xa.f64flag[q] == 0;
+  };
+  constexpr uint32_t b_bytes = (uint32_t)Sh::L_BW;
+  if (warp == 0 && lane == 0) {
+    // ---- MMA issuer
+    const uint64_t da_stage0 = make_desc(smem_u32(At), Sh::LBO_A, Sh::SBO_A);
+    const uint64_t db_buf0 = make_desc(smem_u32(Bt), 128, 256);
+    int gc = 0, it = 0;
+    for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+      const int q = (t % tiles_per_pass) / tiles_per_quasar;
+      const QuasarMeta meta = args.meta[q];
+      if (!tile_live(q, meta)) continue;
+      if (it > 0) mbar_wait_d(bar_tfree, (it - 1) & 1, xa.status, 23, nullptr, 100);
+      for (int c = 0; c < meta.nchunks; ++c, ++gc) {
+        const int stage = gc % C_STAGES;
+        mbar_wait_d(&bar_full[stage], (gc / C_STAGES) & 1, xa.status, 22, nullptr);
+        asm volatile("tcgen05.fence::after_thread_sync;");
+        const uint64_t da0 = da_stage0 + (uint64_t)(uint32_t)(stage * (Sh::A_TILE >> 4));
+        const uint64_t db0 = db_buf0 + (uint64_t)(uint32_t)(stage * (Sh::L_BW >> 4));
+        issue_chunk_mmas_fixed<Sh, L, Sh::NW>(tmem_base, da0, db0, c > 0);
+        mma_commit_multicast(&bar_empty[stage], (uint16_t)((1u << CLUSTER) - 1));
+      }
+      mma_commit(bar_acc);
+      ++it;
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ---- loader: a quarter of the A tile to all four CTAs, this CTA's B block to itself
+    int gc = 0;
+    for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+      const int pass = t / tiles_per_pass, qt = t % tiles_per_pass;
+      const int q = qt / tiles_per_quasar;
+      const QuasarMeta meta = args.meta[q];
+      if (!tile_live(q, meta)) continue;
+      const int slot = WCTAS + CLUSTER * pass + (int)rank;
+      const uint8_t* asrc = xa.adig + (int64_t)qt * (args.NPIX / KC) * Sh::A_TILE + rank * Sh::ROWBLOCK;
+      const uint8_t* bsrc = xa.bop + (int64_t)q * (args.NPIX / KC) * Sh::CHUNK_BYTES + Sh::b_offset(slot);
+      for (int c = 0; c < meta.nchunks; ++c, ++gc) {
+        const int stage = gc % C_STAGES;
+        // the stage is free in ALL four CTAs (every CTA's MMAs of chunk gc - C_STAGES have committed to every peer)
+        mbar_wait_d(&bar_empty[stage], ((gc / C_STAGES) & 1) ^ 1, xa.status, 21, nullptr, 50);
+        mbar_expect_tx(&bar_full[stage], (uint32_t)Sh::A_TILE + b_bytes);
+        tma_load_1d_multicast(smem_u32(At + stage * Sh::A_TILE) + rank * Sh::ROWBLOCK, asrc + (int64_t)c * Sh::A_TILE, Sh::ROWBLOCK,
+                              smem_u32(&bar_full[stage]), (uint16_t)((1u << CLUSTER) - 1));
+        tma_load_1d(Bt + stage * Sh::L_BW, bsrc + (int64_t)c * Sh::CHUNK_BYTES, b_bytes, &bar_full[stage]);
+      }
+    }
+  } else if (warp >= 4) {
+    // ---- epilogue: TMEM lane quarter e = rows 32 e .. 32 e + 31 of the tile (a warp may only read the quarter warp % 4)
+    const int e = warp & 3, half = (warp - 4) >> 2;
+    constexpr int CHALF = (Sh::NW / 2 + 7) / 8 * 8;
+    const uint32_t taddr0 = tmem_base + ((uint32_t)(e * 32) << 16);
+    int it = 0;
+    for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+      const int pass = t / tiles_per_pass, qt = t % tiles_per_pass;
+      const int q = qt / tiles_per_quasar;
+      const QuasarMeta meta = args.meta[q];
+      if (!tile_live(q, meta)) continue;
+      const int slot = WCTAS + CLUSTER * pass + (int)rank;
+      if (lane == 0) mbar_wait_d(bar_acc, it & 1, xa.status, 24, nullptr, 200);
+      __syncwarp();
+      asm volatile("tcgen05.fence::after_thread_sync;");
+      const int64_t row = (int64_t)(qt % tiles_per_quasar) * TM + e * 32 + lane;
+      drain_to_gram<Sh, L>(taddr0, Sh::NW, slot, xa.colscale + (int64_t)q * Sh::NCOLTAB + slot * Sh::NMAX,
+                           args.gram + ((int64_t)q * args.gram_rows + row) * Sh::G::NCOL, half * CHALF, (half + 1) * CHALF);
+      asm volatile("tcgen05.fence::before_thread_sync;");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tfree);
+      ++it;
+    }
+  }
+  __syncwarp();
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  cluster_sync_all();
+  asm volatile("tcgen05.fence::after_thread_sync;");
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
+}
+
 template <int K, int L>
 struct PShape {
   using Sh = Shape<K, L>;
@@ -459,7 +649,8 @@ dla_loglik_i8p_kernel(LoglikArgs args, I8Args xa, int num_quasars, int tiles_per
   int* s_so = s_part + 3 * TS;                                             // [TS]  sample index of every tile row
 
   if (tid == 0) {
-    for (int i = 0; i < STAGES; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], CLUSTER); mbar_init(&bar_rows[i], NPROD); }
+    // EXT: a stage is free once the four MMAs have read it AND the sender's store of its W'' block to global memory has
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], CLUSTER + (Sh::EXT ? 1 : 0)); mbar_init(&bar_rows[i], NPROD); }
     for (int i = 0; i < 2; ++i) { mbar_init(&bar_pfull[i], 1); mbar_init(&bar_pempty[i], 1); mbar_init(&bar_sq[i], NPROD); }
     mbar_init(bar_acc, 1); mbar_init(bar_tfree, 4); mbar_init(bar_csfull, CLUSTER);
     for (int i = 0; i < CLUSTER; ++i) mbar_init(&bar_csfree[i], 4);
@@ -476,7 +667,8 @@ dla_loglik_i8p_kernel(LoglikArgs args, I8Args xa, int num_quasars, int tiles_per
   cluster_sync_all();
 
   const int N = rank < WCTAS ? Sh::NW : Sh::NU;
-  const uint32_t b_bytes = (uint32_t)Sh::b_bytes(rank);
+  const int slot = Sh::slot_of_rank((int)rank);
+  const uint32_t b_bytes = (uint32_t)Sh::b_bytes(slot);
   // a tile is skipped by every role alike when its quasar has no usable pixel or is inactive
   auto tile_quasar = [&](int t) { return t / tiles_per_quasar; };
   auto tile_live = [&](int q, const QuasarMeta& m) {
@@ -505,11 +697,20 @@ dla_loglik_i8p_kernel(LoglikArgs args, I8Args xa, int num_quasars, int tiles_per
       }
       if (lane == 0) {
         mbar_wait_d(bar_acc, it & 1, xa.status, 6, phase_ptr(xa), 500);   // latency-insensitive: poll rarely
-        if (it > 0) mbar_wait_cluster(&bar_csfree[e], (it - 1) & 1, xa.status, 10, phase_ptr(xa));   // CTA e is done with its previous triangle
+        if (!Sh::EXT && it > 0) mbar_wait_cluster(&bar_csfree[e], (it - 1) & 1, xa.status, 10, phase_ptr(xa));   // CTA e is done with its previous triangle
       }
       __syncwarp();
       asm volatile("tcgen05.fence::after_thread_sync;");
-      const double* cs = xa.colscale + (int64_t)q * Sh::NCOLTAB + rank * Sh::NMAX;
+      const double* cs = xa.colscale + (int64_t)q * Sh::NCOLTAB + slot * Sh::NMAX;
+      if constexpr (Sh::EXT) {
+        // accumulators of this CTA's column block, rows of CTA e's samples -> global staging rows (cholesky_kernel)
+        drain_to_gram<Sh, L>(taddr0, N, slot, cs, args.gram + ((int64_t)q * args.gram_rows + (s0 - (int64_t)rank * TS) + e * 32 + lane) * Sh::G::NCOL);
+        asm volatile("tcgen05.fence::before_thread_sync;");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_tfree);
+        ++it;
+        continue;
+      }
       for (int c0 = 0; c0 < ((PROBE & 8) ? 0 : N); c0 += 8) {
         uint32_t v[L][8];
 #pragma unroll
@@ -541,7 +742,9 @@ dla_loglik_i8p_kernel(LoglikArgs args, I8Args xa, int num_quasars, int tiles_per
         mbar_wait_d(&bar_sq[it & 1], (it >> 1) & 1, xa.status, 12, phase_ptr(xa), 200);            // my producers' scalars
       }
       __syncwarp();
-      if (!(PROBE & 8)) factor_staged<K, CSTR>(Cs, s_q + (it & 1) * TS, s_ld + (it & 1) * TS, e * 8, lane, meta, args, q, s0);
+      if constexpr (!Sh::EXT) {
+        if (!(PROBE & 8)) factor_staged<K, CSTR>(Cs, s_q + (it & 1) * TS, s_ld + (it & 1) * TS, e * 8, lane, meta, args, q, s0);
+      }
       __syncwarp();
       if (lane == 0) {
         const uint32_t freebar = smem_u32(&bar_csfree[rank]);
@@ -732,10 +935,17 @@ dla_loglik_i8p_kernel(LoglikArgs args, I8Args xa, int num_quasars, int tiles_per
       for (int ss = 0; ss < SPB; ++ss) {
         const double qs = warp_sum(qacc[ss]);
         const double ld = warp_sum(log(ldm[ss]) + (double)lde[ss] * 0.693147180559945309417);
-        if (lane == 0) { s_q[(it & 1) * TS + row0 + ss] = qs; s_ld[(it & 1) * TS + row0 + ss] = ld; }
+        if (lane == 0) {
+          if (Sh::EXT) {   // straight to cholesky_kernel's scalars
+            double* qd = args.qld + ((int64_t)q * args.gram_rows + s0 + row0 + ss) * 2;
+            qd[0] = qs; qd[1] = ld;
+          } else {
+            s_q[(it & 1) * TS + row0 + ss] = qs; s_ld[(it & 1) * TS + row0 + ss] = ld;
+          }
+        }
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_sq[it & 1]);
+      if (!Sh::EXT && lane == 0) mbar_arrive(&bar_sq[it & 1]);
       if (GPDLA_I8P_PHASES && xa.phase && pr == 0 && lane == 0) atomicAdd(&xa.phase[7], 1ull);
       ++it;
     }
@@ -776,7 +986,7 @@ dla_loglik_i8p_kernel(LoglikArgs args, I8Args xa, int num_quasars, int tiles_per
         const int q = tile_quasar(t);
         const QuasarMeta meta = args.meta[q];
         if (!tile_live(q, meta)) continue;
-        const uint8_t* bsrc = xa.bop + (int64_t)q * (args.NPIX / KC) * Sh::CHUNK_BYTES + Sh::b_offset(rank);
+        const uint8_t* bsrc = xa.bop + (int64_t)q * (args.NPIX / KC) * Sh::CHUNK_BYTES + Sh::b_offset(slot);
         for (int c = 0; c < meta.nchunks; ++c, ++gc) {
           const int buf = gc & 1;
           if (gc >= 2) mbar_wait_d(&bar_pempty[buf], ((gc >> 1) - 1) & 1, xa.status, 4, phase_ptr(xa), 100);
@@ -804,6 +1014,16 @@ dla_loglik_i8p_kernel(LoglikArgs args, I8Args xa, int num_quasars, int tiles_per
             dsmem_bulk_copy(mapa(dst_off, peer), src, Sh::ROWBLOCK, mapa(fullbar, peer));
           }
           mbar_arrive_expect_tx(&bar_full[stage], (CLUSTER - 1) * Sh::ROWBLOCK);
+          if constexpr (Sh::EXT) {
+            // this CTA's W'' block of the chunk -> its place in the stored digit tile (the contract-only passes read whole
+            // tiles); the stage is released only after the copy engine has read the block
+            uint8_t* gdst = xa.adig + (((int64_t)q * tiles_per_quasar + (t % tiles_per_quasar)) * (args.NPIX / KC) + c) * Sh::A_TILE +
+                            rank * Sh::ROWBLOCK;
+            bulk_store_global(gdst, (rank < WCTAS) ? dst_off : other_rows, Sh::ROWBLOCK);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            mbar_arrive(&bar_empty[stage]);
+          }
         }
       }
     }

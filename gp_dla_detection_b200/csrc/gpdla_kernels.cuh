@@ -1042,65 +1042,99 @@ struct CholArgs {
 };
 
 constexpr int CHOL_SAMPLES = 16;              // samples per CTA of cholesky_kernel
-constexpr int CHOL_STRIDE = CHOL_SAMPLES + 4;  // == 4 (mod 16): quad lanes read consecutive entries conflict-free
+constexpr int CHOL_LANES = 8;                 // lanes per sample
+constexpr int CHOL_THREADS = CHOL_SAMPLES * CHOL_LANES;
 template <int K>
-constexpr size_t cholesky_smem_bytes() { return (size_t)((K + 1) * (K + 2) / 2) * CHOL_STRIDE * 8; }
+constexpr size_t cholesky_smem_bytes() { return (size_t)((K + 1) * (K + 2) / 2) * CHOL_SAMPLES * 8; }
+// Staging: entry (p, q) of sample s at Cs[chol_slot(aug_index(p, q), s)] -- 16 samples per entry, no padding (k = 40:
+// 110 KB, two CTAs per SM), the sample position rotated by 2 * (entry mod 8): the 8 lanes of a sample read 8
+// consecutive entries and a half-warp holds two samples, which then fall into 16 different 8-byte bank pairs.
+__device__ __forceinline__ int chol_slot(int entry, int s) { return entry * CHOL_SAMPLES + ((s + 2 * (entry & 7)) & (CHOL_SAMPLES - 1)); }
 
+// Left-looking Cholesky, TWO rows (p, p + 1) per step: lane l of a sample owns the columns p + l + 8 j of both rows, so
+// every entry of a finished row r that it loads updates two accumulators (loads per FMA halved; the kernel is bound by
+// shared-memory loads).  Round 1's version (4 lanes per sample, one row per step, 138 KB per CTA: 64 threads per SM)
+// took 12.4 ms per 37 quasars x 10^4 samples at k = 40, three times the Gram itself on the INT8 path.
 template <int K>
-__global__ void __launch_bounds__(CHOL_SAMPLES * 4) cholesky_kernel(CholArgs a) {
+__global__ void __launch_bounds__(CHOL_THREADS) cholesky_kernel(CholArgs a) {
   using G = GramShape<K>;
-  constexpr int NQ = (K + 3) / 4 + 1;            // columns per quad lane, upper bound
+  static_assert(K % 2 == 0, "rows are processed in pairs");
+  constexpr int NQ = (K + 1 + CHOL_LANES - 1) / CHOL_LANES;      // columns per lane, upper bound
   const int q = (int)blockIdx.y + a.q_offset;
   const QuasarMeta meta = a.meta[q];
   if (meta.nchunks == 0 || (a.active != nullptr && a.active[q] == 0)) return;   // NaNs already written
-  extern __shared__ __align__(16) double Cs[];   // [aug entries][CHOL_STRIDE]
-  const int tid = threadIdx.x, l4 = tid & 3, sl = tid >> 2;
+  extern __shared__ __align__(16) double Cs[];
+  const int tid = threadIdx.x, l8 = tid & (CHOL_LANES - 1), sl = tid / CHOL_LANES;
   const int64_t row0 = (int64_t)blockIdx.x * CHOL_SAMPLES;
   // stage the accumulator rows: coalesced along columns, scattered into the augmented triangle
   const double* g0 = a.gram + ((int64_t)q * a.gram_rows + row0) * G::NCOL;
-  for (int c = tid; c < G::NCOL; c += CHOL_SAMPLES * 4) {   // one (divergent) table lookup per column
+  for (int c = tid; c < G::NCOL; c += CHOL_THREADS) {   // one (divergent) table lookup per column
     const int idx = stage_index_table<K>()[c];
     if (idx >= 0) {
 #pragma unroll 8
-      for (int r = 0; r < CHOL_SAMPLES; ++r) Cs[idx * CHOL_STRIDE + r] = g0[(int64_t)r * G::NCOL + c];
+      for (int r = 0; r < CHOL_SAMPLES; ++r) Cs[chol_slot(idx, r)] = g0[(int64_t)r * G::NCOL + c];
     }
   }
   __syncthreads();
-  double* Bs = Cs + sl;                           // entry (p, q) at Bs[aug_index<K>(p, q) * CHOL_STRIDE]
+  const unsigned gmask = 0xffu << ((tid & 31) & ~(CHOL_LANES - 1));   // the lanes of this sample
+  const int lane0 = (tid & 31) & ~(CHOL_LANES - 1);
   double prod[4] = {1.0, 1.0, 1.0, 1.0};
-  for (int p = 0; p < K; ++p) {
-    const int base_p = aug_index<K>(p, p);
-    double dpp = Bs[base_p * CHOL_STRIDE] + 1.0;                                   // :23
-    double v[NQ];
+  for (int p = 0; p < K; p += 2) {
+    const int base_p = aug_index<K>(p, p) - p, base_p1 = aug_index<K>(p + 1, p + 1) - (p + 1);   // entry (p, x) at base_p + x
+    double v0[NQ], v1[NQ];
 #pragma unroll
     for (int j = 0; j < NQ; ++j) {
-      const int qq = p + 1 + l4 + 4 * j;
-      v[j] = (qq <= K) ? Bs[(base_p + (qq - p)) * CHOL_STRIDE] : 0.0;
+      const int qq = p + l8 + CHOL_LANES * j;
+      v0[j] = (qq <= K) ? Cs[chol_slot(base_p + qq, sl)] : 0.0;
+      v1[j] = (qq <= K && qq >= p + 1) ? Cs[chol_slot(base_p1 + qq, sl)] : 0.0;
     }
+    if (l8 == 0) v0[0] += 1.0;                                                     // B = I + C   (:23)
+    if (l8 == 1) v1[0] += 1.0;
+    // finished rows r < p.  The 8 j-entries of a lane are 8 entries apart, so they share one rotated sample slot: one
+    // address per (lane, r) and immediate offsets; entry (r, x) sits at base_r + x with base_(r+1) = base_r + K - r
+    const int nj = (K - p - l8) / CHOL_LANES + 1;      // columns p + l8 + 8 j <= K
+    int base_r = 0;
 #pragma unroll 2
     for (int r = 0; r < p; ++r) {
-      const int base_r = aug_index<K>(r, r) - r;                                   // entry (r, x) at base_r + x
-      const double c = Bs[(base_r + p) * CHOL_STRIDE];
-      dpp = fma(-c, c, dpp);
+      const int ec = base_r + p, ex = ec + l8;
+      const double c0 = Cs[chol_slot(ec, sl)], c1 = Cs[chol_slot(ec + 1, sl)];
+      const double* px = Cs + chol_slot(ex, sl);
 #pragma unroll
       for (int j = 0; j < NQ; ++j) {
-        const int qq = p + 1 + l4 + 4 * j;
-        if (qq <= K) v[j] = fma(-c, Bs[(base_r + qq) * CHOL_STRIDE], v[j]);
+        if (j < nj) {
+          const double x = px[j * CHOL_LANES * CHOL_SAMPLES];
+          v0[j] = fma(-c0, x, v0[j]);
+          v1[j] = fma(-c1, x, v1[j]);
+        }
       }
+      base_r += K - r;
     }
-    prod[p & 3] *= dpp;
-    const double inv = rsqrt(dpp);
+    // row p: pivot at lane 0, then its entry (p, p + 1) (lane 1) updates row p + 1
+    const double d0 = __shfl_sync(gmask, v0[0], lane0);
+    prod[(p >> 1) & 1] *= d0;
+    const double i0 = rsqrt(d0);
+#pragma unroll
+    for (int j = 0; j < NQ; ++j) v0[j] *= i0;
+    const double c01 = __shfl_sync(gmask, v0[0], lane0 + 1);
+#pragma unroll
+    for (int j = 0; j < NQ; ++j) v1[j] = fma(-c01, v0[j], v1[j]);
+    const double d1 = __shfl_sync(gmask, v1[0], lane0 + 1);
+    prod[2 + ((p >> 1) & 1)] *= d1;
+    const double i1 = rsqrt(d1);
 #pragma unroll
     for (int j = 0; j < NQ; ++j) {
-      const int qq = p + 1 + l4 + 4 * j;
-      if (qq <= K) Bs[(base_p + (qq - p)) * CHOL_STRIDE] = v[j] * inv;
+      const int qq = p + l8 + CHOL_LANES * j;
+      if (qq <= K && qq > p) Cs[chol_slot(base_p + qq, sl)] = v0[j];
+      if (qq <= K && qq > p + 1) Cs[chol_slot(base_p1 + qq, sl)] = v1[j] * i1;
     }
     __syncwarp();
   }
   double zsum = 0.0;
-  for (int p = 0; p < K; ++p) { const double zp = Bs[aug_index<K>(p, K) * CHOL_STRIDE]; zsum = fma(zp, zp, zsum); }
+  for (int p = l8; p < K; p += CHOL_LANES) { const double zp = Cs[chol_slot(aug_index<K>(p, K), sl)]; zsum = fma(zp, zp, zsum); }
+#pragma unroll
+  for (int o = CHOL_LANES / 2; o > 0; o >>= 1) zsum += __shfl_xor_sync(gmask, zsum, o);
   const int64_t row = row0 + sl;
-  if (l4 == 0) {
+  if (l8 == 0) {
     const double* qd = a.qld + ((int64_t)q * a.gram_rows + row) * 2;
     const double quad = qd[0] - zsum;                                            // :28
     const double logdet = qd[1] + (log(prod[0]) + log(prod[1])) + (log(prod[2]) + log(prod[3]));   // :30
