@@ -93,6 +93,22 @@ def test_multi_against_oracle(api, synthetic_inputs):
     assert np.array_equal(np.argmax(res["model_posteriors"], axis=1), np.argmax(ref["model_posteriors"], axis=1))
 
 
+def test_multi_rank_40(api, synthetic_inputs):
+    """The level loop at k = 40: MODE 1 / MODE 2 of the INT8 producing kernel with its contract-only passes, against
+    the oracle with the oracle's resampling indices, and against the FP64 DMMA path."""
+    from gp_dla_detection_b200 import synthetic as syn
+    from oracle import process_qsos_multi_oracle as MO
+    si = synthetic_inputs
+    m40 = syn.make_model(40)
+    samples = syn.make_samples(700, with_lls=True)
+    sp = syn.make_spectra(m40, 2, seed=6, dla_fraction=1.0, meanflux=True, max_injected=2)
+    ref = MO.process_qsos_multi(m40, samples, sp, si["prior"], Z_lls=samples["Z_lls"], Z_dla=samples["Z_dla"], max_dlas=3)
+    for digits in (6, -1):
+        res = api.process_qsos_multiple_dlas_meanflux(m40, samples, sp, si["prior"], max_dlas=3, gram_digits=digits,
+                                                      base_sample_inds=ref["base_sample_inds"])
+        assert_multi_parity(res, ref)
+
+
 def test_multi_empty_and_batched(api, synthetic_inputs):
     from gp_dla_detection_b200 import synthetic as syn
     si = synthetic_inputs

@@ -248,6 +248,37 @@ def test_rank_and_sample_count_sweep(api, synthetic_inputs):
                   O.process_qsos(si["model"], s30k, sp1, si["prior"], engine="c"))
 
 
+def test_rank_40_int8_contract_passes(api, synthetic_inputs):
+    """k = 40 on the INT8 path (default): the producing kernel covers three column blocks and the projection, the
+    contract-only kernel the other eight from the stored digit tiles, cholesky_kernel finishes.  Against the oracle and
+    against the FP64 DMMA path at full sample count; a zero-noise-variance quasar takes the FP64 list kernel and the
+    same Cholesky launch; sample counts that leave partial 128-row tiles."""
+    from gp_dla_detection_b200 import synthetic as syn
+    from oracle import process_qsos_oracle as O
+    si = synthetic_inputs
+    m40 = syn.make_model(40)
+    sp = syn.make_spectra(m40, 4, seed=43, dla_fraction=0.5)
+    sp["all_pixel_mask"][2][::3] = True
+    nv = sp["all_noise_variance"][3]
+    w = np.asarray(sp["all_wavelengths"][3]) / (1 + sp["z_qsos"][3])
+    used = np.flatnonzero(~np.asarray(sp["all_pixel_mask"][3]) & (w >= 911.75) & (w <= 1215.75))
+    nv[used[[-2, -4]]] = 0.0                                      # quasar 3 -> FP64 fallback list (pixels no DLA saturates)
+    res = {d: api.process_qsos(m40, si["samples"], sp, si["prior"], gram_digits=d) for d in (6, -1)}
+    ref = O.process_qsos(m40, si["samples"], sp, si["prior"], engine="c")
+    b = ref["sample_log_likelihoods_dla"]
+    for d in (6, -1):
+        a = res[d]["sample_log_likelihoods_dla"]
+        assert np.max(np.abs(a - b) / np.abs(b)) < 1e-11, (d, np.max(np.abs(a - b) / np.abs(b)))
+        assert_parity(res[d], ref)
+    a6, af = res[6]["sample_log_likelihoods_dla"], res[-1]["sample_log_likelihoods_dla"]
+    assert np.max(np.abs(a6 - af) / np.abs(af)) < 2e-12
+    assert np.array_equal(a6[3], af[3])                            # the flagged quasar ran the same FP64 kernels
+    for S in (1, 127, 129, 300):
+        sub = {k: v[np.arange(S) * 5 + 1] for k, v in si["samples"].items()}
+        sp2 = {k: v[:2] for k, v in sp.items()}
+        assert_parity(api.process_qsos(m40, sub, sp2, si["prior"]), O.process_qsos(m40, sub, sp2, si["prior"], engine="c"))
+
+
 def test_tiny_and_odd_sample_counts(api, synthetic_inputs):
     """Sample tiles are 32 wide: S = 1, 5, 33 exercise the partial-tile and null-slot handling."""
     from oracle import process_qsos_oracle as O
