@@ -456,8 +456,8 @@ static i8::I8Args i8_args(gpdla_ctx* c) {
     if (!c->d_phase) { cudaMalloc(&c->d_phase, 24 * sizeof(unsigned long long)); cudaMemset(c->d_phase, 0, 24 * sizeof(unsigned long long)); }
     unsigned long long h[24];
     cudaMemcpy(h, c->d_phase, sizeof h, cudaMemcpyDeviceToHost);
-    if (h[7]) fprintf(stderr, "[i8 persistent waits, mean cycles per tile] producer: stage empty (per thread) %llu | mma: A full %llu, B full %llu, TMEM drained %llu | loader %llu | sender %llu | epilogue (per warp): acc final %llu, triangle free %llu, triangle full %llu, scalars %llu\n",
-                      h[9] / h[7] / 256, h[10] / h[7], h[11] / h[7], h[21] / h[7], h[12] / h[7], h[13] / h[7], h[14] / h[7] / 4, h[18] / h[7] / 4, h[19] / h[7] / 4, h[20] / h[7] / 4);
+    if (h[7]) fprintf(stderr, "[i8 persistent waits, mean cycles per tile] producer: stage empty (per warp) %llu | mma: A full %llu, B full %llu, TMEM drained %llu | loader %llu | sender %llu | epilogue (per warp): acc final %llu, triangle free %llu, triangle full %llu, scalars %llu | stage B waits for A (per warp) %llu, A for B %llu | tile (MMA issuer) %llu\n",
+                      h[9] / h[7] / 8, h[10] / h[7], h[11] / h[7], h[21] / h[7], h[12] / h[7], h[13] / h[7], h[14] / h[7] / 4, h[18] / h[7] / 4, h[19] / h[7] / 4, h[20] / h[7] / 4, h[22] / h[7] / 8, h[23] / h[7] / 8, h[6] / h[7]);
     cudaMemset(c->d_phase, 0, sizeof h);
     xa.phase = c->d_phase;
   }

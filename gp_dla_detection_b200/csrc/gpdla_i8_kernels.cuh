@@ -52,6 +52,12 @@ constexpr int TMEM_COLS = 512;
 constexpr int PROBE = GPDLA_I8P_PROBE;
 // Barrier-wait accounting (-DGPDLA_I8P_PHASES=1 and GPDLA_I8_PHASES=1 in the environment): compiled out of the product
 // build -- the null-pointer test and the clock reads around every wait cost the producers issue slots.
+#ifndef GPDLA_I8P_PF
+#define GPDLA_I8P_PF 0      // 1: stage A fetches the table cell of the next chunk a chunk ahead (measured 6 % SLOWER: 58.2 against 54.7 ms)
+#endif
+#ifndef GPDLA_I8P_NCA
+#define GPDLA_I8P_NCA 4
+#endif
 #ifndef GPDLA_I8P_PHASES
 #define GPDLA_I8P_PHASES 0
 #endif
@@ -389,9 +395,9 @@ __global__ void __launch_bounds__(NTHREADS) i8_build_operand_kernel(const Quasar
 // Hand-overs: accumulators final (tcgen05.commit -> bar_acc), TMEM drained (bar_tfree), staging triangle delivered
 // (remote arrivals on the owner's bar_csfull) and free again (remote arrivals on every writer's bar_csfree[owner]),
 // per-sample scalars (bar_sq, double-buffered).  All main-loop barriers run on a chunk counter that spans tiles.
-constexpr int P_THREADS = 32 * (NCTRL + NPROD + 4);
-constexpr int REG_CTRL = 48, REG_PROD = 168, REG_EPI = 128;
-static_assert(REG_CTRL * 128 + REG_PROD * 256 + REG_EPI * 128 <= 65536, "register budgets exceed the register file");
+constexpr int P_THREADS = 32 * (NCTRL + 2 * NPROD + 4);
+constexpr int REG_CTRL = 40, REG_A = 96, REG_B = 80, REG_EPI = 88;
+static_assert(REG_CTRL * 128 + (REG_A + REG_B) * 256 + REG_EPI * 128 <= 80 * P_THREADS, "register budgets exceed the register file");
 
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t remote_bar) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote_bar) : "memory");
@@ -605,8 +611,9 @@ struct PShape {
   using Sh = Shape<K, L>;
   static constexpr size_t OFF_MISC = Sh::OFF_MISC;
   __host__ __device__ static constexpr size_t smem_bytes(int num_lines) {
-    // per-sample arrays: nhi, q[2], ld[2], mult[num_lines + 1]; 64 barriers; partner indices
-    return OFF_MISC + (size_t)TS * (num_lines + 6) * 8 + 64 * 8 + 4 * TS * 4 + 64;
+    // per-sample arrays: nhi, q[2], ld[2], mult[num_lines + 1]; 128 barriers; partner indices; the stage A -> B hand-over
+    // buffers (2 slots x 4 samples x 32 pixels per warp pair)
+    return OFF_MISC + (size_t)TS * (num_lines + 6) * 8 + 128 * 8 + 4 * TS * 4 + 64 + (size_t)NPROD * 2 * SPB * KC * 8;
   }
 };
 
@@ -645,14 +652,18 @@ dla_loglik_i8p_kernel(LoglikArgs args, I8Args xa, int num_quasars, int tiles_per
   uint64_t* bar_csfull = bar_sq + 2;            // this CTA's staging triangle is complete
   uint64_t* bar_csfree = bar_csfull + 1;        // [CLUSTER] CTA w has finished factorising: its triangle may be rewritten
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 32);
-  int* s_part = reinterpret_cast<int*>(bars + 64);                         // [3][TS]
+  uint64_t* bar_hfull = bars + 64;              // [NPROD][2] absorption of a chunk handed over by the pair's stage-A warp
+  uint64_t* bar_hempty = bar_hfull + 2 * NPROD; // [NPROD][2] ... consumed by its stage-B warp
+  int* s_part = reinterpret_cast<int*>(bars + 128);                        // [3][TS]
   int* s_so = s_part + 3 * TS;                                             // [TS]  sample index of every tile row
+  double* hbuf = reinterpret_cast<double*>(s_so + TS + 16);                // [NPROD][2][SPB][KC]
 
   if (tid == 0) {
     // EXT: a stage is free once the four MMAs have read it AND the sender's store of its W'' block to global memory has
     for (int i = 0; i < STAGES; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], CLUSTER + (Sh::EXT ? 1 : 0)); mbar_init(&bar_rows[i], NPROD); }
     for (int i = 0; i < 2; ++i) { mbar_init(&bar_pfull[i], 1); mbar_init(&bar_pempty[i], 1); mbar_init(&bar_sq[i], NPROD); }
     mbar_init(bar_acc, 1); mbar_init(bar_tfree, 4); mbar_init(bar_csfull, CLUSTER);
+    for (int i = 0; i < 2 * NPROD; ++i) { mbar_init(&bar_hfull[i], 1); mbar_init(&bar_hempty[i], 1); }
     for (int i = 0; i < CLUSTER; ++i) mbar_init(&bar_csfree[i], 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -667,6 +678,11 @@ dla_loglik_i8p_kernel(LoglikArgs args, I8Args xa, int num_quasars, int tiles_per
   cluster_sync_all();
 
   const int N = rank < WCTAS ? Sh::NW : Sh::NU;
+  // where the instrument convolution runs: in stage B for the single-DLA pass (stage A is the longer one), in stage A
+  // when the convolved absorption is also cached for the later levels (MODE 1); MODE 2 has none
+  // (NCA of a pair's 4 samples are convolved by stage A, the others by stage B: the split that balances the two stages)
+  constexpr int NCA = (MODE == 0) ? GPDLA_I8P_NCA : SPB;
+  constexpr bool CONV_B = NCA < SPB;
   const int slot = Sh::slot_of_rank((int)rank);
   const uint32_t b_bytes = (uint32_t)Sh::b_bytes(slot);
   // a tile is skipped by every role alike when its quasar has no usable pixel or is inactive
@@ -675,10 +691,10 @@ dla_loglik_i8p_kernel(LoglikArgs args, I8Args xa, int num_quasars, int tiles_per
     return m.nchunks > 0 && !(args.active != nullptr && args.active[q] == 0) && xa.f64flag[q] == 0;
   };
 
-  if (warp >= NCTRL + NPROD) {
+  if (warp >= NCTRL + 2 * NPROD) {
     // =========================================================================== EPILOGUE WARPGROUP
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REG_EPI));
-    const int e = warp - NCTRL - NPROD;              // TMEM lane quarter = samples 32 e .. 32 e + 31 = CTA e's samples
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REG_EPI));
+    const int e = warp - NCTRL - 2 * NPROD;          // TMEM lane quarter = samples 32 e .. 32 e + 31 = CTA e's samples
     const uint32_t cs_remote = mapa(smem_u32(Cs), (uint32_t)e) + (uint32_t)lane * 8;
     const uint32_t csfull_remote = mapa(smem_u32(bar_csfull), (uint32_t)e);
     const uint32_t taddr0 = tmem_base + ((uint32_t)(e * 32) << 16);
@@ -752,10 +768,14 @@ dla_loglik_i8p_kernel(LoglikArgs args, I8Args xa, int num_quasars, int tiles_per
       }
       ++it;
     }
-  } else if (warp >= NCTRL) {
-    // =========================================================================== PRODUCERS
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REG_PROD));
-    const int pr = warp - NCTRL;
+  } else if (warp >= NCTRL + NPROD) {
+    // =========================================================================== PRODUCERS, STAGE B: weights and digits
+    // The producers are a two-stage pipeline of warp pairs (A: absorption, B: weights and digits).  One warp doing both
+    // (round 1 .. mid round 2, 8 warps at 168 registers) spent half of its time on dependency and load latency that two
+    // warps per sub-partition could not cover; the split doubles the warps in flight at the same register total, with
+    // the absorption of a warp's 4 samples x 32 pixels handed over through a 2-slot shared-memory buffer per pair.
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REG_B));
+    const int pr = warp - NCTRL - NPROD;
     const int row0 = pr * SPB;
     const uint32_t own_block = rank * Sh::ROWBLOCK;
     uint8_t* const wdst0 = (rank < WCTAS) ? At + own_block : Sx;
@@ -766,127 +786,77 @@ dla_loglik_i8p_kernel(LoglikArgs args, I8Args xa, int num_quasars, int tiles_per
     constexpr uint64_t BIAS = Sh::digit_bias();
     const double MAGIC = Sh::magic();
     const uint64_t KADD = BIAS - (uint64_t)__double_as_longlong(MAGIC);
-    double* myraw = rawbuf + row0 * RAWS;
-    int gc = 0, it = 0;                               // chunk counter across tiles, live-tile counter
-    int stage = 0;                                    // = gc % STAGES
+    const double* hb = hbuf + pr * (2 * SPB * KC) + lane;
+    uint64_t* const hfull = bar_hfull + 2 * pr;
+    uint64_t* const hempty = bar_hempty + 2 * pr;
+    double* myraw = rawbuf + row0 * RAWS;             // CONV_B: this warp's raw-profile rows
+    int it = 0;                                       // live-tile counter
+    int stage = 0;                                    // = gc % STAGES (gc: chunk counter across tiles)
     uint32_t empty_parity = 1;                        // = ((gc / STAGES) & 1) ^ 1
+    uint32_t gh = 0;                                  // hand-over counter across tiles
+    long long w_empty = 0, w_hand = 0;
     for (int t = cluster_id; t < num_tiles; t += num_clusters) {
       const int q = tile_quasar(t);
       const QuasarMeta meta = args.meta[q];
       if (!tile_live(q, meta)) continue;
       const int64_t s0 = (int64_t)(t % tiles_per_quasar) * TM + (int64_t)rank * TS;
       const int nchunks = meta.nchunks;
-      // per-sample parameters of this warp's four samples (rows private to the warp)
-      __syncwarp();
-      if (lane < SPB) {
-        const int i = row0 + lane;
-        const int64_t s = s0 + i;
-        const bool is_null = s >= S;
-        const int64_t so = sample_at(args, is_null ? S - 1 : s);   // the null-model slot borrows a redshift (a == 1 anyway)
-        const double z = __dadd_rn(meta.min_z_dla, __dmul_rn(meta.max_z_dla - meta.min_z_dla, args.offset_samples[so]));
-        s_nhi[i] = is_null ? -1.0 : args.nhi_samples[so];
-        s_K[i] = rest_table_offset(args.rt, z, meta.lam_ref);
-        s_so[i] = (int)so;
-        for (int j = 0; j < num_lines; ++j) s_mult[j * TS + i] = line_multiplier(j, z);
-        if (MODE == 2) {
-          for (int j = 0; j < args.num_partners; ++j)
-            s_part[j * TS + i] = is_null ? 0 : args.partners[((int64_t)q * 3 + j) * S + so];
-        }
-      }
-      __syncwarp();
-      const double* lam = args.lam_pad + (int64_t)q * (args.NPIX + 8);
-      const double2* pix8 = reinterpret_cast<const double2*>(xa.pix8 + (int64_t)q * args.NPIX * 8);
-      double* const cache_q = (MODE != 0) ? args.acache + (int64_t)q * S * args.NPIX : nullptr;
-
-      // tau / N: from the rest-frame table (one cell per lane serves the warp's four samples), directly where the
-      // cell is near a line centre or the four samples are too far apart in redshift
-      const double* lamh = args.lamh + (int64_t)q * (args.NPIX + 8);
-      double K_mid;
-      const int tab_mode = (MODE != 2) ? group_cell<SPB>(args.rt, s_K + row0, K_mid) : 0;
-      auto eval_raw = [&](double lambda, double lh, double (&e)[SPB]) {   // voigt.c:282-292, 4 samples at one wavelength
-        double tau[SPB];
-        tau_samples<NL, SPB>(args.rt, tab_mode, K_mid, lambda, lh, s_mult + row0, TS, s_K + row0, num_lines, tau);
-        raw_from_tau<SPB, false>(tau, s_nhi + row0, e);   // polynomial exponential: see exp_nonpos
-      };
-      if (MODE != 2) {   // leading pad pixels p = 0..5
-        double e[SPB];
-        eval_raw(lam[lane < 6 ? lane : 5], lamh[lane < 6 ? lane : 5], e);
-        if (lane < 6) {
-#pragma unroll
-          for (int ss = 0; ss < SPB; ++ss) myraw[ss * RAWS + lane] = e[ss];
-        }
-      }
+      const double2* prec = reinterpret_cast<const double2*>(xa.pix8 + (int64_t)q * args.NPIX * 8) + (int64_t)lane * 4;
       double qacc[SPB], ldm[SPB];
       int lde[SPB];
 #pragma unroll
       for (int ss = 0; ss < SPB; ++ss) { qacc[ss] = 0.0; ldm[ss] = 1.0; lde[ss] = 0; }
-      double rows_n[4][SPB];   // MODE 2: cached absorption rows (sample, partners) of the next chunk
-      auto load_rows = [&](int ipix) {
-#pragma unroll
-        for (int ss = 0; ss < SPB; ++ss) rows_n[0][ss] = cache_q[(int64_t)s_so[row0 + ss] * args.NPIX + ipix];
-#pragma unroll
-        for (int j = 0; j < 3; ++j)
-          if (j < args.num_partners) {
-#pragma unroll
-            for (int ss = 0; ss < SPB; ++ss) rows_n[1 + j][ss] = cache_q[(int64_t)s_part[j * TS + row0 + ss] * args.NPIX + ipix];
-          }
-      };
-      if (MODE == 2) load_rows(lane);
       // pixel data of the next chunk is fetched one chunk ahead (global/L2 latency off the critical path)
-      const double2* prec = pix8 + (int64_t)lane * 4;
-      double2 plln = prec[0], p01n = prec[1], p23n = prec[2], p45n = prec[3];
-      for (int c = 0; c < nchunks; ++c, ++gc) {
-        const int i = c * KC + lane;
-        const double lambda = plln.x, lh = plln.y;
+      double2 p01n = prec[1], p23n = prec[2], p45n = prec[3];
+      if (CONV_B) {   // the six pad pixels in front of the window: a hand-over of their own (lanes 0..5)
+        const uint32_t slot = gh & 1u;
+        mbar_wait_d(&hfull[slot], (gh >> 1) & 1u, xa.status, 14);
+        if (lane < 6) {
+#pragma unroll
+          for (int ss = NCA; ss < SPB; ++ss) myraw[ss * RAWS + lane] = hb[(slot * SPB + ss) * KC];
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&hempty[slot]);
+        ++gh;
+      }
+      for (int c = 0; c < nchunks; ++c) {
         const double y = p01n.x, v = p01n.y, mu = p23n.x, om2 = p23n.y, cw = p45n.x, cu = p45n.y;
         if (c + 1 < nchunks) {
           prec += KC * 4;
-          plln = prec[0]; p01n = prec[1]; p23n = prec[2]; p45n = prec[3];
+          p01n = prec[1]; p23n = prec[2]; p45n = prec[3];
         }
+        // absorption of this chunk from the pair's stage-A warp
+        const uint32_t slot = gh & 1u;
+        long long tw0 = GPDLA_I8P_PHASES ? clock64() : 0;
+        mbar_wait_d(&hfull[slot], (gh >> 1) & 1u, xa.status, 14);
+        if (GPDLA_I8P_PHASES) w_hand += clock64() - tw0;
         double a[SPB];
-        if (MODE != 2) {
-          double e[SPB];
-          eval_raw(lambda, lh, e);
-          if (PROBE & 64) {   // no instrument convolution: no raw-row traffic through shared memory
 #pragma unroll
-            for (int ss = 0; ss < SPB; ++ss) a[ss] = (__double2hiint(s_nhi[row0 + ss]) < 0) ? 1.0 : e[ss];
-          } else {
+        for (int ss = 0; ss < SPB; ++ss) a[ss] = hb[(slot * SPB + ss) * KC];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&hempty[slot]);
+        ++gh;
+        if (CONV_B) {
+          // what arrived is the raw profile exp(-N tau) (-1 marks the rows of the null model): instrument convolution
+          // over the warp's private rows (6 pixels carried over from the previous chunk)   voigt.c:297-299
 #pragma unroll
-          for (int ss = 0; ss < SPB; ++ss) myraw[ss * RAWS + 6 + lane] = e[ss];
+          for (int ss = NCA; ss < SPB; ++ss) myraw[ss * RAWS + 6 + lane] = a[ss];
           __syncwarp();
           double carry[SPB];
 #pragma unroll
-          for (int ss = 0; ss < SPB; ++ss) {
+          for (int ss = NCA; ss < SPB; ++ss) {
             const double* rb = myraw + ss * RAWS;
             double acc_a = 0.0;
 #pragma unroll
-            for (int tt = 0; tt < 7; ++tt) acc_a = fma(rb[lane + tt], c_lines.ip[tt], acc_a);   // voigt.c:297-299
+            for (int tt = 0; tt < 7; ++tt) acc_a = fma(rb[lane + tt], c_lines.ip[tt], acc_a);
             carry[ss] = rb[KC + (lane < 6 ? lane : 0)];
-            a[ss] = (__double2hiint(s_nhi[row0 + ss]) < 0) ? 1.0 : acc_a;   // null model (N marked negative)
+            a[ss] = (__double2hiint(a[ss]) < 0) ? 1.0 : acc_a;
           }
           __syncwarp();
           if (lane < 6) {
 #pragma unroll
-            for (int ss = 0; ss < SPB; ++ss) myraw[ss * RAWS + lane] = carry[ss];
+            for (int ss = NCA; ss < SPB; ++ss) myraw[ss * RAWS + lane] = carry[ss];
           }
-          }
-          if (MODE == 1) {
-#pragma unroll
-            for (int ss = 0; ss < SPB; ++ss)
-              if (s0 + row0 + ss < S) cache_q[(int64_t)s_so[row0 + ss] * args.NPIX + i] = a[ss];
-          }
-        } else {
-          // absorption = voigt(sample) .* voigt(partner 1) .* ...   (...meanflux.m:342-351): cached rows, fetched one
-          // chunk ahead (HBM latency: the cache is 100 MB per quasar, and a producer has nothing else to overlap it with)
-#pragma unroll
-          for (int ss = 0; ss < SPB; ++ss) a[ss] = rows_n[0][ss];
-#pragma unroll
-          for (int j = 0; j < 3; ++j)
-            if (j < args.num_partners) {
-#pragma unroll
-              for (int ss = 0; ss < SPB; ++ss) a[ss] = a[ss] * rows_n[1 + j][ss];
-            }
-          if (c + 1 < nchunks) load_rows(i + KC);
         }
         uint64_t xw[SPB], xu[SPB];
 #pragma unroll
@@ -903,7 +873,9 @@ dla_loglik_i8p_kernel(LoglikArgs args, I8Args xa, int num_quasars, int tiles_per
           qacc[ss] = fma(r, t1, qacc[ss]);
           ldm[ss] *= d;
         }
-        mbar_wait_d(&bar_empty[stage], empty_parity, xa.status, 1, phase_ptr(xa));
+        tw0 = GPDLA_I8P_PHASES ? clock64() : 0;
+        mbar_wait_d(&bar_empty[stage], empty_parity, xa.status, 1);
+        if (GPDLA_I8P_PHASES) w_empty += clock64() - tw0;
         uint8_t* dW = wdst0 + stage * wstride + rowoff;
         uint8_t* dU = udst0 + stage * ustride + rowoff;
         if (PROBE & 4) {   // keep the digits alive without storing them
@@ -946,8 +918,172 @@ dla_loglik_i8p_kernel(LoglikArgs args, I8Args xa, int num_quasars, int tiles_per
       }
       __syncwarp();
       if (!Sh::EXT && lane == 0) mbar_arrive(&bar_sq[it & 1]);
-      if (GPDLA_I8P_PHASES && xa.phase && pr == 0 && lane == 0) atomicAdd(&xa.phase[7], 1ull);
+      if (GPDLA_I8P_PHASES && xa.phase && lane == 0) {   // per-warp wait cycles of this tile
+        atomicAdd(&xa.phase[8 + 1], (unsigned long long)w_empty); atomicAdd(&xa.phase[8 + 14], (unsigned long long)w_hand);
+        w_empty = w_hand = 0;
+        if (pr == 0) atomicAdd(&xa.phase[7], 1ull);
+      }
       ++it;
+    }
+  } else if (warp >= NCTRL) {
+    // =========================================================================== PRODUCERS, STAGE A: absorption
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REG_A));
+    const int pr = warp - NCTRL;
+    const int row0 = pr * SPB;
+    double* myraw = rawbuf + row0 * RAWS;
+    double* hb = hbuf + pr * (2 * SPB * KC) + lane;
+    uint64_t* const hfull = bar_hfull + 2 * pr;
+    uint64_t* const hempty = bar_hempty + 2 * pr;
+    uint32_t gh = 0;                                  // hand-over counter across tiles
+    long long w_hand = 0;
+    for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+      const int q = tile_quasar(t);
+      const QuasarMeta meta = args.meta[q];
+      if (!tile_live(q, meta)) continue;
+      const int64_t s0 = (int64_t)(t % tiles_per_quasar) * TM + (int64_t)rank * TS;
+      const int nchunks = meta.nchunks;
+      // per-sample parameters of this warp's four samples (rows private to the warp)
+      __syncwarp();
+      if (lane < SPB) {
+        const int i = row0 + lane;
+        const int64_t s = s0 + i;
+        const bool is_null = s >= S;
+        const int64_t so = sample_at(args, is_null ? S - 1 : s);   // the null-model slot borrows a redshift (a == 1 anyway)
+        const double z = __dadd_rn(meta.min_z_dla, __dmul_rn(meta.max_z_dla - meta.min_z_dla, args.offset_samples[so]));
+        s_nhi[i] = is_null ? -1.0 : args.nhi_samples[so];
+        s_K[i] = rest_table_offset(args.rt, z, meta.lam_ref);
+        s_so[i] = (int)so;
+        for (int j = 0; j < num_lines; ++j) s_mult[j * TS + i] = line_multiplier(j, z);
+        if (MODE == 2) {
+          for (int j = 0; j < args.num_partners; ++j)
+            s_part[j * TS + i] = is_null ? 0 : args.partners[((int64_t)q * 3 + j) * S + so];
+        }
+      }
+      __syncwarp();
+      const double* lam = args.lam_pad + (int64_t)q * (args.NPIX + 8);
+      const double2* pix8 = reinterpret_cast<const double2*>(xa.pix8 + (int64_t)q * args.NPIX * 8);
+      double* const cache_q = (MODE != 0) ? args.acache + (int64_t)q * S * args.NPIX : nullptr;
+
+      // tau / N: from the rest-frame table (one cell per lane serves the warp's four samples), directly where the
+      // cell is near a line centre or the four samples are too far apart in redshift
+      const double* lamh = args.lamh + (int64_t)q * (args.NPIX + 8);
+      double K_mid;
+      const int tab_mode = (MODE != 2) ? group_cell<SPB>(args.rt, s_K + row0, K_mid) : 0;
+      auto eval_raw = [&](double lambda, double lh, double (&e)[SPB], const RestCell* cell = nullptr) {   // voigt.c:282-292, 4 samples at one wavelength
+        double tau[SPB];
+        tau_samples<NL, SPB>(args.rt, tab_mode, K_mid, lambda, lh, s_mult + row0, TS, s_K + row0, num_lines, tau, cell);
+        raw_from_tau<SPB, false>(tau, s_nhi + row0, e);   // polynomial exponential: see exp_nonpos
+      };
+      if (MODE != 2) {   // leading pad pixels p = 0..5
+        double e[SPB];
+        eval_raw(lam[lane < 6 ? lane : 5], lamh[lane < 6 ? lane : 5], e);
+        if (CONV_B) {
+          const uint32_t slot = gh & 1u;
+          mbar_wait_d(&hempty[slot], ((gh >> 1) & 1u) ^ 1u, xa.status, 15);
+#pragma unroll
+          for (int ss = NCA; ss < SPB; ++ss) hb[(slot * SPB + ss) * KC] = e[ss];
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&hfull[slot]);
+          ++gh;
+        }
+        if (lane < 6) {
+#pragma unroll
+          for (int ss = 0; ss < NCA; ++ss) myraw[ss * RAWS + lane] = e[ss];
+        }
+      }
+      double rows_n[4][SPB];   // MODE 2: cached absorption rows (sample, partners) of the next chunk
+      auto load_rows = [&](int ipix) {
+#pragma unroll
+        for (int ss = 0; ss < SPB; ++ss) rows_n[0][ss] = cache_q[(int64_t)s_so[row0 + ss] * args.NPIX + ipix];
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+          if (j < args.num_partners) {
+#pragma unroll
+            for (int ss = 0; ss < SPB; ++ss) rows_n[1 + j][ss] = cache_q[(int64_t)s_part[j * TS + row0 + ss] * args.NPIX + ipix];
+          }
+      };
+      if (MODE == 2) load_rows(lane);
+      // wavelength and grid position are fetched two chunks ahead, the table cell of the next chunk one chunk ahead: the
+      // table (230 KB) lives in L2 -- shared memory leaves the L1 a few KB -- and stage A is the longer stage
+      const double2* prec = pix8 + (int64_t)lane * 4;
+      double2 plln = prec[0];
+      double2 plln2 = prec[nchunks > 1 ? KC * 4 : 0];
+      RestCell cell_n;
+      const bool use_cell = GPDLA_I8P_PF && MODE != 2 && tab_mode == 1;
+      if (use_cell) rest_table_fetch(args.rt, plln.y, K_mid, cell_n);
+      for (int c = 0; c < nchunks; ++c) {
+        const int i = c * KC + lane;
+        const double lambda = plln.x, lh = plln.y;
+        const RestCell cell = cell_n;
+        plln = plln2;
+        if (c + 2 < nchunks) {
+          prec += KC * 4;
+          plln2 = prec[KC * 4];
+        }
+        if (use_cell && c + 1 < nchunks) rest_table_fetch(args.rt, plln.y, K_mid, cell_n);
+        double a[SPB];
+        if (MODE != 2) {
+          double e[SPB];
+          eval_raw(lambda, lh, e, use_cell ? &cell : nullptr);
+          if (PROBE & 64) {   // no instrument convolution: no raw-row traffic through shared memory
+#pragma unroll
+            for (int ss = 0; ss < SPB; ++ss) a[ss] = (__double2hiint(s_nhi[row0 + ss]) < 0) ? 1.0 : e[ss];
+          } else {
+            // stage B convolves the samples ss >= NCA: their raw profile goes over, the rows of the null model (N marked
+            // negative) as -1
+#pragma unroll
+            for (int ss = NCA; ss < SPB; ++ss) a[ss] = (__double2hiint(s_nhi[row0 + ss]) < 0) ? -1.0 : e[ss];
+            if (NCA > 0) {
+#pragma unroll
+              for (int ss = 0; ss < NCA; ++ss) myraw[ss * RAWS + 6 + lane] = e[ss];
+              __syncwarp();
+              double carry[SPB];
+#pragma unroll
+              for (int ss = 0; ss < NCA; ++ss) {
+                const double* rb = myraw + ss * RAWS;
+                double acc_a = 0.0;
+#pragma unroll
+                for (int tt = 0; tt < 7; ++tt) acc_a = fma(rb[lane + tt], c_lines.ip[tt], acc_a);   // voigt.c:297-299
+                carry[ss] = rb[KC + (lane < 6 ? lane : 0)];
+                a[ss] = (__double2hiint(s_nhi[row0 + ss]) < 0) ? 1.0 : acc_a;   // null model (N marked negative)
+              }
+              __syncwarp();
+              if (lane < 6) {
+#pragma unroll
+                for (int ss = 0; ss < NCA; ++ss) myraw[ss * RAWS + lane] = carry[ss];
+              }
+            }
+          }
+          if (MODE == 1) {
+#pragma unroll
+            for (int ss = 0; ss < SPB; ++ss)
+              if (s0 + row0 + ss < S) cache_q[(int64_t)s_so[row0 + ss] * args.NPIX + i] = a[ss];
+          }
+        } else {
+          // absorption = voigt(sample) .* voigt(partner 1) .* ...   (...meanflux.m:342-351): cached rows, fetched one
+          // chunk ahead (HBM latency: the cache is 100 MB per quasar, and a producer has nothing else to overlap it with)
+#pragma unroll
+          for (int ss = 0; ss < SPB; ++ss) a[ss] = rows_n[0][ss];
+#pragma unroll
+          for (int j = 0; j < 3; ++j)
+            if (j < args.num_partners) {
+#pragma unroll
+              for (int ss = 0; ss < SPB; ++ss) a[ss] = a[ss] * rows_n[1 + j][ss];
+            }
+          if (c + 1 < nchunks) load_rows(i + KC);
+        }
+        // hand the chunk's absorption to the pair's stage-B warp
+        const uint32_t slot = gh & 1u;
+        const long long tw0 = GPDLA_I8P_PHASES ? clock64() : 0;
+        mbar_wait_d(&hempty[slot], ((gh >> 1) & 1u) ^ 1u, xa.status, 15);
+        if (GPDLA_I8P_PHASES) w_hand += clock64() - tw0;
+#pragma unroll
+        for (int ss = 0; ss < SPB; ++ss) hb[(slot * SPB + ss) * KC] = a[ss];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&hfull[slot]);
+        ++gh;
+      }
+      if (GPDLA_I8P_PHASES && xa.phase && lane == 0) { atomicAdd(&xa.phase[8 + 15], (unsigned long long)w_hand); w_hand = 0; }
     }
   } else {
     // =========================================================================== CONTROL WARPGROUP
@@ -962,6 +1098,7 @@ dla_loglik_i8p_kernel(LoglikArgs args, I8Args xa, int num_quasars, int tiles_per
         const int q = tile_quasar(t);
         const QuasarMeta meta = args.meta[q];
         if (!tile_live(q, meta)) continue;
+        const long long tile_t0 = GPDLA_I8P_PHASES ? clock64() : 0;
         if (it > 0) mbar_wait_d(bar_tfree, (it - 1) & 1, xa.status, 13, phase_ptr(xa), 100);   // accumulators of the previous tile read out
         for (int c = 0; c < meta.nchunks; ++c, ++gc) {
           const int stage = gc % STAGES, buf = gc & 1;
@@ -977,6 +1114,7 @@ dla_loglik_i8p_kernel(LoglikArgs args, I8Args xa, int num_quasars, int tiles_per
           mma_commit(&bar_pempty[buf]);
         }
         mma_commit(bar_acc);
+        if (GPDLA_I8P_PHASES && xa.phase) atomicAdd(&xa.phase[6], (unsigned long long)(clock64() - tile_t0));
         ++it;
       }
     } else if (warp == 1 && lane == 0) {

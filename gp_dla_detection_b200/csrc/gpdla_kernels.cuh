@@ -668,14 +668,16 @@ __device__ __noinline__ TauRow<SPB> tau_own_cells(const RestTable& rt, double lh
 // per sample, 0 = no table.  Where a cell is near a line centre the whole warp evaluates directly.  The coefficient
 // loads hit L1 when the warps of a CTA work on neighbouring redshifts (a line holds 16 cells and is used by every warp
 // for one or two chunks); all 32 lanes must call this together.
+// `cell`: the group's cell when the caller fetched it ahead of time (tab_mode 1 only), else nullptr
 template <int NL, int SPB>
 __device__ __forceinline__ void tau_samples(const RestTable& rt, int tab_mode, double K_mid, double lambda, double lh,
                                             const double* mymult, int mstride, const double* myK, int num_lines,
-                                            double (&tau)[SPB]) {
+                                            double (&tau)[SPB], const RestCell* cell = nullptr) {
   bool direct = tab_mode == 0;
   if (tab_mode == 1) {
     RestCell rc;
-    rest_table_fetch(rt, lh, K_mid, rc);
+    if (cell) rc = *cell;
+    else rest_table_fetch(rt, lh, K_mid, rc);
     direct = tau_from_cell<SPB>(rc, myK, tau);
   } else if (tab_mode == 2) {
     const TauRow<SPB> r = tau_own_cells<SPB>(rt, lh, myK);

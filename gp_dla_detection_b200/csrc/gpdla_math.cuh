@@ -254,6 +254,9 @@ __device__ __forceinline__ void rest_table_fetch(const RestTable& rt, double lh,
   int ci = __double2loint(um);                  // round-to-nearest-even integer of lh - K_mid
   rc.base = lh - (um - RT_MAGIC);               // exact
   ci = min(max(ci, 0), rt.ncell - 1);
+#ifdef GPDLA_PROBE_RT_FIXED
+  ci = 100 + (threadIdx.x & 31);   // timing probe: always the same (L1-resident) cells; results are wrong
+#endif
   static_assert(RT_DEG_DEV == 8 && RT_CELL_STRIDE == 10, "four 128-bit loads and one 64-bit load per cell");
   const double2* cp = reinterpret_cast<const double2*>(rt.coef + (size_t)ci * RT_CELL_STRIDE);
 #pragma unroll
