@@ -848,7 +848,8 @@ dla_loglik_i8p_kernel(LoglikArgs args, I8Args xa, int num_quasars, int tiles_per
             const double* rb = myraw + ss * RAWS;
             double acc_a = 0.0;
 #pragma unroll
-            for (int tt = 0; tt < 7; ++tt) acc_a = fma(rb[lane + tt], c_lines.ip[tt], acc_a);
+            for (int tt = 0; tt < 6; ++tt) acc_a = fma(rb[lane + tt], c_lines.ip[tt], acc_a);
+            acc_a = fma(a[ss], c_lines.ip[6], acc_a);   // the lane's own pixel is still in its register
             carry[ss] = rb[KC + (lane < 6 ? lane : 0)];
             a[ss] = (__double2hiint(a[ss]) < 0) ? 1.0 : acc_a;
           }
@@ -1043,7 +1044,8 @@ dla_loglik_i8p_kernel(LoglikArgs args, I8Args xa, int num_quasars, int tiles_per
                 const double* rb = myraw + ss * RAWS;
                 double acc_a = 0.0;
 #pragma unroll
-                for (int tt = 0; tt < 7; ++tt) acc_a = fma(rb[lane + tt], c_lines.ip[tt], acc_a);   // voigt.c:297-299
+                for (int tt = 0; tt < 6; ++tt) acc_a = fma(rb[lane + tt], c_lines.ip[tt], acc_a);   // voigt.c:297-299
+                acc_a = fma(e[ss], c_lines.ip[6], acc_a);   // the lane's own pixel is still in its register
                 carry[ss] = rb[KC + (lane < 6 ? lane : 0)];
                 a[ss] = (__double2hiint(s_nhi[row0 + ss]) < 0) ? 1.0 : acc_a;   // null model (N marked negative)
               }

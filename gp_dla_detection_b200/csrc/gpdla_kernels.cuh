@@ -887,7 +887,8 @@ __device__ __forceinline__ void ws_tile(const LoglikArgs& args, const int q) {
             const double* rb = myraw + ss * RAWS;
             double acc_a = 0.0;
 #pragma unroll
-            for (int t = 0; t < 7; ++t) acc_a = fma(rb[lane + t], c_lines.ip[t], acc_a);
+            for (int t = 0; t < 6; ++t) acc_a = fma(rb[lane + t], c_lines.ip[t], acc_a);
+            acc_a = fma(e[ss], c_lines.ip[6], acc_a);   // the lane's own pixel is still in its register
             carry[ss] = rb[KC + (lane < 6 ? lane : 0)];
             a[ss] = (__double2hiint(s_nhi[row0 + ss]) < 0) ? 1.0 : acc_a;   // null model (N marked negative)
           }
