@@ -40,7 +40,7 @@ def fp64_peak():
 def ncu_traffic(i8):
     """DRAM bytes of one fused log-likelihood launch (296-quasar batch) from the committed ncu --set full capture."""
     try:
-        d = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_loglik_i8_full.json" if i8 else "r02_ncu_loglik_ws_full.json")))
+        d = json.load(open(os.path.join(ROOT, "profiles", "r02f_ncu_loglik_i8_full.json" if i8 else "r02_ncu_loglik_ws_full.json")))
         return d["dram_bytes_per_launch"], d["Grid Size"]["value"]
     except Exception:
         return None, None
@@ -352,8 +352,8 @@ def main():
             roof.update({
                 "kernel": "dla_loglik_i8p_kernel (fused optical depth from a rest-frame table + instrument convolution + "
                           "exact-product INT8 tcgen05 Gram, %d signed 8-bit digits per factor, s32 TMEM accumulators + "
-                          "Cholesky; persistent 4-CTA clusters, DSMEM row-block exchange, epilogue warpgroup, merged "
-                          "slice-pair MMAs, MN-major digit tiles)" % digits,
+                          "Cholesky; persistent 4-CTA clusters, two-stage producer warp pairs, DSMEM row-block exchange, "
+                          "epilogue warpgroup, merged slice-pair MMAs, MN-major digit tiles)" % digits,
                 "note": "achieved/peak = FP64-equivalent Gram rate (S n k(k+3) per quasar, SURVEY 8(d)) over the "
                         "builder-measured FP64 DMMA peak (MEASURED_PEAKS.json has no FP64 entry; nominal 40 beside it); "
                         "the contraction itself runs as exact INT8 slice products on the tcgen05 tensor pipe, see "
