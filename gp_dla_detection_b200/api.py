@@ -70,7 +70,7 @@ class DLAProcessor:
     def __init__(self, model: Dict, samples: Dict, prior: Dict, params: Parameters = DEFAULT, device: int = 0,
                  batch_quasars: int = 0, gram_digits: int = 0, rest_table: int = 0):
         """``gram_digits``: arithmetic of the Gram contraction -- 0 default (exact-product INT8 tensor-core path
-        with 6 digits for k = 20, FP64 DMMA otherwise), -1 FP64 DMMA, 5 / 6 INT8 path with that many digits.
+        with 6 digits for k = 20 and 40, FP64 DMMA for k = 10), -1 FP64 DMMA, 5 / 6 INT8 path with that many digits (k = 40: 6).
         ``rest_table``: 0 default (optical depth from the rest-frame table away from the line centres), -1 direct
         evaluation of the line sum everywhere (``gpdla_params.rest_table``)."""
         self._lib = _lib.load()

@@ -532,6 +532,13 @@ static int launch_loglik_i8(gpdla_ctx* c, LoglikArgs la, int nq, cudaStream_t st
     std::lock_guard<std::mutex> lock(g_dev[dev].mu);
     int& n = g_dev[dev].clusters[(const void*)kern];
     if (n == 0) {
+      // setmaxnreg.inc can only draw on registers the CTA owned at launch (bench_micro/setmaxnreg_pool.cu): a build whose
+      // launch allocation is smaller than the warpgroups' budgets would block forever -- refuse it instead
+      cudaFuncAttributes fa;
+      if (cudaFuncGetAttributes(&fa, kern) == cudaSuccess && fa.numRegs * i8::P_THREADS < i8::REG_BUDGET_TOTAL) {
+        c->err = "dla_loglik_i8p_kernel: launch register allocation below the setmaxnreg budgets (rebuild with matching REG_*)";
+        return GPDLA_ERR_CUDA;
+      }
       n = max_resident_clusters(kern, smem, i8::P_THREADS);
       const char* e = getenv("GPDLA_I8_CLUSTERS");   // tuning aid: grid size only, same arithmetic
       if (e) n = atoi(e);

@@ -12,14 +12,19 @@
 // Gram to 4e-15 of its scale (log-likelihoods to 8e-14), L = 5 to 9e-13 (1.4e-11).
 //
 // Schedule: a cluster of 4 CTAs owns 128 samples (MMA M) of one quasar.  Every CTA *produces* the W'' and U''
-// digits of 32 samples per 32-pixel chunk (8 producer warps: Voigt profile, instrument convolution, weights,
-// digits -- the FP64 work that remains) and ships its 32-row block to the peers that contract it with one bulk
-// shared-memory-to-shared-memory copy each (DSMEM, completion on the receiver's mbarrier).  CTAs 0..2
+// digits of 32 samples per 32-pixel chunk (8 pairs of producer warps -- stage A: optical depth from the rest-frame
+// table, exponential, instrument convolution; stage B: weights, digits -- the FP64 work that remains) and ships its
+// 32-row block to the peers that contract it with one bulk shared-memory-to-shared-memory copy each (DSMEM,
+// completion on the receiver's mbarrier).  CTAs 0..2
 // contract W'' with a third of the Gram columns each (N = 80), CTA 3 contracts U'' with M'' (N = 32): TMEM
 // holds L diagonals x N columns per CTA.  The P''/M'' digit chunk arrives by 1-D TMA.  One tcgen05.mma spans up
 // to three consecutive digit planes / diagonals (issue_chunk_mmas_fixed: 9 instructions for the 21 slice pairs).  After
 // the last chunk the accumulators are recombined, sent to the CTA that produced the sample (DSMEM stores) and
 // factorised there (factor_staged, the same Cholesky as the FP64 kernels).
+//
+// Ranks whose pair columns exceed one cluster's TMEM (k = 40, Shape::EXT) also store their W'' digit tiles;
+// gram_contract_i8_kernel contracts those with the remaining column blocks (no producers), and the accumulators of both
+// kernels leave through global staging rows to cholesky_kernel (gpdla_kernels.cuh).
 //
 // dla_loglik_i8p_kernel keeps the clusters resident and overlaps the epilogue of a tile with the main loop of the
 // next one (own warpgroup, setmaxnreg).  Measurements, failed variants and the interference probes: DESIGN.md 4.3;
@@ -388,16 +393,21 @@ __global__ void __launch_bounds__(NTHREADS) i8_build_operand_kernel(const Quasar
 
 // ------------------------------------------------------------------------------------------
 // Persistent variant (shipped).  The grid holds as many 4-CTA clusters as the GPU can keep resident; each cluster
-// walks the (quasar, 128-sample tile) list with stride = number of clusters.  A CTA has 16 warps in four
-// warpgroups with their own register budgets (setmaxnreg): control (MMA issuer, B loader, row-block sender; 48
-// registers), two producer warpgroups (168) and an EPILOGUE warpgroup (128) that recombines the TMEM accumulators
-// and runs the Cholesky of tile t while the producers and the tensor pipe are already working on tile t + 1.
+// walks the (quasar, 128-sample tile) list with stride = number of clusters.  A CTA has 24 warps in six
+// warpgroups with their own register budgets (setmaxnreg): control (MMA issuer, B loader, row-block sender; 40
+// registers), two producer warpgroups of stage A (96: optical depth, exponential, convolution), two of stage B (80:
+// weights, digit planes) and an EPILOGUE warpgroup (88) that recombines the TMEM accumulators and runs the Cholesky
+// of tile t while the producers and the tensor pipe are already working on tile t + 1.
 // Hand-overs: accumulators final (tcgen05.commit -> bar_acc), TMEM drained (bar_tfree), staging triangle delivered
 // (remote arrivals on the owner's bar_csfull) and free again (remote arrivals on every writer's bar_csfree[owner]),
 // per-sample scalars (bar_sq, double-buffered).  All main-loop barriers run on a chunk counter that spans tiles.
 constexpr int P_THREADS = 32 * (NCTRL + 2 * NPROD + 4);
 constexpr int REG_CTRL = 40, REG_A = 96, REG_B = 80, REG_EPI = 88;
-static_assert(REG_CTRL * 128 + (REG_A + REG_B) * 256 + REG_EPI * 128 <= 80 * P_THREADS, "register budgets exceed the register file");
+constexpr int REG_BUDGET_TOTAL = REG_CTRL * 128 + (REG_A + REG_B) * 256 + REG_EPI * 128;
+// 80 = the launch allocation ptxas gives a 768-thread CTA (65536 / 768 rounded down to a multiple of 8): setmaxnreg.inc can
+// only draw on what the CTA owned at launch, not on the SM's spare registers (bench_micro/setmaxnreg_pool.cu; the host
+// checks cudaFuncAttributes::numRegs against REG_BUDGET_TOTAL before the first launch)
+static_assert(REG_BUDGET_TOTAL <= 80 * P_THREADS, "register budgets exceed the CTA's launch allocation");
 
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t remote_bar) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote_bar) : "memory");

@@ -56,10 +56,11 @@ typedef struct {
   int32_t batch_quasars;        /* quasars processed per launch group (workspace size); 0 = default */
   int32_t gram_digits;          /* arithmetic of the Gram/projection contraction (log_mvnpdf_low_rank.m:22-28):
                                  *  0 = default: exact-product INT8 tensor-core path with 6 signed 8-bit digits per
-                                 *      factor (47 fractional bits; k = 20 only -- other ranks use FP64 DMMA; a quasar
+                                 *      factor (47 fractional bits; k = 20 and k = 40 -- k = 10 uses FP64 DMMA; a quasar
                                  *      with a used pixel of zero noise variance falls back to FP64 DMMA by itself)
                                  * -1 = FP64 DMMA tensor cores
-                                 *  5, 6 = INT8 path with that many digits (5: 39 fractional bits, ~1e-11 relative) */
+                                 *  5, 6 = INT8 path with that many digits (5: 39 fractional bits, ~1e-11 relative;
+                                 *      k = 40 always uses 6) */
   int32_t rest_table;           /* evaluation of the optical depth tau(lambda_obs / (1 + z_dla)) of voigt.c:282-290 inside
                                  * the fused kernels:  0 = default: per-cell polynomials of a rest-frame table wherever the
                                  *      pixel is >= 13 pixels from every line centre (5e-13 relative), direct evaluation
