@@ -57,6 +57,9 @@ constexpr int TMEM_COLS = 512;
 constexpr int PROBE = GPDLA_I8P_PROBE;
 // Barrier-wait accounting (-DGPDLA_I8P_PHASES=1 and GPDLA_I8_PHASES=1 in the environment): compiled out of the product
 // build -- the null-pointer test and the clock reads around every wait cost the producers issue slots.
+#ifndef GPDLA_I8P_SHFL_CONV
+#define GPDLA_I8P_SHFL_CONV 0   // 1: instrument convolution through warp shuffles instead of shared-memory rows (measured 7 % SLOWER: 58.3 against 54.3 ms)
+#endif
 #ifndef GPDLA_I8P_PF
 #define GPDLA_I8P_PF 0      // 1: stage A fetches the table cell of the next chunk a chunk ahead (measured 6 % SLOWER: 58.2 against 54.7 ms)
 #endif
@@ -693,6 +696,7 @@ dla_loglik_i8p_kernel(LoglikArgs args, I8Args xa, int num_quasars, int tiles_per
   // (NCA of a pair's 4 samples are convolved by stage A, the others by stage B: the split that balances the two stages)
   constexpr int NCA = (MODE == 0) ? GPDLA_I8P_NCA : SPB;
   constexpr bool CONV_B = NCA < SPB;
+  constexpr bool SHFL_CONV = GPDLA_I8P_SHFL_CONV && !CONV_B && MODE != 2;
   const int slot = Sh::slot_of_rank((int)rank);
   const uint32_t b_bytes = (uint32_t)Sh::b_bytes(slot);
   // a tile is skipped by every role alike when its quasar has no usable pixel or is inactive
@@ -985,6 +989,7 @@ dla_loglik_i8p_kernel(LoglikArgs args, I8Args xa, int num_quasars, int tiles_per
         tau_samples<NL, SPB>(args.rt, tab_mode, K_mid, lambda, lh, s_mult + row0, TS, s_K + row0, num_lines, tau, cell);
         raw_from_tau<SPB, false>(tau, s_nhi + row0, e);   // polynomial exponential: see exp_nonpos
       };
+      double eprev[SPB];       // SHFL_CONV: raw profile of the previous chunk (this lane's pixel)
       if (MODE != 2) {   // leading pad pixels p = 0..5
         double e[SPB];
         eval_raw(lam[lane < 6 ? lane : 5], lamh[lane < 6 ? lane : 5], e);
@@ -997,7 +1002,10 @@ dla_loglik_i8p_kernel(LoglikArgs args, I8Args xa, int num_quasars, int tiles_per
           if (lane == 0) mbar_arrive(&hfull[slot]);
           ++gh;
         }
-        if (lane < 6) {
+        if (SHFL_CONV) {   // the six pad pixels sit in front of pixel 0: lanes 26..31 of the "previous chunk"
+#pragma unroll
+          for (int ss = 0; ss < SPB; ++ss) eprev[ss] = __shfl_sync(0xffffffffu, e[ss], (lane + 6) & 31);
+        } else if (lane < 6) {
 #pragma unroll
           for (int ss = 0; ss < NCA; ++ss) myraw[ss * RAWS + lane] = e[ss];
         }
@@ -1044,7 +1052,24 @@ dla_loglik_i8p_kernel(LoglikArgs args, I8Args xa, int num_quasars, int tiles_per
             // negative) as -1
 #pragma unroll
             for (int ss = NCA; ss < SPB; ++ss) a[ss] = (__double2hiint(s_nhi[row0 + ss]) < 0) ? -1.0 : e[ss];
-            if (NCA > 0) {
+            if (SHFL_CONV) {
+              // instrument convolution through warp shuffles (voigt.c:297-299, same summation order): pixel i needs the
+              // raw profile of pixels i - 6 .. i; what lies before lane 0 is the previous chunk's lanes 26..31.  No
+              // shared-memory round trip: the convolution's loads were 40 % of a chunk's shared-memory wavefronts
+#pragma unroll
+              for (int ss = 0; ss < SPB; ++ss) {
+                double acc_a = 0.0;
+#pragma unroll
+                for (int tt = 0; tt < 6; ++tt) {
+                  const int d = 6 - tt;
+                  const double x = (lane >= 32 - d) ? eprev[ss] : e[ss];
+                  acc_a = fma(__shfl_sync(0xffffffffu, x, (lane - d) & 31), c_lines.ip[tt], acc_a);
+                }
+                acc_a = fma(e[ss], c_lines.ip[6], acc_a);
+                eprev[ss] = e[ss];
+                a[ss] = (__double2hiint(s_nhi[row0 + ss]) < 0) ? 1.0 : acc_a;   // null model (N marked negative)
+              }
+            } else if (NCA > 0) {
 #pragma unroll
               for (int ss = 0; ss < NCA; ++ss) myraw[ss * RAWS + 6 + lane] = e[ss];
               __syncwarp();
