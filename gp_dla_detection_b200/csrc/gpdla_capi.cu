@@ -358,9 +358,9 @@ static int ensure_rest_table(gpdla_ctx* c) {
   const RestTableHost t = build_rest_table(c->params.num_lines, c->params.pixel_spacing, RT_NEAR_PIXELS, lc.tw, lc.lc,
                                            lc.gam, kSigma, kC);
   // device layout: the coefficients of a cell side by side (RestTable)
-  std::vector<double> cells((size_t)t.ncell * RT_CELL_STRIDE, 0.0);
+  std::vector<double> cells((size_t)RT_PLANES * t.ncell * 2, 0.0);   // [plane][cell] pairs
   for (int p = 0; p <= RT_DEG_DEV; ++p)
-    for (int ci = 0; ci < t.ncell; ++ci) cells[(size_t)ci * RT_CELL_STRIDE + p] = t.coef[(size_t)p * t.ncell + ci];
+    for (int ci = 0; ci < t.ncell; ++ci) cells[((size_t)(p / 2) * t.ncell + ci) * 2 + (p & 1)] = t.coef[(size_t)p * t.ncell + ci];
   int rc = dev_upload(&c->d_rt, cells.data(), cells.size(), c->err);
   if (rc) return rc;
   c->rt_ncell = t.ncell; c->rt_h = t.h; c->rt_num_lines = c->params.num_lines; c->rt_pixel_spacing = c->params.pixel_spacing;

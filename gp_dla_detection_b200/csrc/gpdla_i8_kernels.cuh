@@ -140,8 +140,8 @@ __constant__ short c_i8_stage[CLUSTER * 128];
 
 struct I8Args {
   double* pix2;            // [Q x NPIX x 2]  (cw, cu)
-  double* pix8;            // [Q x NPIX x 8]  the producers' per-pixel record (lambda, lh, y, v, mu, omega2, cw, cu): one
-                           // address and four 128-bit loads per lane and chunk
+  double* pix8;            // [Q x 4 x NPIX] double2: the producers' per-pixel data as four planes (lambda, lh), (y, v),
+                           // (mu, omega2), (cw, cu) -- a warp's 128-bit load of a plane is one contiguous 512-byte run
   uint8_t* bop;            // [Q x NPIX/KC x CHUNK_BYTES]  digit planes of P'' (ranks 0..2) and M'' (rank 3)
   double* colscale;        // [Q x 4 x NMAX]  2^(e_c - 2F + 8(L-1)): accumulator -> Gram entry
   double* colinv;          // [Q x 4 x NMAX]  2^-e_c
@@ -281,8 +281,8 @@ __global__ void __launch_bounds__(NTHREADS) i8_scales_kernel(const QuasarMeta* _
     unbounded |= !(v > 0.0) || !isfinite(b) || !isfinite(cw);
     const double cu = (yy > 0.0 && isfinite(b)) ? CAP / (b * yy) : 0.0;
     p2[i * 2 + 0] = cw; p2[i * 2 + 1] = cu;
-    p8[i * 4 + 0] = make_double2(lq[i], lhq[i]); p8[i * 4 + 1] = make_double2(y, v);
-    p8[i * 4 + 2] = make_double2(mu, om2); p8[i * 4 + 3] = make_double2(cw, cu);
+    p8[i] = make_double2(lq[i], lhq[i]); p8[NPIX + i] = make_double2(y, v);
+    p8[2 * NPIX + i] = make_double2(mu, om2); p8[3 * NPIX + i] = make_double2(cw, cu);
   }
   if (__syncthreads_or(unbounded) && tid == 0 && meta[q].nchunks > 0) {
     xa.f64flag[q] = 1;
@@ -815,13 +815,14 @@ dla_loglik_i8p_kernel(LoglikArgs args, I8Args xa, int num_quasars, int tiles_per
       if (!tile_live(q, meta)) continue;
       const int64_t s0 = (int64_t)(t % tiles_per_quasar) * TM + (int64_t)rank * TS;
       const int nchunks = meta.nchunks;
-      const double2* prec = reinterpret_cast<const double2*>(xa.pix8 + (int64_t)q * args.NPIX * 8) + (int64_t)lane * 4;
+      const double2* prec = reinterpret_cast<const double2*>(xa.pix8 + (int64_t)q * args.NPIX * 8) + lane;
+      const int64_t PL = args.NPIX;   // plane stride
       double qacc[SPB], ldm[SPB];
       int lde[SPB];
 #pragma unroll
       for (int ss = 0; ss < SPB; ++ss) { qacc[ss] = 0.0; ldm[ss] = 1.0; lde[ss] = 0; }
       // pixel data of the next chunk is fetched one chunk ahead (global/L2 latency off the critical path)
-      double2 p01n = prec[1], p23n = prec[2], p45n = prec[3];
+      double2 p01n = prec[PL], p23n = prec[2 * PL], p45n = prec[3 * PL];
       if (CONV_B) {   // the six pad pixels in front of the window: a hand-over of their own (lanes 0..5)
         const uint32_t slot = gh & 1u;
         mbar_wait_d(&hfull[slot], (gh >> 1) & 1u, xa.status, 14);
@@ -836,8 +837,8 @@ dla_loglik_i8p_kernel(LoglikArgs args, I8Args xa, int num_quasars, int tiles_per
       for (int c = 0; c < nchunks; ++c) {
         const double y = p01n.x, v = p01n.y, mu = p23n.x, om2 = p23n.y, cw = p45n.x, cu = p45n.y;
         if (c + 1 < nchunks) {
-          prec += KC * 4;
-          p01n = prec[1]; p23n = prec[2]; p45n = prec[3];
+          prec += KC;
+          p01n = prec[PL]; p23n = prec[2 * PL]; p45n = prec[3 * PL];
         }
         // absorption of this chunk from the pair's stage-A warp
         const uint32_t slot = gh & 1u;
@@ -1024,9 +1025,9 @@ dla_loglik_i8p_kernel(LoglikArgs args, I8Args xa, int num_quasars, int tiles_per
       if (MODE == 2) load_rows(lane);
       // wavelength and grid position are fetched two chunks ahead, the table cell of the next chunk one chunk ahead: the
       // table (230 KB) lives in L2 -- shared memory leaves the L1 a few KB -- and stage A is the longer stage
-      const double2* prec = pix8 + (int64_t)lane * 4;
+      const double2* prec = pix8 + lane;
       double2 plln = prec[0];
-      double2 plln2 = prec[nchunks > 1 ? KC * 4 : 0];
+      double2 plln2 = prec[nchunks > 1 ? KC : 0];
       RestCell cell_n;
       const bool use_cell = GPDLA_I8P_PF && MODE != 2 && tab_mode == 1;
       if (use_cell) rest_table_fetch(args.rt, plln.y, K_mid, cell_n);
@@ -1036,8 +1037,8 @@ dla_loglik_i8p_kernel(LoglikArgs args, I8Args xa, int num_quasars, int tiles_per
         const RestCell cell = cell_n;
         plln = plln2;
         if (c + 2 < nchunks) {
-          prec += KC * 4;
-          plln2 = prec[KC * 4];
+          prec += KC;
+          plln2 = prec[KC];
         }
         if (use_cell && c + 1 < nchunks) rest_table_fetch(args.rt, plln.y, K_mid, cell_n);
         double a[SPB];

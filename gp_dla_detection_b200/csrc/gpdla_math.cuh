@@ -227,11 +227,15 @@ __device__ __noinline__ double tau_sum_3_exact(double lambda, double m0, double 
 // a chunk ahead, and each sample evaluates the polynomial at its own s.  NaN coefficients mark the cells near a line
 // centre (and the two end cells, which catch clamped indices): the warp then evaluates directly.
 constexpr int RT_DEG_DEV = 8;
-constexpr int RT_CELL_STRIDE = 10;      // doubles per cell on the device: the 9 coefficients of a cell side by side, 16-byte
-                                        // aligned -- one address per lane and 128-bit loads with immediate offsets
+// Device layout of the table: five planes of coefficient PAIRS, [5][ncell] double2 = (c0,c1), (c2,c3), (c4,c5), (c6,c7),
+// (c8,-).  A warp's lanes read neighbouring cells, so a 128-bit load of one plane is one contiguous 512-byte run: 4
+// LSU wavefronts.  (Round 2 first kept the 9 coefficients of a cell side by side -- one address, immediate offsets, but
+// an 80-byte stride between lanes: 20 wavefronts per load, 100 per cell fetch against 18 now; the kernel is bound by
+// LSU wavefronts, shared and global together: profiles/r02f_ncu_loglik_i8_full.json.)
+constexpr int RT_PLANES = 5;
 constexpr double RT_MAX_SPREAD = 1.0;   // = 2 (RT_HALF_WIDTH - 1/2): largest K_max - K_min one cell can serve
 struct RestTable {
-  const double* coef;   // [ncell][RT_CELL_STRIDE]; nullptr = table disabled
+  const double* coef;   // [RT_PLANES][ncell] double2; nullptr = table disabled
   int ncell;
   double inv_h;         // 1 / (pixel spacing in ln units)
   double lam_lo;        // rest wavelength of cell 0 (Angstrom)
@@ -257,14 +261,14 @@ __device__ __forceinline__ void rest_table_fetch(const RestTable& rt, double lh,
 #ifdef GPDLA_PROBE_RT_FIXED
   ci = 100 + (threadIdx.x & 31);   // timing probe: always the same (L1-resident) cells; results are wrong
 #endif
-  static_assert(RT_DEG_DEV == 8 && RT_CELL_STRIDE == 10, "four 128-bit loads and one 64-bit load per cell");
-  const double2* cp = reinterpret_cast<const double2*>(rt.coef + (size_t)ci * RT_CELL_STRIDE);
+  static_assert(RT_DEG_DEV == 8 && RT_PLANES == 5, "four 128-bit loads and one 64-bit load per cell");
+  const double2* cp = reinterpret_cast<const double2*>(rt.coef) + ci;
 #pragma unroll
   for (int p = 0; p < 4; ++p) {
-    const double2 c2 = __ldg(cp + p);
+    const double2 c2 = __ldg(cp + (size_t)p * rt.ncell);
     rc.cf[2 * p] = c2.x; rc.cf[2 * p + 1] = c2.y;
   }
-  rc.cf[8] = __ldg(reinterpret_cast<const double*>(cp + 4));
+  rc.cf[8] = __ldg(reinterpret_cast<const double*>(cp + (size_t)4 * rt.ncell));
 }
 // tau / N of one sample in the fetched cell; NaN (hi word >= 0x7ff00000) where the caller must evaluate directly
 __device__ __forceinline__ double rest_table_eval(const RestCell& rc, double K) {
