@@ -40,7 +40,7 @@ def fp64_peak():
 def ncu_traffic(i8):
     """DRAM bytes of one fused log-likelihood launch (296-quasar batch) from the committed ncu --set full capture."""
     try:
-        d = json.load(open(os.path.join(ROOT, "profiles", "r02f_ncu_loglik_i8_full.json" if i8 else "r02_ncu_loglik_ws_full.json")))
+        d = json.load(open(os.path.join(ROOT, "profiles", "r02h_ncu_loglik_i8_full.json" if i8 else "r02_ncu_loglik_ws_full.json")))
         return d["dram_bytes_per_launch"], d["Grid Size"]["value"]
     except Exception:
         return None, None
