@@ -135,6 +135,29 @@ static void fill_i8_stage_index(short* tab) {
   }
 }
 
+// Compile-time proof that the column blocks of the INT8 path tile the Gram exactly: every pair column and every projection
+// column of GramShape<K> is the image of exactly one (block, n), and the blocks beyond the producing cluster's three come in
+// whole cluster passes of the contract-only kernel.
+template <int K>
+constexpr bool i8_blocks_tile_the_gram() {
+  using Sh = i8::Shape<K, 6>;
+  using G = GramShape<K>;
+  int hits[G::NCOL] = {};
+  for (int slot = 0; slot < Sh::NSLOT; ++slot)
+    for (int n = 0; n < Sh::NMAX; ++n) {
+      const int c = Sh::gram_column(slot, n);
+      if (c >= G::NCOL) return false;
+      if (c >= 0) hits[c]++;
+    }
+  for (int c = 0; c < G::NCOL; ++c) {
+    const bool wanted = c < G::NPAIR || (c >= G::WT * 8 && c < G::WT * 8 + K);
+    if (hits[c] != (wanted ? 1 : 0)) return false;
+  }
+  return (Sh::WBLOCKS - i8::WCTAS) % i8::CLUSTER == 0 && Sh::CPASSES * i8::CLUSTER + i8::WCTAS == Sh::WBLOCKS;
+}
+static_assert(i8_blocks_tile_the_gram<20>() && i8_blocks_tile_the_gram<40>(), "INT8 column blocks must tile the Gram columns");
+static_assert(!i8::Shape<20, 6>::EXT && i8::Shape<40, 6>::EXT && i8::Shape<40, 6>::WBLOCKS == 11 && i8::Shape<40, 6>::CPASSES == 2, "column-block plan");
+
 constexpr int I8_K = 20;   // rank whose INT8 tensor-core Gram fits one cluster's TMEM (shared-memory Cholesky epilogue)
 constexpr int I8_K_EXT = 40;   // rank whose Gram columns take contract-only passes as well (i8::Shape::EXT)
 // (rank, digits) combinations of the INT8 path compiled into the library
